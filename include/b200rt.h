@@ -1,0 +1,191 @@
+/* b200rt.h — C ABI of the B200-native frame hot path (libb200rt.so).
+ *
+ * The reference (expenses/ray-tracing-gallery) has no FFI of its own: the seam
+ * is the set of Rust calls that reach the Vulkan driver.  Each export below
+ * replaces one of those call sites (cited per function, paths relative to the
+ * reference root).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (RtStatus);
+ *     rt_last_error() gives the message.  Nothing throws or aborts across the
+ *     ABI (the reference logs `anyhow` errors and keeps looping,
+ *     src/main.rs:1030-1032).
+ *   - the caller owns every input array; it is copied during the call (like
+ *     the reference's staging buffers, src/util_functions.rs:289-294).
+ *   - one host thread per context; calls are ordered on the context's CUDA
+ *     stream and asynchronous unless stated otherwise.
+ *   - there is NO CPU fallback: without a CUDA device rt_create fails.
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include "rt_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RtContext RtContext;
+
+typedef enum RtStatus {
+    RT_OK = 0,
+    RT_ERR_INVALID_ARGUMENT = -1,
+    RT_ERR_CUDA = -2,
+    RT_ERR_OUT_OF_RANGE = -3,
+    RT_ERR_NOT_BUILT = -4,      /* render/update before rt_build_tlas */
+    RT_ERR_NO_DEVICE = -5
+} RtStatus;
+
+/* Texel formats of the bindless image table.
+ * vk::Format::R8G8B8A8_UNORM / R8G8B8A8_SRGB: src/util_functions.rs:239-265,
+ * R32G32B32A32_SFLOAT (1x1 constants): src/util_functions.rs:216-237. */
+typedef enum RtFormat {
+    RT_FORMAT_RGBA8_UNORM = 0,
+    RT_FORMAT_RGBA8_SRGB = 1,
+    RT_FORMAT_RGBA32_SFLOAT = 2
+} RtFormat;
+
+/* One geometry = one glTF material's triangles (src/util_structs.rs:911-916). */
+typedef struct RtGeometryDesc {
+    const uint32_t*  indices;       /* 3 per triangle, already rebased to the model's vertex arrays */
+    uint32_t         num_indices;
+    uint8_t          opaque;        /* alphaMode == OPAQUE (src/util_structs.rs:992); 0 => any-hit alpha clip */
+    uint8_t          _pad[3];
+    RtGeometryImages images;
+} RtGeometryDesc;
+
+/* `ModelArrays`, src/util_structs.rs:903-909. */
+typedef struct RtModelDesc {
+    const float*          positions;   /* num_vertices * 3 */
+    const float*          normals;     /* num_vertices * 3 */
+    const float*          uvs;         /* num_vertices * 2 */
+    uint32_t              num_vertices;
+    uint32_t              num_geometries;
+    const RtGeometryDesc* geometries;
+} RtModelDesc;
+
+typedef enum RtUpdateMode {
+    RT_UPDATE_AUTO = 0,     /* library picks (rebuild when many instances moved) */
+    RT_UPDATE_REFIT = 1,    /* keep topology, refit boxes: VK mode UPDATE, src/util_structs.rs:309 */
+    RT_UPDATE_REBUILD = 2   /* full LBVH rebuild */
+} RtUpdateMode;
+
+typedef enum RtPipeline {
+    RT_PIPELINE_WAVEFRONT = 0,  /* ray-gen/trace -> compacted hit + ray queues -> shade/shadow */
+    RT_PIPELINE_MEGAKERNEL = 1  /* one thread per pixel runs the whole segment loop (A/B baseline) */
+} RtPipeline;
+
+enum {
+    RT_RENDER_COUNTERS = 1u     /* also count nodes/instances/triangles visited (slower; for the roofline audit) */
+};
+
+/* What `cmd_trace_rays(width, height, 1)` + the hard-coded shader constants
+ * mean (src/command_buffer_recording.rs:116-126, lib.rs:144,
+ * closest_hit_textured.glsl:195). */
+typedef struct RtRenderParams {
+    uint32_t width, height;     /* gl_LaunchSizeEXT: ALWAYS the full image, also when rendering a tile */
+    uint32_t max_segments;      /* ray-gen loop bound; reference = 3 */
+    uint32_t shadow_rays;       /* shadow rays per textured hit; reference = 2 */
+    uint32_t tile_x0, tile_y0;  /* rectangle of global pixel coords to render; */
+    uint32_t tile_w, tile_h;    /*   tile_w == 0 => full image */
+    uint32_t strip_height;      /* >0: rows of the tile are dealt to `strip_count` ranks in strips */
+    uint32_t strip_count;       /*   of this height, round-robin; this call renders strips with */
+    uint32_t strip_index;       /*   (strip % strip_count) == strip_index.  0 => no interleave */
+    uint32_t pipeline;          /* RtPipeline */
+    uint32_t flags;             /* RT_RENDER_* */
+    uint32_t _reserved[3];
+} RtRenderParams;
+
+/* Output arrays are compact over the rendered rows (ascending global y), row
+ * pitch = tile_w pixels.  Any pointer may be NULL. */
+typedef struct RtFrameOutputs {
+    uint8_t*  rgba8;        /* [rows][tile_w][4]  linear_to_srgb + UNORM8 store, alpha 255 (lib.rs:188-190) */
+    float*    radiance;     /* [rows][tile_w][3]  payload.colour before the sRGB encode */
+    uint32_t* hit_ids;      /* [rows][tile_w][max_segments][3] = (gl_InstanceID, gl_GeometryIndexEXT,
+                               gl_PrimitiveID) per ray-gen segment; 0xFFFFFFFF x3 = miss / segment not traced */
+    uint64_t* ray_counts;   /* [2] trace calls issued: {ray-gen segments, shadow rays} */
+} RtFrameOutputs;
+
+typedef struct RtStats {
+    uint64_t primary_rays;      /* ray-gen trace calls of the last render */
+    uint64_t shadow_rays;
+    uint64_t textured_hits;
+    uint64_t nodes_visited;     /* the next four only with RT_RENDER_COUNTERS */
+    uint64_t instances_entered;
+    uint64_t triangles_tested;
+    uint64_t anyhit_calls;
+    float    last_render_ms;    /* CUDA-event time of the last rt_render*, valid after rt_sync */
+    float    last_tlas_ms;      /* CUDA-event time of the last rt_build_tlas / rt_update_tlas */
+    uint32_t tlas_nodes;        /* 128-byte wide nodes in the current TLAS */
+    uint32_t blas_nodes;        /* over all models */
+    uint32_t num_instances;
+    uint32_t num_triangles;     /* over all models */
+} RtStats;
+
+/* Device/allocator creation: src/main.rs:157-204,337.  One context per GPU. */
+int  rt_create(int cuda_device, RtContext** out);
+/* Explicit teardown, like the reference's cleanup() chain, src/main.rs:997-1023. */
+void rt_destroy(RtContext* ctx);
+/* Message of the last failed call on this context (ctx may be NULL: last rt_create failure). */
+const char* rt_last_error(const RtContext* ctx);
+/* Run this context's work on a caller-owned cudaStream_t (e.g. torch's current stream). */
+int  rt_set_stream(RtContext* ctx, void* cuda_stream);
+
+/* load_png_image_from_bytes / create_single_colour_image + ImageManager::push_image
+ * (src/util_functions.rs:216-265, src/util_structs.rs:1330-1349).  Indices are
+ * dense in push order; the reference pushes green, pink, blue-noise, GGX LUT
+ * as 0..3 first (src/main.rs:416-460).  linear_filter: the sampler choice of
+ * src/util_structs.rs:954-955.  texels: w*h*4 bytes (RGBA8) or w*h*16 (RGBA32F). */
+int  rt_push_image(RtContext* ctx, const void* texels, uint32_t width, uint32_t height,
+                   uint32_t format, int linear_filter, uint32_t* out_index);
+
+/* Model::new + AccelerationStructure::build_blas + ModelInfo push
+ * (src/util_structs.rs:1158-1236, 140-224, 1148-1153).  out_model_id is the
+ * index into ModelInfo[] (= instance custom index); out_blas_handle is what
+ * the host writes into instance bytes 56..64. */
+int  rt_create_model(RtContext* ctx, const RtModelDesc* desc,
+                     uint32_t* out_model_id, uint64_t* out_blas_handle);
+
+/* build_tlas (src/util_functions.rs:453-510; caller src/main.rs:524-530). */
+int  rt_build_tlas(RtContext* ctx, const RtInstance* instances, uint32_t count);
+
+/* Buffer::write_mapped on the instance buffer (src/scene.rs:177-181) ... */
+int  rt_update_instances(RtContext* ctx, uint32_t first, uint32_t count, const RtInstance* host_records);
+/* ... same, from device memory (e.g. the landing buffer of an NCCL broadcast). */
+int  rt_update_instances_device(RtContext* ctx, uint32_t first, uint32_t count, const void* device_records);
+/* ... then AccelerationStructure::update_tlas + the AS-write -> RT-read barrier
+ * (src/util_structs.rs:285-357, src/scene.rs:183-201).  Stream-ordered. */
+int  rt_update_tlas(RtContext* ctx, uint32_t mode /* RtUpdateMode */);
+
+/* Uniforms write + push constants + cmd_trace_rays
+ * (src/main.rs:942-948, src/command_buffer_recording.rs:102-126).
+ * rt_render: `out` holds HOST pointers (or is NULL); the frame is rendered into
+ * the context's own device framebuffer, copied to the host arrays, and the call
+ * returns when they are filled.
+ * rt_render_device: `out` holds DEVICE pointers supplied by the caller; the call
+ * only enqueues work on the context's stream. */
+int  rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params,
+               const RtFrameOutputs* out);
+int  rt_render_device(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params,
+                      const RtFrameOutputs* out);
+/* Storage-image copy / present (src/command_buffer_recording.rs:165-179): copy the
+ * RGBA8 rows of the last rt_render(…, NULL) / rt_render frame to host memory (blocking). */
+int  rt_readback(RtContext* ctx, void* host_rgba8, size_t capacity_bytes);
+/* Fence wait (src/main.rs:919-923). */
+int  rt_sync(RtContext* ctx);
+
+int  rt_get_stats(RtContext* ctx, RtStats* out);
+/* The three device addresses the reference pushes as push constants
+ * (ModelInfo[] table, Uniforms copy, TLAS root) — exposed for layout parity checks. */
+int  rt_get_push_constants(RtContext* ctx, RtPushConstantBufferAddresses* out);
+/* Copy `count` ModelInfo / `count` GeometryInfo records of a model back (tests: the
+ * device tables carry the reference's 32/24-byte layouts). */
+int  rt_debug_read_model_info(RtContext* ctx, uint32_t model_id, RtModelInfo* out_info,
+                              RtGeometryInfo* out_geoms, uint32_t max_geoms);
+/* Library/ABI version: (major << 16) | minor. */
+uint32_t rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RT_H */
