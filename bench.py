@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s (primary + shadow) and ms/frame of the frame hot path.
+
+  python bench.py --gpus N --steps K --warmup W [--workload c1..c5] [--pipeline wavefront|mega]
+  python bench.py --impl reference ...     # the CPU restatement of the reference shaders (oracle)
+
+A step is one frame of the workload: (TLAS update, when the scene is dynamic) + one
+`cmd_trace_rays(width, height)` + (N > 1) the gather of the framebuffer strips to rank 0.
+Default workload: BASELINE.json configs[1] — lain.glb textured PBR with 4 blue-noise soft-shadow
+rays per hit at 1920x1080 (the config the metric is quoted on that fits one GPU).
+One JSON line on rank 0.  Timing: CUDA events per step on the launching stream, L2 flushed between
+timed steps, barrier + synchronize around the timed region, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/s (primary+shadow)"
+UNIT = "Mrays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "default"])
+    ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "mega"])
+    ap.add_argument("--instances", type=int, default=0, help="override the instance count of c3/c4/c5")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--update-mode", default="rebuild", choices=["rebuild", "refit"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(setup, args, extra=None):
+    cfg = {
+        "workload": f"{setup.name}: {setup.description}",
+        "resolution": f"{setup.width}x{setup.height}",
+        "shadow_rays_per_hit": setup.shadow_rays,
+        "sun_radius": setup.sun_radius,
+        "max_segments": setup.max_segments,
+        "instances": int(len(setup.instances)),
+        "frame_index": "1..K (animated blue noise)" if setup.sun_radius > 0 else 1,
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(gpu_index), "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def oracle_sample(args, setup_builder, threads=0, steps=1, warmup=0):
+    """Time the CPU restatement (oracle/) on a bounded sample of the workload.  Returns (Mrays/s, info)."""
+    from oracle.binding import Oracle
+
+    orc = Oracle(threads=threads)
+    s = setup_builder(orc)
+    # bounded sample: the full frame when it finishes in seconds, else a centred tile of the same launch
+    tile = {}
+    if s.name in ("c4", "c5"):
+        tw, th = 960, 270
+        tile = dict(tile_x0=(s.width - tw) // 2, tile_y0=(s.height - th) // 2 + s.height // 8, tile_w=tw, tile_h=th)
+    p = s.params(**tile)
+    rays, secs = 0, 0.0
+    for i in range(warmup + steps):
+        u = s.uniforms(frame_index=1 + i)
+        t0 = time.perf_counter()
+        r = orc.render(u, p, want=("rgba8", "ray_counts"))
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            rays += int(r["ray_counts"].sum())
+            secs += dt
+    cores = orc.threads
+    orc.close()
+    sample = (f"{steps} frame(s) of {s.name} at {s.width}x{s.height}" +
+              (f", tile {tile['tile_w']}x{tile['tile_h']} of the launch" if tile else ", full frame") + f", {rays} rays in {secs:.2f} s")
+    return rays / secs / 1e6, {"cores": cores, "sample": sample, "ms_per_step": secs / steps * 1e3, "rays": rays}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    from ray_tracing_gallery_b200.scene import build_scene
+
+    holder = {}
+
+    def builder(backend):
+        holder["s"] = build_scene(backend, args.workload, args.width or None, args.height or None, num_instances=args.instances or None)
+        return holder["s"]
+
+    steps = max(1, min(args.steps, 5))
+    warm = max(0, min(args.warmup, 1))
+    value, info = oracle_sample(args, builder, steps=steps, warmup=warm)
+    s = holder["s"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic: reference assets (glb/png), seeded instance transforms",
+        "config": workload_config(s, args, {"note": "CPU restatement of the reference shaders (oracle/); the reference itself needs Rust + "
+                                            "Vulkan ray tracing (lavapipe / host rust-gpu unavailable: no Vulkan ICD, no Rust toolchain)"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def algorithmic_bytes(st, setup, pixels):
+    """Algorithmic bytes of one frame per kernel class (DESIGN.md 'Roofline accounting')."""
+    n = setup.shadow_rays
+    trav = [80 * st.nodes_visited[k] + 64 * st.instances_entered[k] + 48 * st.triangles_tested[k] + 52 * st.anyhit_calls[k] for k in (0, 1)]
+    bounces = st.primary_rays - pixels
+    trace_b = trav[0] + 64 * bounces + 112 * bounces + 48 * st.textured_hits + 4 * (pixels - st.textured_hits)
+    shade_b = trav[1] + st.textured_hits * (48 + 32 + 24 + 12 + 96 + 64 + 48 + 2 * 16 + 4 * 2 * n + 4)
+    return {"trace": int(trace_b), "shade": int(shade_b), "mega": int(trace_b + shade_b - 48 * 2 * st.textured_hits - 64 * bounces)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from ray_tracing_gallery_b200 import abi, native
+    from ray_tracing_gallery_b200.dist import Partition, broadcast_instances, deinterleave
+    from ray_tracing_gallery_b200.scene import build_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    args.warmup = max(args.warmup, 3)
+
+    gpu = native.Renderer(local_rank)  # raises if libb200rt.so is missing: there is no fallback
+    stream = torch.cuda.current_stream()
+    gpu.set_stream(stream.cuda_stream)
+    s = build_scene(gpu, args.workload, args.width or None, args.height or None, num_instances=args.instances or None)
+    W, H = s.width, s.height
+    part = Partition.make(W, H, world, rank)
+    pipeline = abi.RT_PIPELINE_MEGAKERNEL if args.pipeline == "mega" else abi.RT_PIPELINE_WAVEFRONT
+    update_mode = abi.RT_UPDATE_REFIT if args.update_mode == "refit" else abi.RT_UPDATE_REBUILD
+    rows = part.local_rows
+    pixels = rows * W
+
+    fb = torch.zeros((rows, W, 4), dtype=torch.uint8, device=dev)
+    gathered = torch.zeros((world, rows, W, 4), dtype=torch.uint8, device=dev) if world > 1 else None
+    rays_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    inst_dev = torch.zeros(len(s.instances) * 64, dtype=torch.uint8, device=dev) if s.dynamic else None
+    inst_pinned = torch.zeros(len(s.instances) * 64, dtype=torch.uint8).pin_memory() if s.dynamic else None
+    host_fb = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
+    host_rays = torch.zeros(2, dtype=torch.int64).pin_memory()
+
+    def params(flags=0):
+        return part.apply(s.params(pipeline=pipeline, flags=flags))
+
+    def frame_inputs(i):
+        return s.uniforms(frame_index=1 + i)
+
+    def update_scene_device(i):
+        """Dynamic scene: rank 0 produces the records, NCCL broadcast lands them in the builder's input."""
+        if rank == 0:
+            rec = s.animate(i + 1)
+            inst_pinned.numpy()[:] = rec.view(np.uint8).reshape(-1)
+            inst_dev.copy_(inst_pinned, non_blocking=True)
+        if world > 1:
+            broadcast_instances(inst_dev, 0)
+        gpu.update_instances_device(0, len(s.instances), inst_dev.data_ptr())
+        gpu.update_tlas(update_mode)
+
+    def step_device(i, flags=0):
+        if s.dynamic:
+            update_scene_device(i)
+        gpu.render_device(frame_inputs(i), params(flags), rgba8=fb.data_ptr(), ray_counts=rays_dev.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
+            if rank == 0:
+                deinterleave(gathered, part)
+
+    # ---- one instrumented frame: deterministic traversal counters for the roofline accounting
+    step_device(0, abi.RT_RENDER_COUNTERS)
+    torch.cuda.synchronize()
+    st_count = gpu.stats()
+    bytes_frame = algorithmic_bytes(st_count, s, pixels)
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, per-step CUDA events on the launching stream, L2 flushed in between
+    launches0 = gpu.lib.rt_kernel_launches()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    total_rays = 0
+    kernel_ms = np.zeros(3)
+    kernel_launches = np.zeros(3, np.int64)
+    tlas_ms = 0.0
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record(stream)
+        step_device(args.warmup + i, abi.RT_RENDER_TIMING)
+        ev[i][1].record(stream)
+        ev[i][1].synchronize()
+        st = gpu.stats()
+        total_rays += int(st.primary_rays + st.shadow_rays)
+        kernel_ms += np.array(list(st.kernel_ms))
+        kernel_launches += np.array(list(st.kernel_launches))
+        tlas_ms += st.last_tlas_ms if s.dynamic else 0.0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    launches = gpu.lib.rt_kernel_launches() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    r = torch.tensor([total_rays], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    total_ms, total_rays_all = float(t.item()), int(r.item())
+    value = total_rays_all / (total_ms * 1e-3) / 1e6
+
+    # ---- e2e: the same steps through the host-facing C ABI, host<->device copies inside the timed region
+    def step_e2e(i):
+        if s.dynamic:
+            if rank == 0 or world == 1:
+                rec = s.animate(i + 1)
+            if world == 1:
+                gpu.update_instances(0, rec)  # rt_update_instances: host records -> device
+                gpu.update_tlas(update_mode)
+            else:
+                update_scene_device(i)
+        if world == 1:
+            gpu.render_to_host(frame_inputs(i), params(), host_fb.data_ptr(), host_rays.data_ptr())  # rt_render, blocking
+        else:
+            gpu.render_device(frame_inputs(i), params(), rgba8=fb.data_ptr(), ray_counts=rays_dev.data_ptr())
+            dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
+            if rank == 0:
+                host_fb.copy_(deinterleave(gathered, part), non_blocking=True)
+            host_rays.copy_(rays_dev, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for i in range(2):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_rays = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+        e2e_rays += int(host_rays.sum().item())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    r = torch.tensor([e2e_rays], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    e2e_value = int(r.item()) / float(t.item()) / 1e6
+    h2d = 176 + (len(s.instances) * 64 if s.dynamic else 0)
+    d2h = (H * W * 4 if rank == 0 else 0) + 16
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        names = ["trace", "shade", "mega"]
+        dom = int(np.argmax(kernel_ms))
+        per_launch_ms = kernel_ms[dom] / max(kernel_launches[dom], 1)
+        launches_per_frame = kernel_launches[dom] / args.steps
+        bytes_per_launch = bytes_frame[names[dom]] / max(launches_per_frame, 1)
+        achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        rays_frame = max(int(st_count.primary_rays + st_count.shadow_rays), 1)
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": {"trace": "k_trace (ray-gen + closest-hit traversal)", "shade": "k_shade (shadow rays + PBR shading)", "mega": "k_mega"}[names[dom]],
+            "peak_source": peak_src,
+            "kernel_ms_per_frame": {n: float(kernel_ms[i] / args.steps) for i, n in enumerate(names)},
+            "kernel_share_of_step": float(kernel_ms[dom] / total_ms) if world == 1 else None,
+            "algorithmic_bytes_per_launch": bytes_per_launch,
+            "launches_per_frame": float(launches_per_frame),
+            "per_ray": {"nodes": float(sum(st_count.nodes_visited)) / rays_frame, "instances": float(sum(st_count.instances_entered)) / rays_frame,
+                        "triangles": float(sum(st_count.triangles_tested)) / rays_frame,
+                        "bytes": float(bytes_frame["trace"] + bytes_frame["shade"]) / rays_frame},
+            "note": "working set of this workload is L2-resident after first touch (SURVEY 8d): the HBM fraction is expected to be small; "
+                    "the kernel is latency/issue bound, see profiles/",
+        }
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            def builder(backend):
+                return build_scene(backend, args.workload, args.width or None, args.height or None, num_instances=args.instances or None)
+            v, info = oracle_sample(args, builder, steps=3 if args.workload in ("c1", "c2", "c3", "default") else 1, warmup=0)
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic: reference assets (glb/png), seeded instance transforms",
+            "config": workload_config(s, args, {
+                "pipeline": args.pipeline, "partition": f"{world} rank(s), row strips of {part.strip_height or H} rows, round-robin",
+                "l2": "flushed between timed steps (256 MiB device write)", "tlas_update": (args.update_mode if s.dynamic else "static"),
+                "rays_per_frame": rays_frame if world == 1 else None}),
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / args.steps * 1e3,
+                    "path": "rt_render (host buffers, pinned)" if world == 1 else "rt_render_device + NCCL all-gather + D2H on rank 0"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "tlas_update_ms_per_step": (tlas_ms / args.steps) if s.dynamic else None,
+        }
+        print(json.dumps(line), flush=True)
+    gpu.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

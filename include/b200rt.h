@@ -76,7 +76,8 @@ typedef enum RtPipeline {
 } RtPipeline;
 
 enum {
-    RT_RENDER_COUNTERS = 1u     /* also count nodes/instances/triangles visited (slower; for the roofline audit) */
+    RT_RENDER_COUNTERS = 1u,    /* also count nodes/instances/triangles visited (slower; for the roofline audit) */
+    RT_RENDER_TIMING = 2u       /* CUDA events around every kernel of the frame -> RtStats.kernel_ms */
 };
 
 /* What `cmd_trace_rays(width, height, 1)` + the hard-coded shader constants
@@ -110,12 +111,16 @@ typedef struct RtStats {
     uint64_t primary_rays;      /* ray-gen trace calls of the last render */
     uint64_t shadow_rays;
     uint64_t textured_hits;
-    uint64_t nodes_visited;     /* the next four only with RT_RENDER_COUNTERS */
-    uint64_t instances_entered;
-    uint64_t triangles_tested;
-    uint64_t anyhit_calls;
+    /* the next four only with RT_RENDER_COUNTERS; [0] = closest-hit rays (ray-gen segments),
+       [1] = shadow rays */
+    uint64_t nodes_visited[2];
+    uint64_t instances_entered[2];
+    uint64_t triangles_tested[2];
+    uint64_t anyhit_calls[2];
     float    last_render_ms;    /* CUDA-event time of the last rt_render*, valid after rt_sync */
     float    last_tlas_ms;      /* CUDA-event time of the last rt_build_tlas / rt_update_tlas */
+    float    kernel_ms[3];      /* with RT_RENDER_TIMING, summed over segments: {trace kernels, shade kernels, megakernel} */
+    uint32_t kernel_launches[3];/* launches behind kernel_ms */
     uint32_t tlas_nodes;        /* 128-byte wide nodes in the current TLAS */
     uint32_t blas_nodes;        /* over all models */
     uint32_t num_instances;
@@ -182,6 +187,8 @@ int  rt_get_push_constants(RtContext* ctx, RtPushConstantBufferAddresses* out);
  * device tables carry the reference's 32/24-byte layouts). */
 int  rt_debug_read_model_info(RtContext* ctx, uint32_t model_id, RtModelInfo* out_info,
                               RtGeometryInfo* out_geoms, uint32_t max_geoms);
+/* Number of this library's own kernels launched so far in the process (all contexts). */
+uint64_t rt_kernel_launches(void);
 /* Library/ABI version: (major << 16) | minor. */
 uint32_t rt_version(void);
 

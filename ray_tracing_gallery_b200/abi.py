@@ -121,12 +121,14 @@ class RtStats(C.Structure):
         ("primary_rays", C.c_uint64),
         ("shadow_rays", C.c_uint64),
         ("textured_hits", C.c_uint64),
-        ("nodes_visited", C.c_uint64),
-        ("instances_entered", C.c_uint64),
-        ("triangles_tested", C.c_uint64),
-        ("anyhit_calls", C.c_uint64),
+        ("nodes_visited", C.c_uint64 * 2),
+        ("instances_entered", C.c_uint64 * 2),
+        ("triangles_tested", C.c_uint64 * 2),
+        ("anyhit_calls", C.c_uint64 * 2),
         ("last_render_ms", C.c_float),
         ("last_tlas_ms", C.c_float),
+        ("kernel_ms", C.c_float * 3),
+        ("kernel_launches", C.c_uint32 * 3),
         ("tlas_nodes", C.c_uint32),
         ("blas_nodes", C.c_uint32),
         ("num_instances", C.c_uint32),
@@ -139,6 +141,7 @@ RT_HIT_TEXTURED, RT_HIT_MIRROR, RT_HIT_PORTAL = 0, 1, 2
 RT_UPDATE_AUTO, RT_UPDATE_REFIT, RT_UPDATE_REBUILD = 0, 1, 2
 RT_PIPELINE_WAVEFRONT, RT_PIPELINE_MEGAKERNEL = 0, 1
 RT_RENDER_COUNTERS = 1
+RT_RENDER_TIMING = 2
 RT_INSTANCE_TRIANGLE_FACING_CULL_DISABLE = 1
 MISS_ID = 0xFFFFFFFF
 

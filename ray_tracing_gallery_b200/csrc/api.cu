@@ -1,0 +1,703 @@
+// api.cu — the C ABI of include/b200rt.h: context, image table, models/BLAS, TLAS, frames.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "bvh_build.h"
+#include "launch_count.h"
+#include "render.h"
+
+using namespace b200rt;
+
+namespace b200rt {
+std::atomic<uint64_t> g_kernel_launches{0};
+}
+
+namespace {
+
+std::string g_create_error;
+
+template <typename T>
+struct DevVec {  // growable device array; indices stay valid across growth
+    T* ptr = nullptr;
+    size_t size = 0, cap = 0;
+    cudaError_t reserve(size_t want, cudaStream_t stream) {
+        if (want <= cap) return cudaSuccess;
+        size_t ncap = cap ? cap : 1024;
+        while (ncap < want) ncap += ncap / 2 + 1024;
+        T* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (size) {
+            e = cudaMemcpyAsync(np, ptr, size * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
+        }
+        if (ptr) cudaFree(ptr);
+        ptr = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        size = cap = 0;
+    }
+};
+
+struct ModelRes {
+    float *positions = nullptr, *normals = nullptr, *uvs = nullptr;
+    RtGeometryInfo* geom_info = nullptr;
+    std::vector<uint32_t*> index_bufs;
+    uint32_t num_geoms = 0;
+    BlasInfo blas{};
+};
+
+struct TexRes {
+    cudaArray_t array = nullptr;
+    cudaTextureObject_t obj = 0;
+};
+
+}  // namespace
+
+struct RtContext {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // render start/stop, tlas start/stop
+    bool render_timed = false, tlas_timed = false;
+    FrameTiming timing;
+    bool timing_ready = false, timing_valid = false;
+    std::string err;
+
+    // images
+    std::vector<TexRes> tex_res;
+    std::vector<TexEntry> tex_host;
+    TexEntry* d_textures = nullptr;
+    float* d_srgb_lut = nullptr;
+    float srgb_lut[256];
+
+    // models
+    std::vector<ModelRes> models;
+    DevVec<RtModelInfo> d_model_info;
+    DevVec<BlasInfo> d_blas_info;
+    DevVec<Node8> blas_nodes;
+    DevVec<TriRec> tris;
+
+    // instances / TLAS
+    uint32_t num_instances = 0, inst_cap = 0;
+    bool tlas_built = false;
+    RtInstance* d_instances = nullptr;
+    InstRT *d_inst_unsorted = nullptr, *d_inst_rt = nullptr;
+    Aabb* d_inst_boxes = nullptr;
+    uint32_t* d_leaf_order = nullptr;
+    Node8* d_tlas_nodes = nullptr;
+    uint32_t tlas_node_cap = 0;
+    uint32_t* d_tlas_node_count = nullptr;
+    BvhBuilder builder;
+
+    // frame
+    RtUniforms* d_uniforms = nullptr;  // copy kept for the push-constant parity view
+    FrameCounters* d_counters = nullptr;
+    RayRec* d_ray_q[2] = {nullptr, nullptr};
+    HitRec* d_hit_q = nullptr;
+    size_t queue_cap = 0;
+    uint8_t* d_fb_rgba8 = nullptr;
+    float* d_fb_radiance = nullptr;
+    uint32_t* d_fb_hit_ids = nullptr;
+    size_t fb_rgba8_cap = 0, fb_radiance_cap = 0, fb_hit_ids_cap = 0;
+    size_t last_rows = 0, last_tw = 0;
+    uint64_t* d_ray_counts = nullptr;
+};
+
+namespace {
+
+int fail(RtContext* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t _e = (call);                                                                                   \
+        if (_e != cudaSuccess) {                                                                                   \
+            (void)cudaGetLastError();                                                                              \
+            return fail(ctx, RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));                     \
+        }                                                                                                          \
+    } while (0)
+#define CK_DEV(ctx) CK(cudaSetDevice((ctx)->device))
+
+template <typename T>
+cudaError_t grow(T*& p, size_t& cap, size_t want) {
+    if (want <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+}
+
+int ensure_instance_capacity(RtContext* ctx, uint32_t n) {
+    if (n <= ctx->inst_cap && ctx->d_instances) return RT_OK;
+    uint32_t cap = n + n / 8 + 16;
+    if (ctx->d_instances) cudaFree(ctx->d_instances);
+    if (ctx->d_inst_unsorted) cudaFree(ctx->d_inst_unsorted);
+    if (ctx->d_inst_rt) cudaFree(ctx->d_inst_rt);
+    if (ctx->d_inst_boxes) cudaFree(ctx->d_inst_boxes);
+    if (ctx->d_leaf_order) cudaFree(ctx->d_leaf_order);
+    if (ctx->d_tlas_nodes) cudaFree(ctx->d_tlas_nodes);
+    ctx->d_instances = nullptr; ctx->d_inst_unsorted = nullptr; ctx->d_inst_rt = nullptr;
+    ctx->d_inst_boxes = nullptr; ctx->d_leaf_order = nullptr; ctx->d_tlas_nodes = nullptr;
+    ctx->inst_cap = 0;
+    CK(cudaMalloc(&ctx->d_instances, sizeof(RtInstance) * cap));
+    CK(cudaMalloc(&ctx->d_inst_unsorted, sizeof(InstRT) * cap));
+    CK(cudaMalloc(&ctx->d_inst_rt, sizeof(InstRT) * cap));
+    CK(cudaMalloc(&ctx->d_inst_boxes, sizeof(Aabb) * cap));
+    CK(cudaMalloc(&ctx->d_leaf_order, sizeof(uint32_t) * cap));
+    ctx->tlas_node_cap = max_wide_nodes(cap);
+    CK(cudaMalloc(&ctx->d_tlas_nodes, sizeof(Node8) * ctx->tlas_node_cap));
+    ctx->inst_cap = cap;
+    return RT_OK;
+}
+
+int build_tlas_now(RtContext* ctx, uint32_t mode) {
+    uint32_t n = ctx->num_instances;
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[2], st));
+    if (mode == RT_UPDATE_REFIT && ctx->tlas_built) {
+        // keep topology: records and boxes are produced directly in leaf order
+        CK(launch_prepare_instances(ctx->d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), ctx->d_leaf_order,
+                                    ctx->d_inst_rt, ctx->d_inst_boxes, st));
+        CK(ctx->builder.refit(ctx->d_inst_boxes, n, ctx->d_tlas_nodes, 0, 0, ctx->d_tlas_node_count, ctx->tlas_node_cap, st));
+    } else {
+        CK(launch_prepare_instances(ctx->d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), nullptr,
+                                    ctx->d_inst_unsorted, ctx->d_inst_boxes, st));
+        CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, ctx->d_tlas_nodes, 0, 0, ctx->d_leaf_order, ctx->d_tlas_node_count, st));
+        CK(launch_gather_instances(ctx->d_inst_unsorted, ctx->d_leaf_order, n, ctx->d_inst_rt, st));
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    ctx->tlas_timed = true;
+    ctx->tlas_built = true;
+    return RT_OK;
+}
+
+struct FramePlan {
+    uint32_t x0, y0, tw, th, rows;
+};
+
+int plan_frame(RtContext* ctx, const RtRenderParams* p, FramePlan& f) {
+    if (!p->width || !p->height) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: zero launch size");
+    if (!p->shadow_rays) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: shadow_rays must be >= 1");
+    if (p->pipeline > RT_PIPELINE_MEGAKERNEL) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: unknown pipeline");
+    f.x0 = p->tile_x0; f.y0 = p->tile_y0; f.tw = p->tile_w; f.th = p->tile_h;
+    if (f.tw == 0) { f.x0 = 0; f.y0 = 0; f.tw = p->width; f.th = p->height; }
+    if ((uint64_t)f.x0 + f.tw > p->width || (uint64_t)f.y0 + f.th > p->height)
+        return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_render: tile outside the image");
+    f.rows = f.th;
+    if (p->strip_height && p->strip_count > 1) {
+        if (p->strip_index >= p->strip_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: strip_index >= strip_count");
+        if (f.th % (p->strip_height * p->strip_count) != 0)
+            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: tile height must be a multiple of strip_height * strip_count");
+        f.rows = f.th / p->strip_count;
+    }
+    if ((uint64_t)f.rows * f.tw > 0x7FFFFFFFull) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_render: too many pixels");
+    return RT_OK;
+}
+
+int render_common(RtContext* ctx, const RtUniforms* u, const RtRenderParams* p, const FramePlan& f, uint8_t* d_rgba8, float* d_radiance,
+                  uint32_t* d_hit_ids, uint64_t* d_ray_counts) {
+    if (!ctx->tlas_built) return fail(ctx, RT_ERR_NOT_BUILT, "rt_render before rt_build_tlas");
+    size_t pixels = (size_t)f.rows * f.tw;
+    if (pixels > ctx->queue_cap) {
+        size_t cap = 0;
+        for (int i = 0; i < 2; i++) { cap = ctx->queue_cap; CK(grow(ctx->d_ray_q[i], cap, pixels)); }
+        cap = ctx->queue_cap;
+        CK(grow(ctx->d_hit_q, cap, pixels));
+        ctx->queue_cap = pixels;
+    }
+    SceneDev S;
+    S.tlas_nodes = ctx->d_tlas_nodes;
+    S.inst_rt = ctx->d_inst_rt;
+    S.instances = ctx->d_instances;
+    S.blas_nodes = ctx->blas_nodes.ptr;
+    S.tris = ctx->tris.ptr;
+    S.model_info = ctx->d_model_info.ptr;
+    S.num_models = (uint32_t)ctx->models.size();
+    S.num_instances = ctx->num_instances;
+    S.textures = ctx->d_textures;
+    S.num_textures = (uint32_t)ctx->tex_host.size();
+    S.srgb_lut = ctx->d_srgb_lut;
+    FrameDev F;
+    memset(&F, 0, sizeof(F));
+    F.uniforms = *u;
+    F.width = p->width; F.height = p->height;
+    F.max_segments = p->max_segments; F.shadow_rays = p->shadow_rays;
+    F.x0 = f.x0; F.y0 = f.y0; F.tw = f.tw; F.rows = f.rows; F.tile_h = f.th;
+    F.strip_height = p->strip_height; F.strip_count = p->strip_count; F.strip_index = p->strip_index;
+    F.cos_sun_radius = cosf(u->sun_radius);
+    F.rgba8 = d_rgba8; F.radiance = d_radiance; F.hit_ids = d_hit_ids;
+    F.counters = ctx->d_counters;
+    F.ray_q[0] = ctx->d_ray_q[0]; F.ray_q[1] = ctx->d_ray_q[1];
+    F.hit_q = ctx->d_hit_q;
+    CK(cudaMemcpyAsync(ctx->d_uniforms, u, sizeof(RtUniforms), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    FrameTiming* timing = nullptr;
+    if (p->flags & RT_RENDER_TIMING) {
+        if (!ctx->timing_ready) {
+            for (int i = 0; i <= FrameTiming::MAX_INTERVALS; i++) CK(cudaEventCreate(&ctx->timing.ev[i]));
+            ctx->timing_ready = true;
+        }
+        timing = &ctx->timing;
+    }
+    ctx->timing_valid = timing != nullptr;
+    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, ctx->sms, d_ray_counts, timing, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->render_timed = true;
+    ctx->last_rows = f.rows;
+    ctx->last_tw = f.tw;
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t rt_version(void) { return (1u << 16) | 0u; }
+
+uint64_t rt_kernel_launches(void) { return g_kernel_launches.load(); }
+
+const char* rt_last_error(const RtContext* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rt_create(int cuda_device, RtContext** out) {
+    RtContext* ctx = nullptr;  // for CK/fail before the context exists
+    if (!out) return fail(nullptr, RT_ERR_INVALID_ARGUMENT, "rt_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, RT_ERR_NO_DEVICE,
+                    std::string("rt_create: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                        "); this library has no CPU fallback");
+    }
+    if (cuda_device < 0 || cuda_device >= count) return fail(nullptr, RT_ERR_INVALID_ARGUMENT, "rt_create: bad device index");
+    CK(cudaSetDevice(cuda_device));
+    RtContext* c = new (std::nothrow) RtContext();
+    if (!c) return fail(nullptr, RT_ERR_CUDA, "rt_create: out of host memory");
+    c->device = cuda_device;
+    ctx = c;
+    cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cuda_device);
+    auto bail = [&](cudaError_t err, const char* what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        rt_destroy(c);
+        return RT_ERR_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (int i = 0; i < 4; i++)
+        if ((e = cudaEventCreate(&c->ev[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(&c->d_textures, sizeof(TexEntry) * RT_MAX_BOUND_IMAGES)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&c->d_srgb_lut, sizeof(float) * 256)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&c->d_uniforms, sizeof(RtUniforms))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&c->d_counters, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&c->d_tlas_node_count, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&c->d_ray_counts, sizeof(uint64_t) * 2)) != cudaSuccess) return bail(e, "cudaMalloc");
+    // sRGB EOTF table (exact per 8-bit code, decode happens before filtering)
+    for (int i = 0; i < 256; i++) {
+        float v = (float)i / 255.0f;
+        c->srgb_lut[i] = v <= 0.04045f ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f);
+    }
+    if ((e = cudaMemcpy(c->d_srgb_lut, c->srgb_lut, sizeof(c->srgb_lut), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+    if ((e = cudaMemset(c->d_counters, 0, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMemset");
+    *out = c;
+    return RT_OK;
+}
+
+void rt_destroy(RtContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& t : ctx->tex_res) {
+        if (t.obj) cudaDestroyTextureObject(t.obj);
+        if (t.array) cudaFreeArray(t.array);
+    }
+    for (auto& m : ctx->models) {
+        cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.geom_info);
+        for (auto* p : m.index_bufs) cudaFree(p);
+    }
+    ctx->d_model_info.release(); ctx->d_blas_info.release(); ctx->blas_nodes.release(); ctx->tris.release();
+    cudaFree(ctx->d_textures); cudaFree(ctx->d_srgb_lut); cudaFree(ctx->d_uniforms); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_instances); cudaFree(ctx->d_inst_unsorted); cudaFree(ctx->d_inst_rt); cudaFree(ctx->d_inst_boxes);
+    cudaFree(ctx->d_leaf_order); cudaFree(ctx->d_tlas_nodes); cudaFree(ctx->d_tlas_node_count); cudaFree(ctx->d_ray_counts);
+    cudaFree(ctx->d_ray_q[0]); cudaFree(ctx->d_ray_q[1]); cudaFree(ctx->d_hit_q);
+    cudaFree(ctx->d_fb_rgba8); cudaFree(ctx->d_fb_radiance); cudaFree(ctx->d_fb_hit_ids);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->timing_ready)
+        for (int i = 0; i <= FrameTiming::MAX_INTERVALS; i++) cudaEventDestroy(ctx->timing.ev[i]);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    (void)cudaGetLastError();
+    delete ctx;
+}
+
+int rt_set_stream(RtContext* ctx, void* cuda_stream) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    CK_DEV(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    ctx->render_timed = ctx->tlas_timed = false;
+    ctx->timing_valid = false;
+    return RT_OK;
+}
+
+int rt_push_image(RtContext* ctx, const void* texels, uint32_t width, uint32_t height, uint32_t format, int linear_filter,
+                  uint32_t* out_index) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!texels || !width || !height || format > RT_FORMAT_RGBA32_SFLOAT) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_push_image: bad argument");
+    if (ctx->tex_host.size() >= RT_MAX_BOUND_IMAGES) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_push_image: image table full (128)");
+    CK_DEV(ctx);
+    TexEntry te;
+    memset(&te, 0, sizeof(te));
+    te.w = width; te.h = height; te.format = format; te.linear = linear_filter ? 1u : 0u;
+    TexRes tr;
+    if (width == 1 && height == 1) {
+        // a 1x1 image samples to its texel under every filter/address mode: keep it as a constant
+        if (format == RT_FORMAT_RGBA32_SFLOAT) {
+            memcpy(te.constant, texels, 16);
+        } else {
+            const uint8_t* p = static_cast<const uint8_t*>(texels);
+            for (int k = 0; k < 3; k++) te.constant[k] = format == RT_FORMAT_RGBA8_SRGB ? ctx->srgb_lut[p[k]] : (float)p[k] / 255.0f;
+            te.constant[3] = (float)p[3] / 255.0f;
+        }
+    } else {
+        bool f32 = format == RT_FORMAT_RGBA32_SFLOAT;
+        cudaChannelFormatDesc cd = f32 ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
+        CK(cudaMallocArray(&tr.array, &cd, width, height));
+        size_t pitch = (size_t)width * (f32 ? 16 : 4);
+        cudaError_t e = cudaMemcpy2DToArray(tr.array, 0, 0, texels, pitch, pitch, height, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFreeArray(tr.array); CK(e); }
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = tr.array;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;  // REPEAT is applied on integer texel coords
+        td.filterMode = cudaFilterModePoint;                          // bilinear weights are applied in fp32 by the shader
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        e = cudaCreateTextureObject(&tr.obj, &rd, &td, nullptr);
+        if (e != cudaSuccess) { cudaFreeArray(tr.array); CK(e); }
+        te.obj = tr.obj;
+    }
+    uint32_t index = (uint32_t)ctx->tex_host.size();
+    cudaError_t e = cudaMemcpyAsync(ctx->d_textures + index, &te, sizeof(te), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (tr.obj) cudaDestroyTextureObject(tr.obj);
+        if (tr.array) cudaFreeArray(tr.array);
+        CK(e);
+    }
+    ctx->tex_host.push_back(te);
+    ctx->tex_res.push_back(tr);
+    if (out_index) *out_index = index;
+    return RT_OK;
+}
+
+int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model_id, uint64_t* out_blas_handle) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!desc || (desc->num_vertices && (!desc->positions || !desc->normals || !desc->uvs)) || (desc->num_geometries && !desc->geometries))
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_create_model: bad argument");
+    CK_DEV(ctx);
+    cudaStream_t st = ctx->stream;
+    uint32_t nv = desc->num_vertices, ng = desc->num_geometries;
+    std::vector<uint32_t> geom_start(ng + 1, 0);
+    std::vector<uint8_t> geom_opaque(ng ? ng : 1, 1);
+    for (uint32_t g = 0; g < ng; g++) {
+        const RtGeometryDesc& gd = desc->geometries[g];
+        if (gd.num_indices && !gd.indices) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_create_model: geometry without indices");
+        for (uint32_t i = 0; i < gd.num_indices; i++)
+            if (gd.indices[i] >= nv) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_create_model: index out of range");
+        geom_start[g + 1] = geom_start[g] + gd.num_indices / 3;
+        geom_opaque[g] = gd.opaque ? 1 : 0;
+    }
+    uint32_t nt = geom_start[ng];
+    ModelRes m;
+    m.num_geoms = ng;
+    auto cleanup = [&]() {
+        cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.geom_info);
+        for (auto* p : m.index_bufs) cudaFree(p);
+    };
+#define CKM(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess) {                                                                           \
+            (void)cudaGetLastError();                                                                      \
+            cleanup();                                                                                     \
+            return fail(ctx, RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));             \
+        }                                                                                                  \
+    } while (0)
+    size_t nvq = nv ? nv : 1;
+    CKM(cudaMalloc(&m.positions, nvq * 12));
+    CKM(cudaMalloc(&m.normals, nvq * 12));
+    CKM(cudaMalloc(&m.uvs, nvq * 8));
+    if (nv) {
+        CKM(cudaMemcpyAsync(m.positions, desc->positions, (size_t)nv * 12, cudaMemcpyHostToDevice, st));
+        CKM(cudaMemcpyAsync(m.normals, desc->normals, (size_t)nv * 12, cudaMemcpyHostToDevice, st));
+        CKM(cudaMemcpyAsync(m.uvs, desc->uvs, (size_t)nv * 8, cudaMemcpyHostToDevice, st));
+    }
+    std::vector<RtGeometryInfo> ginfo(ng ? ng : 1);
+    for (uint32_t g = 0; g < ng; g++) {
+        const RtGeometryDesc& gd = desc->geometries[g];
+        uint32_t* d_idx = nullptr;
+        CKM(cudaMalloc(&d_idx, (size_t)(gd.num_indices ? gd.num_indices : 3) * 4));
+        m.index_bufs.push_back(d_idx);
+        if (gd.num_indices) CKM(cudaMemcpyAsync(d_idx, gd.indices, (size_t)gd.num_indices * 4, cudaMemcpyHostToDevice, st));
+        ginfo[g].index_buffer_address = (uint64_t)(uintptr_t)d_idx;
+        ginfo[g].images = gd.images;
+    }
+    CKM(cudaMalloc(&m.geom_info, sizeof(RtGeometryInfo) * (ng ? ng : 1)));
+    if (ng) CKM(cudaMemcpyAsync(m.geom_info, ginfo.data(), sizeof(RtGeometryInfo) * ng, cudaMemcpyHostToDevice, st));
+
+    // ---- BLAS
+    uint32_t node_offset = (uint32_t)ctx->blas_nodes.size, prim_offset = (uint32_t)ctx->tris.size;
+    CKM(ctx->blas_nodes.reserve(ctx->blas_nodes.size + max_wide_nodes(nt), st));
+    CKM(ctx->tris.reserve(ctx->tris.size + (nt ? nt : 1), st));
+    uint32_t** d_index_ptrs = nullptr;
+    uint32_t* d_geom_start = nullptr;
+    uint8_t* d_geom_opaque = nullptr;
+    Aabb* d_boxes = nullptr;
+    uint32_t* d_leaf_order = nullptr;
+    uint32_t* d_count = nullptr;
+    auto cleanup_tmp = [&]() {
+        cudaFree(d_index_ptrs); cudaFree(d_geom_start); cudaFree(d_geom_opaque); cudaFree(d_boxes); cudaFree(d_leaf_order); cudaFree(d_count);
+    };
+#define CKT(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess) {                                                                           \
+            (void)cudaGetLastError();                                                                      \
+            cleanup_tmp();                                                                                 \
+            cleanup();                                                                                     \
+            return fail(ctx, RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));             \
+        }                                                                                                  \
+    } while (0)
+    CKT(cudaMalloc(&d_index_ptrs, sizeof(uint32_t*) * (ng ? ng : 1)));
+    CKT(cudaMalloc(&d_geom_start, sizeof(uint32_t) * (ng + 1)));
+    CKT(cudaMalloc(&d_geom_opaque, ng ? ng : 1));
+    CKT(cudaMalloc(&d_boxes, sizeof(Aabb) * (nt ? nt : 1)));
+    CKT(cudaMalloc(&d_leaf_order, sizeof(uint32_t) * (nt ? nt : 1)));
+    CKT(cudaMalloc(&d_count, sizeof(uint32_t)));
+    if (ng) CKT(cudaMemcpyAsync(d_index_ptrs, m.index_bufs.data(), sizeof(uint32_t*) * ng, cudaMemcpyHostToDevice, st));
+    CKT(cudaMemcpyAsync(d_geom_start, geom_start.data(), sizeof(uint32_t) * (ng + 1), cudaMemcpyHostToDevice, st));
+    if (ng) CKT(cudaMemcpyAsync(d_geom_opaque, geom_opaque.data(), ng, cudaMemcpyHostToDevice, st));
+    ModelGeomDev M;
+    M.positions = m.positions; M.indices = d_index_ptrs; M.geom_start = d_geom_start; M.geom_opaque = d_geom_opaque;
+    M.num_geoms = ng; M.num_tris = nt; M.num_vertices = nv;
+    CKT(launch_triangle_boxes(M, d_boxes, st));
+    CKT(ctx->builder.build(d_boxes, nt, 4, ctx->blas_nodes.ptr, node_offset, prim_offset, d_leaf_order, d_count, st));
+    CKT(launch_gather_triangles(M, d_leaf_order, ctx->tris.ptr + prim_offset, st));
+    uint32_t node_count = 0;
+    Node8 root;
+    CKT(cudaMemcpyAsync(&node_count, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CKT(cudaMemcpyAsync(&root, ctx->blas_nodes.ptr + node_offset, sizeof(Node8), cudaMemcpyDeviceToHost, st));
+    CKT(cudaStreamSynchronize(st));
+    cleanup_tmp();
+    ctx->blas_nodes.size += node_count;
+    ctx->tris.size += nt;
+    m.blas.root = node_offset;
+    m.blas.num_tris = nt;
+    for (int k = 0; k < 3; k++) { m.blas.lo[k] = root.lo[k]; m.blas.hi[k] = root.hi[k]; }
+
+    // ---- ModelInfo / BlasInfo tables (reference layout, device pointers in the u64 fields)
+    uint32_t id = (uint32_t)ctx->models.size();
+    RtModelInfo mi;
+    mi.position_buffer_address = (uint64_t)(uintptr_t)m.positions;
+    mi.normal_buffer_address = (uint64_t)(uintptr_t)m.normals;
+    mi.uv_buffer_address = (uint64_t)(uintptr_t)m.uvs;
+    mi.geometry_info_address = (uint64_t)(uintptr_t)m.geom_info;
+    CKM(ctx->d_model_info.reserve(id + 1, st));
+    CKM(ctx->d_blas_info.reserve(id + 1, st));
+    CKM(cudaMemcpyAsync(ctx->d_model_info.ptr + id, &mi, sizeof(mi), cudaMemcpyHostToDevice, st));
+    CKM(cudaMemcpyAsync(ctx->d_blas_info.ptr + id, &m.blas, sizeof(BlasInfo), cudaMemcpyHostToDevice, st));
+    CKM(cudaStreamSynchronize(st));
+    ctx->d_model_info.size = id + 1;
+    ctx->d_blas_info.size = id + 1;
+    ctx->models.push_back(m);
+    if (out_model_id) *out_model_id = id;
+    if (out_blas_handle) *out_blas_handle = (0xB200ull << 48) | (uint64_t)(id + 1);
+    return RT_OK;
+#undef CKM
+#undef CKT
+}
+
+int rt_build_tlas(RtContext* ctx, const RtInstance* instances, uint32_t count) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (count && !instances) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_build_tlas: instances is NULL");
+    CK_DEV(ctx);
+    int rc = ensure_instance_capacity(ctx, count);
+    if (rc) return rc;
+    ctx->num_instances = count;
+    ctx->tlas_built = false;
+    if (count) CK(cudaMemcpyAsync(ctx->d_instances, instances, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    rc = build_tlas_now(ctx, RT_UPDATE_REBUILD);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));  // the caller may free `instances` now
+    return RT_OK;
+}
+
+int rt_update_instances(RtContext* ctx, uint32_t first, uint32_t count, const RtInstance* host_records) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if ((uint64_t)first + count > ctx->num_instances) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_update_instances: range outside the instance buffer");
+    if (count && !host_records) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_instances: records is NULL");
+    CK_DEV(ctx);
+    if (count) {
+        CK(cudaMemcpyAsync(ctx->d_instances + first, host_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // pageable source: the caller owns it again on return
+    }
+    return RT_OK;
+}
+
+int rt_update_instances_device(RtContext* ctx, uint32_t first, uint32_t count, const void* device_records) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if ((uint64_t)first + count > ctx->num_instances) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_update_instances_device: range outside the instance buffer");
+    if (count && !device_records) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_instances_device: records is NULL");
+    CK_DEV(ctx);
+    if (count) CK(cudaMemcpyAsync(ctx->d_instances + first, device_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyDeviceToDevice, ctx->stream));
+    return RT_OK;
+}
+
+int rt_update_tlas(RtContext* ctx, uint32_t mode) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (mode > RT_UPDATE_REBUILD) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_tlas: unknown mode");
+    if (!ctx->tlas_built) return fail(ctx, RT_ERR_NOT_BUILT, "rt_update_tlas before rt_build_tlas");
+    CK_DEV(ctx);
+    if (mode == RT_UPDATE_AUTO) mode = RT_UPDATE_REBUILD;
+    return build_tlas_now(ctx, mode);
+}
+
+int rt_render_device(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params, const RtFrameOutputs* out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!uniforms || !params) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_device: NULL argument");
+    CK_DEV(ctx);
+    FramePlan f;
+    int rc = plan_frame(ctx, params, f);
+    if (rc) return rc;
+    return render_common(ctx, uniforms, params, f, out ? out->rgba8 : nullptr, out ? out->radiance : nullptr, out ? out->hit_ids : nullptr,
+                         out ? out->ray_counts : nullptr);
+}
+
+int rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params, const RtFrameOutputs* out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!uniforms || !params) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: NULL argument");
+    CK_DEV(ctx);
+    FramePlan f;
+    int rc = plan_frame(ctx, params, f);
+    if (rc) return rc;
+    size_t pixels = (size_t)f.rows * f.tw;
+    bool want_rad = out && out->radiance, want_ids = out && out->hit_ids;
+    CK(grow(ctx->d_fb_rgba8, ctx->fb_rgba8_cap, pixels * 4 + 16));
+    if (want_rad) CK(grow(ctx->d_fb_radiance, ctx->fb_radiance_cap, pixels * 3 + 4));
+    if (want_ids) CK(grow(ctx->d_fb_hit_ids, ctx->fb_hit_ids_cap, pixels * 3 * params->max_segments + 4));
+    rc = render_common(ctx, uniforms, params, f, ctx->d_fb_rgba8, want_rad ? ctx->d_fb_radiance : nullptr,
+                       want_ids ? ctx->d_fb_hit_ids : nullptr, ctx->d_ray_counts);
+    if (rc) return rc;
+    if (out) {
+        cudaStream_t st = ctx->stream;
+        if (out->rgba8) CK(cudaMemcpyAsync(out->rgba8, ctx->d_fb_rgba8, pixels * 4, cudaMemcpyDeviceToHost, st));
+        if (want_rad) CK(cudaMemcpyAsync(out->radiance, ctx->d_fb_radiance, pixels * 12, cudaMemcpyDeviceToHost, st));
+        if (want_ids) CK(cudaMemcpyAsync(out->hit_ids, ctx->d_fb_hit_ids, pixels * 12 * params->max_segments, cudaMemcpyDeviceToHost, st));
+        if (out->ray_counts) CK(cudaMemcpyAsync(out->ray_counts, ctx->d_ray_counts, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return RT_OK;
+}
+
+int rt_readback(RtContext* ctx, void* host_rgba8, size_t capacity_bytes) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!host_rgba8) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_readback: NULL destination");
+    size_t bytes = ctx->last_rows * ctx->last_tw * 4;
+    if (!ctx->d_fb_rgba8 || bytes == 0) return fail(ctx, RT_ERR_NOT_BUILT, "rt_readback: no frame rendered by rt_render yet");
+    if (capacity_bytes < bytes) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_readback: destination too small");
+    CK_DEV(ctx);
+    CK(cudaMemcpyAsync(host_rgba8, ctx->d_fb_rgba8, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_sync(RtContext* ctx) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    CK_DEV(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_get_stats(RtContext* ctx, RtStats* out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!out) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_get_stats: NULL");
+    CK_DEV(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    FrameCounters fc;
+    CK(cudaMemcpy(&fc, ctx->d_counters, sizeof(fc), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->primary_rays = fc.primary_rays;
+    out->shadow_rays = fc.shadow_rays;
+    out->textured_hits = fc.textured_hits;
+    for (int k = 0; k < 2; k++) {
+        out->nodes_visited[k] = fc.nodes_visited[k];
+        out->instances_entered[k] = fc.instances_entered[k];
+        out->triangles_tested[k] = fc.triangles_tested[k];
+        out->anyhit_calls[k] = fc.anyhit_calls[k];
+    }
+    if (ctx->timing_valid) {
+        for (int i = 0; i < ctx->timing.n; i++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ctx->timing.ev[i], ctx->timing.ev[i + 1]));
+            out->kernel_ms[ctx->timing.kind[i]] += ms;
+            out->kernel_launches[ctx->timing.kind[i]]++;
+        }
+    }
+    if (fc.stack_overflow) return fail(ctx, RT_ERR_OUT_OF_RANGE, "traversal stack overflow in the last frame");
+    if (ctx->render_timed) CK(cudaEventElapsedTime(&out->last_render_ms, ctx->ev[0], ctx->ev[1]));
+    if (ctx->tlas_timed) CK(cudaEventElapsedTime(&out->last_tlas_ms, ctx->ev[2], ctx->ev[3]));
+    if (ctx->tlas_built) CK(cudaMemcpy(&out->tlas_nodes, ctx->d_tlas_node_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    out->blas_nodes = (uint32_t)ctx->blas_nodes.size;
+    out->num_instances = ctx->num_instances;
+    out->num_triangles = (uint32_t)ctx->tris.size;
+    return RT_OK;
+}
+
+int rt_get_push_constants(RtContext* ctx, RtPushConstantBufferAddresses* out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!out) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_get_push_constants: NULL");
+    out->model_info = (uint64_t)(uintptr_t)ctx->d_model_info.ptr;
+    out->uniforms = (uint64_t)(uintptr_t)ctx->d_uniforms;
+    out->acceleration_structure = (uint64_t)(uintptr_t)ctx->d_tlas_nodes;
+    return RT_OK;
+}
+
+int rt_debug_read_model_info(RtContext* ctx, uint32_t model_id, RtModelInfo* out_info, RtGeometryInfo* out_geoms, uint32_t max_geoms) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (model_id >= ctx->models.size()) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_debug_read_model_info: no such model");
+    CK_DEV(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (out_info) CK(cudaMemcpy(out_info, ctx->d_model_info.ptr + model_id, sizeof(RtModelInfo), cudaMemcpyDeviceToHost));
+    if (out_geoms) {
+        uint32_t n = ctx->models[model_id].num_geoms < max_geoms ? ctx->models[model_id].num_geoms : max_geoms;
+        if (n) CK(cudaMemcpy(out_geoms, ctx->models[model_id].geom_info, sizeof(RtGeometryInfo) * n, cudaMemcpyDeviceToHost));
+    }
+    return RT_OK;
+}
+
+}  // extern "C"

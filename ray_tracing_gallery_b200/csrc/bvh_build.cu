@@ -1,0 +1,669 @@
+// bvh_build.cu — LBVH -> SAH-guided collapse -> compressed 8-wide BVH, entirely on the GPU.
+//
+//   1. centroid bounds            k_centroid_bounds    (warp shuffles + ordered-int atomics)
+//   2. 63-bit Morton keys         k_morton
+//   3. radix sort                 cub::DeviceRadixSort::SortPairs (64-bit key, 32-bit payload)
+//   4. binary radix tree          k_hierarchy          (Karras 2012, index tie-break for duplicates)
+//   5. bottom-up AABB fit         k_fit                (one atomic flag per internal node)
+//   6. collapse to 8-wide nodes   k_collapse_coop      (breadth-first, one cooperative launch:
+//                                                      task index == wide-node index, so the BFS
+//                                                      queue IS the node array; grid.sync per level)
+//      - children chosen by greedy largest-surface-area expansion of the binary tree
+//      - slots assigned by child-centre octant => front-to-back order is (slot XOR ray octant)
+//      - boxes quantised to 8 bits on an exactly representable power-of-two grid
+//   7. refit (TLAS update)        k_refit              (bottom-up over wide nodes)
+//
+// What the Vulkan driver does for the reference at src/util_structs.rs:269-274 / :345-354.
+#include <cooperative_groups.h>
+#include <math_constants.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "bvh_build.h"
+#include "launch_count.h"
+
+namespace cg = cooperative_groups;
+
+namespace b200rt {
+namespace {
+
+enum { ST_LEVEL_BEGIN = 0, ST_LEVEL_END = 1, ST_WIDE_COUNT = 2, ST_PRIM_CURSOR = 3 };
+
+__device__ __forceinline__ int f2ord(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+__device__ __forceinline__ bool box_valid(const Aabb& b) {
+    return b.lo[0] <= b.hi[0] && b.lo[1] <= b.hi[1] && b.lo[2] <= b.hi[2] && isfinite(b.lo[0]) && isfinite(b.lo[1]) &&
+           isfinite(b.lo[2]) && isfinite(b.hi[0]) && isfinite(b.hi[1]) && isfinite(b.hi[2]);
+}
+__device__ __forceinline__ Aabb box_empty() {
+    Aabb b;
+    b.lo[0] = b.lo[1] = b.lo[2] = CUDART_INF_F;
+    b.hi[0] = b.hi[1] = b.hi[2] = -CUDART_INF_F;
+    return b;
+}
+__device__ __forceinline__ void box_grow(Aabb& a, const Aabb& b) {
+    if (!box_valid(b)) return;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        a.lo[k] = fminf(a.lo[k], b.lo[k]);
+        a.hi[k] = fmaxf(a.hi[k], b.hi[k]);
+    }
+}
+__device__ __forceinline__ float box_area(const Aabb& b) {
+    if (!box_valid(b)) return 0.0f;
+    float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+__device__ __forceinline__ Aabb ldcg_box(const Aabb* p) {
+    Aabb b;
+    const float* f = reinterpret_cast<const float*>(p);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        b.lo[k] = __ldcg(f + k);
+        b.hi[k] = __ldcg(f + 3 + k);
+    }
+    return b;
+}
+
+// ------------------------------------------------------------------------------------ 1, 2
+__global__ void k_init_state(int* bounds, uint32_t* state) {
+    int t = threadIdx.x;
+    if (t < 3) bounds[t] = f2ord(CUDART_INF_F);
+    else if (t < 6) bounds[t] = f2ord(-CUDART_INF_F);
+    if (t == 0) {
+        for (int i = 0; i < 8; i++) state[i] = 0;
+        state[ST_LEVEL_BEGIN] = 0;
+        state[ST_LEVEL_END] = 1;
+        state[ST_WIDE_COUNT] = 1;
+        state[ST_PRIM_CURSOR] = 0;
+    }
+}
+
+__global__ void k_centroid_bounds(const Aabb* __restrict__ boxes, uint32_t n, int* bounds) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
+    float hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    if (i < n) {
+        Aabb b = boxes[i];
+        if (box_valid(b)) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) lo[k] = hi[k] = 0.5f * b.lo[k] + 0.5f * b.hi[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            atomicMin(&bounds[k], f2ord(lo[k]));
+            atomicMax(&bounds[3 + k], f2ord(hi[k]));
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint64_t x) {
+    x &= 0x1FFFFFull;
+    x = (x | x << 32) & 0x1F00000000FFFFull;
+    x = (x | x << 16) & 0x1F0000FF0000FFull;
+    x = (x | x << 8) & 0x100F00F00F00F00Full;
+    x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const Aabb* __restrict__ boxes, uint32_t n, const int* __restrict__ bounds, uint64_t* keys,
+                         uint32_t* vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Aabb b = boxes[i];
+    uint64_t key = 0x7FFFFFFFFFFFFFFFull;  // invalid boxes sort last
+    if (box_valid(b)) {
+        uint64_t q[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float lo = ord2f(bounds[k]), hi = ord2f(bounds[3 + k]);
+            float c = 0.5f * b.lo[k] + 0.5f * b.hi[k];
+            float ext = hi - lo;
+            float f = ext > 0.0f ? (c - lo) / ext : 0.0f;
+            f = fminf(fmaxf(f, 0.0f), 1.0f);
+            q[k] = (uint64_t)(f * 2097151.0f);
+        }
+        key = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    }
+    keys[i] = key;
+    vals[i] = i;
+}
+
+// ------------------------------------------------------------------------------------ 4
+struct Tree2 {
+    const uint64_t* keys;   // sorted
+    const uint32_t* vals;   // sorted position -> input primitive
+    int* left;              // internal node -> child ref (>=0 internal, <0: ~leaf position)
+    int* right;
+    int* parent_int;        // parent of an internal node (-1 for root)
+    int* parent_leaf;       // parent of a leaf position
+    uint32_t* first;        // primitive range of an internal node (sorted positions)
+    uint32_t* last;
+    Aabb* ibox;             // internal node boxes
+    uint32_t* flags;
+    const Aabb* boxes;      // input boxes (by input primitive)
+    int n;
+};
+
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ k, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = k[i], b = k[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_hierarchy(Tree2 T) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = T.n;
+    if (i >= n - 1) return;
+    const uint64_t* k = T.keys;
+    int d = (delta(k, n, i, i + 1) - delta(k, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(k, n, i, i - d);
+    int lmax = 2;
+    while (delta(k, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(k, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(k, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(k, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int lref, rref;
+    if (lo == gamma) { lref = ~gamma; T.parent_leaf[gamma] = i; } else { lref = gamma; T.parent_int[gamma] = i; }
+    if (hi == gamma + 1) { rref = ~(gamma + 1); T.parent_leaf[gamma + 1] = i; } else { rref = gamma + 1; T.parent_int[gamma + 1] = i; }
+    T.left[i] = lref;
+    T.right[i] = rref;
+    T.first[i] = (uint32_t)lo;
+    T.last[i] = (uint32_t)hi;
+    if (i == 0) T.parent_int[0] = -1;
+}
+
+// ------------------------------------------------------------------------------------ 5
+__device__ __forceinline__ Aabb ref_box_cg(const Tree2& T, int ref) {
+    if (ref < 0) return T.boxes[T.vals[~ref]];
+    return ldcg_box(&T.ibox[ref]);
+}
+
+__global__ void k_fit(Tree2 T) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= T.n) return;
+    int cur = T.parent_leaf[p];
+    while (cur >= 0) {
+        __threadfence();
+        unsigned old = atomicAdd(&T.flags[cur], 1u);
+        if (old == 0) return;
+        Aabb b = box_empty();
+        box_grow(b, ref_box_cg(T, T.left[cur]));
+        box_grow(b, ref_box_cg(T, T.right[cur]));
+        float* f = reinterpret_cast<float*>(&T.ibox[cur]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            __stcg(f + k, b.lo[k]);
+            __stcg(f + 3 + k, b.hi[k]);
+        }
+        cur = T.parent_int[cur];
+    }
+}
+
+// ------------------------------------------------------------------------------------ quantisation
+// Choose the grid (origin, exponent) of one axis so that lo..hi spans <= 254 cells (one cell of
+// slack for the outward rounding fix-up) and every plane origin + q*2^e is exactly representable.
+__device__ __forceinline__ void axis_grid(float lo, float hi, float& origin, int& e) {
+    float s = (hi - lo) / 253.0f;
+    int es = -126, em = -126;
+    if (s > 0.0f) frexpf(s, &es);  // s = m * 2^es, m in [0.5,1)  =>  2^es > s
+    float mx = fmaxf(fabsf(lo), fabsf(hi));
+    if (mx > 0.0f) frexpf(mx, &em);  // mx < 2^em
+    e = max(max(es, em - 22), -100);
+    for (;;) {
+        origin = ldexpf(floorf(ldexpf(lo, -e)), e);
+        float top = ceilf(ldexpf(hi - origin, -e));
+        if (top <= 254.0f || e >= 120) break;
+        e++;
+    }
+}
+
+// Fill geometry fields of `nd` (origin, exp, qlo, qhi, lo, hi) from the per-slot child boxes.
+__device__ void quantise_node(Node8& nd, const Aabb* cb, uint32_t present) {
+    Aabb nb = box_empty();
+    for (int s = 0; s < 8; s++)
+        if (present >> s & 1) box_grow(nb, cb[s]);
+    bool any = box_valid(nb);
+    float org[3] = {0.f, 0.f, 0.f};
+    int ex[3] = {0, 0, 0};
+    if (any) {
+        for (int k = 0; k < 3; k++) axis_grid(nb.lo[k], nb.hi[k], org[k], ex[k]);
+    }
+    for (int k = 0; k < 3; k++) {
+        nd.origin[k] = org[k];
+        nd.exp[k] = (int8_t)ex[k];
+        nd.lo[k] = nb.lo[k];
+        nd.hi[k] = nb.hi[k];
+    }
+    for (int s = 0; s < 8; s++) {
+        bool ok = (present >> s & 1) && box_valid(cb[s]);
+        for (int k = 0; k < 3; k++) {
+            uint8_t ql = 255, qh = 0;
+            if (ok) {
+                float cell = ldexpf(1.0f, ex[k]);
+                float a = floorf(ldexpf(cb[s].lo[k] - org[k], -ex[k]));
+                a = fminf(fmaxf(a, 0.0f), 255.0f);
+                while (a > 0.0f && fmaf(a, cell, org[k]) > cb[s].lo[k]) a -= 1.0f;
+                float b = ceilf(ldexpf(cb[s].hi[k] - org[k], -ex[k]));
+                b = fminf(fmaxf(b, 0.0f), 255.0f);
+                while (b < 255.0f && fmaf(b, cell, org[k]) < cb[s].hi[k]) b += 1.0f;
+                ql = (uint8_t)a;
+                qh = (uint8_t)b;
+            }
+            nd.qlo[k][s] = ql;
+            nd.qhi[k][s] = qh;
+        }
+    }
+}
+
+__device__ __forceinline__ void store_node(Node8* dst, const Node8& nd) {
+    const uint4* s = reinterpret_cast<const uint4*>(&nd);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------ 6
+struct CollapseArgs {
+    Tree2 T;
+    int* task_node;        // wide index -> binary subtree ref
+    uint32_t* task_parent; // wide index -> parent wide index | slot << 29
+    uint32_t* state;
+    Node8* nodes;          // pool base
+    uint32_t node_offset, prim_offset, max_leaf;
+    uint32_t* leaf_order;
+};
+
+__device__ __forceinline__ uint32_t ref_count(const Tree2& T, int r) { return r < 0 ? 1u : T.last[r] - T.first[r] + 1u; }
+__device__ __forceinline__ uint32_t ref_first(const Tree2& T, int r) { return r < 0 ? (uint32_t)~r : T.first[r]; }
+__device__ __forceinline__ Aabb ref_box(const Tree2& T, int r) { return r < 0 ? T.boxes[T.vals[~r]] : T.ibox[r]; }
+
+__device__ void collapse_task(const CollapseArgs& A, uint32_t w) {
+    const Tree2& T = A.T;
+    int ch[8];
+    int cnt;
+    int r = A.task_node[w];
+    if (r < 0) { ch[0] = r; cnt = 1; }
+    else { ch[0] = T.left[r]; ch[1] = T.right[r]; cnt = 2; }
+    // greedy expansion by surface area: first only subtrees too big to be a leaf, then any subtree
+    for (int pass = 0; pass < 2; pass++) {
+        while (cnt < 8) {
+            int best = -1;
+            float best_area = -1.0f;
+            for (int j = 0; j < cnt; j++) {
+                int c = ch[j];
+                if (c < 0) continue;
+                if (pass == 0 && ref_count(T, c) <= A.max_leaf) continue;
+                float a = box_area(T.ibox[c]);
+                if (a > best_area) { best_area = a; best = j; }
+            }
+            if (best < 0) break;
+            int c = ch[best];
+            ch[best] = T.left[c];
+            ch[cnt++] = T.right[c];
+        }
+    }
+    Aabb cb[8];
+    Aabb nb = box_empty();
+    for (int j = 0; j < cnt; j++) {
+        cb[j] = ref_box(T, ch[j]);
+        box_grow(nb, cb[j]);
+    }
+    // slot assignment by octant of the child centre
+    int child_at[8];
+    for (int s = 0; s < 8; s++) child_at[s] = -1;
+    float cn[3];
+    for (int k = 0; k < 3; k++) cn[k] = 0.5f * nb.lo[k] + 0.5f * nb.hi[k];
+    for (int j = 0; j < cnt; j++) {
+        int pref = 0;
+        if (box_valid(cb[j])) {
+            for (int k = 0; k < 3; k++)
+                if (0.5f * cb[j].lo[k] + 0.5f * cb[j].hi[k] > cn[k]) pref |= 1 << k;
+        }
+        int best = -1, best_cost = 99;
+        for (int s = 0; s < 8; s++) {
+            if (child_at[s] >= 0) continue;
+            int cost = __popc(pref ^ s) * 8 + (pref ^ s);
+            if (cost < best_cost) { best_cost = cost; best = s; }
+        }
+        child_at[best] = j;
+    }
+    uint32_t k_int = 0, total_prims = 0;
+    for (int j = 0; j < cnt; j++) {
+        uint32_t c = ref_count(T, ch[j]);
+        if (ch[j] >= 0 && c > A.max_leaf) k_int++;
+        else total_prims += c;
+    }
+    uint32_t base = k_int ? atomicAdd(&A.state[ST_WIDE_COUNT], k_int) : 0u;
+    uint32_t pbase = total_prims ? atomicAdd(&A.state[ST_PRIM_CURSOR], total_prims) : 0u;
+
+    Node8 nd;
+    memset(&nd, 0, sizeof(nd));
+    Aabb sb[8];
+    uint32_t present = 0, imask = 0, lmask = 0, rank = 0, off = 0;
+    for (int s = 0; s < 8; s++) {
+        int j = child_at[s];
+        if (j < 0) continue;
+        present |= 1u << s;
+        sb[s] = cb[j];
+        uint32_t c = ref_count(T, ch[j]);
+        if (ch[j] >= 0 && c > A.max_leaf) {
+            imask |= 1u << s;
+            nd.meta[s] = 0xFF;
+            A.task_node[base + rank] = ch[j];
+            A.task_parent[base + rank] = w | ((uint32_t)s << 29);
+            rank++;
+        } else {
+            lmask |= 1u << s;
+            uint32_t f = ref_first(T, ch[j]);
+            for (uint32_t k = 0; k < c; k++) A.leaf_order[pbase + off + k] = T.vals[f + k];
+            nd.meta[s] = (uint8_t)(off | (c << 5));
+            off += c;
+        }
+    }
+    quantise_node(nd, sb, present);
+    nd.imask = (uint8_t)imask;
+    nd.lmask = lmask;
+    nd.child_base = A.node_offset + base;
+    nd.prim_base = A.prim_offset + pbase;
+    if (w == 0) { nd.parent = 0xFFFFFFFFu; nd.parent_slot = 0; }
+    else {
+        uint32_t tp = A.task_parent[w];
+        nd.parent = A.node_offset + (tp & 0x1FFFFFFFu);
+        nd.parent_slot = tp >> 29;
+    }
+    store_node(&A.nodes[A.node_offset + w], nd);
+}
+
+__global__ void __launch_bounds__(128) k_collapse_coop(CollapseArgs A) {
+    cg::grid_group grid = cg::this_grid();
+    uint32_t begin = 0, end = 1;
+    uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    while (begin < end) {
+        for (uint32_t w = begin + gtid; w < end; w += gsize) collapse_task(A, w);
+        grid.sync();
+        begin = end;
+        end = *((volatile uint32_t*)&A.state[ST_WIDE_COUNT]);
+        grid.sync();  // nobody may bump WIDE_COUNT before everyone has read it
+    }
+}
+
+// Fallback: one launch per level, the level range lives in A.state.
+__global__ void k_collapse_level(CollapseArgs A, uint32_t begin, uint32_t end) {
+    uint32_t w = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < end) collapse_task(A, w);
+}
+
+__global__ void k_empty_root(Node8* nodes, uint32_t node_offset, uint32_t prim_offset, uint32_t* state) {
+    Node8 nd;
+    memset(&nd, 0, sizeof(nd));
+    Aabb sb[8];
+    quantise_node(nd, sb, 0);
+    nd.child_base = node_offset;
+    nd.prim_base = prim_offset;
+    nd.parent = 0xFFFFFFFFu;
+    store_node(&nodes[node_offset], nd);
+    state[ST_WIDE_COUNT] = 1;
+}
+
+__global__ void k_single_leaf_task(int* task_node, uint32_t* task_parent) {
+    task_node[0] = ~0;  // leaf position 0
+    task_parent[0] = 0;
+}
+__global__ void k_root_task(int* task_node, uint32_t* task_parent) {
+    task_node[0] = 0;  // binary root
+    task_parent[0] = 0;
+}
+__global__ void k_copy_u32(const uint32_t* src, uint32_t* dst) { *dst = *src; }
+
+// ------------------------------------------------------------------------------------ 7
+struct RefitArgs {
+    Node8* nodes;
+    uint32_t node_offset, prim_offset;
+    const uint32_t* node_count;
+    const Aabb* boxes;  // by leaf position
+    uint32_t* counters;
+};
+
+__global__ void k_refit(RefitArgs A) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= *A.node_count) return;
+    Node8* nd = &A.nodes[A.node_offset + w];
+    if (nd->imask != 0) return;  // only bottom nodes start
+    for (;;) {
+        Node8 cur;
+        {
+            const uint4* s = reinterpret_cast<const uint4*>(nd);
+            uint4* d = reinterpret_cast<uint4*>(&cur);
+#pragma unroll
+            for (int i = 0; i < 8; i++) d[i] = __ldcg(s + i);
+        }
+        Aabb sb[8];
+        uint32_t present = cur.imask | cur.lmask, rank = 0;
+        for (int s = 0; s < 8; s++) {
+            if (cur.imask >> s & 1) {
+                const Node8* c = &A.nodes[cur.child_base + rank++];
+                const float* f = reinterpret_cast<const float*>(c) + 20;  // lo at byte 80
+                for (int k = 0; k < 3; k++) { sb[s].lo[k] = __ldcg(f + k); sb[s].hi[k] = __ldcg(f + 3 + k); }
+            } else if (cur.lmask >> s & 1) {
+                uint32_t off = cur.meta[s] & 31u, c = cur.meta[s] >> 5;
+                Aabb b = box_empty();
+                for (uint32_t k = 0; k < c; k++) box_grow(b, A.boxes[cur.prim_base - A.prim_offset + off + k]);
+                sb[s] = b;
+            }
+        }
+        quantise_node(cur, sb, present);
+        {
+            const uint4* s = reinterpret_cast<const uint4*>(&cur);
+            uint4* d = reinterpret_cast<uint4*>(nd);
+#pragma unroll
+            for (int i = 0; i < 8; i++) __stcg(d + i, s[i]);
+        }
+        if (cur.parent == 0xFFFFFFFFu) return;
+        __threadfence();
+        uint32_t pl = cur.parent - A.node_offset;
+        Node8* pn = &A.nodes[cur.parent];
+        uint32_t need = __popc((uint32_t)__ldcg(reinterpret_cast<const unsigned char*>(pn) + 15));
+        uint32_t old = atomicAdd(&A.counters[pl], 1u);
+        if (old + 1 != need) return;
+        nd = pn;
+    }
+}
+
+template <typename T>
+T* carve(char*& p, size_t count) {
+    uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255);
+    T* r = reinterpret_cast<T*>(a);
+    p = reinterpret_cast<char*>(a + count * sizeof(T));
+    return r;
+}
+
+struct Scratch {
+    int* bounds;
+    uint32_t* state;
+    uint64_t *keys_in, *keys_out;
+    uint32_t *vals_in, *vals_out;
+    int *left, *right, *parent_int, *parent_leaf;
+    uint32_t *first, *last, *flags;
+    Aabb* ibox;
+    int* task_node;
+    uint32_t* task_parent;
+    uint32_t* refit_counters;
+    void* cub_temp;
+};
+
+size_t layout(char* base, uint32_t n, size_t cub_bytes, Scratch& s) {
+    char* p = base;
+    uint32_t maxw = max_wide_nodes(n);
+    s.bounds = carve<int>(p, 8);
+    s.state = carve<uint32_t>(p, 8);
+    s.keys_in = carve<uint64_t>(p, n);
+    s.keys_out = carve<uint64_t>(p, n);
+    s.vals_in = carve<uint32_t>(p, n);
+    s.vals_out = carve<uint32_t>(p, n);
+    s.left = carve<int>(p, n);
+    s.right = carve<int>(p, n);
+    s.parent_int = carve<int>(p, n);
+    s.parent_leaf = carve<int>(p, n);
+    s.first = carve<uint32_t>(p, n);
+    s.last = carve<uint32_t>(p, n);
+    s.flags = carve<uint32_t>(p, n);
+    s.ibox = carve<Aabb>(p, n);
+    s.task_node = carve<int>(p, maxw);
+    s.task_parent = carve<uint32_t>(p, maxw);
+    s.refit_counters = carve<uint32_t>(p, maxw);
+    s.cub_temp = carve<char>(p, cub_bytes);
+    return (size_t)(p - base) + 256;
+}
+
+}  // namespace
+
+BvhBuilder::~BvhBuilder() {
+    if (scratch_) cudaFree(scratch_);
+}
+
+cudaError_t BvhBuilder::reserve(uint32_t n) {
+    if (n < 2) n = 2;
+    if (n <= cap_) return cudaSuccess;
+    uint32_t cap = n + n / 8 + 64;
+    size_t cub_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)cap, 0, 63);
+    if (e != cudaSuccess) return e;
+    Scratch s;
+    size_t bytes = layout(nullptr, cap, cub_bytes, s);
+    if (scratch_) cudaFree(scratch_);
+    scratch_ = nullptr;
+    cap_ = 0;
+    e = cudaMalloc(&scratch_, bytes);
+    if (e != cudaSuccess) return e;
+    scratch_bytes_ = bytes;
+    cub_bytes_ = cub_bytes;
+    cap_ = cap;
+    if (coop_blocks_ == 0) {
+        int dev = 0, sms = 0, per_sm = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse_coop, 128, 0);
+        coop_blocks_ = sms * (per_sm > 0 ? per_sm : 1);
+        coop_ok_ = coop != 0 && per_sm > 0;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
+                              uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, cudaStream_t stream) {
+    cudaError_t e = reserve(n);
+    if (e != cudaSuccess) return e;
+    Scratch s;
+    layout(static_cast<char*>(scratch_), cap_, cub_bytes_, s);
+    const int TB = 256;
+    k_init_state<<<1, 32, 0, stream>>>(s.bounds, s.state);
+    note_launch();
+    if (n == 0) {
+        k_empty_root<<<1, 1, 0, stream>>>(nodes_pool, node_offset, prim_offset, s.state);
+        note_launch();
+        if (d_node_count) { k_copy_u32<<<1, 1, 0, stream>>>(&s.state[ST_WIDE_COUNT], d_node_count); note_launch(); }
+        return cudaGetLastError();
+    }
+    uint32_t blocks = (n + TB - 1) / TB;
+    k_centroid_bounds<<<blocks, TB, 0, stream>>>(d_boxes, n, s.bounds);
+    k_morton<<<blocks, TB, 0, stream>>>(d_boxes, n, s.bounds, s.keys_in, s.vals_in);
+    note_launch(2);
+    size_t cub_bytes = cub_bytes_;
+    e = cub::DeviceRadixSort::SortPairs(s.cub_temp, cub_bytes, s.keys_in, s.keys_out, s.vals_in, s.vals_out, (int)n, 0, 63,
+                                        stream);
+    if (e != cudaSuccess) return e;
+    Tree2 T;
+    T.keys = s.keys_out; T.vals = s.vals_out;
+    T.left = s.left; T.right = s.right; T.parent_int = s.parent_int; T.parent_leaf = s.parent_leaf;
+    T.first = s.first; T.last = s.last; T.ibox = s.ibox; T.flags = s.flags;
+    T.boxes = d_boxes; T.n = (int)n;
+    if (n >= 2) {
+        cudaMemsetAsync(s.flags, 0, sizeof(uint32_t) * n, stream);
+        k_hierarchy<<<blocks, TB, 0, stream>>>(T);
+        k_fit<<<blocks, TB, 0, stream>>>(T);
+        k_root_task<<<1, 1, 0, stream>>>(s.task_node, s.task_parent);
+        note_launch(3);
+    } else {
+        k_single_leaf_task<<<1, 1, 0, stream>>>(s.task_node, s.task_parent);
+        note_launch();
+    }
+    CollapseArgs A;
+    A.T = T; A.task_node = s.task_node; A.task_parent = s.task_parent; A.state = s.state;
+    A.nodes = nodes_pool; A.node_offset = node_offset; A.prim_offset = prim_offset; A.max_leaf = max_leaf;
+    A.leaf_order = d_leaf_order;
+    bool done = false;
+    if (coop_ok_) {
+        void* args[] = {&A};
+        uint32_t want = (max_wide_nodes(n) + 127) / 128;
+        uint32_t grid = want < (uint32_t)coop_blocks_ ? (want ? want : 1u) : (uint32_t)coop_blocks_;
+        cudaError_t ce = cudaLaunchCooperativeKernel((void*)k_collapse_coop, dim3(grid), dim3(128), args, 0, stream);
+        if (ce == cudaSuccess) { done = true; note_launch(); }
+        else { (void)cudaGetLastError(); coop_ok_ = false; }
+    }
+    if (!done) {
+        // level-synchronous fallback (host reads the level range back)
+        uint32_t begin = 0, end = 1;
+        while (begin < end) {
+            k_collapse_level<<<(end - begin + 127) / 128, 128, 0, stream>>>(A, begin, end);
+            note_launch();
+            uint32_t cnt = 0;
+            e = cudaMemcpyAsync(&cnt, &s.state[ST_WIDE_COUNT], sizeof(cnt), cudaMemcpyDeviceToHost, stream);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) return e;
+            begin = end;
+            end = cnt;
+        }
+    }
+    if (d_node_count) { k_copy_u32<<<1, 1, 0, stream>>>(&s.state[ST_WIDE_COUNT], d_node_count); note_launch(); }
+    return cudaGetLastError();
+}
+
+cudaError_t BvhBuilder::refit(const Aabb* d_boxes_leaf_order, uint32_t n, Node8* nodes_pool, uint32_t node_offset,
+                              uint32_t prim_offset, const uint32_t* d_node_count, uint32_t node_capacity,
+                              cudaStream_t stream) {
+    cudaError_t e = reserve(n);
+    if (e != cudaSuccess) return e;
+    Scratch s;
+    layout(static_cast<char*>(scratch_), cap_, cub_bytes_, s);
+    uint32_t maxw = max_wide_nodes(cap_);
+    if (node_capacity > maxw) node_capacity = maxw;
+    cudaMemsetAsync(s.refit_counters, 0, sizeof(uint32_t) * node_capacity, stream);
+    RefitArgs A;
+    A.nodes = nodes_pool; A.node_offset = node_offset; A.prim_offset = prim_offset; A.node_count = d_node_count;
+    A.boxes = d_boxes_leaf_order; A.counters = s.refit_counters;
+    k_refit<<<(node_capacity + 127) / 128, 128, 0, stream>>>(A);
+    note_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace b200rt

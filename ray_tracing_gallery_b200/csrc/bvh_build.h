@@ -1,0 +1,47 @@
+// bvh_build.h — GPU builder of the compressed 8-wide BVH (used for every BLAS and for the TLAS).
+//
+// Replaces what the Vulkan driver does behind vkCmdBuildAccelerationStructuresKHR
+// (reference call sites: src/util_structs.rs:269-274 BLAS/TLAS build, :345-354 TLAS update).
+#pragma once
+#include "rt_types.h"
+
+namespace b200rt {
+
+// Upper bound on wide nodes for n primitives: every non-bottom node absorbs 7 binary nodes,
+// every bottom node holds >= 2 primitives.
+inline uint32_t max_wide_nodes(uint32_t n) { return n / 2 + n / 7 + 8; }
+
+class BvhBuilder {
+public:
+    BvhBuilder() = default;
+    ~BvhBuilder();
+    BvhBuilder(const BvhBuilder&) = delete;
+    BvhBuilder& operator=(const BvhBuilder&) = delete;
+
+    // Grow scratch for up to n primitives (no-op if already large enough).
+    cudaError_t reserve(uint32_t n);
+
+    // Build over `n` primitive boxes (device memory).  Writes wide nodes to
+    // nodes_pool[node_offset ...] (root = node_offset; at most max_wide_nodes(n) are written),
+    // child indices are absolute pool indices, prim_base values are prim_offset + position in
+    // leaf order.  d_leaf_order[i] = index of the input primitive stored at leaf position i.
+    // d_node_count (device, optional) receives the number of wide nodes written.
+    // Everything is enqueued on `stream`; no host synchronisation.
+    cudaError_t build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
+                      uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, cudaStream_t stream);
+
+    // Refit in place: recompute boxes bottom-up for a tree built by build() whose leaf order is
+    // unchanged.  d_boxes_leaf_order[i] = new box of the primitive at leaf position i.
+    cudaError_t refit(const Aabb* d_boxes_leaf_order, uint32_t n, Node8* nodes_pool, uint32_t node_offset,
+                      uint32_t prim_offset, const uint32_t* d_node_count, uint32_t node_capacity, cudaStream_t stream);
+
+private:
+    uint32_t cap_ = 0;
+    void* scratch_ = nullptr;
+    size_t scratch_bytes_ = 0;
+    size_t cub_bytes_ = 0;
+    int coop_blocks_ = 0;
+    bool coop_ok_ = true;
+};
+
+}  // namespace b200rt

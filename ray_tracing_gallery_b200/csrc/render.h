@@ -1,0 +1,37 @@
+// render.h — frame launch (render.cu) and scene-preparation kernels (scene_kernels.cu).
+#pragma once
+#include "rt_types.h"
+
+namespace b200rt {
+
+// Optional per-kernel timing of one frame: ev[0] is recorded before the first kernel, ev[i+1]
+// after the i-th timed kernel, kind[i] = 0 trace / 1 shade / 2 megakernel.
+struct FrameTiming {
+    enum { MAX_INTERVALS = 40 };
+    cudaEvent_t ev[MAX_INTERVALS + 1];
+    int kind[MAX_INTERVALS];
+    int n;
+};
+
+// Enqueue one frame on `stream`.  d_ray_counts (device, optional) receives {ray-gen segments, shadow rays}.
+cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, int sms, uint64_t* d_ray_counts,
+                         FrameTiming* timing, cudaStream_t stream);
+
+// BLAS input: per flattened triangle (geometry-major) the padded AABB.
+struct ModelGeomDev {
+    const float* positions;         // float3 per vertex
+    const uint32_t* const* indices; // per geometry
+    const uint32_t* geom_start;     // [num_geoms + 1] flattened triangle offsets
+    const uint8_t* geom_opaque;     // [num_geoms]
+    uint32_t num_geoms, num_tris, num_vertices;
+};
+cudaError_t launch_triangle_boxes(const ModelGeomDev& M, Aabb* boxes, cudaStream_t stream);
+cudaError_t launch_gather_triangles(const ModelGeomDev& M, const uint32_t* leaf_order, TriRec* out, cudaStream_t stream);
+
+// TLAS input: per instance the inverse transform, traversal record and padded world AABB.
+// leaf_order == nullptr: output slot i = instance i;  otherwise slot i = instance leaf_order[i].
+cudaError_t launch_prepare_instances(const RtInstance* instances, uint32_t n, const BlasInfo* blas, uint32_t num_models,
+                                     const uint32_t* leaf_order, InstRT* out_rt, Aabb* out_boxes, cudaStream_t stream);
+cudaError_t launch_gather_instances(const InstRT* in, const uint32_t* leaf_order, uint32_t n, InstRT* out, cudaStream_t stream);
+
+}  // namespace b200rt

@@ -1,0 +1,137 @@
+// rt_types.h — device-side records of libb200rt (internal; the public layouts are in include/rt_abi.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200rt.h"
+
+namespace b200rt {
+
+// ---------------------------------------------------------------------------------------------
+// Compressed 8-wide BVH node.  One 128-byte, 128-byte-aligned record = one L2 line.
+// Traversal reads bytes 0..79 as five ld.global.nc.v4; bytes 80..127 are build/refit state.
+//
+// Child boxes are quantised to 8 bits per plane on a power-of-two grid anchored at `origin`:
+//     plane = origin[k] + q * 2^exp[k]
+// The origin is snapped onto that grid and exp is clamped so that every plane is exactly
+// representable in fp32 (builder: quantise_node).  lo planes are rounded down, hi planes up.
+// Slots are assigned by the octant of the child centre relative to the node centre, so that
+// visiting hit slots in order of (slot XOR ray_octant) is front-to-back without sorting.
+// Internal children are stored contiguously from `child_base` in slot order
+// (child index = child_base + popc(imask & ((1<<slot)-1))); leaf primitives are stored
+// contiguously from `prim_base`: meta[slot] = offset (5 bits) | count << 5 (count 1..7) for a leaf
+// slot, 0xFF for an internal slot, 0 for an empty slot (which also has qlo = 255, qhi = 0).
+struct __align__(128) Node8 {
+    float    origin[3];   //  0
+    int8_t   exp[3];      // 12
+    uint8_t  imask;       // 15  bit s: slot s is an internal child
+    uint32_t child_base;  // 16
+    uint32_t prim_base;   // 20
+    uint8_t  meta[8];     // 24
+    uint8_t  qlo[3][8];   // 32  [axis][slot]
+    uint8_t  qhi[3][8];   // 56
+    // ---- not read by traversal
+    float    lo[3];       // 80  exact bounds of this node
+    float    hi[3];       // 92
+    uint32_t parent;      // 104 wide-node index of the parent (0xFFFFFFFF for the root)
+    uint32_t parent_slot; // 108
+    uint32_t lmask;       // 112 bit s: slot s is a leaf child
+    uint32_t _pad[3];
+};
+static_assert(sizeof(Node8) == 128, "Node8 must be one 128-byte line");
+
+// Triangle record in BVH leaf order: three float4.
+struct __align__(16) TriRec {
+    float v0[3];  uint32_t prim;        // gl_PrimitiveID
+    float e1[3];  uint32_t geom_flags;  // gl_GeometryIndexEXT | (non-opaque ? 0x80000000 : 0)
+    float e2[3];  uint32_t _pad;
+};
+static_assert(sizeof(TriRec) == 48, "TriRec is 48 bytes");
+#define RT_TRI_NON_OPAQUE 0x80000000u
+
+// Per-instance traversal record in TLAS leaf order: four float4.
+struct __align__(16) InstRT {
+    float    inv[12];      // world -> object, row-major 3x4
+    uint32_t blas_root;    // index into the BLAS node pool, 0xFFFFFFFF = no geometry
+    uint32_t instance_id;  // gl_InstanceID (index of the 64-byte record)
+    uint32_t custom_sbt;   // custom_index (24 low) | sbt_offset (8 high)
+    uint32_t mask;         // visibility mask (8 bits)
+};
+static_assert(sizeof(InstRT) == 64, "InstRT is 64 bytes");
+
+struct BlasInfo {
+    uint32_t root;       // wide-node index of the BLAS root in the pool
+    uint32_t num_tris;
+    float    lo[3], hi[3];
+};
+
+// Bindless image table entry (<= RT_MAX_BOUND_IMAGES).
+struct __align__(16) TexEntry {
+    cudaTextureObject_t obj;  // point-sampled, unnormalised coords; 0 for 1x1 constants
+    uint32_t w, h;
+    uint32_t format;          // RtFormat
+    uint32_t linear;          // sampler choice
+    float    constant[4];     // decoded texel of a 1x1 image
+};
+
+// Generic AABB used by the builder.
+struct Aabb {
+    float lo[3];
+    float hi[3];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Wavefront queues.
+struct __align__(16) RayRec {   // 32 B: a ray-gen segment waiting to be traced
+    float ox, oy, oz; uint32_t pixel;
+    float dx, dy, dz; uint32_t _pad;
+};
+struct __align__(16) HitRec {   // 48 B: a textured hit waiting for shadow rays + shading
+    uint32_t pixel, inst_pos, geom, prim;
+    float    u, v, t; uint32_t _pad;
+    float    dx, dy, dz; uint32_t _pad2;
+};
+
+struct FrameCounters {
+    unsigned long long primary_rays, shadow_rays, textured_hits;
+    // [0] closest-hit rays (k_trace), [1] shadow rays (k_shade)
+    unsigned long long nodes_visited[2], instances_entered[2], triangles_tested[2], anyhit_calls[2];
+    unsigned int hit_count;       // HitRec queue fill
+    unsigned int ray_count[2];    // RayRec ping-pong queue fill
+    unsigned int work_next[4];    // persistent-kernel work cursors
+    unsigned int stack_overflow;  // traversal stack overflow events (must stay 0)
+    unsigned int _pad;
+};
+
+// Everything a render kernel needs, passed by value (< 4 KB).
+struct SceneDev {
+    const Node8*      tlas_nodes;
+    const InstRT*     inst_rt;       // TLAS leaf order
+    const RtInstance* instances;     // original 64-byte records, by gl_InstanceID
+    const Node8*      blas_nodes;
+    const TriRec*     tris;
+    const RtModelInfo* model_info;   // reference layout, device pointers inside
+    uint32_t          num_models;
+    uint32_t          num_instances;
+    const TexEntry*   textures;
+    uint32_t          num_textures;
+    const float*      srgb_lut;      // 256 floats
+};
+
+struct FrameDev {
+    RtUniforms uniforms;
+    uint32_t width, height;         // launch size
+    uint32_t max_segments, shadow_rays;
+    uint32_t x0, y0, tw, rows;      // rendered rectangle: tw columns, `rows` compact rows
+    uint32_t tile_h;
+    uint32_t strip_height, strip_count, strip_index;
+    float    cos_sun_radius;
+    uint8_t*  rgba8;
+    float*    radiance;
+    uint32_t* hit_ids;
+    FrameCounters* counters;
+    RayRec*   ray_q[2];
+    HitRec*   hit_q;
+};
+
+}  // namespace b200rt

@@ -1,0 +1,354 @@
+// shade.cuh — the reference's shader stages as device functions.
+//
+//   sample_texture            Vulkan sampler rules at LOD 0 (src/util_structs.rs:1306-1320;
+//                             only OpImageSampleExplicitLod in the shipped .spv files)
+//   anyhit_accepts            shaders/any_hit_alpha_clip.glsl:11-28
+//   shade_textured_*          shaders/closest_hit_textured.glsl:13-226 + shaders/pbr.glsl:25-211
+//   shade_mirror              shaders/closest_hit_mirror.glsl:11-29
+//   shade_portal              shaders/ray-tracing/src/lib.rs:300-312
+//   miss_colour               shaders/ray-tracing/src/lib.rs:40-51
+//   linear_to_srgb / unorm8   shaders/ray-tracing/src/lib.rs:85-92, :188-190
+//   primary_ray               shaders/ray-tracing/src/lib.rs:126-142
+//
+// Geometry that decides which primitive a later ray hits (ray generation, barycentric
+// interpolation, normal transform, reflect, the shadow-terminator origin) follows the arithmetic
+// contract of contract.cuh; BRDF and texture filtering are plain fp32.
+#pragma once
+#include "contract.cuh"
+#include "rt_types.h"
+
+namespace b200rt {
+
+#define RT_PI 3.141592653589793f
+
+struct F4 { float r, g, b, a; };
+
+__device__ __forceinline__ int wrap_i(int i, int n) {
+    int m = i % n;
+    return m < 0 ? m + n : m;
+}
+
+__device__ __forceinline__ F4 fetch_texel(const SceneDev& S, const TexEntry& t, int x, int y) {
+    F4 r;
+    if (t.format == RT_FORMAT_RGBA32_SFLOAT) {
+        float4 c = tex2D<float4>(t.obj, (float)x + 0.5f, (float)y + 0.5f);
+        r.r = c.x; r.g = c.y; r.b = c.z; r.a = c.w;
+        return r;
+    }
+    uchar4 c = tex2D<uchar4>(t.obj, (float)x + 0.5f, (float)y + 0.5f);
+    if (t.format == RT_FORMAT_RGBA8_SRGB) {
+        r.r = __ldg(S.srgb_lut + c.x); r.g = __ldg(S.srgb_lut + c.y); r.b = __ldg(S.srgb_lut + c.z);
+    } else {
+        r.r = __fdiv_rn((float)c.x, 255.0f); r.g = __fdiv_rn((float)c.y, 255.0f); r.b = __fdiv_rn((float)c.z, 255.0f);
+    }
+    r.a = __fdiv_rn((float)c.w, 255.0f);
+    return r;
+}
+
+// REPEAT addressing, normalised coordinates, texel centres at +0.5, sRGB decode before filtering.
+__device__ __forceinline__ F4 sample_texture_one(const SceneDev& S, uint32_t index, float u, float v);
+
+// Bindless fetch with a per-lane image index (`nonuniformEXT`, closest_hit_textured.glsl:50-52).
+// A TEX instruction takes its texture header from a uniform register; when lanes of a warp hold
+// different handles, the loop nvcc 12.9 generates for sm_100a returned texels of the wrong image
+// for some lanes (measured: compacted wavefront warps mixing lain/fence hits).  So the fetch is made
+// uniform by hand: the converged lanes elect a leader, the lanes sharing the leader's index sample
+// and leave, the rest go round again.
+__device__ __forceinline__ F4 sample_texture(const SceneDev& S, uint32_t index, float u, float v) {
+    F4 r;
+    r.r = r.g = r.b = r.a = 0.0f;
+    if (index >= S.num_textures) return r;  // robustness2 null descriptor, src/main.rs:183-184
+    for (;;) {
+        uint32_t m = __activemask();
+        uint32_t cur = __shfl_sync(m, index, __ffs(m) - 1);
+        if (cur == index) {
+            r = sample_texture_one(S, cur, u, v);
+            break;
+        }
+    }
+    return r;
+}
+// Same, for an index that is uniform by construction (the blue-noise image named by the Uniforms).
+__device__ __forceinline__ F4 sample_texture_uniform(const SceneDev& S, uint32_t index, float u, float v) {
+    return sample_texture_one(S, index, u, v);
+}
+__device__ __forceinline__ F4 sample_texture_one(const SceneDev& S, uint32_t index, float u, float v) {
+    F4 r;
+    r.r = r.g = r.b = r.a = 0.0f;
+    if (index >= S.num_textures) return r;  // robustness2 null descriptor, src/main.rs:183-184
+    const TexEntry t = S.textures[index];
+    if (t.w == 1 && t.h == 1) {
+        r.r = t.constant[0]; r.g = t.constant[1]; r.b = t.constant[2]; r.a = t.constant[3];
+        return r;
+    }
+    if (!t.linear) {
+        int x = wrap_i((int)floorf(u * (float)t.w), (int)t.w);
+        int y = wrap_i((int)floorf(v * (float)t.h), (int)t.h);
+        return fetch_texel(S, t, x, y);
+    }
+    float fx = u * (float)t.w - 0.5f, fy = v * (float)t.h - 0.5f;
+    float flx = floorf(fx), fly = floorf(fy);
+    float ax = fx - flx, ay = fy - fly;
+    int x0 = wrap_i((int)flx, (int)t.w), y0 = wrap_i((int)fly, (int)t.h);
+    int x1 = wrap_i(x0 + 1, (int)t.w), y1 = wrap_i(y0 + 1, (int)t.h);
+    F4 t00 = fetch_texel(S, t, x0, y0), t10 = fetch_texel(S, t, x1, y0);
+    F4 t01 = fetch_texel(S, t, x0, y1), t11 = fetch_texel(S, t, x1, y1);
+    float w00 = (1.0f - ax) * (1.0f - ay), w10 = ax * (1.0f - ay), w01 = (1.0f - ax) * ay, w11 = ax * ay;
+    r.r = t00.r * w00 + t10.r * w10 + t01.r * w01 + t11.r * w11;
+    r.g = t00.g * w00 + t10.g * w10 + t01.g * w01 + t11.g * w11;
+    r.b = t00.b * w00 + t10.b * w10 + t01.b * w01 + t11.b * w11;
+    r.a = t00.a * w00 + t10.a * w10 + t01.a * w01 + t11.a * w11;
+    return r;
+}
+
+// ---- bindless vertex fetch through the reference-layout ModelInfo / GeometryInfo tables
+struct TriAttr {
+    V3 pa, pb, pc, na, nb, nc;
+    V2 ta, tb, tc;
+};
+
+__device__ __forceinline__ V3 ld_v3(const float* p, uint32_t i) { return v3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)); }
+__device__ __forceinline__ V2 ld_v2(const float* p, uint32_t i) { V2 r; r.x = __ldg(p + 2 * i); r.y = __ldg(p + 2 * i + 1); return r; }
+
+__device__ __forceinline__ bool load_geometry(const SceneDev& S, uint32_t custom_index, uint32_t geom, RtModelInfo& mi, RtGeometryInfo& gi) {
+    if (custom_index >= S.num_models) return false;
+    mi = S.model_info[custom_index];
+    gi = reinterpret_cast<const RtGeometryInfo*>(mi.geometry_info_address)[geom];
+    return true;
+}
+__device__ __forceinline__ void load_indices(const RtGeometryInfo& gi, uint32_t prim, uint32_t& ia, uint32_t& ib, uint32_t& ic) {
+    const uint32_t* idx = reinterpret_cast<const uint32_t*>(gi.index_buffer_address);
+    ia = __ldg(idx + 3 * prim); ib = __ldg(idx + 3 * prim + 1); ic = __ldg(idx + 3 * prim + 2);
+}
+
+// any_hit_alpha_clip.glsl:11-28 — true = keep the candidate
+__device__ __noinline__ bool anyhit_accepts(const SceneDev& S, uint32_t custom_index, uint32_t geom, uint32_t prim, float u, float v) {
+    RtModelInfo mi; RtGeometryInfo gi;
+    if (!load_geometry(S, custom_index, geom, mi, gi)) return true;
+    uint32_t ia, ib, ic;
+    load_indices(gi, prim, ia, ib, ic);
+    const float* uvs = reinterpret_cast<const float*>(mi.uv_buffer_address);
+    V2 uv = interp2(ld_v2(uvs, ia), ld_v2(uvs, ib), ld_v2(uvs, ic), bary_weights(u, v));
+    float alpha = sample_texture(S, gi.images.diffuse_image_index, uv.x, uv.y).a;
+    return !(alpha < 0.5f);
+}
+
+// ---- pbr.glsl
+struct DotParams { float NoH, NoV, NoL, LoH, roughness; };
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ float pdot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float compute_f90(const DotParams& p) { return 0.5f + 2.0f * p.roughness * p.LoH * p.LoH; }
+__device__ __forceinline__ float schlick1(float u, float f0, float f90) { return f0 + (f90 - f0) * powf(1.0f - u, 5.0f); }
+
+// pbr.glsl:174-211
+__device__ __forceinline__ V3 brdf(V3 normal, V3 view, V3 light, V3 base, float perceptual_roughness, float metallic, float sun_factor) {
+    V3 hs = v3(view.x + light.x, view.y + light.y, view.z + light.z);
+    float hl = sqrtf(pdot(hs, hs));
+    V3 h = v3(hs.x / hl, hs.y / hl, hs.z / hl);
+    DotParams p;
+    p.roughness = perceptual_roughness * perceptual_roughness;
+    p.NoV = clampf(pdot(normal, view), 10.0e-10f, 1.0f);
+    p.NoH = clampf(pdot(normal, h), 0.0f, 1.0f);
+    p.NoL = clampf(pdot(normal, light), 0.0f, 1.0f);
+    p.LoH = clampf(pdot(light, h), 0.0f, 1.0f);
+    // D_GGX, :44-51
+    float a = p.NoH * p.roughness;
+    float k = p.roughness / (1.0f - p.NoH * p.NoH + a * a);
+    float D = k * k * (1.0f / RT_PI);
+    // f0, :190-193 (perceptual_dielectric_reflectance = 0.5, closest_hit_textured.glsl:217)
+    float dielectric_f0 = 0.16f * 0.5f * 0.5f;
+    float f0x = dielectric_f0 * (1.0f - metallic) + base.x * metallic;
+    float f0y = dielectric_f0 * (1.0f - metallic) + base.y * metallic;
+    float f0z = dielectric_f0 * (1.0f - metallic) + base.z * metallic;
+    float f90 = compute_f90(p);
+    float fw = powf(1.0f - p.LoH, 5.0f);
+    float Fx = f0x + (f90 - f0x) * fw, Fy = f0y + (f90 - f0y) * fw, Fz = f0z + (f90 - f0z) * fw;
+    // V_SmithGGXCorrelated, :56-65
+    float a2 = p.roughness * p.roughness;
+    float GGXV = p.NoL * sqrtf(p.NoV * p.NoV * (1.0f - a2) + a2);
+    float GGXL = p.NoV * sqrtf(p.NoL * p.NoL * (1.0f - a2) + a2);
+    float G = 0.5f / (GGXV + GGXL);
+    float DG = D * G;
+    // Fd_Burley, :95-103
+    float fd = schlick1(p.NoL, 1.0f, f90) * schlick1(p.NoV, 1.0f, f90) * (1.0f / RT_PI);
+    return v3(sun_factor * p.NoL * (base.x * fd + DG * Fx), sun_factor * p.NoL * (base.y * fd + DG * Fy),
+              sun_factor * p.NoL * (base.z * fd + DG * Fz));
+}
+
+// ---- closest_hit_textured.glsl
+// :13-19
+__device__ __forceinline__ V3 project_onto_tangent_plane(V3 point, V3 vpos, V3 vnormal) {
+    V3 vtp = sub3(point, vpos);
+    float dp = fminf(0.0f, dot3(vtp, vnormal));
+    return v3(fmaf(-dp, vnormal.x, vtp.x), fmaf(-dp, vnormal.y, vtp.y), fmaf(-dp, vnormal.z, vtp.z));
+}
+// :25-39
+__device__ __forceinline__ V3 terminator_origin(const TriAttr& a, V3 p, V3 w, const float* o2w) {
+    V3 oa = project_onto_tangent_plane(p, a.pa, a.na);
+    V3 ob = project_onto_tangent_plane(p, a.pb, a.nb);
+    V3 oc = project_onto_tangent_plane(p, a.pc, a.nc);
+    V3 off = interp3(oa, ob, oc, w);
+    return xform_point(o2w, add3(p, off));
+}
+// :99-120
+__device__ __forceinline__ V2 blue_noise_xi(const SceneDev& S, uint32_t tex, uint32_t px, uint32_t py, uint32_t iteration, uint32_t frame_index) {
+    uint32_t ox1 = iteration * 2u * 13u, oy1 = iteration * 2u * 41u;
+    uint32_t ox2 = (iteration * 2u + 1u) * 13u, oy2 = (iteration * 2u + 1u) * 41u;
+    float a = sample_texture_uniform(S, tex, __fdiv_rn((float)(px + ox1), 64.0f), __fdiv_rn((float)(py + oy1), 64.0f)).r;
+    float b = sample_texture_uniform(S, tex, __fdiv_rn((float)(px + ox2), 64.0f), __fdiv_rn((float)(py + oy2), 64.0f)).r;
+    float k = mul_((float)(frame_index % 32u), 0.618033988749f);
+    float sa = add_(a, k), sb = add_(b, k);
+    V2 r; r.x = sub_(sa, floorf(sa)); r.y = sub_(sb, floorf(sb));
+    return r;
+}
+// :77-94
+__device__ __forceinline__ V3 sample_directional_light(V2 rng, V3 center, float radius) {
+    float r = __fsqrt_rn(rng.x);
+    float angle = mul_(mul_(rng.y, 2.0f), RT_PI);
+    float px = mul_(mul_(r, cosf(angle)), radius), py = mul_(mul_(r, sinf(angle)), radius);
+    V3 tangent = normalize3(cross3(center, v3(0.f, 1.f, 0.f)));
+    V3 bitangent = normalize3(cross3(tangent, center));
+    return normalize3(v3(add_(add_(center.x, mul_(px, tangent.x)), mul_(py, bitangent.x)),
+                         add_(add_(center.y, mul_(px, tangent.y)), mul_(py, bitangent.y)),
+                         add_(add_(center.z, mul_(px, tangent.z)), mul_(py, bitangent.z))));
+}
+
+struct TexturedHit {       // what the textured closest-hit needs after traversal
+    uint32_t px, py;       // gl_LaunchIDEXT.xy
+    uint32_t inst_pos;     // TLAS leaf position (-> InstRT)
+    uint32_t geom, prim;
+    float u, v;
+    V3 dir;                // gl_WorldRayDirectionEXT
+};
+
+struct ShadeCtx {          // state kept between the shadow-ray phase and the BRDF phase
+    TriAttr tri;
+    RtGeometryInfo gi;
+    V3 w;
+    V2 uv;
+    V3 inrm;
+    uint32_t instance_id;
+};
+
+// First half of closest_hit_textured main(): fetch the triangle, build the shadow-ray origin.
+__device__ __forceinline__ bool shade_textured_begin(const SceneDev& S, const TexturedHit& h, ShadeCtx& c, V3& shadow_origin) {
+    const InstRT* ir = S.inst_rt + h.inst_pos;
+    uint32_t custom = __ldg(&ir->custom_sbt) & 0xFFFFFFu;
+    c.instance_id = __ldg(&ir->instance_id);
+    RtModelInfo mi;
+    if (!load_geometry(S, custom, h.geom, mi, c.gi)) return false;
+    uint32_t ia, ib, ic;
+    load_indices(c.gi, h.prim, ia, ib, ic);
+    const float* pos = reinterpret_cast<const float*>(mi.position_buffer_address);
+    const float* nrm = reinterpret_cast<const float*>(mi.normal_buffer_address);
+    const float* uvs = reinterpret_cast<const float*>(mi.uv_buffer_address);
+    c.tri.pa = ld_v3(pos, ia); c.tri.pb = ld_v3(pos, ib); c.tri.pc = ld_v3(pos, ic);
+    c.tri.na = ld_v3(nrm, ia); c.tri.nb = ld_v3(nrm, ib); c.tri.nc = ld_v3(nrm, ic);
+    c.tri.ta = ld_v2(uvs, ia); c.tri.tb = ld_v2(uvs, ib); c.tri.tc = ld_v2(uvs, ic);
+    c.w = bary_weights(h.u, h.v);
+    V3 ipos = interp3(c.tri.pa, c.tri.pb, c.tri.pc, c.w);
+    c.inrm = interp3(c.tri.na, c.tri.nb, c.tri.nc, c.w);
+    c.uv = interp2(c.tri.ta, c.tri.tb, c.tri.tc, c.w);
+    float o2w[12];
+    const float* tr = S.instances[c.instance_id].transform;
+#pragma unroll
+    for (int i = 0; i < 12; i++) o2w[i] = __ldg(tr + i);
+    shadow_origin = terminator_origin(c.tri, ipos, c.w, o2w);
+    return true;
+}
+
+// Second half: material, normal, BRDF, ambient.  Returns primary_payload.colour.
+__device__ __forceinline__ V3 shade_textured_end(const SceneDev& S, const RtUniforms& U, const TexturedHit& h, const ShadeCtx& c, float sun_factor) {
+    F4 dcol = sample_texture(S, c.gi.images.diffuse_image_index, c.uv.x, c.uv.y);
+    F4 mr = sample_texture(S, c.gi.images.metallic_roughness_image_index, c.uv.x, c.uv.y);
+    float metallic = mr.b, roughness = mr.g;  // `.bg` swizzle, closest_hit_textured.glsl:54-60
+    float inv[12];
+    const float* ip = S.inst_rt[h.inst_pos].inv;
+#pragma unroll
+    for (int i = 0; i < 12; i++) inv[i] = __ldg(ip + i);
+    V3 normal;
+    if (c.gi.images.normal_map_image_index < 0) {
+        normal = normalize3(xform_normal(inv, c.inrm));
+    } else {
+        F4 nm = sample_texture(S, (uint32_t)c.gi.images.normal_map_image_index, c.uv.x, c.uv.y);
+        V3 mn = v3(nm.r * 2.0f - 1.0f, nm.g * 2.0f - 1.0f, nm.b * 2.0f - 1.0f);
+        // compute_cotangent_frame, :123-139
+        V3 dp1 = sub3(c.tri.pb, c.tri.pa), dp2 = sub3(c.tri.pc, c.tri.pa);
+        float du1x = c.tri.tb.x - c.tri.ta.x, du1y = c.tri.tb.y - c.tri.ta.y;
+        float du2x = c.tri.tc.x - c.tri.ta.x, du2y = c.tri.tc.y - c.tri.ta.y;
+        V3 dp2perp = cross3(dp2, c.inrm), dp1perp = cross3(c.inrm, dp1);
+        V3 T = add3(scale3(dp2perp, du1x), scale3(dp1perp, du2x));
+        V3 B = add3(scale3(dp2perp, du1y), scale3(dp1perp, du2y));
+        float invmax = 1.0f / sqrtf(fmaxf(dot3(T, T), dot3(B, B)));
+        V3 mnn = normalize3(mn);
+        V3 Ts = scale3(T, invmax), Bs = scale3(B, invmax);
+        V3 local = v3(Ts.x * mnn.x + Bs.x * mnn.y + c.inrm.x * mnn.z, Ts.y * mnn.x + Bs.y * mnn.y + c.inrm.y * mnn.z,
+                      Ts.z * mnn.x + Bs.z * mnn.y + c.inrm.z * mnn.z);
+        normal = normalize3(xform_normal(inv, local));
+    }
+    V3 sun = v3(U.sun_dir[0], U.sun_dir[1], U.sun_dir[2]);
+    V3 lo = brdf(normal, v3(-h.dir.x, -h.dir.y, -h.dir.z), sun, v3(dcol.r, dcol.g, dcol.b), roughness, metallic, sun_factor);
+    return v3(lo.x + 0.1f * dcol.r, lo.y + 0.1f * dcol.g, lo.z + 0.1f * dcol.b);
+}
+
+// closest_hit_mirror.glsl:11-29.  Returns false if the model tables cannot be resolved.
+__device__ __forceinline__ bool shade_mirror(const SceneDev& S, uint32_t inst_pos, uint32_t geom, uint32_t prim, float u, float v,
+                                             float t, V3 o, V3 d, V3& new_o, V3& new_d) {
+    const InstRT* ir = S.inst_rt + inst_pos;
+    uint32_t custom = __ldg(&ir->custom_sbt) & 0xFFFFFFu;
+    RtModelInfo mi; RtGeometryInfo gi;
+    if (!load_geometry(S, custom, geom, mi, gi)) return false;
+    uint32_t ia, ib, ic;
+    load_indices(gi, prim, ia, ib, ic);
+    const float* nrm = reinterpret_cast<const float*>(mi.normal_buffer_address);
+    V3 n = interp3(ld_v3(nrm, ia), ld_v3(nrm, ib), ld_v3(nrm, ic), bary_weights(u, v));
+    float inv[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) inv[i] = __ldg(ir->inv + i);
+    n = normalize3(xform_normal(inv, n));
+    float k = mul_(2.0f, dot3(n, d));  // reflect(I,N) = I - 2 dot(N,I) N
+    new_d = v3(fmaf(-k, n.x, d.x), fmaf(-k, n.y, d.y), fmaf(-k, n.z, d.z));
+    new_o = v3(fmaf(d.x, t, o.x), fmaf(d.y, t, o.y), fmaf(d.z, t, o.z));
+    return true;
+}
+
+// lib.rs:300-312
+__device__ __forceinline__ void shade_portal(float t, V3 o, V3 d, V3& new_o, V3& new_d) {
+    new_d = d;
+    new_o = v3(fmaf(d.x, t, o.x), add_(fmaf(d.y, t, o.y), 5.0f), fmaf(d.z, t, o.z));
+}
+
+// lib.rs:40-51 (cos(sun_radius) is evaluated once on the host)
+__device__ __forceinline__ V3 miss_colour(const RtUniforms& U, float cos_sun_radius, V3 d) {
+    V3 sun = v3(U.sun_dir[0], U.sun_dir[1], U.sun_dir[2]);
+    if (dot3(d, sun) > cos_sun_radius) return v3(1.0f, 1.0f, 1.0f);
+    return v3(0.0f, 0.0f, 0.05f);
+}
+
+// lib.rs:85-92
+__device__ __forceinline__ float linear_to_srgb1(float c) {
+    return c <= 0.0031308f ? c * 12.92f : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+}
+// UNORM8 image store: clamp, round to nearest, NaN -> 0
+__device__ __forceinline__ uint32_t unorm8(float c) {
+    if (!(c > 0.0f)) return 0u;
+    if (c >= 1.0f) return 255u;
+    return (uint32_t)floorf(c * 255.0f + 0.5f);
+}
+
+// lib.rs:126-142
+__device__ __forceinline__ void primary_ray(const RtUniforms& U, uint32_t x, uint32_t y, uint32_t W, uint32_t H, V3& o, V3& d) {
+    float pcx = add_((float)x, 0.5f), pcy = add_((float)y, 0.5f);
+    float ndx = sub_(mul_(div_(pcx, (float)W), 2.0f), 1.0f), ndy = sub_(mul_(div_(pcy, (float)H), 2.0f), 1.0f);
+    const float* V = U.view_inverse;
+    const float* P = U.proj_inverse;
+    o = v3(V[12], V[13], V[14]);
+    V3 target = v3(fmaf(P[12], 1.0f, fmaf(P[8], 1.0f, fmaf(P[4], ndy, mul_(P[0], ndx)))),
+                   fmaf(P[13], 1.0f, fmaf(P[9], 1.0f, fmaf(P[5], ndy, mul_(P[1], ndx)))),
+                   fmaf(P[14], 1.0f, fmaf(P[10], 1.0f, fmaf(P[6], ndy, mul_(P[2], ndx)))));
+    V3 ld = normalize3(target);
+    d = v3(fmaf(V[8], ld.z, fmaf(V[4], ld.y, mul_(V[0], ld.x))), fmaf(V[9], ld.z, fmaf(V[5], ld.y, mul_(V[1], ld.x))),
+           fmaf(V[10], ld.z, fmaf(V[6], ld.y, mul_(V[2], ld.x))));
+}
+
+}  // namespace b200rt

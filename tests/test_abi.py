@@ -1,0 +1,108 @@
+"""Struct layouts and the C-ABI surface.  CPU only: no compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+from ray_tracing_gallery_b200 import abi, native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def off(struct, field):
+    return getattr(struct, field).offset
+
+
+def test_uniforms_layout():
+    # shared-structs/src/lib.rs:10-19 == hit_shader_common.glsl:3-13 (scalar layout)
+    assert C.sizeof(abi.RtUniforms) == 176
+    assert off(abi.RtUniforms, "view_inverse") == 0
+    assert off(abi.RtUniforms, "proj_inverse") == 64
+    assert off(abi.RtUniforms, "sun_dir") == 128
+    assert off(abi.RtUniforms, "sun_radius") == 144
+    assert off(abi.RtUniforms, "blue_noise_texture_index") == 148
+    assert off(abi.RtUniforms, "ggx_lut_texture_index") == 152
+    assert off(abi.RtUniforms, "frame_index") == 156
+    assert off(abi.RtUniforms, "show_heatmap") == 160
+
+
+def test_model_geometry_push_constant_layouts():
+    assert C.sizeof(abi.RtModelInfo) == 32
+    assert [off(abi.RtModelInfo, f) for f in ("position_buffer_address", "normal_buffer_address", "uv_buffer_address", "geometry_info_address")] == [0, 8, 16, 24]
+    assert C.sizeof(abi.RtGeometryInfo) == 24 and off(abi.RtGeometryInfo, "images") == 8
+    assert C.sizeof(abi.RtGeometryImages) == 16
+    assert C.sizeof(abi.RtPushConstantBufferAddresses) == 24
+
+
+def test_instance_layout():
+    # src/gpu_structs.rs:20-25 == VkAccelerationStructureInstanceKHR
+    assert C.sizeof(abi.RtInstance) == 64
+    assert off(abi.RtInstance, "instance_custom_index_and_mask") == 48
+    assert off(abi.RtInstance, "sbt_record_offset_and_flags") == 52
+    assert off(abi.RtInstance, "acceleration_structure_device_address") == 56
+    assert abi.INSTANCE_DTYPE.itemsize == 64
+    assert abi.INSTANCE_DTYPE.fields["custom_index_and_mask"][1] == 48
+    assert abi.INSTANCE_DTYPE.fields["blas"][1] == 56
+
+
+def test_instance_packing_matches_reference_constructor():
+    from ray_tracing_gallery_b200.scene import make_instance, mat_translation
+
+    rec = make_instance(mat_translation(1, 2, 3), model_id=5, blas_handle=0xABCDEF, hit_shader=abi.RT_HIT_MIRROR, double_sided=True)
+    t = rec["transform"].reshape(3, 4)
+    assert np.allclose(t[:, 3], [1, 2, 3]) and np.allclose(t[:, :3], np.eye(3))
+    assert int(rec["custom_index_and_mask"]) == 5 | (0xFF << 24)
+    assert int(rec["sbt_offset_and_flags"]) == 1 | (1 << 24)
+    assert int(rec["blas"]) == 0xABCDEF
+
+
+def test_headers_compile_as_c_and_cxx(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "b200rt.h"\nint main(void){return (int)sizeof(RtUniforms)-176;}\n')
+    for cc, std in (("gcc", "-std=c11"), ("g++", "-std=c++17")):
+        subprocess.check_call([cc, std, "-x", "c" if cc == "gcc" else "c++", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "t")])
+        assert subprocess.call([str(tmp_path / "t")]) == 0
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "b200rt.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 18
+    assert sorted(native.EXPORTS) == names
+    lib = native.load()
+    for n in names:
+        getattr(lib, n)  # raises AttributeError if the symbol is missing
+    assert lib.rt_version() >> 16 == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    from ray_tracing_gallery_b200.backend import RtError
+
+    try:
+        native.Renderer(0)
+    except RtError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("Renderer() must fail loudly without a CUDA device")
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "ray_tracing_gallery_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liborc" not in text and "rt_oracle" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert not re.search(r'#include\s+"[^"]*oracle', text), f

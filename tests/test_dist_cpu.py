@@ -1,0 +1,75 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the strip partition, instance broadcast and
+frame gather, with the oracle standing in for the per-rank renderer."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from ray_tracing_gallery_b200 import abi
+from ray_tracing_gallery_b200.dist import Partition, choose_strip_height, deinterleave
+
+
+def test_strip_height_choice():
+    assert choose_strip_height(1080, 1) == 8
+    assert choose_strip_height(1080, 2) == 4
+    assert choose_strip_height(1080, 8) == 1
+    assert choose_strip_height(2160, 8) == 2
+    assert choose_strip_height(2160, 4) == 4
+    with pytest.raises(ValueError):
+        choose_strip_height(1081, 2)
+
+
+def test_deinterleave_inverts_the_partition():
+    H, W, world = 48, 5, 4
+    img = np.arange(H * W * 4, dtype=np.uint32).reshape(H, W, 4)
+    parts = [Partition.make(W, H, world, r) for r in range(world)]
+    slabs = np.stack([img[p.global_rows()] for p in parts])
+    assert np.array_equal(deinterleave(slabs, parts[0]), img)
+    rows = np.concatenate([p.global_rows() for p in parts])
+    assert sorted(rows.tolist()) == list(range(H))
+
+
+def _worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.binding import Oracle
+    from ray_tracing_gallery_b200.dist import broadcast_instances, gather_frame
+    from ray_tracing_gallery_b200.scene import build_scene
+
+    W, H = 64, 32
+    o = Oracle(threads=2)
+    s = build_scene(o, "c3", W, H, num_instances=8)
+    # rank 0 owns the authoritative instance records; the others start from garbage
+    rec = s.instances.copy()
+    if rank != 0:
+        rec["transform"] = 0
+    t = torch.from_numpy(rec.view(np.uint8).reshape(-1))
+    broadcast_instances(t, 0)
+    o.update_instances(0, rec)
+    o.update_tlas(abi.RT_UPDATE_REBUILD)
+    part = Partition.make(W, H, world, rank)
+    p = part.apply(s.params())
+    local = o.render(s.uniforms(), p, want=("rgba8",))["rgba8"]
+    assert local.shape == (part.local_rows, W, 4)
+    frame = gather_frame(torch.from_numpy(local), part).numpy()
+    if rank == 0:
+        full = o.render(s.uniforms(), s.params(), want=("rgba8",))["rgba8"]
+        np.save(os.path.join(tmp, "ok.npy"), np.array([np.array_equal(frame, full)]))
+    dist.barrier()
+    dist.destroy_process_group()
+    o.close()
+
+
+def test_two_rank_gloo_frame(tmp_path):
+    import torch.multiprocessing as mp
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert np.load(tmp_path / "ok.npy")[0]

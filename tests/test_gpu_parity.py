@@ -1,0 +1,269 @@
+"""Parity of the CUDA path (through the C ABI of libb200rt.so) against the CPU oracle.
+
+Bars (BASELINE.json north_star): hit IDs bit-exact except tie/edge pixels (>= 99.99 %), radiance
+within 1e-3 relative per pixel or PSNR >= 50 dB, identical blue-noise sequences.  The oracle is the
+checker only; everything under test goes through `native.Renderer` (ctypes -> rt_*)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import make_oracle, make_renderer
+from ray_tracing_gallery_b200 import abi
+from ray_tracing_gallery_b200.backend import RtError
+from ray_tracing_gallery_b200.dist import Partition, deinterleave
+from ray_tracing_gallery_b200.scene import (build_scene, load_model, make_instance, mat_identity, mat_scale, mat_translation,
+                                            push_builtin_images)
+
+pytestmark = pytest.mark.gpu
+
+PIPELINES = [abi.RT_PIPELINE_WAVEFRONT, abi.RT_PIPELINE_MEGAKERNEL]
+REL_TOL = 1e-3        # north_star: radiance within 1e-3 relative per pixel ...
+PSNR_MIN_DB = 50.0    # ... or PSNR >= 50 dB
+ID_AGREEMENT = 0.9999
+
+
+def psnr(a, b):
+    fin = np.isfinite(a) & np.isfinite(b)
+    mse = np.mean(np.where(fin, a.astype(np.float64) - b.astype(np.float64), 0.0) ** 2)
+    return 999.0 if mse == 0 else 10 * np.log10(1.0 / mse)
+
+
+def check_parity(gpu_out, cpu_out, strict_ids=True):
+    ids_ok = np.all(gpu_out["hit_ids"] == cpu_out["hit_ids"], axis=(2, 3))
+    assert ids_ok.mean() >= (1.0 if strict_ids else ID_AGREEMENT), f"hit-ID agreement {ids_ok.mean():.6f}"
+    a, b = gpu_out["radiance"].astype(np.float64), cpu_out["radiance"].astype(np.float64)
+    rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
+    within = np.mean(np.all((rel <= REL_TOL) | ~np.isfinite(b), axis=2))
+    assert within >= 0.999 or psnr(a, b) >= PSNR_MIN_DB, f"radiance: {within:.6f} of pixels within 1e-3, PSNR {psnr(a, b):.1f} dB"
+    assert psnr(a, b) >= PSNR_MIN_DB
+    d8 = np.abs(gpu_out["rgba8"].astype(int) - cpu_out["rgba8"].astype(int))
+    assert np.mean(d8.max(axis=2) <= 1) >= 0.999
+    assert np.array_equal(gpu_out["ray_counts"], cpu_out["ray_counts"])
+    return ids_ok.mean(), within
+
+
+def both(cfg, w, h, **kw):
+    orc, gpu = make_oracle(), make_renderer()
+    return orc, build_scene(orc, cfg, w, h, **kw), gpu, build_scene(gpu, cfg, w, h, **kw)
+
+
+@pytest.mark.parametrize("cfg,size,kw", [
+    ("c1", (1280, 720), {}),                          # BASELINE configs[0], full size
+    ("c2", (1920, 1080), {}),                         # configs[1], full size
+    ("c3", (1920, 1080), {}),                         # configs[2], full size
+    ("default", (1280, 720), {}),                     # the reference's own DefaultScene (portal, lain, fence, 100 tori)
+])
+def test_frame_parity_full_size(cfg, size, kw):
+    orc, so, gpu, sg = both(cfg, *size, **kw)
+    want = orc.render(so.uniforms(), so.params())
+    for pipeline in PIPELINES:
+        got = gpu.render(sg.uniforms(), sg.params(pipeline=pipeline))
+        gpu.stats()  # raises on traversal-stack overflow
+        check_parity(got, want)
+    orc.close(); gpu.close()
+
+
+def test_pipelines_agree_bit_for_bit():
+    gpu = make_renderer()
+    s = build_scene(gpu, "default", 640, 360)
+    a = gpu.render(s.uniforms(), s.params(pipeline=abi.RT_PIPELINE_WAVEFRONT))
+    b = gpu.render(s.uniforms(), s.params(pipeline=abi.RT_PIPELINE_MEGAKERNEL))
+    c = gpu.render(s.uniforms(), s.params(pipeline=abi.RT_PIPELINE_WAVEFRONT))
+    for k in ("hit_ids", "rgba8", "ray_counts"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])
+    assert np.array_equal(a["radiance"].view(np.uint32), b["radiance"].view(np.uint32))
+    assert np.array_equal(a["radiance"].view(np.uint32), c["radiance"].view(np.uint32))  # run-to-run deterministic
+    gpu.close()
+
+
+def test_blue_noise_sequence_over_frames():
+    """Soft shadows must follow the reference's deterministic sequence: frame f and f+32 are identical,
+    other frames differ, and every frame matches the oracle."""
+    orc, so, gpu, sg = both("c2", 480, 270)
+    frames = {}
+    for f in (1, 2, 17, 33):
+        want = orc.render(so.uniforms(frame_index=f), so.params())
+        got = gpu.render(sg.uniforms(frame_index=f), sg.params())
+        check_parity(got, want)
+        frames[f] = got["radiance"]
+    assert np.array_equal(frames[1], frames[33])
+    assert not np.array_equal(frames[1], frames[2])
+    orc.close(); gpu.close()
+
+
+def test_hard_shadow_config_is_exact_in_ids_and_counts():
+    """C1 (sun_radius 0): the shadow direction is exactly normalize(sun_dir), so every ray of the frame is
+    reproducible; only pow/cos ulps remain in the radiance."""
+    orc, so, gpu, sg = both("c1", 640, 360)
+    want, got = orc.render(so.uniforms(), so.params()), gpu.render(sg.uniforms(), sg.params())
+    assert np.array_equal(got["hit_ids"], want["hit_ids"])
+    lit_gpu = got["radiance"].sum(axis=2) > 0.2 * 0.3
+    lit_cpu = want["radiance"].sum(axis=2) > 0.2 * 0.3
+    assert np.array_equal(lit_gpu, lit_cpu)
+    assert np.max(np.abs(got["radiance"] - want["radiance"]) / np.maximum(want["radiance"], 1e-3)) < 1e-4
+    orc.close(); gpu.close()
+
+
+def test_tiles_and_strips_reassemble_the_full_frame():
+    gpu = make_renderer()
+    W, H = 320, 192
+    s = build_scene(gpu, "default", W, H)
+    full = gpu.render(s.uniforms(), s.params())
+    # a tile uses global pixel coordinates (gl_LaunchIDEXT) for rays and blue noise
+    tile = gpu.render(s.uniforms(), s.params(tile_x0=40, tile_y0=64, tile_w=120, tile_h=72))
+    assert np.array_equal(tile["rgba8"], full["rgba8"][64:136, 40:160])
+    assert np.array_equal(tile["hit_ids"], full["hit_ids"][64:136, 40:160])
+    for world in (2, 4, 8):
+        parts = [Partition.make(W, H, world, r) for r in range(world)]
+        slabs, rays = [], np.zeros(2, np.uint64)
+        for part in parts:
+            out = gpu.render(s.uniforms(), part.apply(s.params()))
+            assert out["rgba8"].shape == (H // world, W, 4)
+            slabs.append(out["rgba8"])
+            rays += out["ray_counts"]
+        assert np.array_equal(deinterleave(np.stack(slabs), parts[0]), full["rgba8"])
+        assert np.array_equal(rays, full["ray_counts"])
+    gpu.close()
+
+
+@pytest.mark.parametrize("mode", [abi.RT_UPDATE_REBUILD, abi.RT_UPDATE_REFIT, abi.RT_UPDATE_AUTO])
+def test_tlas_update_parity(mode):
+    """C4 in small: every transform changes each tick, then rt_update_instances + rt_update_tlas
+    (src/scene.rs:167-204).  Result must equal the oracle after the same update, for rebuild and refit."""
+    orc, so, gpu, sg = both("c4", 480, 270, num_instances=1500)
+    for tick in (1, 2, 5):
+        rec_o, rec_g = so.animate(tick), sg.animate(tick)
+        orc.update_instances(0, rec_o); orc.update_tlas(mode)
+        gpu.update_instances(0, rec_g); gpu.update_tlas(mode)
+        want, got = orc.render(so.uniforms(), so.params()), gpu.render(sg.uniforms(), sg.params())
+        gpu.stats()
+        check_parity(got, want)
+    # partial update: one 64-byte record, like the reference's lain rotation
+    one = sg.animate(9)[7:8]
+    gpu.update_instances(7, one); gpu.update_tlas(mode)
+    orc.update_instances(7, so.animate(9)[7:8]); orc.update_tlas(mode)
+    check_parity(gpu.render(sg.uniforms(), sg.params()), orc.render(so.uniforms(), so.params()))
+    orc.close(); gpu.close()
+
+
+def test_many_instances_tile_parity():
+    """C5 in small (50k instances, 16 soft-shadow rays): a tile of the 4K launch against the oracle."""
+    orc, so, gpu, sg = both("c5", 3840, 2160, num_instances=50000)
+    tile = dict(tile_x0=1700, tile_y0=1200, tile_w=256, tile_h=96)
+    want = orc.render(so.uniforms(), so.params(**tile))
+    got = gpu.render(sg.uniforms(), sg.params(**tile))
+    gpu.stats()
+    check_parity(got, want, strict_ids=False)
+    orc.close(); gpu.close()
+
+
+def test_device_tables_keep_the_reference_layout():
+    gpu = make_renderer()
+    s = build_scene(gpu, "default", 64, 36)
+    pc = gpu.push_constants()
+    assert pc.model_info and pc.uniforms and pc.acceleration_structure
+    for name, (mid, handle, arrays) in s.models.items():
+        info, geoms = gpu.read_model_info(mid)
+        assert info.position_buffer_address and info.normal_buffer_address and info.uv_buffer_address and info.geometry_info_address
+        for g, gi in zip(arrays.geometries, geoms):
+            assert gi.index_buffer_address
+            assert (gi.images.diffuse_image_index, gi.images.metallic_roughness_image_index, gi.images.normal_map_image_index) == (
+                g.diffuse_image_index, g.metallic_roughness_image_index, g.normal_map_image_index)
+    st = gpu.stats()
+    assert st.num_instances == 105 and st.num_triangles == 2 + 2304 + 45448 + 2 and st.tlas_nodes >= 1
+    gpu.close()
+
+
+def test_edge_cases():
+    orc, gpu = make_oracle(), make_renderer()
+    setups = []
+    for b in (orc, gpu):
+        push_builtin_images(b)
+        pid, ph, _ = load_model(b, "plane.glb", 0)
+        tid, th, _ = load_model(b, "tori.glb", 1)
+        setups.append((pid, ph, tid, th))
+    from ray_tracing_gallery_b200.scene import Camera, SceneSetup, Sun
+
+    def scene(b, ids, inst):
+        s = SceneSetup("edge", inst, Camera(), Sun(), 160, 90, shadow_rays=2, sun_radius=0.05)
+        b.build_tlas(inst)
+        return s
+
+    def records(ids):
+        pid, ph, tid, th = ids
+        hidden = make_instance(mat_translation(0, 1, 0), tid, th, abi.RT_HIT_TEXTURED)
+        hidden["custom_index_and_mask"] = tid  # visibility mask 0: never hit
+        singular = make_instance(mat_scale(0.0), tid, th, abi.RT_HIT_TEXTURED)
+        bad_handle = make_instance(mat_identity(), tid, 0x1234, abi.RT_HIT_TEXTURED)
+        out_of_table = make_instance(mat_translation(3, 1, 2), tid, th, 7)  # hit group 7: payload untouched -> black
+        return np.stack([make_instance(mat_scale(10.0), pid, ph, abi.RT_HIT_TEXTURED), hidden, singular, bad_handle, out_of_table])
+
+    so, sg = scene(orc, setups[0], records(setups[0])), scene(gpu, setups[1], records(setups[1]))
+    want, got = orc.render(so.uniforms(), so.params()), gpu.render(sg.uniforms(), sg.params())
+    check_parity(got, want)
+    assert set(np.unique(got["hit_ids"][:, :, 0, 0]).tolist()) <= {0, 4, abi.MISS_ID}
+    # empty TLAS: every pixel is sky
+    for b in (orc, gpu):
+        b.build_tlas(np.zeros(0, abi.INSTANCE_DTYPE))
+    got = gpu.render(sg.uniforms(), sg.params())
+    assert np.array_equal(got["rgba8"], orc.render(so.uniforms(), so.params())["rgba8"])
+    assert np.all(got["hit_ids"] == abi.MISS_ID) and got["ray_counts"].tolist() == [160 * 90, 0]
+    # ragged sizes: width/height not multiples of the 8x4 warp tile, max_segments 1, 5 shadow rays
+    for b, ids in ((orc, setups[0]), (gpu, setups[1])):
+        b.build_tlas(records(ids))
+    po, pg = so.params(width=75, height=41, max_segments=1, shadow_rays=5), sg.params(width=75, height=41, max_segments=1, shadow_rays=5)
+    check_parity(gpu.render(sg.uniforms(width=75, height=41), pg), orc.render(so.uniforms(width=75, height=41), po))
+    orc.close(); gpu.close()
+
+
+def test_error_behaviour():
+    gpu = make_renderer()
+    push_builtin_images(gpu)
+    from ray_tracing_gallery_b200.scene import Camera, Sun, make_uniforms
+
+    u = make_uniforms(Camera(), Sun(), 64, 36, 0.05, 1)
+    p = abi.RtRenderParams(width=64, height=36, max_segments=3, shadow_rays=2)
+    with pytest.raises(RtError, match="before rt_build_tlas"):
+        gpu.render(u, p)
+    with pytest.raises(RtError):
+        gpu.update_tlas(abi.RT_UPDATE_REBUILD)
+    gpu.build_tlas(np.zeros(0, abi.INSTANCE_DTYPE))
+    with pytest.raises(RtError, match="shadow_rays"):
+        gpu.render(u, abi.RtRenderParams(width=64, height=36, max_segments=3, shadow_rays=0))
+    with pytest.raises(RtError, match="tile outside"):
+        gpu.render(u, abi.RtRenderParams(width=64, height=36, max_segments=3, shadow_rays=1, tile_x0=60, tile_w=10, tile_h=4))
+    with pytest.raises(RtError, match="range outside"):
+        gpu.update_instances(0, np.zeros(1, abi.INSTANCE_DTYPE))
+    assert gpu.lib.rt_render(gpu.ctx, None, None, None) == -1
+    gpu.render(u, p)  # the context stays usable after errors
+    for _ in range(130):
+        try:
+            gpu.push_image(np.zeros((1, 1, 4), np.uint8), abi.RT_FORMAT_RGBA8_UNORM, False)
+        except RtError as e:
+            assert "table full" in str(e)
+            break
+    else:
+        raise AssertionError("image table must be capped at 128 (src/main.rs:44)")
+    gpu.close()
+
+
+def test_device_output_path_and_readback():
+    import torch
+
+    gpu = make_renderer()
+    s = build_scene(gpu, "c1", 320, 180)
+    host = gpu.render(s.uniforms(), s.params())
+    assert np.array_equal(gpu.readback(180, 320), host["rgba8"])
+    gpu.set_stream(torch.cuda.current_stream().cuda_stream)
+    fb = torch.zeros((180, 320, 4), dtype=torch.uint8, device="cuda")
+    rad = torch.zeros((180, 320, 3), dtype=torch.float32, device="cuda")
+    rays = torch.zeros(2, dtype=torch.int64, device="cuda")
+    before = gpu.lib.rt_kernel_launches()
+    gpu.render_device(s.uniforms(), s.params(), rgba8=fb.data_ptr(), radiance=rad.data_ptr(), ray_counts=rays.data_ptr())
+    torch.cuda.synchronize()
+    assert gpu.lib.rt_kernel_launches() > before
+    assert np.array_equal(fb.cpu().numpy(), host["rgba8"])
+    assert np.array_equal(rad.cpu().numpy().view(np.uint32), host["radiance"].view(np.uint32))
+    assert rays.cpu().numpy().astype(np.uint64).tolist() == host["ray_counts"].tolist()
+    gpu.close()

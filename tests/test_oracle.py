@@ -1,0 +1,310 @@
+"""Pins for the CPU oracle: the reference's only unit test, constants of the shipped .spv files,
+independent float64 re-derivations of every shader formula, BVH-vs-brute-force equality, and the
+committed golden fixtures (tests/golden/, made by tests/golden/make_golden.py)."""
+import hashlib
+import json
+import math
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import make_oracle
+from ray_tracing_gallery_b200 import abi
+from ray_tracing_gallery_b200.gltf import load_png_file_rgba8
+from ray_tracing_gallery_b200.scene import ASSET_DIR, Camera, Sun, build_scene, make_uniforms
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PHI = np.float32(0.618033988749)
+
+
+@pytest.fixture(scope="module")
+def orc():
+    o = make_oracle()
+    from ray_tracing_gallery_b200.scene import push_builtin_images
+
+    push_builtin_images(o)
+    yield o
+    o.close()
+
+
+# ---------------------------------------------------------------- reference KAT + .spv constants
+def test_ggx_division_by_zero(orc):
+    """shaders/ray-tracing/src/pbr.rs:52-69 — V_SmithGGXCorrelated is finite at roughness 0."""
+    v = orc.v_smith_ggx((0, 1, 0), (1, 0, 0), (0, 1, 0), 0.0)
+    assert math.isfinite(v)
+    # NoV clamps to 10.0e-10 (pbr.glsl:33), NoL = 1: V = 0.5 / (1*sqrt(NoV^2) + NoV*1) = 0.25 / NoV
+    assert v == pytest.approx(0.25 / 1e-9, rel=1e-5)
+
+
+def _spv_constants(path):
+    words = np.frombuffer(open(path, "rb").read(), dtype="<u4")
+    assert words[0] == 0x07230203
+    i, floats, ints = 5, [], []
+    while i < len(words):
+        wc, op = int(words[i]) >> 16, int(words[i]) & 0xFFFF
+        if op == 43 and wc == 4:  # OpConstant (32-bit)
+            ints.append(int(words[i + 3]))
+            floats.append(struct.unpack("<f", struct.pack("<I", int(words[i + 3])))[0])
+        i += max(wc, 1)
+    return floats, ints
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/shaders/closest_hit_textured.spv"), reason="reference tree not present")
+def test_shipped_spirv_constants_match_the_restatement():
+    floats, ints = _spv_constants("/root/reference/shaders/closest_hit_textured.spv")
+    for want in (0.618033988749, 1e-9, 0.1, 0.04, 0.001, 10000.0, 64.0, 0.5):
+        assert any(abs(f - want) <= 1e-6 * max(1.0, abs(want)) for f in floats), want
+    for want in (13, 41, 32, 2):  # blue-noise offsets, frame modulus, shadow-ray loop bound
+        assert want in ints
+    floats, ints = _spv_constants("/root/reference/shaders/ray_generation.spv")
+    for want in (0.01, 10000.0, 0.0031308, 12.92, 1.055, 0.055):
+        assert any(abs(f - want) <= 1e-6 * max(1.0, abs(want)) for f in floats), want
+
+
+# ---------------------------------------------------------------- shading formulas in float64
+def brdf64(n, v, l, base, pr, m, sun):
+    n, v, l, base = (np.asarray(x, np.float64) for x in (n, v, l, base))
+    h = (v + l) / np.linalg.norm(v + l)
+    a = pr * pr
+    NoV = min(max(n @ v, 1e-9), 1.0)
+    NoH, NoL, LoH = (min(max(x, 0.0), 1.0) for x in (n @ h, n @ l, l @ h))
+    D = (a / (1 - NoH * NoH + (NoH * a) ** 2)) ** 2 / math.pi
+    V = 0.5 / (NoL * math.sqrt(NoV * NoV * (1 - a * a) + a * a) + NoV * math.sqrt(NoL * NoL * (1 - a * a) + a * a))
+    f90 = 0.5 + 2 * a * LoH * LoH
+    f0 = 0.04 * (1 - m) + base * m
+    F = f0 + (f90 - f0) * (1 - LoH) ** 5
+    Fd = (1 + (f90 - 1) * (1 - NoL) ** 5) * (1 + (f90 - 1) * (1 - NoV) ** 5) / math.pi
+    return sun * NoL * (base * Fd + D * V * F)
+
+
+def test_brdf_against_float64(orc):
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        v = rng.normal(size=3); v /= np.linalg.norm(v)
+        l = rng.normal(size=3); l /= np.linalg.norm(l)
+        if n @ v < 0.05 or n @ l < 0.05:
+            continue
+        base, pr, m, sun = rng.uniform(0, 1, 3), rng.uniform(0.05, 1), rng.uniform(0, 1), rng.choice([0.0, 0.5, 1.0])
+        got = orc.brdf(n, v, l, base, float(pr), float(m), float(sun))
+        want = brdf64(n.astype(np.float32), v.astype(np.float32), l.astype(np.float32), base.astype(np.float32), np.float32(pr), np.float32(m), sun)
+        assert np.allclose(got, want, rtol=2e-4, atol=1e-6)
+
+
+def test_linear_to_srgb_and_unorm8(orc):
+    lib = orc.lib
+    assert lib.orc_linear_to_srgb(0.0) == 0.0
+    assert lib.orc_linear_to_srgb(0.0031308) == pytest.approx(0.0031308 * 12.92, rel=1e-6)
+    assert lib.orc_linear_to_srgb(1.0) == pytest.approx(1.0, abs=1e-6)
+    for c in (0.004, 0.05, 0.2, 0.5, 0.9):
+        assert lib.orc_linear_to_srgb(c) == pytest.approx(1.055 * c ** (1 / 2.4) - 0.055, rel=1e-5)
+    # SKY_COLOUR (0,0,0.05) -> navy (0,0,63), lib.rs:38
+    assert lib.orc_unorm8(lib.orc_linear_to_srgb(0.05)) == 63
+    assert lib.orc_unorm8(-1.0) == 0 and lib.orc_unorm8(2.0) == 255 and lib.orc_unorm8(float("nan")) == 0
+    assert lib.orc_unorm8(0.5) == 128
+
+
+def test_blue_noise_sequence(orc):
+    """closest_hit_textured.glsl:99-120: texel (px + k*(13,41)) mod 64, fract(bn + (frame % 32) * phi)."""
+    tex = load_png_file_rgba8(os.path.join(ASSET_DIR, "blue_noise_64x64.png"))[..., 0].astype(np.float32) / np.float32(255)
+    for px, py, it, frame in [(0, 0, 0, 1), (5, 7, 1, 1), (1279, 719, 3, 31), (100, 200, 15, 32), (63, 64, 2, 77)]:
+        k = np.float32(frame % 32) * PHI
+        a = tex[(py + 2 * it * 41) % 64, (px + 2 * it * 13) % 64] + k
+        b = tex[(py + (2 * it + 1) * 41) % 64, (px + (2 * it + 1) * 13) % 64] + k
+        want = np.array([a - np.floor(a), b - np.floor(b)], np.float32)
+        assert np.array_equal(orc.blue_noise_xi(px, py, it, frame), want)
+
+
+def test_blue_noise_png_is_16_bit_grey_narrowed_by_shift():
+    from PIL import Image
+
+    img = Image.open(os.path.join(ASSET_DIR, "blue_noise_64x64.png"))
+    assert img.size == (64, 64) and img.mode.startswith("I")
+    raw = np.asarray(img).astype(np.uint32)
+    rgba = load_png_file_rgba8(os.path.join(ASSET_DIR, "blue_noise_64x64.png"))
+    assert np.array_equal(rgba[..., 0], (raw >> 8).astype(np.uint8)) and np.all(rgba[..., 3] == 255)
+
+
+def test_sample_directional_light(orc):
+    c = np.array([0.7384603, 0.47942555, 0.47415987], np.float32)
+    # radius 0 (hard shadows, C1): the jitter vanishes exactly, whatever the blue-noise sample
+    d0 = orc.sample_directional_light((0.3, 0.8), c, 0.0)
+    assert np.array_equal(d0, orc.sample_directional_light((0.9, 0.1), c, 0.0))
+    assert np.allclose(d0, c / np.linalg.norm(c), atol=1e-7)
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        xi = rng.uniform(0, 1, 2)
+        d = orc.sample_directional_light(xi, c, 0.05).astype(np.float64)
+        assert abs(np.linalg.norm(d) - 1) < 1e-6
+        cn = c.astype(np.float64) / np.linalg.norm(c)
+        t = np.cross(cn, [0, 1, 0]); t /= np.linalg.norm(t)
+        b = np.cross(t, cn); b /= np.linalg.norm(b)
+        r, ang = math.sqrt(np.float32(xi[0])), float(np.float32(xi[1])) * 2 * math.pi
+        want = c.astype(np.float64) + 0.05 * r * (math.cos(ang) * t + math.sin(ang) * b)
+        want /= np.linalg.norm(want)
+        assert np.allclose(d, want, atol=2e-6)
+
+
+def test_texture_sampling_rules():
+    o = make_oracle()
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, size=(4, 8, 4), dtype=np.uint8)
+    lin_unorm = o.push_image(img, abi.RT_FORMAT_RGBA8_UNORM, True)
+    near_srgb = o.push_image(img, abi.RT_FORMAT_RGBA8_SRGB, False)
+    const = o.push_image(np.array([[[1.0, 0.5, 0.25, 1.0]]], np.float32), abi.RT_FORMAT_RGBA32_SFLOAT, False)
+    f = img.astype(np.float64) / 255
+
+    def srgb(c):
+        return np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+
+    for u, v in [(0.1, 0.2), (0.99, 0.01), (-0.3, 1.7), (3.25, -2.5), (0.5, 0.5), (0.0625, 0.125)]:
+        x, y = u * 8 - 0.5, v * 4 - 0.5
+        x0, y0 = math.floor(x), math.floor(y)
+        ax, ay = x - x0, y - y0
+        t = lambda i, j: f[(y0 + j) % 4, (x0 + i) % 8]
+        want = t(0, 0) * (1 - ax) * (1 - ay) + t(1, 0) * ax * (1 - ay) + t(0, 1) * (1 - ax) * ay + t(1, 1) * ax * ay
+        assert np.allclose(o.sample_texture(lin_unorm, u, v), want, atol=3e-6)
+        tx = f[math.floor(v * 4) % 4, math.floor(u * 8) % 8]
+        want_n = np.concatenate([srgb(tx[:3]), tx[3:]])
+        assert np.allclose(o.sample_texture(near_srgb, u, v), want_n, atol=3e-6)
+        assert np.array_equal(o.sample_texture(const, u, v), [1.0, 0.5, 0.25, 1.0])
+    assert np.array_equal(o.sample_texture(99, 0.5, 0.5), [0, 0, 0, 0])  # null descriptor
+    o.close()
+
+
+def test_intersection_and_inverse_against_float64(orc):
+    rng = np.random.default_rng(5)
+    hits = 0
+    for _ in range(400):
+        a, b, c = rng.uniform(-1, 1, (3, 3)).astype(np.float32)
+        o = rng.uniform(-3, 3, 3).astype(np.float32)
+        tgt = (a + b + c) / 3 + rng.normal(scale=0.3, size=3)
+        d = (tgt - o).astype(np.float32)
+        hit, tuv = orc.intersect_triangle(o, d, a, b, c)
+        A, B, Cc, O, D = (x.astype(np.float64) for x in (a, b, c, o, d))
+        M = np.stack([-D, B - A, Cc - A], axis=1)
+        if abs(np.linalg.det(M)) < 1e-9:
+            continue
+        t, u, v = np.linalg.solve(M, O - A)
+        inside = u >= 0 and v >= 0 and u + v <= 1
+        if min(abs(u), abs(v), abs(1 - u - v)) < 1e-4:
+            continue
+        assert hit == inside
+        if hit:
+            hits += 1
+            assert np.allclose(tuv, [t, u, v], rtol=1e-4, atol=1e-5)
+    assert hits > 50
+    for _ in range(50):
+        m = np.concatenate([rng.normal(size=(3, 3)) + 2 * np.eye(3), rng.normal(size=(3, 1))], axis=1).astype(np.float32)
+        inv = orc.invert_3x4(m).reshape(3, 4)
+        full = np.vstack([m.astype(np.float64), [0, 0, 0, 1]])
+        assert np.allclose(inv, np.linalg.inv(full)[:3], rtol=1e-4, atol=1e-5)
+
+
+def test_primary_ray_matches_camera_model(orc):
+    cam, sun = Camera(), Sun()
+    u = make_uniforms(cam, sun, 1280, 720, 0.05, 1)
+    o, d = orc.primary_ray(u, 640, 360, 1280, 720)
+    assert np.allclose(o, [0, 2, -5], atol=1e-6)
+    # yaw = pi looks down +z; image row 0 is up (Vulkan clip space, reversed-z projection)
+    assert np.allclose(d, [0, 0, 1], atol=2e-3)
+    _, d_top = orc.primary_ray(u, 640, 0, 1280, 720)
+    _, d_right = orc.primary_ray(u, 1279, 360, 1280, 720)
+    assert d_top[1] > 0.4 and abs(np.linalg.norm(d_top) - 1) < 1e-6
+    half = math.tan(math.radians(59) / 2)
+    assert d_top[1] / d_top[2] == pytest.approx(half * (1 - 1 / 720), rel=1e-4)
+    assert abs(d_right[0] / d_right[2]) == pytest.approx(half * 1280 / 720 * (1 - 1 / 1280), rel=1e-4)
+
+
+def test_shadow_terminator_fix(orc):
+    """RTG-II 4.3 (closest_hit_textured.glsl:13-39): flat normals -> no offset; curved normals -> the
+    origin moves to the convex side of the triangle."""
+    pos = [0, 0, 0, 1, 0, 0, 0, 1, 0]
+    ident = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]
+    bary = (0.2, 0.3, 0.5)
+    flat = orc.terminator_origin(pos, [0, 0, 1] * 3, bary, ident)
+    assert np.allclose(flat, [0.3, 0.5, 0.0], atol=1e-7)
+    curved = orc.terminator_origin(pos, [-0.5, -0.5, 1, 0.8, 0, 1, 0, 0.8, 1], bary, ident)
+    assert curved[2] > 1e-3
+    moved = orc.terminator_origin(pos, [0, 0, 1] * 3, bary, [2, 0, 0, 5, 0, 2, 0, 6, 0, 0, 2, 7])
+    assert np.allclose(moved, [5.6, 7.0, 7.0], atol=1e-6)
+
+
+# ---------------------------------------------------------------- trace semantics
+def test_bvh_equals_brute_force():
+    for cfg, kw in (("c3", {"num_instances": 30}), ("default", {"num_instances": 12})):
+        a, b = make_oracle(), make_oracle(brute_force=True)
+        sa, sb = build_scene(a, cfg, 96, 54, **kw), build_scene(b, cfg, 96, 54, **kw)
+        ra, rb = a.render(sa.uniforms(), sa.params()), b.render(sb.uniforms(), sb.params())
+        assert np.array_equal(ra["hit_ids"], rb["hit_ids"])
+        assert np.array_equal(ra["radiance"].view(np.uint32), rb["radiance"].view(np.uint32))
+        assert np.array_equal(ra["ray_counts"], rb["ray_counts"])
+        a.close(); b.close()
+
+
+def test_interval_is_exclusive_and_ties_go_to_lowest_ids():
+    from ray_tracing_gallery_b200.scene import load_model, make_instance, mat_identity, mat_translation, push_builtin_images
+
+    o = make_oracle()
+    push_builtin_images(o)
+    pid, ph, _ = load_model(o, "plane.glb", 0)
+    # two coincident planes: instance 0 must win the exact tie; plane is y = 0, x,z in [-1,1]
+    o.build_tlas(np.stack([make_instance(mat_identity(), pid, ph, 0), make_instance(mat_identity(), pid, ph, 0)]))
+    hit, ids, tuv = o.trace((0.25, 1, 0.25), (0, -1, 0), 0.01, 100.0)
+    assert hit and ids[0] == 0 and tuv[0] == 1.0
+    hit, ids, _ = o.trace((0.25, 1, 0.25), (0, -1, 0), 1.0, 100.0)  # t == tmin is not a hit
+    assert not hit
+    hit, ids, _ = o.trace((0.25, 1, 0.25), (0, -1, 0), 0.01, 1.0)  # t == tmax is not a hit
+    assert not hit
+    # no face culling: the plane is hit from below too
+    hit, ids, _ = o.trace((0.25, -1, 0.25), (0, 1, 0), 0.01, 100.0)
+    assert hit
+    # direction is not normalised and t is preserved through the instance transform
+    o.build_tlas(np.stack([make_instance(mat_translation(0, -3, 0), pid, ph, 0)]))
+    hit, ids, tuv = o.trace((0, 1, 0), (0, -2, 0), 0.01, 100.0)
+    assert hit and tuv[0] == 2.0
+    o.close()
+
+
+def test_ray_counts_and_segments():
+    o = make_oracle()
+    s = build_scene(o, "c1", 160, 90)
+    r = o.render(s.uniforms(), s.params())
+    hit_px = int(np.sum(r["hit_ids"][:, :, 0, 0] != abi.MISS_ID))
+    assert r["ray_counts"][0] == 160 * 90  # no mirrors in C1: one segment per pixel
+    assert r["ray_counts"][1] == hit_px * s.shadow_rays
+    sky = r["rgba8"][0, 0]
+    assert tuple(sky) == (0, 0, 63, 255)
+    o.close()
+
+
+def test_alpha_clip_anyhit_lets_rays_through_the_fence():
+    o = make_oracle()
+    s = build_scene(o, "c3", 64, 36, num_instances=0)
+    fence_idx = 1  # second instance in c3
+    # straight at the fence quad centred at (2, 1, 2): some rays pass (alpha < 0.5), some stop
+    seen = set()
+    for i in range(40):
+        x = 1.1 + 1.8 * i / 39
+        hit, ids, _ = o.trace((x, 1.0, -3.0), (0, 0, 1), 0.01, 100.0)
+        seen.add(ids[0] if hit else None)
+    assert fence_idx in seen and (seen - {fence_idx}), seen
+    o.close()
+
+
+# ---------------------------------------------------------------- committed golden fixtures
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "default"])
+def test_golden_fixture(cfg):
+    from PIL import Image
+
+    meta = json.load(open(os.path.join(GOLDEN, f"{cfg}.json")))
+    o = make_oracle()
+    s = build_scene(o, cfg, meta["width"], meta["height"], **meta.get("kwargs", {}))
+    r = o.render(s.uniforms(), s.params())
+    assert hashlib.sha256(r["hit_ids"].tobytes()).hexdigest() == meta["hit_ids_sha256"]
+    assert [int(x) for x in r["ray_counts"]] == meta["ray_counts"]
+    want = np.asarray(Image.open(os.path.join(GOLDEN, f"{cfg}.png")))
+    assert np.abs(r["rgba8"].astype(int) - want.astype(int)).max() <= 1
+    o.close()
