@@ -191,9 +191,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     args.warmup = max(args.warmup, 3)
+    torch.cuda.synchronize()
 
     gpu = native.Renderer(local_rank)  # raises if libb200rt.so is missing: there is no fallback
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # one stream for the library's kernels, NCCL and the timing events
+    torch.cuda.set_stream(stream)
     gpu.set_stream(stream.cuda_stream)
     s = build_scene(gpu, args.workload, args.width or None, args.height or None, num_instances=args.instances or None)
     W, H = s.width, s.height

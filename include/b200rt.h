@@ -133,7 +133,8 @@ int  rt_create(int cuda_device, RtContext** out);
 void rt_destroy(RtContext* ctx);
 /* Message of the last failed call on this context (ctx may be NULL: last rt_create failure). */
 const char* rt_last_error(const RtContext* ctx);
-/* Run this context's work on a caller-owned cudaStream_t (e.g. torch's current stream). */
+/* Run this context's work on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the
+ * context's own non-blocking stream.  NULL names the legacy default stream, as in the CUDA runtime. */
 int  rt_set_stream(RtContext* ctx, void* cuda_stream);
 
 /* load_png_image_from_bytes / create_single_colour_image + ImageManager::push_image

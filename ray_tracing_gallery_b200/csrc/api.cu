@@ -78,6 +78,8 @@ struct RtContext {
     std::vector<TexRes> tex_res;
     std::vector<TexEntry> tex_host;
     TexEntry* d_textures = nullptr;
+    std::vector<uint32_t> real_tex_host;
+    uint32_t* d_real_textures = nullptr;
     float* d_srgb_lut = nullptr;
     float srgb_lut[256];
 
@@ -231,6 +233,8 @@ int render_common(RtContext* ctx, const RtUniforms* u, const RtRenderParams* p, 
     S.num_instances = ctx->num_instances;
     S.textures = ctx->d_textures;
     S.num_textures = (uint32_t)ctx->tex_host.size();
+    S.num_real_textures = (uint32_t)ctx->real_tex_host.size();
+    S.real_textures = ctx->d_real_textures;
     S.srgb_lut = ctx->d_srgb_lut;
     FrameDev F;
     memset(&F, 0, sizeof(F));
@@ -301,6 +305,7 @@ int rt_create(int cuda_device, RtContext** out) {
     for (int i = 0; i < 4; i++)
         if ((e = cudaEventCreate(&c->ev[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&c->d_textures, sizeof(TexEntry) * RT_MAX_BOUND_IMAGES)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&c->d_real_textures, sizeof(uint32_t) * RT_MAX_BOUND_IMAGES)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_srgb_lut, sizeof(float) * 256)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_uniforms, sizeof(RtUniforms))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_counters, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -330,7 +335,7 @@ void rt_destroy(RtContext* ctx) {
         for (auto* p : m.index_bufs) cudaFree(p);
     }
     ctx->d_model_info.release(); ctx->d_blas_info.release(); ctx->blas_nodes.release(); ctx->tris.release();
-    cudaFree(ctx->d_textures); cudaFree(ctx->d_srgb_lut); cudaFree(ctx->d_uniforms); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_textures); cudaFree(ctx->d_real_textures); cudaFree(ctx->d_srgb_lut); cudaFree(ctx->d_uniforms); cudaFree(ctx->d_counters);
     cudaFree(ctx->d_instances); cudaFree(ctx->d_inst_unsorted); cudaFree(ctx->d_inst_rt); cudaFree(ctx->d_inst_boxes);
     cudaFree(ctx->d_leaf_order); cudaFree(ctx->d_tlas_nodes); cudaFree(ctx->d_tlas_node_count); cudaFree(ctx->d_ray_counts);
     cudaFree(ctx->d_ray_q[0]); cudaFree(ctx->d_ray_q[1]); cudaFree(ctx->d_hit_q);
@@ -349,13 +354,8 @@ int rt_set_stream(RtContext* ctx, void* cuda_stream) {
     CK_DEV(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (cuda_stream) {
-        ctx->stream = (cudaStream_t)cuda_stream;
-        ctx->own_stream = false;
-    } else {
-        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->own_stream = true;
-    }
+    ctx->stream = (cudaStream_t)cuda_stream;  // NULL names the legacy default stream, as in the CUDA runtime
+    ctx->own_stream = false;
     ctx->render_timed = ctx->tlas_timed = false;
     ctx->timing_valid = false;
     return RT_OK;
@@ -403,6 +403,8 @@ int rt_push_image(RtContext* ctx, const void* texels, uint32_t width, uint32_t h
     }
     uint32_t index = (uint32_t)ctx->tex_host.size();
     cudaError_t e = cudaMemcpyAsync(ctx->d_textures + index, &te, sizeof(te), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && tr.obj)
+        e = cudaMemcpyAsync(ctx->d_real_textures + ctx->real_tex_host.size(), &index, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         if (tr.obj) cudaDestroyTextureObject(tr.obj);
@@ -411,6 +413,7 @@ int rt_push_image(RtContext* ctx, const void* texels, uint32_t width, uint32_t h
     }
     ctx->tex_host.push_back(te);
     ctx->tex_res.push_back(tr);
+    if (tr.obj) ctx->real_tex_host.push_back(index);
     if (out_index) *out_index = index;
     return RT_OK;
 }

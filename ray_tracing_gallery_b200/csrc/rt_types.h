@@ -115,6 +115,8 @@ struct SceneDev {
     uint32_t          num_instances;
     const TexEntry*   textures;
     uint32_t          num_textures;
+    uint32_t          num_real_textures;  // images that need a TEX fetch (not 1x1 constants)
+    const uint32_t*   real_textures;      // their indices, ascending
     const float*      srgb_lut;      // 256 floats
 };
 

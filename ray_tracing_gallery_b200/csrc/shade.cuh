@@ -28,15 +28,19 @@ __device__ __forceinline__ int wrap_i(int i, int n) {
     return m < 0 ? m + n : m;
 }
 
-__device__ __forceinline__ F4 fetch_texel(const SceneDev& S, const TexEntry& t, int x, int y) {
+// One texel of image `k`.  `k` MUST be warp-uniform (see sample_texture).
+__device__ __forceinline__ F4 fetch_texel_uniform(const SceneDev& S, uint32_t k, int x, int y) {
+    const TexEntry* t = S.textures + k;
+    cudaTextureObject_t obj = t->obj;
+    uint32_t format = t->format;
     F4 r;
-    if (t.format == RT_FORMAT_RGBA32_SFLOAT) {
-        float4 c = tex2D<float4>(t.obj, (float)x + 0.5f, (float)y + 0.5f);
+    if (format == RT_FORMAT_RGBA32_SFLOAT) {
+        float4 c = tex2D<float4>(obj, (float)x + 0.5f, (float)y + 0.5f);
         r.r = c.x; r.g = c.y; r.b = c.z; r.a = c.w;
         return r;
     }
-    uchar4 c = tex2D<uchar4>(t.obj, (float)x + 0.5f, (float)y + 0.5f);
-    if (t.format == RT_FORMAT_RGBA8_SRGB) {
+    uchar4 c = tex2D<uchar4>(obj, (float)x + 0.5f, (float)y + 0.5f);
+    if (format == RT_FORMAT_RGBA8_SRGB) {
         r.r = __ldg(S.srgb_lut + c.x); r.g = __ldg(S.srgb_lut + c.y); r.b = __ldg(S.srgb_lut + c.z);
     } else {
         r.r = __fdiv_rn((float)c.x, 255.0f); r.g = __fdiv_rn((float)c.y, 255.0f); r.b = __fdiv_rn((float)c.z, 255.0f);
@@ -45,60 +49,66 @@ __device__ __forceinline__ F4 fetch_texel(const SceneDev& S, const TexEntry& t, 
     return r;
 }
 
-// REPEAT addressing, normalised coordinates, texel centres at +0.5, sRGB decode before filtering.
-__device__ __forceinline__ F4 sample_texture_one(const SceneDev& S, uint32_t index, float u, float v);
-
-// Bindless fetch with a per-lane image index (`nonuniformEXT`, closest_hit_textured.glsl:50-52).
-// A TEX instruction takes its texture header from a uniform register; when lanes of a warp hold
-// different handles, the loop nvcc 12.9 generates for sm_100a returned texels of the wrong image
-// for some lanes (measured: compacted wavefront warps mixing lain/fence hits).  So the fetch is made
-// uniform by hand: the converged lanes elect a leader, the lanes sharing the leader's index sample
-// and leave, the rest go round again.
-__device__ __forceinline__ F4 sample_texture(const SceneDev& S, uint32_t index, float u, float v) {
-    F4 r;
-    r.r = r.g = r.b = r.a = 0.0f;
-    if (index >= S.num_textures) return r;  // robustness2 null descriptor, src/main.rs:183-184
-    for (;;) {
-        uint32_t m = __activemask();
-        uint32_t cur = __shfl_sync(m, index, __ffs(m) - 1);
-        if (cur == index) {
-            r = sample_texture_one(S, cur, u, v);
-            break;
-        }
+// Sampling of image `k` (warp-uniform) at per-lane coordinates.  REPEAT addressing, normalised
+// coordinates, texel centres at +0.5, sRGB decode before filtering (Vulkan rules at LOD 0).
+__device__ __forceinline__ F4 sample_image_uniform(const SceneDev& S, uint32_t k, float u, float v) {
+    const TexEntry* t = S.textures + k;
+    int w = (int)t->w, h = (int)t->h;
+    if (!t->linear) {
+        int x = wrap_i((int)floorf(u * (float)w), w);
+        int y = wrap_i((int)floorf(v * (float)h), h);
+        return fetch_texel_uniform(S, k, x, y);
     }
-    return r;
-}
-// Same, for an index that is uniform by construction (the blue-noise image named by the Uniforms).
-__device__ __forceinline__ F4 sample_texture_uniform(const SceneDev& S, uint32_t index, float u, float v) {
-    return sample_texture_one(S, index, u, v);
-}
-__device__ __forceinline__ F4 sample_texture_one(const SceneDev& S, uint32_t index, float u, float v) {
-    F4 r;
-    r.r = r.g = r.b = r.a = 0.0f;
-    if (index >= S.num_textures) return r;  // robustness2 null descriptor, src/main.rs:183-184
-    const TexEntry t = S.textures[index];
-    if (t.w == 1 && t.h == 1) {
-        r.r = t.constant[0]; r.g = t.constant[1]; r.b = t.constant[2]; r.a = t.constant[3];
-        return r;
-    }
-    if (!t.linear) {
-        int x = wrap_i((int)floorf(u * (float)t.w), (int)t.w);
-        int y = wrap_i((int)floorf(v * (float)t.h), (int)t.h);
-        return fetch_texel(S, t, x, y);
-    }
-    float fx = u * (float)t.w - 0.5f, fy = v * (float)t.h - 0.5f;
+    float fx = u * (float)w - 0.5f, fy = v * (float)h - 0.5f;
     float flx = floorf(fx), fly = floorf(fy);
     float ax = fx - flx, ay = fy - fly;
-    int x0 = wrap_i((int)flx, (int)t.w), y0 = wrap_i((int)fly, (int)t.h);
-    int x1 = wrap_i(x0 + 1, (int)t.w), y1 = wrap_i(y0 + 1, (int)t.h);
-    F4 t00 = fetch_texel(S, t, x0, y0), t10 = fetch_texel(S, t, x1, y0);
-    F4 t01 = fetch_texel(S, t, x0, y1), t11 = fetch_texel(S, t, x1, y1);
+    int x0 = wrap_i((int)flx, w), y0 = wrap_i((int)fly, h);
+    int x1 = wrap_i(x0 + 1, w), y1 = wrap_i(y0 + 1, h);
+    F4 t00 = fetch_texel_uniform(S, k, x0, y0), t10 = fetch_texel_uniform(S, k, x1, y0);
+    F4 t01 = fetch_texel_uniform(S, k, x0, y1), t11 = fetch_texel_uniform(S, k, x1, y1);
     float w00 = (1.0f - ax) * (1.0f - ay), w10 = ax * (1.0f - ay), w01 = (1.0f - ax) * ay, w11 = ax * ay;
+    F4 r;
     r.r = t00.r * w00 + t10.r * w10 + t01.r * w01 + t11.r * w11;
     r.g = t00.g * w00 + t10.g * w10 + t01.g * w01 + t11.g * w11;
     r.b = t00.b * w00 + t10.b * w10 + t01.b * w01 + t11.b * w11;
     r.a = t00.a * w00 + t10.a * w10 + t01.a * w01 + t11.a * w11;
     return r;
+}
+
+// Bindless fetch with a per-lane image index (`nonuniformEXT`, closest_hit_textured.glsl:50-52).
+// A TEX instruction takes its texture header from a uniform register.  When lanes of a warp hold
+// different handles, the serialising loop nvcc 12.9 generates for sm_100a returned texels of the
+// wrong image for some lanes (measured on B200 with compacted wavefront warps mixing lain and fence
+// hits; an __activemask()/__shfl_sync election did not cure it, diverged groups re-merge inside the
+// sampled block).  So the handle is made *provably* uniform: 1x1 images are constants in the table
+// and need no TEX; for the others the loop below walks the short list of real images with a
+// warp-uniform counter and each lane samples in the iteration that matches its index.
+__device__ __forceinline__ F4 sample_texture(const SceneDev& S, uint32_t index, float u, float v) {
+    F4 r;
+    r.r = r.g = r.b = r.a = 0.0f;
+    if (index >= S.num_textures) return r;  // robustness2 null descriptor, src/main.rs:183-184
+    const TexEntry* t = S.textures + index;
+    if (t->obj == 0) {
+        r.r = t->constant[0]; r.g = t->constant[1]; r.b = t->constant[2]; r.a = t->constant[3];
+        return r;
+    }
+    for (uint32_t j = 0; j < S.num_real_textures; j++) {
+        uint32_t k = S.real_textures[j];
+        if (k == index) r = sample_image_uniform(S, k, u, v);
+    }
+    return r;
+}
+// Same, for an index that is uniform by construction (the blue-noise image named by the Uniforms).
+__device__ __forceinline__ F4 sample_texture_uniform(const SceneDev& S, uint32_t index, float u, float v) {
+    F4 r;
+    r.r = r.g = r.b = r.a = 0.0f;
+    if (index >= S.num_textures) return r;
+    const TexEntry* t = S.textures + index;
+    if (t->obj == 0) {
+        r.r = t->constant[0]; r.g = t->constant[1]; r.b = t->constant[2]; r.a = t->constant[3];
+        return r;
+    }
+    return sample_image_uniform(S, index, u, v);
 }
 
 // ---- bindless vertex fetch through the reference-layout ModelInfo / GeometryInfo tables
