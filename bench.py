@@ -162,14 +162,33 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+KERNELS = ["trace", "prep", "shadow", "resolve", "mega"]
+KERNEL_DESC = {"trace": "k_trace (ray-gen + closest-hit traversal)", "prep": "k_prep (triangle fetch, textures, BRDF terms)",
+               "shadow": "k_shadow (blue-noise shadow rays, first-hit traversal)", "resolve": "k_resolve (sun factor, sRGB store)",
+               "mega": "k_mega (one thread per pixel)"}
+
+
 def algorithmic_bytes(st, setup, pixels):
-    """Algorithmic bytes of one frame per kernel class (DESIGN.md 'Roofline accounting')."""
+    """Algorithmic bytes of one frame per kernel (DESIGN.md 'Roofline accounting').
+
+    Traversal: 80 B read per node visit (the five 16-byte words the box test needs), 64 B per instance entered,
+    48 B per triangle tested, 12 + 24 + 16 B per any-hit call (indices, 3 uvs, one bilinear tap)."""
     n = setup.shadow_rays
     trav = [80 * st.nodes_visited[k] + 64 * st.instances_entered[k] + 48 * st.triangles_tested[k] + 52 * st.anyhit_calls[k] for k in (0, 1)]
+    hits = st.textured_hits
     bounces = st.primary_rays - pixels
-    trace_b = trav[0] + 64 * bounces + 112 * bounces + 48 * st.textured_hits + 4 * (pixels - st.textured_hits)
-    shade_b = trav[1] + st.textured_hits * (48 + 32 + 24 + 12 + 96 + 64 + 48 + 2 * 16 + 4 * 2 * n + 4)
-    return {"trace": int(trace_b), "shade": int(shade_b), "mega": int(trace_b + shade_b - 48 * 2 * st.textured_hits - 64 * bounces)}
+    # k_trace: + ray queue (32 B written and read per bounce), mirror shading (12 B indices + 36 B normals + 64 B instance),
+    #          48 B hit record per textured hit, 4 B framebuffer per pixel finished here
+    trace_b = trav[0] + 64 * bounces + 112 * bounces + 48 * hits + 4 * (pixels - hits)
+    # k_prep: hit record 48 B in, ModelInfo 32 + GeometryInfo 24 + indices 12 + 3 vertices x 32, instance transform 48 + inverse 64,
+    #         two bilinear taps (4 texels x 4 B each), 64 B record out
+    prep_b = hits * (48 + 32 + 24 + 12 + 96 + 48 + 64 + 2 * 16 + 64)
+    # k_shadow: per ray 20 B of the hit record (pixel + origin), two blue-noise texels, 4 B atomic on `lit`
+    shadow_b = trav[1] + st.shadow_rays * (20 + 8 + 4)
+    # k_resolve: 52 B of the record, 4 B framebuffer
+    resolve_b = hits * (52 + 4)
+    mega_b = trav[0] + trav[1] + 112 * bounces + hits * (32 + 24 + 12 + 96 + 48 + 64 + 2 * 16 + 8 * n) + 4 * pixels
+    return {"trace": int(trace_b), "prep": int(prep_b), "shadow": int(shadow_b), "resolve": int(resolve_b), "mega": int(mega_b)}
 
 
 def run_ours(args):
@@ -259,8 +278,8 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     total_rays = 0
-    kernel_ms = np.zeros(3)
-    kernel_launches = np.zeros(3, np.int64)
+    kernel_ms = np.zeros(len(KERNELS))
+    kernel_launches = np.zeros(len(KERNELS), np.int64)
     tlas_ms = 0.0
     for i in range(args.steps):
         flush.zero_()
@@ -336,7 +355,7 @@ def run_ours(args):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        names = ["trace", "shade", "mega"]
+        names = KERNELS
         dom = int(np.argmax(kernel_ms))
         per_launch_ms = kernel_ms[dom] / max(kernel_launches[dom], 1)
         launches_per_frame = kernel_launches[dom] / args.steps
@@ -345,7 +364,7 @@ def run_ours(args):
         rays_frame = max(int(st_count.primary_rays + st_count.shadow_rays), 1)
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "kernel": {"trace": "k_trace (ray-gen + closest-hit traversal)", "shade": "k_shade (shadow rays + PBR shading)", "mega": "k_mega"}[names[dom]],
+            "kernel": KERNEL_DESC[names[dom]],
             "peak_source": peak_src,
             "kernel_ms_per_frame": {n: float(kernel_ms[i] / args.steps) for i, n in enumerate(names)},
             "kernel_share_of_step": float(kernel_ms[dom] / total_ms) if world == 1 else None,
@@ -353,7 +372,7 @@ def run_ours(args):
             "launches_per_frame": float(launches_per_frame),
             "per_ray": {"nodes": float(sum(st_count.nodes_visited)) / rays_frame, "instances": float(sum(st_count.instances_entered)) / rays_frame,
                         "triangles": float(sum(st_count.triangles_tested)) / rays_frame,
-                        "bytes": float(bytes_frame["trace"] + bytes_frame["shade"]) / rays_frame},
+                        "bytes": float(bytes_frame["mega"] if args.pipeline == "mega" else sum(bytes_frame[k] for k in KERNELS[:4])) / rays_frame},
             "note": "working set of this workload is L2-resident after first touch (SURVEY 8d): the HBM fraction is expected to be small; "
                     "the kernel is latency/issue bound, see profiles/",
         }

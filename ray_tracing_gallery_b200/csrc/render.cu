@@ -6,10 +6,15 @@
 //                miss -> sky colour to the framebuffer; mirror/portal -> next ray pushed to the
 //                compacted ray queue; textured hit -> HitRec pushed to the compacted hit queue
 //                (warp ballot + one atomic per warp).
-//   k_shade      one thread per queued textured hit (all lanes busy): shadow-terminator origin,
-//                N blue-noise shadow rays (first-hit traversal), textures, BRDF, framebuffer write.
-// Both are persistent kernels: warps pull 32-item batches from a device-side cursor, so a launch
-// never needs the queue length on the host.
+//   k_prep       one thread per queued textured hit: triangle fetch, shadow-terminator origin,
+//                textures, normal, BRDF terms; the HitRec is rewritten in place.
+//   k_shadow     one thread per shadow ray (hit x sample): blue-noise direction + first-hit
+//                traversal; unshadowed rays are counted into HitRec.lit.
+//   k_resolve    one thread per hit: sun_factor, final colour, sRGB encode, framebuffer write.
+// Small kernels on purpose: the one-pass shade kernel of the first version was instruction-fetch
+// bound (profiles/r01a_shade_details.txt: 31 % of issue stalls "no instruction", 128 registers).
+// All are persistent kernels: warps pull 32-item batches from a device-side cursor, so a launch
+// never needs a queue length on the host.
 // Megakernel (A/B baseline): one thread per pixel runs the whole segment loop.
 #include "launch_count.h"
 #include "render.h"
@@ -92,42 +97,59 @@ __device__ __forceinline__ void flush_ray_counters(const FrameDev& F, uint32_t n
     warp_add(&F.counters->textured_hits, n_textured);
 }
 
-// The textured closest-hit: shadow rays + shading.  closest_hit_textured.glsl:174-226
+// cast_shadow_ray for sample `i` of a textured hit (closest_hit_textured.glsl:159-172, :195-201):
+// TerminateOnFirstHit | SkipClosestHit, tmin 0.001, tmax 10000.  Returns 1 - shadowed.
+template <bool COUNT>
+__device__ __forceinline__ bool shadow_sample_lit(const SceneDev& S, const FrameDev& F, const SunFrame& sun, uint32_t px, uint32_t py,
+                                                  uint32_t i, V3 origin, TraceCounters& tc) {
+    V2 xi = blue_noise_xi(S, F.uniforms.blue_noise_texture_index, px, py, i, F.uniforms.frame_index);
+    V3 dir = sample_directional_light(xi, sun, F.uniforms.sun_radius);
+    Hit sh;
+    return !trace_ray<true, COUNT>(S, origin, dir, 0.001f, 10000.0f, sh, tc);
+}
+
+// The textured closest-hit in one pass (megakernel).  closest_hit_textured.glsl:174-226
 template <bool COUNT>
 __device__ __forceinline__ V3 shade_textured(const SceneDev& S, const FrameDev& F, const TexturedHit& th, uint32_t& n_shadow, TraceCounters& tc /* shadow-ray counters */) {
     ShadeCtx ctx;
-    V3 shadow_origin;
-    if (!shade_textured_begin(S, th, ctx, shadow_origin)) return v3(0.f, 0.f, 0.f);
-    V3 sun = v3(F.uniforms.sun_dir[0], F.uniforms.sun_dir[1], F.uniforms.sun_dir[2]);
-    float sum = 0.0f;
-    for (uint32_t i = 0; i < F.shadow_rays; i++) {
-        V2 xi = blue_noise_xi(S, F.uniforms.blue_noise_texture_index, th.px, th.py, i, F.uniforms.frame_index);
-        V3 dir = sample_directional_light(xi, sun, F.uniforms.sun_radius);
-        Hit sh;
-        // cast_shadow_ray: TerminateOnFirstHit | SkipClosestHit, tmin 0.001, tmax 10000 (:159-172)
-        bool shadowed = trace_ray<true, COUNT>(S, shadow_origin, dir, 0.001f, 10000.0f, sh, tc);
-        sum += shadowed ? 0.0f : 1.0f;
-    }
+    if (!shade_textured_load(S, th, ctx)) return v3(0.f, 0.f, 0.f);
+    V3 shadow_origin = shade_textured_shadow_origin(S, ctx);
+    SunFrame sun = make_sun_frame(F.uniforms);
+    uint32_t lit = 0;
+    for (uint32_t i = 0; i < F.shadow_rays; i++) lit += shadow_sample_lit<COUNT>(S, F, sun, th.px, th.py, i, shadow_origin, tc) ? 1u : 0u;
     n_shadow += F.shadow_rays;
-    float sun_factor = sum / (float)F.shadow_rays;
-    return shade_textured_end(S, F.uniforms, th, ctx, sun_factor);
+    float sun_factor = div_((float)lit, (float)F.shadow_rays);
+    V3 base;
+    BrdfTerms bt = shade_textured_terms(S, F.uniforms, th, ctx, base);
+    return shade_finish(sun_factor, bt.NoL, bt.comb, base);
 }
 
 // ------------------------------------------------------------------------------------ wavefront
+enum { K_TRACE = 0, K_PREP = 1, K_SHADOW = 2, K_RESOLVE = 3, K_MEGA = 4 };
+
+__device__ __forceinline__ SegCounters* seg_counters(const FrameDev& F, uint32_t seg) { return &F.counters->seg[seg & (RT_SEG_SLOTS - 1u)]; }
+
+// warp-wide grab of 32 work items; returns false when the cursor has passed `total`
+__device__ __forceinline__ bool grab32(unsigned int* cursor, uint32_t total, uint32_t& item) {
+    uint32_t base = 0;
+    if (lane_id() == 0) base = atomicAdd(cursor, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    item = base + lane_id();
+    return base < total;
+}
+
+// Ray generation (segment 0) or ray-queue read, closest-hit traversal, miss / mirror / portal shaders,
+// textured hits -> hit queue.
 template <bool SEG0, bool COUNT>
 __global__ void __launch_bounds__(128) k_trace(SceneDev S, FrameDev F, uint32_t seg, uint32_t total_seg0) {
     TraceCounters tc = {0, 0, 0, 0, 0};
     uint32_t n_primary = 0;
     const RayRec* __restrict__ in_q = F.ray_q[(seg + 1u) & 1u];
     RayRec* __restrict__ out_q = F.ray_q[seg & 1u];
-    unsigned int* cursor = &F.counters->work_next[0];
-    const uint32_t total = SEG0 ? total_seg0 : *((volatile unsigned int*)&F.counters->ray_count[(seg + 1u) & 1u]);
-    for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= total) break;
-        uint32_t item = base + lane_id();
+    SegCounters* sc = seg_counters(F, seg);
+    const uint32_t total = SEG0 ? total_seg0 : *((volatile unsigned int*)&seg_counters(F, seg - 1u)->ray_count);
+    uint32_t item;
+    while (grab32(&sc->work_next[K_TRACE], total, item)) {
         bool active = false;
         uint32_t pixel = 0;
         V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
@@ -172,14 +194,14 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev S, FrameDev F, uint32_t 
             V3 c = got ? v3(0.f, 0.f, 0.f) : miss_colour(F.uniforms, F.cos_sun_radius, d);
             write_pixel(F, pixel, c);
         }
-        uint32_t hslot = warp_push(&F.counters->hit_count, textured);
+        uint32_t hslot = warp_push(&sc->hit_count, textured);
         if (textured) {
             HitRec* hr = F.hit_q + hslot;
             reinterpret_cast<uint4*>(hr)[0] = make_uint4(pixel, h.inst_pos, h.geom, h.prim);
             reinterpret_cast<float4*>(hr)[1] = make_float4(h.u, h.v, h.t, 0.f);
             reinterpret_cast<float4*>(hr)[2] = make_float4(d.x, d.y, d.z, 0.f);
         }
-        uint32_t rslot = warp_push(&F.counters->ray_count[seg & 1u], bounce);
+        uint32_t rslot = warp_push(&sc->ray_count, bounce);
         if (bounce) {
             float4* rp = reinterpret_cast<float4*>(out_q + rslot);
             rp[0] = make_float4(no.x, no.y, no.z, __uint_as_float(pixel));
@@ -190,44 +212,102 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev S, FrameDev F, uint32_t 
     flush_trace_counters<COUNT>(F, 0, tc);
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shade(SceneDev S, FrameDev F) {
-    TraceCounters tc = {0, 0, 0, 0, 0};
-    uint32_t n_shadow = 0, n_textured = 0;
-    unsigned int* cursor = &F.counters->work_next[1];
-    const uint32_t total = *((volatile unsigned int*)&F.counters->hit_count);
-    for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= total) break;
-        uint32_t item = base + lane_id();
+// closest_hit_textured.glsl:174-221 for every queued hit, minus the shadow rays: triangle fetch,
+// shadow-terminator origin, material textures, normal, BRDF terms.  Rewrites the HitRec in place.
+__global__ void __launch_bounds__(128) k_prep(SceneDev S, FrameDev F, uint32_t seg) {
+    SegCounters* sc = seg_counters(F, seg);
+    const uint32_t total = *((volatile unsigned int*)&sc->hit_count);
+    uint32_t n_textured = 0;
+    uint32_t item;
+    while (grab32(&sc->work_next[K_PREP], total, item)) {
         if (item < total) {
-            const HitRec* hr = F.hit_q + item;
-            uint4 a = __ldg(reinterpret_cast<const uint4*>(hr));
-            float4 b = __ldg(reinterpret_cast<const float4*>(hr) + 1);
-            float4 c = __ldg(reinterpret_cast<const float4*>(hr) + 2);
+            HitRec* hr = F.hit_q + item;
+            uint4 a = __ldcg(reinterpret_cast<const uint4*>(hr));
+            float4 b = __ldcg(reinterpret_cast<const float4*>(hr) + 1);
+            float4 c = __ldcg(reinterpret_cast<const float4*>(hr) + 2);
             TexturedHit th;
             uint32_t ly = a.x / F.tw, lx = a.x - ly * F.tw;
             th.px = F.x0 + lx; th.py = global_y(F, ly);
             th.inst_pos = a.y; th.geom = a.z; th.prim = a.w;
             th.u = b.x; th.v = b.y;
             th.dir = v3(c.x, c.y, c.z);
-            V3 col = shade_textured<COUNT>(S, F, th, n_shadow, tc);
+            ShadeCtx ctx;
+            float4 r0 = make_float4(__uint_as_float(a.x), 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, 0.f), r2 = r1, r3 = r1;
+            if (shade_textured_load(S, th, ctx)) {
+                V3 so = shade_textured_shadow_origin(S, ctx);
+                V3 base;
+                BrdfTerms bt = shade_textured_terms(S, F.uniforms, th, ctx, base);
+                r0.y = bt.NoL;
+                r1 = make_float4(bt.comb.x, bt.comb.y, bt.comb.z, 0.f);  // .w: lit = 0
+                r2 = make_float4(base.x, base.y, base.z, 0.f);
+                r3 = make_float4(so.x, so.y, so.z, __uint_as_float(1u));
+            }
+            reinterpret_cast<float4*>(hr)[0] = r0;
+            reinterpret_cast<float4*>(hr)[1] = r1;
+            reinterpret_cast<float4*>(hr)[2] = r2;
+            reinterpret_cast<float4*>(hr)[3] = r3;
             n_textured++;
-            write_pixel(F, a.x, col);
         }
     }
-    flush_ray_counters(F, 0, n_shadow, n_textured);
+    flush_ray_counters(F, 0, 0, n_textured);
+}
+
+// One thread per shadow ray: item = hit * shadow_rays + sample, so the samples of one hit sit in
+// adjacent lanes (same origin, directions inside the sun's cone: coherent traversal).
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow(SceneDev S, FrameDev F, uint32_t seg) {
+    TraceCounters tc = {0, 0, 0, 0, 0};
+    SegCounters* sc = seg_counters(F, seg);
+    const uint32_t n = F.shadow_rays;
+    const uint32_t total = *((volatile unsigned int*)&sc->hit_count) * n;
+    const SunFrame sun = make_sun_frame(F.uniforms);
+    uint32_t n_shadow = 0;
+    uint32_t item;
+    while (grab32(&sc->work_next[K_SHADOW], total, item)) {
+        if (item < total) {
+            uint32_t hi = item / n, i = item - hi * n;
+            HitRec* hr = F.hit_q + hi;
+            uint32_t pixel = __ldg(&hr->pixel);
+            float4 so = __ldg(reinterpret_cast<const float4*>(hr) + 3);
+            if (__float_as_uint(so.w)) {
+                uint32_t ly = pixel / F.tw, lx = pixel - ly * F.tw;
+                bool lit = shadow_sample_lit<COUNT>(S, F, sun, F.x0 + lx, global_y(F, ly), i, v3(so.x, so.y, so.z), tc);
+                if (lit) atomicAdd(&hr->lit, 1u);
+                n_shadow++;
+            }
+        }
+    }
+    flush_ray_counters(F, 0, n_shadow, 0);
     flush_trace_counters<COUNT>(F, 1, tc);
 }
 
-// between segments: the hit queue and the next output ray queue start empty, cursors rewind
-__global__ void k_next_segment(FrameCounters* c, uint32_t next_seg) {
-    c->hit_count = 0;
-    c->ray_count[next_seg & 1u] = 0;
-    c->work_next[0] = 0;
-    c->work_next[1] = 0;
+// sun_factor = lit / N, colour = sun_factor * NoL * comb + 0.1 * base (closest_hit_textured.glsl:203, :222-225),
+// then the ray-gen tail: linear_to_srgb + image store (lib.rs:188-190).
+__global__ void __launch_bounds__(128) k_resolve(FrameDev F, uint32_t seg) {
+    SegCounters* sc = seg_counters(F, seg);
+    const uint32_t total = *((volatile unsigned int*)&sc->hit_count);
+    uint32_t item;
+    while (grab32(&sc->work_next[K_RESOLVE], total, item)) {
+        if (item < total) {
+            const HitRec* hr = F.hit_q + item;
+            float4 r0 = __ldcg(reinterpret_cast<const float4*>(hr));
+            float4 r1 = __ldcg(reinterpret_cast<const float4*>(hr) + 1);
+            float4 r2 = __ldcg(reinterpret_cast<const float4*>(hr) + 2);
+            uint32_t valid = __ldcg(&hr->shadow_valid);
+            V3 col = v3(0.f, 0.f, 0.f);
+            if (valid) {
+                float sun_factor = div_((float)__float_as_uint(r1.w), (float)F.shadow_rays);
+                col = shade_finish(sun_factor, r0.y, v3(r1.x, r1.y, r1.z), v3(r2.x, r2.y, r2.z));
+            }
+            write_pixel(F, __float_as_uint(r0.x), col);
+        }
+    }
+}
+
+// segments >= RT_SEG_SLOTS reuse a counter slot
+__global__ void k_reset_segment(FrameCounters* c, uint32_t seg) {
+    SegCounters z = {};
+    c->seg[seg & (RT_SEG_SLOTS - 1u)] = z;
 }
 
 // ------------------------------------------------------------------------------------ megakernel
@@ -318,30 +398,36 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
     if (pipeline == RT_PIPELINE_MEGAKERNEL) {
         if (count) k_mega<true><<<(total + 127) / 128, 128, 0, stream>>>(S, F, total);
         else k_mega<false><<<(total + 127) / 128, 128, 0, stream>>>(S, F, total);
-        mark(2);
+        mark(K_MEGA);
     } else {
-        static int g_trace0[2] = {0, 0}, g_trace[2] = {0, 0}, g_shade[2] = {0, 0};
+        static int g_trace0[2] = {0, 0}, g_trace[2] = {0, 0}, g_shadow[2] = {0, 0}, g_prep = 0, g_resolve = 0;
         int ci = count ? 1 : 0;
         if (!g_trace0[ci]) {
             g_trace0[ci] = count ? persistent_grid(k_trace<true, true>, sms) : persistent_grid(k_trace<true, false>, sms);
             g_trace[ci] = count ? persistent_grid(k_trace<false, true>, sms) : persistent_grid(k_trace<false, false>, sms);
-            g_shade[ci] = count ? persistent_grid(k_shade<true>, sms) : persistent_grid(k_shade<false>, sms);
+            g_shadow[ci] = count ? persistent_grid(k_shadow<true>, sms) : persistent_grid(k_shadow<false>, sms);
+            g_prep = persistent_grid(k_prep, sms);
+            g_resolve = persistent_grid(k_resolve, sms);
         }
+        int cap = (int)((total + 127) / 128);  // no more blocks than there could be work
+        auto fit = [&](int g, uint32_t per_item) { long long c = (long long)cap * per_item; return (int)(c < g ? c : g); };
         for (uint32_t seg = 0; seg < F.max_segments; seg++) {
+            if (seg >= RT_SEG_SLOTS) { k_reset_segment<<<1, 1, 0, stream>>>(F.counters, seg); note_launch(); }
             if (seg == 0) {
-                int grid = (int)((total + 127) / 128) < g_trace0[ci] ? (int)((total + 127) / 128) : g_trace0[ci];
-                if (count) k_trace<true, true><<<grid, 128, 0, stream>>>(S, F, 0, total);
-                else k_trace<true, false><<<grid, 128, 0, stream>>>(S, F, 0, total);
+                if (count) k_trace<true, true><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, 0, total);
+                else k_trace<true, false><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, 0, total);
             } else {
-                k_next_segment<<<1, 1, 0, stream>>>(F.counters, seg);
-                note_launch();
-                if (count) k_trace<false, true><<<g_trace[ci], 128, 0, stream>>>(S, F, seg, 0);
-                else k_trace<false, false><<<g_trace[ci], 128, 0, stream>>>(S, F, seg, 0);
+                if (count) k_trace<false, true><<<fit(g_trace[ci], 1), 128, 0, stream>>>(S, F, seg, 0);
+                else k_trace<false, false><<<fit(g_trace[ci], 1), 128, 0, stream>>>(S, F, seg, 0);
             }
-            mark(0);
-            if (count) k_shade<true><<<g_shade[ci], 128, 0, stream>>>(S, F);
-            else k_shade<false><<<g_shade[ci], 128, 0, stream>>>(S, F);
-            mark(1);
+            mark(K_TRACE);
+            k_prep<<<fit(g_prep, 1), 128, 0, stream>>>(S, F, seg);
+            mark(K_PREP);
+            if (count) k_shadow<true><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, seg);
+            else k_shadow<false><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, seg);
+            mark(K_SHADOW);
+            k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, seg);
+            mark(K_RESOLVE);
         }
     }
     if (d_ray_counts) { k_export_counts<<<1, 1, 0, stream>>>(F.counters, d_ray_counts); note_launch(); }

@@ -86,20 +86,30 @@ struct __align__(16) RayRec {   // 32 B: a ray-gen segment waiting to be traced
     float ox, oy, oz; uint32_t pixel;
     float dx, dy, dz; uint32_t _pad;
 };
-struct __align__(16) HitRec {   // 48 B: a textured hit waiting for shadow rays + shading
-    uint32_t pixel, inst_pos, geom, prim;
-    float    u, v, t; uint32_t _pad;
-    float    dx, dy, dz; uint32_t _pad2;
+// 64 B: a textured hit on its way through k_trace -> k_prep -> k_shadow -> k_resolve.
+// k_trace writes the hit (words 0..11); k_prep replaces it in place by what the later stages need.
+struct __align__(16) HitRec {
+    uint32_t pixel; uint32_t a1, a2, a3;  // k_trace: inst_pos, geom, prim       k_prep: NoL, -, -
+    float    b0, b1, b2; uint32_t lit;    // k_trace: u, v, t                    k_prep: comb.xyz; lit = unshadowed rays (k_shadow, atomic)
+    float    c0, c1, c2; uint32_t _pad;   // k_trace: gl_WorldRayDirectionEXT    k_prep: base colour
+    float    sox, soy, soz; uint32_t shadow_valid;  // k_prep: shadow-ray origin; 0 = triangle not resolvable
 };
+static_assert(sizeof(HitRec) == 64, "HitRec is 64 bytes");
 
+// Per ray-gen segment: queue fills and the work cursors of the persistent kernels.
+#define RT_SEG_SLOTS 8
+struct SegCounters {
+    unsigned int hit_count;      // HitRec queue fill (k_trace)
+    unsigned int ray_count;      // RayRec queue fill: rays for the NEXT segment (k_trace)
+    unsigned int work_next[4];   // cursors: trace, prep, shadow, resolve
+    unsigned int _pad[2];
+};
 struct FrameCounters {
     unsigned long long primary_rays, shadow_rays, textured_hits;
-    // [0] closest-hit rays (k_trace), [1] shadow rays (k_shade)
+    // [0] closest-hit rays (k_trace), [1] shadow rays (k_shadow)
     unsigned long long nodes_visited[2], instances_entered[2], triangles_tested[2], anyhit_calls[2];
-    unsigned int hit_count;       // HitRec queue fill
-    unsigned int ray_count[2];    // RayRec ping-pong queue fill
-    unsigned int work_next[4];    // persistent-kernel work cursors
-    unsigned int stack_overflow;  // traversal stack overflow events (must stay 0)
+    SegCounters seg[RT_SEG_SLOTS];  // slot = segment % RT_SEG_SLOTS
+    unsigned int stack_overflow;    // traversal stack overflow events (must stay 0)
     unsigned int _pad;
 };
 

@@ -150,8 +150,14 @@ __device__ __forceinline__ float pdot(V3 a, V3 b) { return a.x * b.x + a.y * b.y
 __device__ __forceinline__ float compute_f90(const DotParams& p) { return 0.5f + 2.0f * p.roughness * p.LoH * p.LoH; }
 __device__ __forceinline__ float schlick1(float u, float f0, float f90) { return f0 + (f90 - f0) * powf(1.0f - u, 5.0f); }
 
-// pbr.glsl:174-211
-__device__ __forceinline__ V3 brdf(V3 normal, V3 view, V3 light, V3 base, float perceptual_roughness, float metallic, float sun_factor) {
+// pbr.glsl:174-211.  The result is light_intensity * NoL * (diffuse + specular) (:200-210); the
+// light-independent part is returned so that the wavefront can finish the product after its shadow
+// rays have been counted (shade_finish), with exactly the operations of the one-pass path.
+struct BrdfTerms {
+    float NoL;
+    V3 comb;   // base * Fd + D * V * F
+};
+__device__ __forceinline__ BrdfTerms brdf_terms(V3 normal, V3 view, V3 light, V3 base, float perceptual_roughness, float metallic) {
     V3 hs = v3(view.x + light.x, view.y + light.y, view.z + light.z);
     float hl = sqrtf(pdot(hs, hs));
     V3 h = v3(hs.x / hl, hs.y / hl, hs.z / hl);
@@ -181,8 +187,15 @@ __device__ __forceinline__ V3 brdf(V3 normal, V3 view, V3 light, V3 base, float 
     float DG = D * G;
     // Fd_Burley, :95-103
     float fd = schlick1(p.NoL, 1.0f, f90) * schlick1(p.NoV, 1.0f, f90) * (1.0f / RT_PI);
-    return v3(sun_factor * p.NoL * (base.x * fd + DG * Fx), sun_factor * p.NoL * (base.y * fd + DG * Fy),
-              sun_factor * p.NoL * (base.z * fd + DG * Fz));
+    BrdfTerms t;
+    t.NoL = p.NoL;
+    t.comb = v3(base.x * fd + DG * Fx, base.y * fd + DG * Fy, base.z * fd + DG * Fz);
+    return t;
+}
+// primary_payload.colour = brdf(params) + 0.1 * base (closest_hit_textured.glsl:222-225), unfused
+__device__ __forceinline__ V3 shade_finish(float sun_factor, float NoL, V3 comb, V3 base) {
+    float k = mul_(sun_factor, NoL);
+    return v3(add_(mul_(k, comb.x), mul_(0.1f, base.x)), add_(mul_(k, comb.y), mul_(0.1f, base.y)), add_(mul_(k, comb.z), mul_(0.1f, base.z)));
 }
 
 // ---- closest_hit_textured.glsl
@@ -211,16 +224,23 @@ __device__ __forceinline__ V2 blue_noise_xi(const SceneDev& S, uint32_t tex, uin
     V2 r; r.x = sub_(sa, floorf(sa)); r.y = sub_(sb, floorf(sb));
     return r;
 }
-// :77-94
-__device__ __forceinline__ V3 sample_directional_light(V2 rng, V3 center, float radius) {
+// :77-94.  The tangent frame depends only on the light direction, so it is built once per thread
+// (same operations, same order as the shader, which rebuilds it per sample).
+struct SunFrame { V3 center, tangent, bitangent; };
+__device__ __forceinline__ SunFrame make_sun_frame(const RtUniforms& U) {
+    SunFrame f;
+    f.center = v3(U.sun_dir[0], U.sun_dir[1], U.sun_dir[2]);
+    f.tangent = normalize3(cross3(f.center, v3(0.f, 1.f, 0.f)));
+    f.bitangent = normalize3(cross3(f.tangent, f.center));
+    return f;
+}
+__device__ __forceinline__ V3 sample_directional_light(V2 rng, const SunFrame& f, float radius) {
     float r = __fsqrt_rn(rng.x);
     float angle = mul_(mul_(rng.y, 2.0f), RT_PI);
     float px = mul_(mul_(r, cosf(angle)), radius), py = mul_(mul_(r, sinf(angle)), radius);
-    V3 tangent = normalize3(cross3(center, v3(0.f, 1.f, 0.f)));
-    V3 bitangent = normalize3(cross3(tangent, center));
-    return normalize3(v3(add_(add_(center.x, mul_(px, tangent.x)), mul_(py, bitangent.x)),
-                         add_(add_(center.y, mul_(px, tangent.y)), mul_(py, bitangent.y)),
-                         add_(add_(center.z, mul_(px, tangent.z)), mul_(py, bitangent.z))));
+    return normalize3(v3(add_(add_(f.center.x, mul_(px, f.tangent.x)), mul_(py, f.bitangent.x)),
+                         add_(add_(f.center.y, mul_(px, f.tangent.y)), mul_(py, f.bitangent.y)),
+                         add_(add_(f.center.z, mul_(px, f.tangent.z)), mul_(py, f.bitangent.z))));
 }
 
 struct TexturedHit {       // what the textured closest-hit needs after traversal
@@ -240,8 +260,8 @@ struct ShadeCtx {          // state kept between the shadow-ray phase and the BR
     uint32_t instance_id;
 };
 
-// First half of closest_hit_textured main(): fetch the triangle, build the shadow-ray origin.
-__device__ __forceinline__ bool shade_textured_begin(const SceneDev& S, const TexturedHit& h, ShadeCtx& c, V3& shadow_origin) {
+// closest_hit_textured main(), part 1: ModelInfo -> GeometryInfo -> load_triangle -> interpolate (:175-188)
+__device__ __forceinline__ bool shade_textured_load(const SceneDev& S, const TexturedHit& h, ShadeCtx& c) {
     const InstRT* ir = S.inst_rt + h.inst_pos;
     uint32_t custom = __ldg(&ir->custom_sbt) & 0xFFFFFFu;
     c.instance_id = __ldg(&ir->instance_id);
@@ -256,19 +276,27 @@ __device__ __forceinline__ bool shade_textured_begin(const SceneDev& S, const Te
     c.tri.na = ld_v3(nrm, ia); c.tri.nb = ld_v3(nrm, ib); c.tri.nc = ld_v3(nrm, ic);
     c.tri.ta = ld_v2(uvs, ia); c.tri.tb = ld_v2(uvs, ib); c.tri.tc = ld_v2(uvs, ic);
     c.w = bary_weights(h.u, h.v);
-    V3 ipos = interp3(c.tri.pa, c.tri.pb, c.tri.pc, c.w);
     c.inrm = interp3(c.tri.na, c.tri.nb, c.tri.nc, c.w);
     c.uv = interp2(c.tri.ta, c.tri.tb, c.tri.tc, c.w);
+    return true;
+}
+// part 2: get_shadow_terminator_fix_shadow_origin (:193)
+__device__ __forceinline__ V3 shade_textured_shadow_origin(const SceneDev& S, const ShadeCtx& c) {
+    V3 ipos = interp3(c.tri.pa, c.tri.pb, c.tri.pc, c.w);
     float o2w[12];
     const float* tr = S.instances[c.instance_id].transform;
 #pragma unroll
     for (int i = 0; i < 12; i++) o2w[i] = __ldg(tr + i);
-    shadow_origin = terminator_origin(c.tri, ipos, c.w, o2w);
+    return terminator_origin(c.tri, ipos, c.w, o2w);
+}
+__device__ __forceinline__ bool shade_textured_begin(const SceneDev& S, const TexturedHit& h, ShadeCtx& c, V3& shadow_origin) {
+    if (!shade_textured_load(S, h, c)) return false;
+    shadow_origin = shade_textured_shadow_origin(S, c);
     return true;
 }
 
-// Second half: material, normal, BRDF, ambient.  Returns primary_payload.colour.
-__device__ __forceinline__ V3 shade_textured_end(const SceneDev& S, const RtUniforms& U, const TexturedHit& h, const ShadeCtx& c, float sun_factor) {
+// part 3: material, normal, BRDF terms (:205-221).  `base` receives the diffuse texel.
+__device__ __forceinline__ BrdfTerms shade_textured_terms(const SceneDev& S, const RtUniforms& U, const TexturedHit& h, const ShadeCtx& c, V3& base) {
     F4 dcol = sample_texture(S, c.gi.images.diffuse_image_index, c.uv.x, c.uv.y);
     F4 mr = sample_texture(S, c.gi.images.metallic_roughness_image_index, c.uv.x, c.uv.y);
     float metallic = mr.b, roughness = mr.g;  // `.bg` swizzle, closest_hit_textured.glsl:54-60
@@ -297,8 +325,8 @@ __device__ __forceinline__ V3 shade_textured_end(const SceneDev& S, const RtUnif
         normal = normalize3(xform_normal(inv, local));
     }
     V3 sun = v3(U.sun_dir[0], U.sun_dir[1], U.sun_dir[2]);
-    V3 lo = brdf(normal, v3(-h.dir.x, -h.dir.y, -h.dir.z), sun, v3(dcol.r, dcol.g, dcol.b), roughness, metallic, sun_factor);
-    return v3(lo.x + 0.1f * dcol.r, lo.y + 0.1f * dcol.g, lo.z + 0.1f * dcol.b);
+    base = v3(dcol.r, dcol.g, dcol.b);
+    return brdf_terms(normal, v3(-h.dir.x, -h.dir.y, -h.dir.z), sun, base, roughness, metallic);
 }
 
 // closest_hit_mirror.glsl:11-29.  Returns false if the model tables cannot be resolved.

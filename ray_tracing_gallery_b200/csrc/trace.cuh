@@ -10,25 +10,33 @@
 //   * candidates on non-opaque geometry run the alpha-clip any-hit (for both ray types);
 //   * shadow rays (ANY = true) stop at the first accepted candidate.
 //
-// Mechanics: one thread per ray.  A node visit is five ld.global.nc.v4 (80 of the node's 128
-// bytes).  The traversal stack holds "node groups" — (child_base, pending-hit mask, imask) — so a
-// node costs one stack slot however many of its children were hit; slots were assigned at build
-// time by child octant, so visiting pending bits in order of (slot XOR ray_octant) is
-// front-to-back with no distance sort.  TLAS leaves (instances) that are hit but not entered yet
-// are stacked as single entries.
+// Mechanics: one thread per ray, written as a resumable state machine (`Traverser::step` = one
+// node visit, instance entry or stack pop) so that persistent warps can swap finished rays for
+// new ones between steps.  A node visit is five ld.global.nc.v4 (80 of the node's 128 bytes).
+// The stack holds "node groups" — (child_base, pending-hit mask, imask) — so a node costs one
+// slot however many of its children were hit; slots were assigned at build time by child octant,
+// so visiting pending bits in order of (slot XOR ray_octant) is front-to-back with no distance
+// sort.  TLAS leaves (instances) that are hit but not entered yet are stacked as single entries.
+//
+// Box test: child planes are bytes q on the node grid, t = q*a + b with a = 2^e/d, b = (origin-o)/d.
+// The byte is dropped into the mantissa of 1.0 (m = 1 + q*2^-15, one PRMT, no int->float convert)
+// and t = fma(m, A, B) with A = 2^15*a, B = b - A.  B's rounding error is <= (|b|+|A|)*2^-24, i.e.
+// at most 1/512 of a grid cell; near planes use B - p and far planes B + p with
+// p = (|b|+|A|)*2^-21, so the test stays conservative.
 #pragma once
 #include "shade.cuh"
 
 namespace b200rt {
 
 #define RT_STACK_SIZE 48
+#define RT_NONE 0xFFFFFFFFu
 
 struct Hit {
     float t, u, v;
-    uint32_t inst_pos;     // TLAS leaf position of the instance (0xFFFFFFFF = miss)
+    uint32_t inst_pos;     // TLAS leaf position of the instance (RT_NONE = miss)
     uint32_t instance_id;  // gl_InstanceID
     uint32_t geom, prim;
-    uint32_t custom_sbt;
+    uint32_t custom_sbt;   // custom index (24 low) | hit-shader kind (8 high)
 };
 
 struct TraceCounters {
@@ -39,11 +47,6 @@ __device__ __forceinline__ float safe_rcp(float x) {
     float ax = fabsf(x);
     if (!(ax >= 1e-12f)) x = copysignf(1e-12f, x);
     return __frcp_rn(x);
-}
-
-// byte `sel` of `w` as float (exact): place the byte in the mantissa of 2^23 and subtract
-__device__ __forceinline__ float byte_f(uint32_t w, uint32_t sel) {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | sel)) - 8388608.0f;
 }
 
 // 8-bit mask of non-zero bytes of (lo, hi)
@@ -61,53 +64,77 @@ __device__ __forceinline__ uint32_t permute_by_octant(uint32_t m, uint32_t oct) 
     return m;
 }
 
+// byte `SEL` of w placed in the mantissa of 1.0f: 1 + q * 2^-15
+template <int SEL>
+__device__ __forceinline__ float byte_m(uint32_t w) {
+    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (SEL << 4)));
+}
+
 template <bool ANY, bool COUNT>
-__device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float tmin, float tmax, Hit& hit, TraceCounters& tc) {
-    uint2 stack[RT_STACK_SIZE];
-    int sp = 0;
+struct Traverser {
+    V3 o, d;    // world-space ray
+    V3 co, cd;  // ray in the current space (world in the TLAS, object inside an instance)
+    float idx, idy, idz;
+    float tmin, tmax;
+    uint32_t oct;
+    uint32_t ng_base, ng_bits;  // current node group: child_base | pending (bits 0..7, priority order) + imask (bits 8..15)
+    uint32_t enter_inst;        // TLAS leaf to enter next, or RT_NONE
+    int sp, inst_sp;            // inst_sp >= 0: inside an instance entered at this stack height
+    uint32_t cur_inst_pos, cur_instance_id, cur_custom_sbt;
+    Hit hit;
 
-    hit.t = tmax;
-    hit.inst_pos = 0xFFFFFFFFu;
-    hit.instance_id = 0xFFFFFFFFu;
-    hit.geom = hit.prim = 0xFFFFFFFFu;
-    hit.u = hit.v = 0.0f;
-    hit.custom_sbt = 0;
+    __device__ __forceinline__ void set_space(V3 no, V3 nd) {
+        co = no; cd = nd;
+        idx = safe_rcp(cd.x); idy = safe_rcp(cd.y); idz = safe_rcp(cd.z);
+        oct = (cd.x < 0.0f ? 1u : 0u) | (cd.y < 0.0f ? 2u : 0u) | (cd.z < 0.0f ? 4u : 0u);
+    }
 
-    const Node8* __restrict__ nodes = S.tlas_nodes;
-    V3 co = o, cd = d;
-    float idx = safe_rcp(cd.x), idy = safe_rcp(cd.y), idz = safe_rcp(cd.z);
-    uint32_t oct = (cd.x < 0.0f ? 1u : 0u) | (cd.y < 0.0f ? 2u : 0u) | (cd.z < 0.0f ? 4u : 0u);
+    __device__ __forceinline__ void begin(V3 ro, V3 rd, float t_min, float t_max) {
+        o = ro; d = rd; tmin = t_min; tmax = t_max;
+        set_space(ro, rd);
+        hit.t = t_max; hit.u = hit.v = 0.0f;
+        hit.inst_pos = RT_NONE; hit.instance_id = RT_NONE; hit.geom = hit.prim = RT_NONE; hit.custom_sbt = 0;
+        sp = 0; inst_sp = -1;
+        cur_inst_pos = cur_instance_id = cur_custom_sbt = 0;
+        enter_inst = RT_NONE;
+        ng_base = 0;                       // TLAS root = slot 0 of a virtual parent
+        ng_bits = (1u << oct) | (1u << 8);
+    }
 
-    bool in_blas = false;
-    int inst_sp = 0;
-    uint32_t cur_inst_pos = 0, cur_instance_id = 0, cur_custom_sbt = 0;
+    __device__ __forceinline__ bool found() const { return hit.inst_pos != RT_NONE; }
 
-    // current node group: root of the TLAS as slot 0 of a virtual parent
-    uint32_t ng_base = 0, ng_bits = (1u << oct) | (1u << 8);
-    uint32_t enter_inst = 0xFFFFFFFFu;  // TLAS leaf to enter next
+    __device__ __forceinline__ void push(uint2* stack, uint32_t x, uint32_t y, TraceCounters& tc) {
+        if (sp < RT_STACK_SIZE) stack[sp++] = make_uint2(x, y);
+        else tc.overflow++;
+    }
 
-    for (;;) {
+    // One traversal step.  Returns true when the ray is finished (then found() tells hit or miss).
+    __device__ __forceinline__ bool step(const SceneDev& S, uint2* stack, TraceCounters& tc) {
         if (ng_bits & 0xFFu) {
             // ---- visit the nearest pending child of the current group
             uint32_t i = __ffs(ng_bits & 0xFFu) - 1;
             ng_bits &= ~(1u << i);
             uint32_t slot = i ^ oct;
-            uint32_t child = ng_base + __popc((ng_bits >> 8) & 0xFFu & ((1u << slot) - 1u));
-            if (ng_bits & 0xFFu) {
-                if (sp < RT_STACK_SIZE) stack[sp++] = make_uint2(ng_base, ng_bits);
-                else tc.overflow++;
-            }
+            uint32_t child = ng_base + __popc((ng_bits >> 8) & ((1u << slot) - 1u));
+            if (ng_bits & 0xFFu) push(stack, ng_base, ng_bits, tc);
+            const Node8* nodes = inst_sp >= 0 ? S.blas_nodes : S.tlas_nodes;
             const uint4* np = reinterpret_cast<const uint4*>(nodes + child);
             uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
             if (COUNT) tc.nodes++;
 
-            float sx = __uint_as_float((uint32_t)((int)(int8_t)(n0.w & 0xFFu) + 127) << 23);
-            float sy = __uint_as_float((uint32_t)((int)(int8_t)((n0.w >> 8) & 0xFFu) + 127) << 23);
-            float sz = __uint_as_float((uint32_t)((int)(int8_t)((n0.w >> 16) & 0xFFu) + 127) << 23);
-            float ax = sx * idx, ay = sy * idy, az = sz * idz;
+            // per-axis: A = 2^15 * 2^e / d, B = (origin - o)/d - A, padded outwards by p
+            float ax = __uint_as_float((uint32_t)((int)(int8_t)(n0.w & 0xFFu) + 127) << 23) * idx;
+            float ay = __uint_as_float((uint32_t)((int)(int8_t)((n0.w >> 8) & 0xFFu) + 127) << 23) * idy;
+            float az = __uint_as_float((uint32_t)((int)(int8_t)((n0.w >> 16) & 0xFFu) + 127) << 23) * idz;
             float bx = (__uint_as_float(n0.x) - co.x) * idx;
             float by = (__uint_as_float(n0.y) - co.y) * idy;
             float bz = (__uint_as_float(n0.z) - co.z) * idz;
+            float Ax = ax * 32768.0f, Ay = ay * 32768.0f, Az = az * 32768.0f;
+            float Bx = fmaf(-32768.0f, ax, bx), By = fmaf(-32768.0f, ay, by), Bz = fmaf(-32768.0f, az, bz);
+            float px = (fabsf(bx) + fabsf(Ax)) * 4.76837158e-7f;
+            float py = (fabsf(by) + fabsf(Ay)) * 4.76837158e-7f;
+            float pz = (fabsf(bz) + fabsf(Az)) * 4.76837158e-7f;
+            float Bnx = Bx - px, Bfx = Bx + px, Bny = By - py, Bfy = By + py, Bnz = Bz - pz, Bfz = Bz + pz;
             // near / far plane words per axis, chosen by ray direction
             uint32_t nx0, nx1, fx0, fx1, ny0, ny1, fy0, fy1, nz0, nz1, fz0, fz1;
             if (oct & 1u) { nx0 = n3.z; nx1 = n3.w; fx0 = n2.x; fx1 = n2.y; } else { nx0 = n2.x; nx1 = n2.y; fx0 = n3.z; fx1 = n3.w; }
@@ -115,19 +142,23 @@ __device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float t
             if (oct & 4u) { nz0 = n4.z; nz1 = n4.w; fz0 = n3.x; fz1 = n3.y; } else { nz0 = n3.x; nz1 = n3.y; fz0 = n4.z; fz1 = n4.w; }
             float tlimit = hit.t;
             uint32_t h = 0;
-#pragma unroll
-            for (int s = 0; s < 8; s++) {
-                uint32_t sel = s & 3;
-                float tnx = fmaf(byte_f(s < 4 ? nx0 : nx1, sel), ax, bx);
-                float tny = fmaf(byte_f(s < 4 ? ny0 : ny1, sel), ay, by);
-                float tnz = fmaf(byte_f(s < 4 ? nz0 : nz1, sel), az, bz);
-                float tfx = fmaf(byte_f(s < 4 ? fx0 : fx1, sel), ax, bx);
-                float tfy = fmaf(byte_f(s < 4 ? fy0 : fy1, sel), ay, by);
-                float tfz = fmaf(byte_f(s < 4 ? fz0 : fz1, sel), az, bz);
-                float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-                float tf = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
-                if (tn <= tf * 1.000002f) h |= 1u << s;
-            }
+#define RT_BOX(SLOT, SEL, WNX, WNY, WNZ, WFX, WFY, WFZ)                                                   \
+    {                                                                                                    \
+        float tn = fmaxf(fmaxf(fmaf(byte_m<SEL>(WNX), Ax, Bnx), fmaf(byte_m<SEL>(WNY), Ay, Bny)),          \
+                         fmaxf(fmaf(byte_m<SEL>(WNZ), Az, Bnz), tmin));                                  \
+        float tf = fminf(fminf(fmaf(byte_m<SEL>(WFX), Ax, Bfx), fmaf(byte_m<SEL>(WFY), Ay, Bfy)),          \
+                         fminf(fmaf(byte_m<SEL>(WFZ), Az, Bfz), tlimit));                                \
+        if (tn <= tf) h |= 1u << SLOT;                                                                   \
+    }
+            RT_BOX(0, 0, nx0, ny0, nz0, fx0, fy0, fz0)
+            RT_BOX(1, 1, nx0, ny0, nz0, fx0, fy0, fz0)
+            RT_BOX(2, 2, nx0, ny0, nz0, fx0, fy0, fz0)
+            RT_BOX(3, 3, nx0, ny0, nz0, fx0, fy0, fz0)
+            RT_BOX(4, 0, nx1, ny1, nz1, fx1, fy1, fz1)
+            RT_BOX(5, 1, nx1, ny1, nz1, fx1, fy1, fz1)
+            RT_BOX(6, 2, nx1, ny1, nz1, fx1, fy1, fz1)
+            RT_BOX(7, 3, nx1, ny1, nz1, fx1, fy1, fz1)
+#undef RT_BOX
             uint32_t imask = n0.w >> 24;
             h &= nonzero_bytes(n1.z, n1.w);
             uint32_t hl = h & ~imask;
@@ -136,7 +167,7 @@ __device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float t
 
             // ---- leaves of this node
             uint64_t meta = ((uint64_t)n1.w << 32) | n1.z;
-            if (in_blas) {
+            if (inst_sp >= 0) {
                 while (hl) {
                     uint32_t s = __ffs(hl) - 1;
                     hl &= hl - 1;
@@ -153,7 +184,7 @@ __device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float t
                         uint32_t geom = gf & ~RT_TRI_NON_OPAQUE;
                         if (!ANY) {
                             if (t > hit.t) continue;
-                            if (t == hit.t && hit.inst_pos != 0xFFFFFFFFu) {
+                            if (t == hit.t && hit.inst_pos != RT_NONE) {
                                 // exact tie: lowest (instance, geometry, primitive) wins
                                 bool lower = cur_instance_id != hit.instance_id ? cur_instance_id < hit.instance_id
                                              : geom != hit.geom                ? geom < hit.geom
@@ -179,59 +210,57 @@ __device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float t
                 while (hl) {
                     s = __ffs(hl) - 1;
                     hl &= hl - 1;
-                    uint32_t pos = n1.y + ((uint32_t)(meta >> (8 * s)) & 31u);
-                    if (sp < RT_STACK_SIZE) stack[sp++] = make_uint2(pos, 0x80000000u);
-                    else tc.overflow++;
+                    push(stack, n1.y + ((uint32_t)(meta >> (8 * s)) & 31u), 0x80000000u, tc);
                 }
             }
         }
 
-        if (enter_inst != 0xFFFFFFFFu) {
+        if (enter_inst != RT_NONE) {
             // ---- enter an instance: world ray -> object ray
             const float4* ip = reinterpret_cast<const float4*>(S.inst_rt + enter_inst);
             float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
             uint32_t pos = enter_inst;
-            enter_inst = 0xFFFFFFFFu;
+            enter_inst = RT_NONE;
             uint32_t root = __float_as_uint(r3.x);
-            if (root != 0xFFFFFFFFu && (__float_as_uint(r3.w) & 0xFFu)) {
+            if (root != RT_NONE && (__float_as_uint(r3.w) & 0xFFu)) {
                 if (COUNT) tc.instances++;
-                if (ng_bits & 0xFFu) {
-                    if (sp < RT_STACK_SIZE) stack[sp++] = make_uint2(ng_base, ng_bits);
-                    else tc.overflow++;
-                }
+                if (ng_bits & 0xFFu) push(stack, ng_base, ng_bits, tc);
                 float inv[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-                co = xform_point(inv, o);
-                cd = xform_vec(inv, d);
-                idx = safe_rcp(cd.x); idy = safe_rcp(cd.y); idz = safe_rcp(cd.z);
-                oct = (cd.x < 0.0f ? 1u : 0u) | (cd.y < 0.0f ? 2u : 0u) | (cd.z < 0.0f ? 4u : 0u);
+                set_space(xform_point(inv, o), xform_vec(inv, d));
                 cur_inst_pos = pos;
                 cur_instance_id = __float_as_uint(r3.y);
                 cur_custom_sbt = __float_as_uint(r3.z);
-                nodes = S.blas_nodes;
                 ng_base = root;
                 ng_bits = (1u << oct) | (1u << 8);
-                in_blas = true;
                 inst_sp = sp;
             }
-            continue;
+            return false;
         }
 
         if ((ng_bits & 0xFFu) == 0u) {
             // ---- current group exhausted: pop
-            if (in_blas && sp == inst_sp) {
-                in_blas = false;
-                nodes = S.tlas_nodes;
-                co = o; cd = d;
-                idx = safe_rcp(cd.x); idy = safe_rcp(cd.y); idz = safe_rcp(cd.z);
-                oct = (cd.x < 0.0f ? 1u : 0u) | (cd.y < 0.0f ? 2u : 0u) | (cd.z < 0.0f ? 4u : 0u);
+            if (inst_sp >= 0 && sp == inst_sp) {
+                inst_sp = -1;
+                set_space(o, d);
             }
-            if (sp == 0) break;
+            if (sp == 0) return true;
             uint2 e = stack[--sp];
             if (e.y & 0x80000000u) enter_inst = e.x;
             else { ng_base = e.x; ng_bits = e.y; }
         }
+        return false;
     }
-    return hit.inst_pos != 0xFFFFFFFFu;
+};
+
+// Run one ray to completion (megakernel path, tests).
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float tmin, float tmax, Hit& hit, TraceCounters& tc) {
+    uint2 stack[RT_STACK_SIZE];
+    Traverser<ANY, COUNT> T;
+    T.begin(o, d, tmin, tmax);
+    while (!T.step(S, stack, tc)) {}
+    hit = T.hit;
+    return T.found();
 }
 
 }  // namespace b200rt
