@@ -162,10 +162,10 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
-KERNELS = ["trace", "prep", "shadow", "resolve", "mega"]
+KERNELS = ["trace", "prep", "shadow", "resolve", "mega", "tail"]
 KERNEL_DESC = {"trace": "k_trace (ray-gen + closest-hit traversal)", "prep": "k_prep (triangle fetch, textures, BRDF terms)",
                "shadow": "k_shadow (blue-noise shadow rays, first-hit traversal)", "resolve": "k_resolve (sun factor, sRGB store)",
-               "mega": "k_mega (one thread per pixel)"}
+               "mega": "k_mega (one thread per pixel)", "tail": "k_tail (bounce segments, cooperative)"}
 
 
 def algorithmic_bytes(st, setup, pixels):
@@ -188,7 +188,8 @@ def algorithmic_bytes(st, setup, pixels):
     # k_resolve: 52 B of the record, 4 B framebuffer
     resolve_b = hits * (52 + 4)
     mega_b = trav[0] + trav[1] + 112 * bounces + hits * (32 + 24 + 12 + 96 + 48 + 64 + 2 * 16 + 8 * n) + 4 * pixels
-    return {"trace": int(trace_b), "prep": int(prep_b), "shadow": int(shadow_b), "resolve": int(resolve_b), "mega": int(mega_b)}
+    return {"trace": int(trace_b), "prep": int(prep_b), "shadow": int(shadow_b), "resolve": int(resolve_b), "mega": int(mega_b),
+            "tail": 0}  # counters are whole-frame: bounce segments (k_tail) are accounted under the four stage names
 
 
 def run_ours(args):
@@ -284,13 +285,11 @@ def run_ours(args):
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record(stream)
-        step_device(args.warmup + i, abi.RT_RENDER_TIMING)
+        step_device(args.warmup + i)
         ev[i][1].record(stream)
         ev[i][1].synchronize()
         st = gpu.stats()
         total_rays += int(st.primary_rays + st.shadow_rays)
-        kernel_ms += np.array(list(st.kernel_ms))
-        kernel_launches += np.array(list(st.kernel_launches))
         tlas_ms += st.last_tlas_ms if s.dynamic else 0.0
     torch.cuda.synchronize()
     if world > 1:
@@ -298,6 +297,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     launches = gpu.lib.rt_kernel_launches() - launches0
+    # ---- per-kernel durations (roofline): a separate pass with CUDA events around every kernel of the frame,
+    #      same stream, L2 flushed between frames; kept out of the timed region because the events serialise launches
+    ksteps = max(3, min(args.steps, 10))
+    for i in range(ksteps):
+        flush.zero_()
+        step_device(args.warmup + i, abi.RT_RENDER_TIMING)
+        st = gpu.stats()
+        kernel_ms += np.array(list(st.kernel_ms))
+        kernel_launches += np.array(list(st.kernel_launches))
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     r = torch.tensor([total_rays], dtype=torch.int64, device=dev)
@@ -358,7 +366,7 @@ def run_ours(args):
         names = KERNELS
         dom = int(np.argmax(kernel_ms))
         per_launch_ms = kernel_ms[dom] / max(kernel_launches[dom], 1)
-        launches_per_frame = kernel_launches[dom] / args.steps
+        launches_per_frame = kernel_launches[dom] / ksteps
         bytes_per_launch = bytes_frame[names[dom]] / max(launches_per_frame, 1)
         achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         rays_frame = max(int(st_count.primary_rays + st_count.shadow_rays), 1)
@@ -366,8 +374,8 @@ def run_ours(args):
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "kernel": KERNEL_DESC[names[dom]],
             "peak_source": peak_src,
-            "kernel_ms_per_frame": {n: float(kernel_ms[i] / args.steps) for i, n in enumerate(names)},
-            "kernel_share_of_step": float(kernel_ms[dom] / total_ms) if world == 1 else None,
+            "kernel_ms_per_frame": {n: float(kernel_ms[i] / ksteps) for i, n in enumerate(names)},
+            "kernel_share_of_step": float((kernel_ms[dom] / ksteps) / (total_ms / args.steps)) if world == 1 else None,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "launches_per_frame": float(launches_per_frame),
             "per_ray": {"nodes": float(sum(st_count.nodes_visited)) / rays_frame, "instances": float(sum(st_count.instances_entered)) / rays_frame,

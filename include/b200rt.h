@@ -119,8 +119,8 @@ typedef struct RtStats {
     uint64_t anyhit_calls[2];
     float    last_render_ms;    /* CUDA-event time of the last rt_render*, valid after rt_sync */
     float    last_tlas_ms;      /* CUDA-event time of the last rt_build_tlas / rt_update_tlas */
-    float    kernel_ms[5];      /* with RT_RENDER_TIMING, summed over segments: {k_trace, k_prep, k_shadow, k_resolve, k_mega} */
-    uint32_t kernel_launches[5];/* launches behind kernel_ms */
+    float    kernel_ms[6];      /* with RT_RENDER_TIMING: {k_trace0, k_prep, k_shadow, k_resolve (segment 0), k_mega, k_tail (segments >= 1)} */
+    uint32_t kernel_launches[6];/* launches behind kernel_ms */
     uint32_t tlas_nodes;        /* 128-byte wide nodes in the current TLAS */
     uint32_t blas_nodes;        /* over all models */
     uint32_t num_instances;

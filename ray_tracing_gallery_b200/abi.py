@@ -127,8 +127,8 @@ class RtStats(C.Structure):
         ("anyhit_calls", C.c_uint64 * 2),
         ("last_render_ms", C.c_float),
         ("last_tlas_ms", C.c_float),
-        ("kernel_ms", C.c_float * 5),
-        ("kernel_launches", C.c_uint32 * 5),
+        ("kernel_ms", C.c_float * 6),
+        ("kernel_launches", C.c_uint32 * 6),
         ("tlas_nodes", C.c_uint32),
         ("blas_nodes", C.c_uint32),
         ("num_instances", C.c_uint32),

@@ -81,7 +81,7 @@ struct RtContext {
     std::vector<uint32_t> real_tex_host;
     uint32_t* d_real_textures = nullptr;
     float* d_srgb_lut = nullptr;
-    float srgb_lut[256];
+    float srgb_lut[512];
 
     // models
     std::vector<ModelRes> models;
@@ -306,7 +306,7 @@ int rt_create(int cuda_device, RtContext** out) {
         if ((e = cudaEventCreate(&c->ev[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&c->d_textures, sizeof(TexEntry) * RT_MAX_BOUND_IMAGES)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_real_textures, sizeof(uint32_t) * RT_MAX_BOUND_IMAGES)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&c->d_srgb_lut, sizeof(float) * 256)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&c->d_srgb_lut, sizeof(float) * 512)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_uniforms, sizeof(RtUniforms))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_counters, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_tlas_node_count, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -315,6 +315,7 @@ int rt_create(int cuda_device, RtContext** out) {
     for (int i = 0; i < 256; i++) {
         float v = (float)i / 255.0f;
         c->srgb_lut[i] = v <= 0.04045f ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f);
+        c->srgb_lut[256 + i] = v;  // UNORM8 decode: code / 255, correctly rounded
     }
     if ((e = cudaMemcpy(c->d_srgb_lut, c->srgb_lut, sizeof(c->srgb_lut), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
     if ((e = cudaMemset(c->d_counters, 0, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMemset");

@@ -16,9 +16,13 @@
 // All are persistent kernels: warps pull 32-item batches from a device-side cursor, so a launch
 // never needs a queue length on the host.
 // Megakernel (A/B baseline): one thread per pixel runs the whole segment loop.
+#include <cooperative_groups.h>
+
 #include "launch_count.h"
 #include "render.h"
 #include "trace.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b200rt {
 namespace {
@@ -125,31 +129,46 @@ __device__ __forceinline__ V3 shade_textured(const SceneDev& S, const FrameDev& 
 }
 
 // ------------------------------------------------------------------------------------ wavefront
-enum { K_TRACE = 0, K_PREP = 1, K_SHADOW = 2, K_RESOLVE = 3, K_MEGA = 4 };
+enum { K_TRACE = 0, K_PREP = 1, K_SHADOW = 2, K_RESOLVE = 3, K_MEGA = 4, K_TAIL = 5 };
+
+#define RT_CHUNK 32u   // work items a warp takes from a queue cursor per atomic (128 measured slower: coarser tail)
 
 __device__ __forceinline__ SegCounters* seg_counters(const FrameDev& F, uint32_t seg) { return &F.counters->seg[seg & (RT_SEG_SLOTS - 1u)]; }
 
-// warp-wide grab of 32 work items; returns false when the cursor has passed `total`
-__device__ __forceinline__ bool grab32(unsigned int* cursor, uint32_t total, uint32_t& item) {
-    uint32_t base = 0;
-    if (lane_id() == 0) base = atomicAdd(cursor, 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    item = base + lane_id();
-    return base < total;
-}
+// Warp-wide work distribution: a warp owns a chunk [next, end) of RT_CHUNK items taken from the
+// device-side cursor with one atomic.  All members are warp-uniform.
+struct WarpChunk {
+    uint32_t next, end;
+    bool exhausted;
+    __device__ __forceinline__ void init() { next = end = 0; exhausted = false; }
+    // make sure the chunk is non-empty; returns false when the queue has run dry
+    __device__ __forceinline__ bool ensure(unsigned int* cursor, uint32_t total) {
+        if (next < end) return true;
+        if (exhausted) return false;
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(cursor, RT_CHUNK);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= total) { exhausted = true; return false; }
+        next = base;
+        end = min(base + RT_CHUNK, total);
+        return true;
+    }
+};
 
 // Ray generation (segment 0) or ray-queue read, closest-hit traversal, miss / mirror / portal shaders,
 // textured hits -> hit queue.
 template <bool SEG0, bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(SceneDev S, FrameDev F, uint32_t seg, uint32_t total_seg0) {
+__device__ __forceinline__ void trace_phase(const SceneDev& S, const FrameDev& F, uint32_t seg, uint32_t total) {
     TraceCounters tc = {0, 0, 0, 0, 0};
     uint32_t n_primary = 0;
     const RayRec* __restrict__ in_q = F.ray_q[(seg + 1u) & 1u];
     RayRec* __restrict__ out_q = F.ray_q[seg & 1u];
     SegCounters* sc = seg_counters(F, seg);
-    const uint32_t total = SEG0 ? total_seg0 : *((volatile unsigned int*)&seg_counters(F, seg - 1u)->ray_count);
-    uint32_t item;
-    while (grab32(&sc->work_next[K_TRACE], total, item)) {
+    WarpChunk wc;
+    wc.init();
+    while (wc.ensure(&sc->work_next[K_TRACE], total)) {
+        uint32_t item = wc.next + lane_id();
+        wc.next += 32u;
         bool active = false;
         uint32_t pixel = 0;
         V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
@@ -164,7 +183,7 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev S, FrameDev F, uint32_t 
             active = item < total;
             if (active) {
                 const float4* rp = reinterpret_cast<const float4*>(in_q + item);
-                float4 a = __ldg(rp), b = __ldg(rp + 1);
+                float4 a = __ldcg(rp), b = __ldcg(rp + 1);
                 o = v3(a.x, a.y, a.z); pixel = __float_as_uint(a.w);
                 d = v3(b.x, b.y, b.z);
             }
@@ -214,56 +233,59 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev S, FrameDev F, uint32_t 
 
 // closest_hit_textured.glsl:174-221 for every queued hit, minus the shadow rays: triangle fetch,
 // shadow-terminator origin, material textures, normal, BRDF terms.  Rewrites the HitRec in place.
-__global__ void __launch_bounds__(128) k_prep(SceneDev S, FrameDev F, uint32_t seg) {
-    SegCounters* sc = seg_counters(F, seg);
-    const uint32_t total = *((volatile unsigned int*)&sc->hit_count);
+// Uniform cost per item: plain grid-stride loop, no cursor.
+__device__ __forceinline__ void prep_phase(const SceneDev& S, const FrameDev& F, uint32_t seg) {
+    const uint32_t total = *((volatile unsigned int*)&seg_counters(F, seg)->hit_count);
     uint32_t n_textured = 0;
-    uint32_t item;
-    while (grab32(&sc->work_next[K_PREP], total, item)) {
-        if (item < total) {
-            HitRec* hr = F.hit_q + item;
-            uint4 a = __ldcg(reinterpret_cast<const uint4*>(hr));
-            float4 b = __ldcg(reinterpret_cast<const float4*>(hr) + 1);
-            float4 c = __ldcg(reinterpret_cast<const float4*>(hr) + 2);
-            TexturedHit th;
-            uint32_t ly = a.x / F.tw, lx = a.x - ly * F.tw;
-            th.px = F.x0 + lx; th.py = global_y(F, ly);
-            th.inst_pos = a.y; th.geom = a.z; th.prim = a.w;
-            th.u = b.x; th.v = b.y;
-            th.dir = v3(c.x, c.y, c.z);
-            ShadeCtx ctx;
-            float4 r0 = make_float4(__uint_as_float(a.x), 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, 0.f), r2 = r1, r3 = r1;
-            if (shade_textured_load(S, th, ctx)) {
-                V3 so = shade_textured_shadow_origin(S, ctx);
-                V3 base;
-                BrdfTerms bt = shade_textured_terms(S, F.uniforms, th, ctx, base);
-                r0.y = bt.NoL;
-                r1 = make_float4(bt.comb.x, bt.comb.y, bt.comb.z, 0.f);  // .w: lit = 0
-                r2 = make_float4(base.x, base.y, base.z, 0.f);
-                r3 = make_float4(so.x, so.y, so.z, __uint_as_float(1u));
-            }
-            reinterpret_cast<float4*>(hr)[0] = r0;
-            reinterpret_cast<float4*>(hr)[1] = r1;
-            reinterpret_cast<float4*>(hr)[2] = r2;
-            reinterpret_cast<float4*>(hr)[3] = r3;
-            n_textured++;
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+        HitRec* hr = F.hit_q + item;
+        uint4 a = __ldcg(reinterpret_cast<const uint4*>(hr));
+        float4 b = __ldcg(reinterpret_cast<const float4*>(hr) + 1);
+        float4 c = __ldcg(reinterpret_cast<const float4*>(hr) + 2);
+        TexturedHit th;
+        uint32_t ly = a.x / F.tw, lx = a.x - ly * F.tw;
+        th.px = F.x0 + lx; th.py = global_y(F, ly);
+        th.inst_pos = a.y; th.geom = a.z; th.prim = a.w;
+        th.u = b.x; th.v = b.y;
+        th.dir = v3(c.x, c.y, c.z);
+        ShadeCtx ctx;
+        float4 r0 = make_float4(__uint_as_float(a.x), 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, 0.f), r2 = r1, r3 = r1;
+        if (shade_textured_load(S, th, ctx)) {
+            V3 so = shade_textured_shadow_origin(S, ctx);
+            V3 base;
+            BrdfTerms bt = shade_textured_terms(S, F.uniforms, th, ctx, base);
+            r0.y = bt.NoL;
+            r1 = make_float4(bt.comb.x, bt.comb.y, bt.comb.z, 0.f);  // .w: lit = 0
+            r2 = make_float4(base.x, base.y, base.z, 0.f);
+            r3 = make_float4(so.x, so.y, so.z, __uint_as_float(1u));
         }
+        reinterpret_cast<float4*>(hr)[0] = r0;
+        reinterpret_cast<float4*>(hr)[1] = r1;
+        reinterpret_cast<float4*>(hr)[2] = r2;
+        reinterpret_cast<float4*>(hr)[3] = r3;
+        n_textured++;
     }
+    // every lane of the warp must reach the warp-wide flush
     flush_ray_counters(F, 0, 0, n_textured);
 }
 
 // One thread per shadow ray: item = hit * shadow_rays + sample, so the samples of one hit sit in
-// adjacent lanes (same origin, directions inside the sun's cone: coherent traversal).
+// adjacent lanes (same origin, directions inside the sun's cone: coherent traversal).  A warp runs
+// its 32 rays to completion before taking the next 32: replacing finished rays lane by lane
+// (persistent threads with ray replacement) was measured slower here — profiles/r01_notes.md.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow(SceneDev S, FrameDev F, uint32_t seg) {
+__device__ __forceinline__ void shadow_phase(const SceneDev& S, const FrameDev& F, uint32_t seg) {
     TraceCounters tc = {0, 0, 0, 0, 0};
     SegCounters* sc = seg_counters(F, seg);
     const uint32_t n = F.shadow_rays;
     const uint32_t total = *((volatile unsigned int*)&sc->hit_count) * n;
     const SunFrame sun = make_sun_frame(F.uniforms);
     uint32_t n_shadow = 0;
-    uint32_t item;
-    while (grab32(&sc->work_next[K_SHADOW], total, item)) {
+    WarpChunk wc;
+    wc.init();
+    while (wc.ensure(&sc->work_next[K_SHADOW], total)) {
+        uint32_t item = wc.next + lane_id();
+        wc.next += 32u;
         if (item < total) {
             uint32_t hi = item / n, i = item - hi * n;
             HitRec* hr = F.hit_q + hi;
@@ -272,7 +294,7 @@ __global__ void __launch_bounds__(128) k_shadow(SceneDev S, FrameDev F, uint32_t
             if (__float_as_uint(so.w)) {
                 uint32_t ly = pixel / F.tw, lx = pixel - ly * F.tw;
                 bool lit = shadow_sample_lit<COUNT>(S, F, sun, F.x0 + lx, global_y(F, ly), i, v3(so.x, so.y, so.z), tc);
-                if (lit) atomicAdd(&hr->lit, 1u);
+                if (lit) atomicAdd(&hr->lit, 1u);  // shadow_ray_miss: shadowed = false (lib.rs:33-36)
                 n_shadow++;
             }
         }
@@ -283,31 +305,59 @@ __global__ void __launch_bounds__(128) k_shadow(SceneDev S, FrameDev F, uint32_t
 
 // sun_factor = lit / N, colour = sun_factor * NoL * comb + 0.1 * base (closest_hit_textured.glsl:203, :222-225),
 // then the ray-gen tail: linear_to_srgb + image store (lib.rs:188-190).
-__global__ void __launch_bounds__(128) k_resolve(FrameDev F, uint32_t seg) {
-    SegCounters* sc = seg_counters(F, seg);
-    const uint32_t total = *((volatile unsigned int*)&sc->hit_count);
-    uint32_t item;
-    while (grab32(&sc->work_next[K_RESOLVE], total, item)) {
-        if (item < total) {
-            const HitRec* hr = F.hit_q + item;
-            float4 r0 = __ldcg(reinterpret_cast<const float4*>(hr));
-            float4 r1 = __ldcg(reinterpret_cast<const float4*>(hr) + 1);
-            float4 r2 = __ldcg(reinterpret_cast<const float4*>(hr) + 2);
-            uint32_t valid = __ldcg(&hr->shadow_valid);
-            V3 col = v3(0.f, 0.f, 0.f);
-            if (valid) {
-                float sun_factor = div_((float)__float_as_uint(r1.w), (float)F.shadow_rays);
-                col = shade_finish(sun_factor, r0.y, v3(r1.x, r1.y, r1.z), v3(r2.x, r2.y, r2.z));
-            }
-            write_pixel(F, __float_as_uint(r0.x), col);
+__device__ __forceinline__ void resolve_phase(const FrameDev& F, uint32_t seg) {
+    const uint32_t total = *((volatile unsigned int*)&seg_counters(F, seg)->hit_count);
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+        const HitRec* hr = F.hit_q + item;
+        float4 r0 = __ldcg(reinterpret_cast<const float4*>(hr));
+        float4 r1 = __ldcg(reinterpret_cast<const float4*>(hr) + 1);
+        float4 r2 = __ldcg(reinterpret_cast<const float4*>(hr) + 2);
+        uint32_t valid = __ldcg(&hr->shadow_valid);
+        V3 col = v3(0.f, 0.f, 0.f);
+        if (valid) {
+            float sun_factor = div_((float)__float_as_uint(r1.w), (float)F.shadow_rays);
+            col = shade_finish(sun_factor, r0.y, v3(r1.x, r1.y, r1.z), v3(r2.x, r2.y, r2.z));
         }
+        write_pixel(F, __float_as_uint(r0.x), col);
     }
 }
 
-// segments >= RT_SEG_SLOTS reuse a counter slot
-__global__ void k_reset_segment(FrameCounters* c, uint32_t seg) {
-    SegCounters z = {};
-    c->seg[seg & (RT_SEG_SLOTS - 1u)] = z;
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace0(SceneDev S, FrameDev F, uint32_t total) { trace_phase<true, COUNT>(S, F, 0, total); }
+__global__ void __launch_bounds__(128) k_prep(SceneDev S, FrameDev F, uint32_t seg) { prep_phase(S, F, seg); }
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow(SceneDev S, FrameDev F, uint32_t seg) { shadow_phase<COUNT>(S, F, seg); }
+__global__ void __launch_bounds__(128) k_resolve(FrameDev F, uint32_t seg) { resolve_phase(F, seg); }
+
+// Segments 1 .. max_segments-1 (mirror / portal bounces) in ONE cooperative launch: the four phases
+// separated by grid-wide barriers.  Most frames have few or no bounce rays; the kernel leaves as soon
+// as a segment's ray queue is empty, so such frames pay one near-empty launch instead of four per
+// segment.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_tail(SceneDev S, FrameDev F) {
+    cg::grid_group grid = cg::this_grid();
+    for (uint32_t seg = 1; seg < F.max_segments; seg++) {
+        const uint32_t rays = *((volatile unsigned int*)&seg_counters(F, seg - 1u)->ray_count);
+        if (rays == 0) break;  // grid-uniform: written before the last barrier (or the previous kernel)
+        if (seg >= RT_SEG_SLOTS) {  // counter slots are reused round-robin
+            if (grid.thread_rank() == 0) {
+                SegCounters z = {};
+                *seg_counters(F, seg) = z;
+            }
+            grid.sync();
+        }
+        trace_phase<false, COUNT>(S, F, seg, rays);
+        grid.sync();
+        const uint32_t hits = *((volatile unsigned int*)&seg_counters(F, seg)->hit_count);
+        if (hits) {
+            prep_phase(S, F, seg);
+            grid.sync();
+            shadow_phase<COUNT>(S, F, seg);
+            grid.sync();
+            resolve_phase(F, seg);
+            grid.sync();  // the next segment's trace phase overwrites the hit queue
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------ megakernel
@@ -400,34 +450,34 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
         else k_mega<false><<<(total + 127) / 128, 128, 0, stream>>>(S, F, total);
         mark(K_MEGA);
     } else {
-        static int g_trace0[2] = {0, 0}, g_trace[2] = {0, 0}, g_shadow[2] = {0, 0}, g_prep = 0, g_resolve = 0;
+        static int g_trace0[2] = {0, 0}, g_shadow[2] = {0, 0}, g_tail[2] = {0, 0}, g_prep = 0, g_resolve = 0;
         int ci = count ? 1 : 0;
         if (!g_trace0[ci]) {
-            g_trace0[ci] = count ? persistent_grid(k_trace<true, true>, sms) : persistent_grid(k_trace<true, false>, sms);
-            g_trace[ci] = count ? persistent_grid(k_trace<false, true>, sms) : persistent_grid(k_trace<false, false>, sms);
+            g_trace0[ci] = count ? persistent_grid(k_trace0<true>, sms) : persistent_grid(k_trace0<false>, sms);
             g_shadow[ci] = count ? persistent_grid(k_shadow<true>, sms) : persistent_grid(k_shadow<false>, sms);
+            g_tail[ci] = count ? persistent_grid(k_tail<true>, sms) : persistent_grid(k_tail<false>, sms);
             g_prep = persistent_grid(k_prep, sms);
             g_resolve = persistent_grid(k_resolve, sms);
         }
         int cap = (int)((total + 127) / 128);  // no more blocks than there could be work
         auto fit = [&](int g, uint32_t per_item) { long long c = (long long)cap * per_item; return (int)(c < g ? c : g); };
-        for (uint32_t seg = 0; seg < F.max_segments; seg++) {
-            if (seg >= RT_SEG_SLOTS) { k_reset_segment<<<1, 1, 0, stream>>>(F.counters, seg); note_launch(); }
-            if (seg == 0) {
-                if (count) k_trace<true, true><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, 0, total);
-                else k_trace<true, false><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, 0, total);
-            } else {
-                if (count) k_trace<false, true><<<fit(g_trace[ci], 1), 128, 0, stream>>>(S, F, seg, 0);
-                else k_trace<false, false><<<fit(g_trace[ci], 1), 128, 0, stream>>>(S, F, seg, 0);
-            }
-            mark(K_TRACE);
-            k_prep<<<fit(g_prep, 1), 128, 0, stream>>>(S, F, seg);
-            mark(K_PREP);
-            if (count) k_shadow<true><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, seg);
-            else k_shadow<false><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, seg);
-            mark(K_SHADOW);
-            k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, seg);
-            mark(K_RESOLVE);
+        if (count) k_trace0<true><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, total);
+        else k_trace0<false><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, total);
+        mark(K_TRACE);
+        k_prep<<<fit(g_prep, 1), 128, 0, stream>>>(S, F, 0);
+        mark(K_PREP);
+        if (count) k_shadow<true><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, 0);
+        else k_shadow<false><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, 0);
+        mark(K_SHADOW);
+        k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, 0);
+        mark(K_RESOLVE);
+        if (F.max_segments > 1) {
+            SceneDev s_arg = S;
+            FrameDev f_arg = F;
+            void* args[] = {&s_arg, &f_arg};
+            cudaError_t ce = cudaLaunchCooperativeKernel(count ? (void*)k_tail<true> : (void*)k_tail<false>, dim3(fit(g_tail[ci], 1)), dim3(128), args, 0, stream);
+            if (ce != cudaSuccess) return ce;
+            mark(K_TAIL);
         }
     }
     if (d_ray_counts) { k_export_counts<<<1, 1, 0, stream>>>(F.counters, d_ray_counts); note_launch(); }

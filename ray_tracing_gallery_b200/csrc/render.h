@@ -5,7 +5,7 @@
 namespace b200rt {
 
 // Optional per-kernel timing of one frame: ev[0] is recorded before the first kernel, ev[i+1]
-// after the i-th timed kernel, kind[i] = 0 k_trace / 1 k_prep / 2 k_shadow / 3 k_resolve / 4 k_mega.
+// after the i-th timed kernel, kind[i] = 0 k_trace / 1 k_prep / 2 k_shadow / 3 k_resolve / 4 k_mega / 5 k_tail.
 struct FrameTiming {
     enum { MAX_INTERVALS = 40 };
     cudaEvent_t ev[MAX_INTERVALS + 1];

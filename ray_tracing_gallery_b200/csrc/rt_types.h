@@ -127,7 +127,7 @@ struct SceneDev {
     uint32_t          num_textures;
     uint32_t          num_real_textures;  // images that need a TEX fetch (not 1x1 constants)
     const uint32_t*   real_textures;      // their indices, ascending
-    const float*      srgb_lut;      // 256 floats
+    const float*      srgb_lut;      // 512 floats: sRGB EOTF per 8-bit code, then code / 255
 };
 
 struct FrameDev {

@@ -24,6 +24,7 @@ namespace b200rt {
 struct F4 { float r, g, b, a; };
 
 __device__ __forceinline__ int wrap_i(int i, int n) {
+    if ((n & (n - 1)) == 0) return i & (n - 1);  // power-of-two images: two's-complement mask == REPEAT
     int m = i % n;
     return m < 0 ? m + n : m;
 }
@@ -40,12 +41,10 @@ __device__ __forceinline__ F4 fetch_texel_uniform(const SceneDev& S, uint32_t k,
         return r;
     }
     uchar4 c = tex2D<uchar4>(obj, (float)x + 0.5f, (float)y + 0.5f);
-    if (format == RT_FORMAT_RGBA8_SRGB) {
-        r.r = __ldg(S.srgb_lut + c.x); r.g = __ldg(S.srgb_lut + c.y); r.b = __ldg(S.srgb_lut + c.z);
-    } else {
-        r.r = __fdiv_rn((float)c.x, 255.0f); r.g = __fdiv_rn((float)c.y, 255.0f); r.b = __fdiv_rn((float)c.z, 255.0f);
-    }
-    r.a = __fdiv_rn((float)c.w, 255.0f);
+    // exact per 8-bit code: [0,256) sRGB EOTF, [256,512) code / 255 (correctly rounded), see rt_create
+    const float* lut = S.srgb_lut + (format == RT_FORMAT_RGBA8_SRGB ? 0 : 256);
+    r.r = __ldg(lut + c.x); r.g = __ldg(lut + c.y); r.b = __ldg(lut + c.z);
+    r.a = __ldg(S.srgb_lut + 256 + c.w);
     return r;
 }
 
@@ -217,8 +216,16 @@ __device__ __forceinline__ V3 terminator_origin(const TriAttr& a, V3 p, V3 w, co
 __device__ __forceinline__ V2 blue_noise_xi(const SceneDev& S, uint32_t tex, uint32_t px, uint32_t py, uint32_t iteration, uint32_t frame_index) {
     uint32_t ox1 = iteration * 2u * 13u, oy1 = iteration * 2u * 41u;
     uint32_t ox2 = (iteration * 2u + 1u) * 13u, oy2 = (iteration * 2u + 1u) * 41u;
-    float a = sample_texture_uniform(S, tex, __fdiv_rn((float)(px + ox1), 64.0f), __fdiv_rn((float)(py + oy1), 64.0f)).r;
-    float b = sample_texture_uniform(S, tex, __fdiv_rn((float)(px + ox2), 64.0f), __fdiv_rn((float)(py + oy2), 64.0f)).r;
+    float a, b;
+    const TexEntry* te = S.textures + tex;
+    if (tex < S.num_textures && te->obj != 0 && te->w == 64u && te->h == 64u && !te->linear) {
+        // the shipped 64x64 nearest-filtered image: coordinate k/64 selects texel k mod 64 exactly
+        a = fetch_texel_uniform(S, tex, (int)((px + ox1) & 63u), (int)((py + oy1) & 63u)).r;
+        b = fetch_texel_uniform(S, tex, (int)((px + ox2) & 63u), (int)((py + oy2) & 63u)).r;
+    } else {
+        a = sample_texture_uniform(S, tex, __fdiv_rn((float)(px + ox1), 64.0f), __fdiv_rn((float)(py + oy1), 64.0f)).r;
+        b = sample_texture_uniform(S, tex, __fdiv_rn((float)(px + ox2), 64.0f), __fdiv_rn((float)(py + oy2), 64.0f)).r;
+    }
     float k = mul_((float)(frame_index % 32u), 0.618033988749f);
     float sa = add_(a, k), sb = add_(b, k);
     V2 r; r.x = sub_(sa, floorf(sa)); r.y = sub_(sb, floorf(sb));
