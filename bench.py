@@ -21,6 +21,14 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 
 import numpy as np  # noqa: E402
 
@@ -158,7 +166,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -407,7 +415,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "tlas_update_ms_per_step": (tlas_ms / args.steps) if s.dynamic else None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     gpu.close()
     if world > 1:
         dist.barrier()
@@ -416,6 +424,12 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner under NCCL_DEBUG,
+    # torch.distributed warnings) are sent to stderr instead.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

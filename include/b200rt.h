@@ -77,7 +77,8 @@ typedef enum RtPipeline {
 
 enum {
     RT_RENDER_COUNTERS = 1u,    /* also count nodes/instances/triangles visited (slower; for the roofline audit) */
-    RT_RENDER_TIMING = 2u       /* CUDA events around every kernel of the frame -> RtStats.kernel_ms */
+    RT_RENDER_TIMING = 2u,      /* CUDA events around every kernel of the frame -> RtStats.kernel_ms */
+    RT_RENDER_SPLIT_TAIL = 4u   /* bounce segments as four launches each instead of the one cooperative k_tail (A/B) */
 };
 
 /* What `cmd_trace_rays(width, height, 1)` + the hard-coded shader constants
@@ -125,6 +126,8 @@ typedef struct RtStats {
     uint32_t blas_nodes;        /* over all models */
     uint32_t num_instances;
     uint32_t num_triangles;     /* over all models */
+    uint32_t segment_rays[8];   /* wavefront: bounce rays queued BY ray-gen segment s (traced in segment s+1) */
+    uint32_t segment_hits[8];   /* wavefront: textured hits queued by ray-gen segment s */
 } RtStats;
 
 /* Device/allocator creation: src/main.rs:157-204,337.  One context per GPU. */

@@ -133,6 +133,8 @@ class RtStats(C.Structure):
         ("blas_nodes", C.c_uint32),
         ("num_instances", C.c_uint32),
         ("num_triangles", C.c_uint32),
+        ("segment_rays", C.c_uint32 * 8),
+        ("segment_hits", C.c_uint32 * 8),
     ]
 
 
@@ -142,6 +144,7 @@ RT_UPDATE_AUTO, RT_UPDATE_REFIT, RT_UPDATE_REBUILD = 0, 1, 2
 RT_PIPELINE_WAVEFRONT, RT_PIPELINE_MEGAKERNEL = 0, 1
 RT_RENDER_COUNTERS = 1
 RT_RENDER_TIMING = 2
+RT_RENDER_SPLIT_TAIL = 4
 RT_INSTANCE_TRIANGLE_FACING_CULL_DISABLE = 1
 MISS_ID = 0xFFFFFFFF
 

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -259,7 +260,7 @@ int render_common(RtContext* ctx, const RtUniforms* u, const RtRenderParams* p, 
         timing = &ctx->timing;
     }
     ctx->timing_valid = timing != nullptr;
-    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, ctx->sms, d_ray_counts, timing, ctx->stream));
+    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, (p->flags & RT_RENDER_SPLIT_TAIL) != 0, ctx->sms, d_ray_counts, timing, ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->render_timed = true;
     ctx->last_rows = f.rows;
@@ -663,6 +664,10 @@ int rt_get_stats(RtContext* ctx, RtStats* out) {
         out->instances_entered[k] = fc.instances_entered[k];
         out->triangles_tested[k] = fc.triangles_tested[k];
         out->anyhit_calls[k] = fc.anyhit_calls[k];
+    }
+    for (int k = 0; k < RT_SEG_SLOTS && k < 8; k++) {
+        out->segment_rays[k] = fc.seg[k].ray_count;
+        out->segment_hits[k] = fc.seg[k].hit_count;
     }
     if (ctx->timing_valid) {
         for (int i = 0; i < ctx->timing.n; i++) {

@@ -272,7 +272,7 @@ __device__ __forceinline__ void prep_phase(const SceneDev& S, const FrameDev& F,
 // One thread per shadow ray: item = hit * shadow_rays + sample, so the samples of one hit sit in
 // adjacent lanes (same origin, directions inside the sun's cone: coherent traversal).  A warp runs
 // its 32 rays to completion before taking the next 32: replacing finished rays lane by lane
-// (persistent threads with ray replacement) was measured slower here — profiles/r01_notes.md.
+// (persistent threads with ray replacement) was measured slower on C2 — profiles/r01_notes.md.
 template <bool COUNT>
 __device__ __forceinline__ void shadow_phase(const SceneDev& S, const FrameDev& F, uint32_t seg) {
     TraceCounters tc = {0, 0, 0, 0, 0};
@@ -324,10 +324,21 @@ __device__ __forceinline__ void resolve_phase(const FrameDev& F, uint32_t seg) {
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace0(SceneDev S, FrameDev F, uint32_t total) { trace_phase<true, COUNT>(S, F, 0, total); }
+// bounce segment as its own launch (RT_RENDER_SPLIT_TAIL): the ray count is read on the device
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_n(SceneDev S, FrameDev F, uint32_t seg) {
+    trace_phase<false, COUNT>(S, F, seg, *((volatile unsigned int*)&seg_counters(F, seg - 1u)->ray_count));
+}
 __global__ void __launch_bounds__(128) k_prep(SceneDev S, FrameDev F, uint32_t seg) { prep_phase(S, F, seg); }
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_shadow(SceneDev S, FrameDev F, uint32_t seg) { shadow_phase<COUNT>(S, F, seg); }
 __global__ void __launch_bounds__(128) k_resolve(FrameDev F, uint32_t seg) { resolve_phase(F, seg); }
+
+// segments >= RT_SEG_SLOTS reuse a counter slot (split-tail path)
+__global__ void k_reset_segment(FrameCounters* c, uint32_t seg) {
+    SegCounters z = {};
+    c->seg[seg & (RT_SEG_SLOTS - 1u)] = z;
+}
 
 // Segments 1 .. max_segments-1 (mirror / portal bounces) in ONE cooperative launch: the four phases
 // separated by grid-wide barriers.  Most frames have few or no bounce rays; the kernel leaves as soon
@@ -423,7 +434,7 @@ static int persistent_grid(K kernel, int sms) {
     return sms * per_sm;
 }
 
-cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, int sms, uint64_t* d_ray_counts,
+cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, int sms, uint64_t* d_ray_counts,
                          FrameTiming* timing, cudaStream_t stream) {
     cudaMemsetAsync(F.counters, 0, sizeof(FrameCounters), stream);
     if (F.hit_ids) cudaMemsetAsync(F.hit_ids, 0xFF, (size_t)F.rows * F.tw * F.max_segments * 3 * sizeof(uint32_t), stream);
@@ -471,7 +482,21 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
         mark(K_SHADOW);
         k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, 0);
         mark(K_RESOLVE);
-        if (F.max_segments > 1) {
+        if (F.max_segments > 1 && split_tail) {
+            for (uint32_t seg = 1; seg < F.max_segments; seg++) {
+                if (seg >= RT_SEG_SLOTS) { k_reset_segment<<<1, 1, 0, stream>>>(F.counters, seg); note_launch(); }
+                if (count) k_trace_n<true><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, seg);
+                else k_trace_n<false><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, seg);
+                mark(K_TRACE);
+                k_prep<<<fit(g_prep, 1), 128, 0, stream>>>(S, F, seg);
+                mark(K_PREP);
+                if (count) k_shadow<true><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, seg);
+                else k_shadow<false><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, seg);
+                mark(K_SHADOW);
+                k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, seg);
+                mark(K_RESOLVE);
+            }
+        } else if (F.max_segments > 1) {
             SceneDev s_arg = S;
             FrameDev f_arg = F;
             void* args[] = {&s_arg, &f_arg};
