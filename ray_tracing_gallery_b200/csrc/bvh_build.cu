@@ -70,8 +70,12 @@ __device__ __forceinline__ Aabb ldcg_box(const Aabb* p) {
 }
 
 // ------------------------------------------------------------------------------------ 1, 2
-__global__ void k_init_state(int* bounds, uint32_t* state) {
+__global__ void k_init_state(int* bounds, uint32_t* state, int* task_node, uint32_t* task_parent, int root_ref) {
     int t = threadIdx.x;
+    if (t == 0) {
+        task_node[0] = root_ref;  // binary root (0) or the only leaf (~0)
+        task_parent[0] = 0;
+    }
     if (t < 3) bounds[t] = f2ord(CUDART_INF_F);
     else if (t < 6) bounds[t] = f2ord(-CUDART_INF_F);
     if (t == 0) {
@@ -121,12 +125,13 @@ __device__ __forceinline__ uint64_t spread21(uint64_t x) {
     return x;
 }
 
-__global__ void k_morton(const Aabb* __restrict__ boxes, uint32_t n, const int* __restrict__ bounds, uint64_t* keys,
+// `shift` drops low key bits so that the radix sort needs fewer passes (key_bits_for)
+__global__ void k_morton(const Aabb* __restrict__ boxes, uint32_t n, const int* __restrict__ bounds, uint32_t shift, uint64_t* keys,
                          uint32_t* vals) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Aabb b = boxes[i];
-    uint64_t key = 0x7FFFFFFFFFFFFFFFull;  // invalid boxes sort last
+    uint64_t key = 0x7FFFFFFFFFFFFFFFull >> shift;  // invalid boxes sort last
     if (box_valid(b)) {
         uint64_t q[3];
 #pragma unroll
@@ -138,7 +143,7 @@ __global__ void k_morton(const Aabb* __restrict__ boxes, uint32_t n, const int* 
             f = fminf(fmaxf(f, 0.0f), 1.0f);
             q[k] = (uint64_t)(f * 2097151.0f);
         }
-        key = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+        key = ((spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2])) >> shift;
     }
     keys[i] = key;
     vals[i] = i;
@@ -298,6 +303,7 @@ struct CollapseArgs {
     Node8* nodes;          // pool base
     uint32_t node_offset, prim_offset, max_leaf;
     uint32_t* leaf_order;
+    uint32_t* node_count_out;  // optional: receives the number of wide nodes written
 };
 
 __device__ __forceinline__ uint32_t ref_count(const Tree2& T, int r) { return r < 0 ? 1u : T.last[r] - T.first[r] + 1u; }
@@ -412,6 +418,7 @@ __global__ void __launch_bounds__(128) k_collapse_coop(CollapseArgs A) {
         end = *((volatile uint32_t*)&A.state[ST_WIDE_COUNT]);
         grid.sync();  // nobody may bump WIDE_COUNT before everyone has read it
     }
+    if (gtid == 0 && A.node_count_out) *A.node_count_out = end;
 }
 
 // Fallback: one launch per level, the level range lives in A.state.
@@ -432,14 +439,6 @@ __global__ void k_empty_root(Node8* nodes, uint32_t node_offset, uint32_t prim_o
     state[ST_WIDE_COUNT] = 1;
 }
 
-__global__ void k_single_leaf_task(int* task_node, uint32_t* task_parent) {
-    task_node[0] = ~0;  // leaf position 0
-    task_parent[0] = 0;
-}
-__global__ void k_root_task(int* task_node, uint32_t* task_parent) {
-    task_node[0] = 0;  // binary root
-    task_parent[0] = 0;
-}
 __global__ void k_copy_u32(const uint32_t* src, uint32_t* dst) { *dst = *src; }
 
 // ------------------------------------------------------------------------------------ 7
@@ -579,13 +578,13 @@ cudaError_t BvhBuilder::reserve(uint32_t n) {
 }
 
 cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
-                              uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, cudaStream_t stream) {
+                              uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, cudaStream_t stream) {
     cudaError_t e = reserve(n);
     if (e != cudaSuccess) return e;
     Scratch s;
     layout(static_cast<char*>(scratch_), cap_, cub_bytes_, s);
     const int TB = 256;
-    k_init_state<<<1, 32, 0, stream>>>(s.bounds, s.state);
+    k_init_state<<<1, 32, 0, stream>>>(s.bounds, s.state, s.task_node, s.task_parent, n >= 2 ? 0 : ~0);
     note_launch();
     if (n == 0) {
         k_empty_root<<<1, 1, 0, stream>>>(nodes_pool, node_offset, prim_offset, s.state);
@@ -595,10 +594,15 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
     }
     uint32_t blocks = (n + TB - 1) / TB;
     k_centroid_bounds<<<blocks, TB, 0, stream>>>(d_boxes, n, s.bounds);
-    k_morton<<<blocks, TB, 0, stream>>>(d_boxes, n, s.bounds, s.keys_in, s.vals_in);
+    // Morton bits per axis: all 21 for a static build; for per-frame rebuilds (fast_sort) enough cells to
+    // separate n primitives with 4 bits to spare (10..21), which saves radix-sort passes
+    uint32_t axis_bits = fast_sort ? 10 : 21;
+    while (axis_bits < 21 && (1ull << (3 * (axis_bits - 4))) < n) axis_bits++;
+    const uint32_t key_bits = 3 * axis_bits;
+    k_morton<<<blocks, TB, 0, stream>>>(d_boxes, n, s.bounds, 63u - key_bits, s.keys_in, s.vals_in);
     note_launch(2);
     size_t cub_bytes = cub_bytes_;
-    e = cub::DeviceRadixSort::SortPairs(s.cub_temp, cub_bytes, s.keys_in, s.keys_out, s.vals_in, s.vals_out, (int)n, 0, 63,
+    e = cub::DeviceRadixSort::SortPairs(s.cub_temp, cub_bytes, s.keys_in, s.keys_out, s.vals_in, s.vals_out, (int)n, 0, (int)key_bits,
                                         stream);
     if (e != cudaSuccess) return e;
     Tree2 T;
@@ -610,23 +614,21 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
         cudaMemsetAsync(s.flags, 0, sizeof(uint32_t) * n, stream);
         k_hierarchy<<<blocks, TB, 0, stream>>>(T);
         k_fit<<<blocks, TB, 0, stream>>>(T);
-        k_root_task<<<1, 1, 0, stream>>>(s.task_node, s.task_parent);
-        note_launch(3);
-    } else {
-        k_single_leaf_task<<<1, 1, 0, stream>>>(s.task_node, s.task_parent);
-        note_launch();
+        note_launch(2);
     }
     CollapseArgs A;
     A.T = T; A.task_node = s.task_node; A.task_parent = s.task_parent; A.state = s.state;
     A.nodes = nodes_pool; A.node_offset = node_offset; A.prim_offset = prim_offset; A.max_leaf = max_leaf;
     A.leaf_order = d_leaf_order;
+    A.node_count_out = d_node_count;
     bool done = false;
+    bool count_written = false;
     if (coop_ok_) {
         void* args[] = {&A};
         uint32_t want = (max_wide_nodes(n) + 127) / 128;
         uint32_t grid = want < (uint32_t)coop_blocks_ ? (want ? want : 1u) : (uint32_t)coop_blocks_;
         cudaError_t ce = cudaLaunchCooperativeKernel((void*)k_collapse_coop, dim3(grid), dim3(128), args, 0, stream);
-        if (ce == cudaSuccess) { done = true; note_launch(); }
+        if (ce == cudaSuccess) { done = true; count_written = true; note_launch(); }
         else { (void)cudaGetLastError(); coop_ok_ = false; }
     }
     if (!done) {
@@ -644,7 +646,7 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
             end = cnt;
         }
     }
-    if (d_node_count) { k_copy_u32<<<1, 1, 0, stream>>>(&s.state[ST_WIDE_COUNT], d_node_count); note_launch(); }
+    if (d_node_count && !count_written) { k_copy_u32<<<1, 1, 0, stream>>>(&s.state[ST_WIDE_COUNT], d_node_count); note_launch(); }
     return cudaGetLastError();
 }
 

@@ -26,9 +26,10 @@ public:
     // child indices are absolute pool indices, prim_base values are prim_offset + position in
     // leaf order.  d_leaf_order[i] = index of the input primitive stored at leaf position i.
     // d_node_count (device, optional) receives the number of wide nodes written.
+    // fast_sort: Morton keys keep only as many bits as n needs (fewer radix passes; per-frame TLAS rebuilds).
     // Everything is enqueued on `stream`; no host synchronisation.
     cudaError_t build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
-                      uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, cudaStream_t stream);
+                      uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, cudaStream_t stream);
 
     // Refit in place: recompute boxes bottom-up for a tree built by build() whose leaf order is
     // unchanged.  d_boxes_leaf_order[i] = new box of the primitive at leaf position i.

@@ -340,24 +340,25 @@ __global__ void k_reset_segment(FrameCounters* c, uint32_t seg) {
     c->seg[seg & (RT_SEG_SLOTS - 1u)] = z;
 }
 
-// Segments 1 .. max_segments-1 (mirror / portal bounces) in ONE cooperative launch: the four phases
-// separated by grid-wide barriers.  Most frames have few or no bounce rays; the kernel leaves as soon
-// as a segment's ray queue is empty, so such frames pay one near-empty launch instead of four per
-// segment.
+// The rest of the frame in ONE cooperative launch: segment 0's resolve phase, then segments
+// 1 .. max_segments-1 (mirror / portal bounces) with the four phases separated by grid-wide barriers,
+// then the ray-count export.  Most frames have few or no bounce rays; the kernel leaves as soon as a
+// segment's ray queue is empty, so such frames pay one launch instead of four per segment plus two.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_tail(SceneDev S, FrameDev F) {
+__global__ void __launch_bounds__(128) k_tail(SceneDev S, FrameDev F, uint64_t* ray_counts_out) {
     cg::grid_group grid = cg::this_grid();
+    resolve_phase(F, 0);
+    bool traced = false;
     for (uint32_t seg = 1; seg < F.max_segments; seg++) {
         const uint32_t rays = *((volatile unsigned int*)&seg_counters(F, seg - 1u)->ray_count);
-        if (rays == 0) break;  // grid-uniform: written before the last barrier (or the previous kernel)
-        if (seg >= RT_SEG_SLOTS) {  // counter slots are reused round-robin
-            if (grid.thread_rank() == 0) {
-                SegCounters z = {};
-                *seg_counters(F, seg) = z;
-            }
-            grid.sync();
+        if (rays == 0) break;  // grid-uniform: written before the last barrier (or by the previous kernel)
+        if (seg >= RT_SEG_SLOTS && grid.thread_rank() == 0) {  // counter slots are reused round-robin
+            SegCounters z = {};
+            *seg_counters(F, seg) = z;
         }
+        grid.sync();  // the previous resolve phase has read the hit queue this segment will overwrite
         trace_phase<false, COUNT>(S, F, seg, rays);
+        traced = true;
         grid.sync();
         const uint32_t hits = *((volatile unsigned int*)&seg_counters(F, seg)->hit_count);
         if (hits) {
@@ -366,7 +367,13 @@ __global__ void __launch_bounds__(128) k_tail(SceneDev S, FrameDev F) {
             shadow_phase<COUNT>(S, F, seg);
             grid.sync();
             resolve_phase(F, seg);
-            grid.sync();  // the next segment's trace phase overwrites the hit queue
+        }
+    }
+    if (ray_counts_out) {
+        if (traced) grid.sync();  // this kernel added to the counters: wait for every warp's flush
+        if (grid.thread_rank() == 0) {
+            ray_counts_out[0] = *((volatile unsigned long long*)&F.counters->primary_rays);
+            ray_counts_out[1] = *((volatile unsigned long long*)&F.counters->shadow_rays);
         }
     }
 }
@@ -480,9 +487,9 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
         if (count) k_shadow<true><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, 0);
         else k_shadow<false><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, 0);
         mark(K_SHADOW);
-        k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, 0);
-        mark(K_RESOLVE);
-        if (F.max_segments > 1 && split_tail) {
+        if (F.max_segments == 1 || split_tail) {
+            k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, 0);
+            mark(K_RESOLVE);
             for (uint32_t seg = 1; seg < F.max_segments; seg++) {
                 if (seg >= RT_SEG_SLOTS) { k_reset_segment<<<1, 1, 0, stream>>>(F.counters, seg); note_launch(); }
                 if (count) k_trace_n<true><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, seg);
@@ -496,13 +503,15 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
                 k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, seg);
                 mark(K_RESOLVE);
             }
-        } else if (F.max_segments > 1) {
+        } else {
             SceneDev s_arg = S;
             FrameDev f_arg = F;
-            void* args[] = {&s_arg, &f_arg};
+            uint64_t* rc_arg = d_ray_counts;
+            void* args[] = {&s_arg, &f_arg, &rc_arg};
             cudaError_t ce = cudaLaunchCooperativeKernel(count ? (void*)k_tail<true> : (void*)k_tail<false>, dim3(fit(g_tail[ci], 1)), dim3(128), args, 0, stream);
             if (ce != cudaSuccess) return ce;
             mark(K_TAIL);
+            return cudaGetLastError();  // k_tail exported the ray counts
         }
     }
     if (d_ray_counts) { k_export_counts<<<1, 1, 0, stream>>>(F.counters, d_ray_counts); note_launch(); }

@@ -48,20 +48,25 @@ struct __align__(16) TriRec {
 };
 static_assert(sizeof(TriRec) == 48, "TriRec is 48 bytes");
 #define RT_TRI_NON_OPAQUE 0x80000000u
+// A BLAS of at most this many triangles (ground planes, quads, billboards) is tested directly on instance entry:
+// its single node would cost more than the triangles it culls.
+#define RT_TINY_BLAS_TRIS 4u
 
 // Per-instance traversal record in TLAS leaf order: four float4.
 struct __align__(16) InstRT {
     float    inv[12];      // world -> object, row-major 3x4
-    uint32_t blas_root;    // index into the BLAS node pool, 0xFFFFFFFF = no geometry
+    uint32_t blas_root;    // index into the BLAS node pool, 0xFFFFFFFF = no geometry; first TriRec for a tiny BLAS
     uint32_t instance_id;  // gl_InstanceID (index of the 64-byte record)
     uint32_t custom_sbt;   // custom_index (24 low) | sbt_offset (8 high)
-    uint32_t mask;         // visibility mask (8 bits)
+    uint32_t mask;         // visibility mask (bits 0..7) | tiny-BLAS triangle count (bits 8..15, 0 = traverse nodes)
 };
 static_assert(sizeof(InstRT) == 64, "InstRT is 64 bytes");
 
 struct BlasInfo {
     uint32_t root;       // wide-node index of the BLAS root in the pool
     uint32_t num_tris;
+    uint32_t tri_first;  // index of the model's first TriRec
+    uint32_t _pad;
     float    lo[3], hi[3];
 };
 

@@ -111,6 +111,10 @@ __global__ void k_prepare_instances(const RtInstance* __restrict__ instances, ui
         BlasInfo bi = blas[model];
         if (bi.num_tris > 0 && bi.lo[0] <= bi.hi[0]) {
             r.blas_root = bi.root;
+            if (bi.num_tris <= RT_TINY_BLAS_TRIS) {
+                r.blas_root = bi.tri_first;
+                r.mask |= bi.num_tris << 8;
+            }
             bool finite = true;
             for (int c = 0; c < 8; c++) {
                 float px = c & 1 ? bi.hi[0] : bi.lo[0], py = c & 2 ? bi.hi[1] : bi.lo[1], pz = c & 4 ? bi.hi[2] : bi.lo[2];

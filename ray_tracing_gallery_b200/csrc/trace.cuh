@@ -108,6 +108,37 @@ struct Traverser {
         else tc.overflow++;
     }
 
+    // Candidate test of TriRec `ti` against the object-space ray (ro, rd) of instance (ipos, iid, isbt):
+    // exclusive interval, closest-t + tie rule (closest-hit rays), any-hit on non-opaque geometry.
+    // Returns true when the candidate was accepted and committed to `hit`.
+    __device__ __forceinline__ bool test_triangle(const SceneDev& S, uint32_t ti, V3 ro, V3 rd, uint32_t ipos, uint32_t iid, uint32_t isbt,
+                                                  TraceCounters& tc) {
+        const float4* tp = reinterpret_cast<const float4*>(S.tris + ti);
+        float4 ta = __ldg(tp), tb = __ldg(tp + 1), tcv = __ldg(tp + 2);
+        if (COUNT) tc.tris++;
+        float t, u, v;
+        if (!tri_candidate(ro, rd, v3(ta.x, ta.y, ta.z), v3(tb.x, tb.y, tb.z), v3(tcv.x, tcv.y, tcv.z), t, u, v)) return false;
+        if (!(t > tmin && t < tmax)) return false;
+        uint32_t prim = __float_as_uint(ta.w), gf = __float_as_uint(tb.w);
+        uint32_t geom = gf & ~RT_TRI_NON_OPAQUE;
+        if (!ANY) {
+            if (t > hit.t) return false;
+            if (t == hit.t && hit.inst_pos != RT_NONE) {
+                // exact tie: lowest (instance, geometry, primitive) wins
+                bool lower = iid != hit.instance_id ? iid < hit.instance_id : geom != hit.geom ? geom < hit.geom : prim < hit.prim;
+                if (!lower) return false;
+            }
+        }
+        if (gf & RT_TRI_NON_OPAQUE) {
+            if (COUNT) tc.anyhits++;
+            if (!anyhit_accepts(S, isbt & 0xFFFFFFu, geom, prim, u, v)) return false;
+        }
+        hit.t = t; hit.u = u; hit.v = v;
+        hit.inst_pos = ipos; hit.instance_id = iid;
+        hit.geom = geom; hit.prim = prim; hit.custom_sbt = isbt;
+        return true;
+    }
+
     // One traversal step.  Returns true when the ray is finished (then found() tells hit or miss).
     __device__ __forceinline__ bool step(const SceneDev& S, uint2* stack, TraceCounters& tc) {
         if (ng_bits & 0xFFu) {
@@ -173,34 +204,8 @@ struct Traverser {
                     hl &= hl - 1;
                     uint32_t m = (uint32_t)(meta >> (8 * s)) & 0xFFu;
                     uint32_t first = n1.y + (m & 31u), cnt = m >> 5;
-                    for (uint32_t k = 0; k < cnt; k++) {
-                        const float4* tp = reinterpret_cast<const float4*>(S.tris + first + k);
-                        float4 ta = __ldg(tp), tb = __ldg(tp + 1), tcv = __ldg(tp + 2);
-                        if (COUNT) tc.tris++;
-                        float t, u, v;
-                        if (!tri_candidate(co, cd, v3(ta.x, ta.y, ta.z), v3(tb.x, tb.y, tb.z), v3(tcv.x, tcv.y, tcv.z), t, u, v)) continue;
-                        if (!(t > tmin && t < tmax)) continue;
-                        uint32_t prim = __float_as_uint(ta.w), gf = __float_as_uint(tb.w);
-                        uint32_t geom = gf & ~RT_TRI_NON_OPAQUE;
-                        if (!ANY) {
-                            if (t > hit.t) continue;
-                            if (t == hit.t && hit.inst_pos != RT_NONE) {
-                                // exact tie: lowest (instance, geometry, primitive) wins
-                                bool lower = cur_instance_id != hit.instance_id ? cur_instance_id < hit.instance_id
-                                             : geom != hit.geom                ? geom < hit.geom
-                                                                               : prim < hit.prim;
-                                if (!lower) continue;
-                            }
-                        }
-                        if (gf & RT_TRI_NON_OPAQUE) {
-                            if (COUNT) tc.anyhits++;
-                            if (!anyhit_accepts(S, cur_custom_sbt & 0xFFFFFFu, geom, prim, u, v)) continue;
-                        }
-                        hit.t = t; hit.u = u; hit.v = v;
-                        hit.inst_pos = cur_inst_pos; hit.instance_id = cur_instance_id;
-                        hit.geom = geom; hit.prim = prim; hit.custom_sbt = cur_custom_sbt;
-                        if (ANY) return true;
-                    }
+                    for (uint32_t k = 0; k < cnt; k++)
+                        if (test_triangle(S, first + k, co, cd, cur_inst_pos, cur_instance_id, cur_custom_sbt, tc) && ANY) return true;
                 }
             } else if (hl) {
                 // TLAS leaves: enter the first now, stack the others
@@ -222,10 +227,19 @@ struct Traverser {
             uint32_t pos = enter_inst;
             enter_inst = RT_NONE;
             uint32_t root = __float_as_uint(r3.x);
-            if (root != RT_NONE && (__float_as_uint(r3.w) & 0xFFu)) {
+            const uint32_t mw = __float_as_uint(r3.w);
+            if (root != RT_NONE && (mw & 0xFFu)) {
                 if (COUNT) tc.instances++;
-                if (ng_bits & 0xFFu) push(stack, ng_base, ng_bits, tc);
                 float inv[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                const uint32_t tiny = (mw >> 8) & 0xFFu;
+                if (tiny) {
+                    // tiny BLAS: its triangles are tested right here, traversal stays in the TLAS
+                    V3 oo = xform_point(inv, o), od = xform_vec(inv, d);
+                    for (uint32_t k = 0; k < tiny; k++)
+                        if (test_triangle(S, root + k, oo, od, pos, __float_as_uint(r3.y), __float_as_uint(r3.z), tc) && ANY) return true;
+                    return false;
+                }
+                if (ng_bits & 0xFFu) push(stack, ng_base, ng_bits, tc);
                 set_space(xform_point(inv, o), xform_vec(inv, d));
                 cur_inst_pos = pos;
                 cur_instance_id = __float_as_uint(r3.y);

@@ -75,6 +75,10 @@ class Renderer(CApiBackend):
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.rt_set_stream(self.ctx, cuda_stream), "set_stream")
 
+    def update_instances_raw(self, first: int, count: int, host_ptr: int):
+        """`rt_update_instances` from a raw host pointer (e.g. pinned memory) to `count` 64-byte records."""
+        self._check(self.lib.rt_update_instances(self.ctx, first, count, host_ptr), "update_instances")
+
     def update_instances_device(self, first: int, count: int, device_ptr: int):
         self._check(self.lib.rt_update_instances_device(self.ctx, first, count, device_ptr), "update_instances_device")
 

@@ -77,6 +77,23 @@ def test_pipelines_agree_bit_for_bit():
     gpu.close()
 
 
+def test_bounce_segments_cooperative_tail_equals_split_launches():
+    """Segments >= 1 run in one cooperative kernel by default; RT_RENDER_SPLIT_TAIL runs them as four launches each.
+    Same phases, same order: the frames must be identical.  Also covers max_segments = 1 (no tail) and > 8 (counter-slot reuse)."""
+    gpu = make_renderer()
+    s = build_scene(gpu, "c3", 640, 360)
+    for segs in (1, 3, 10):
+        a = gpu.render(s.uniforms(), s.params(max_segments=segs))
+        if segs == 3:
+            assert gpu.stats().segment_rays[0] > 0, "the config must have bounce rays for this test to mean anything"
+        b = gpu.render(s.uniforms(), s.params(max_segments=segs, flags=abi.RT_RENDER_SPLIT_TAIL))
+        m = gpu.render(s.uniforms(), s.params(max_segments=segs, pipeline=abi.RT_PIPELINE_MEGAKERNEL))
+        for k in ("hit_ids", "rgba8", "ray_counts"):
+            assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], m[k]), (segs, k)
+        assert np.array_equal(a["radiance"].view(np.uint32), b["radiance"].view(np.uint32))
+    gpu.close()
+
+
 def test_blue_noise_sequence_over_frames():
     """Soft shadows must follow the reference's deterministic sequence: frame f and f+32 are identical,
     other frames differ, and every frame matches the oracle."""

@@ -19,6 +19,8 @@ ap.add_argument("--pipeline", default="wavefront")
 ap.add_argument("--frames", type=int, default=5)
 ap.add_argument("--shadow-rays", type=int, default=0)
 ap.add_argument("--split-tail", action="store_true")
+ap.add_argument("--tile", default="", help="x0,y0,w,h")
+ap.add_argument("--emulate-rank-of", type=int, default=1, help="render only the strips rank 0 of N would render")
 a = ap.parse_args()
 gpu = native.Renderer(0)
 s = build_scene(gpu, a.workload, a.width or None, a.height or None, num_instances=a.instances or None)
@@ -37,8 +39,14 @@ for k, nm in enumerate(("closest-hit", "shadow")):
 print("  segment bounce rays", list(st.segment_rays)[:4], "segment hits", list(st.segment_hits)[:4])
 acc = np.zeros(6)
 tot = 0.0
+from ray_tracing_gallery_b200.dist import Partition  # noqa: E402
+part = Partition.make(s.width, s.height, a.emulate_rank_of, 0)
+tile = {}
+if a.tile:
+    x0, y0, w, h = (int(v) for v in a.tile.split(","))
+    tile = dict(tile_x0=x0, tile_y0=y0, tile_w=w, tile_h=h)
 for i in range(a.frames):
-    gpu.render(s.uniforms(frame_index=2 + i), s.params(pipeline=pipe, flags=abi.RT_RENDER_TIMING | (abi.RT_RENDER_SPLIT_TAIL if a.split_tail else 0)), want=("rgba8",))
+    gpu.render(s.uniforms(frame_index=2 + i), part.apply(s.params(pipeline=pipe, flags=abi.RT_RENDER_TIMING | (abi.RT_RENDER_SPLIT_TAIL if a.split_tail else 0), **tile)), want=("rgba8",))
     st = gpu.stats()
     acc += np.array(list(st.kernel_ms))
     tot += st.last_render_ms
