@@ -332,34 +332,50 @@ def run_ours(args):
     total_ms, total_rays_all = float(t.item()), int(r.item())
     value = total_rays_all / (total_ms * 1e-3) / 1e6
 
-    # ---- e2e: the same steps through the host-facing C ABI, host<->device copies inside the timed region
-    def step_e2e(i):
-        if s.dynamic:
-            if world == 1:
-                gpu.update_instances_raw(0, len(s.instances), rec_pinned[i % n_frames].data_ptr())  # rt_update_instances: host -> device
-                gpu.update_tlas(update_mode)
-            else:
-                update_scene_device(i, from_host=True)
-        if world == 1:
-            gpu.render_to_host(frame_inputs(i), params(), host_fb.data_ptr(), host_rays.data_ptr())  # rt_render, blocking
-        else:
-            gpu.render_device(frame_inputs(i), params(), rgba8=fb.data_ptr(), ray_counts=rays_dev.data_ptr())
-            dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
-            if rank == 0:
-                host_fb.copy_(deinterleave(gathered, part), non_blocking=True)
-            host_rays.copy_(rays_dev, non_blocking=True)
-            torch.cuda.synchronize()
+    # ---- e2e: the same steps through the host-facing C ABI, host<->device copies inside the timed region.
+    #      N = 1: rt_render_async, two frames in flight like the reference (src/main.rs:917-928): every step copies its
+    #      uniforms (and instance records) H2D and its finished frame + ray counts D2H into pinned host memory; the copy
+    #      of frame i overlaps the rendering of frame i+1; the step's result is consumed after rt_wait_frame.
+    host_fbs = [host_fb, torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()] if world == 1 else [host_fb]
+    host_rays2 = [host_rays, torch.zeros(2, dtype=torch.int64).pin_memory()]
 
-    for i in range(2):
-        step_e2e(i)
+    def e2e_run(first, count):
+        rays, pending = 0, []
+        for k in range(count):
+            i = first + k
+            if s.dynamic:
+                if world == 1:
+                    gpu.update_instances_raw(0, len(s.instances), rec_pinned[i % n_frames].data_ptr())  # rt_update_instances: host -> device
+                    gpu.update_tlas(update_mode)
+                else:
+                    update_scene_device(i, from_host=True)
+            if world == 1:
+                b = k & 1
+                slot = gpu.render_async(frame_inputs(i), params(), host_fbs[b].data_ptr(), host_rays2[b].data_ptr())
+                pending.append((slot, b))
+                if len(pending) == 2:
+                    sl, pb = pending.pop(0)
+                    gpu.wait_frame(sl)
+                    rays += int(host_rays2[pb].sum().item())
+            else:
+                gpu.render_device(frame_inputs(i), params(), rgba8=fb.data_ptr(), ray_counts=rays_dev.data_ptr())
+                dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
+                if rank == 0:
+                    host_fb.copy_(deinterleave(gathered, part), non_blocking=True)
+                host_rays.copy_(rays_dev, non_blocking=True)
+                torch.cuda.synchronize()
+                rays += int(host_rays.sum().item())
+        for sl, pb in pending:
+            gpu.wait_frame(sl)
+            rays += int(host_rays2[pb].sum().item())
+        return rays
+
+    e2e_run(0, 2)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e2e_rays = 0
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(args.warmup + i)
-        e2e_rays += int(host_rays.sum().item())
+    e2e_rays = e2e_run(args.warmup, args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -416,7 +432,7 @@ def run_ours(args):
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / args.steps * 1e3,
-                    "path": "rt_render (host buffers, pinned)" if world == 1 else "rt_render_device + NCCL all-gather + D2H on rank 0"},
+                    "path": "rt_render_async (pinned host buffers, two frames in flight) + rt_wait_frame" if world == 1 else "rt_render_device + NCCL all-gather + D2H on rank 0"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -177,6 +177,17 @@ int  rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams*
                const RtFrameOutputs* out);
 int  rt_render_device(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params,
                       const RtFrameOutputs* out);
+/* Two frames in flight, like the reference's PerFrameResources + one fence per frame
+ * (src/command_buffer_recording.rs:22-30, src/main.rs:917-928).  rt_render_async enqueues the frame into
+ * the next of two frame slots and returns at once: the render runs on the context's stream, the
+ * copy of the finished RGBA8 rows (and ray counts) to `out`'s HOST pointers on a second stream, so the
+ * copy of frame i overlaps the rendering of frame i+1.  The host arrays (use pinned memory) are valid
+ * after rt_wait_frame(slot).  If the slot is still busy with the frame from two calls ago, the call
+ * waits for it first (the reference's wait_for_fences).  Only out->rgba8 and out->ray_counts are
+ * supported here. */
+int  rt_render_async(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params,
+                     const RtFrameOutputs* out, uint32_t* out_slot);
+int  rt_wait_frame(RtContext* ctx, uint32_t slot);
 /* Storage-image copy / present (src/command_buffer_recording.rs:165-179): copy the
  * RGBA8 rows of the last rt_render(…, NULL) / rt_render frame to host memory (blocking). */
 int  rt_readback(RtContext* ctx, void* host_rgba8, size_t capacity_bytes);

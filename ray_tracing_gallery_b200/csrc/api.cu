@@ -115,6 +115,17 @@ struct RtContext {
     size_t fb_rgba8_cap = 0, fb_radiance_cap = 0, fb_hit_ids_cap = 0;
     size_t last_rows = 0, last_tw = 0;
     uint64_t* d_ray_counts = nullptr;
+
+    // two frames in flight (rt_render_async)
+    struct FrameSlot {
+        uint8_t* d_rgba8 = nullptr;
+        size_t cap = 0;
+        uint64_t* d_ray_counts = nullptr;
+        cudaEvent_t rendered = nullptr, copied = nullptr;
+        bool pending = false;
+    } slots[2];
+    cudaStream_t copy_stream = nullptr;
+    uint32_t next_slot = 0;
 };
 
 namespace {
@@ -328,6 +339,12 @@ void rt_destroy(RtContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (auto& sl : ctx->slots) {
+        cudaFree(sl.d_rgba8); cudaFree(sl.d_ray_counts);
+        if (sl.rendered) cudaEventDestroy(sl.rendered);
+        if (sl.copied) cudaEventDestroy(sl.copied);
+    }
     for (auto& t : ctx->tex_res) {
         if (t.obj) cudaDestroyTextureObject(t.obj);
         if (t.array) cudaFreeArray(t.array);
@@ -631,6 +648,53 @@ int rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* 
     return RT_OK;
 }
 
+int rt_render_async(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params, const RtFrameOutputs* out, uint32_t* out_slot) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!uniforms || !params) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_async: NULL argument");
+    if (out && (out->radiance || out->hit_ids)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_async: only rgba8 and ray_counts outputs");
+    CK_DEV(ctx);
+    FramePlan f;
+    int rc = plan_frame(ctx, params, f);
+    if (rc) return rc;
+    size_t pixels = (size_t)f.rows * f.tw;
+    uint32_t si = ctx->next_slot;
+    RtContext::FrameSlot& sl = ctx->slots[si];
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!sl.rendered) {
+        CK(cudaEventCreateWithFlags(&sl.rendered, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+        CK(cudaMalloc(&sl.d_ray_counts, 16));
+    }
+    if (sl.pending) {  // the frame rendered into this slot two calls ago: its fence
+        CK(cudaEventSynchronize(sl.copied));
+        sl.pending = false;
+    }
+    CK(grow(sl.d_rgba8, sl.cap, pixels * 4 + 16));
+    rc = render_common(ctx, uniforms, params, f, sl.d_rgba8, nullptr, nullptr, sl.d_ray_counts);
+    if (rc) return rc;
+    CK(cudaEventRecord(sl.rendered, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, sl.rendered, 0));
+    if (out && out->rgba8) CK(cudaMemcpyAsync(out->rgba8, sl.d_rgba8, pixels * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (out && out->ray_counts) CK(cudaMemcpyAsync(out->ray_counts, sl.d_ray_counts, 16, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(sl.copied, ctx->copy_stream));
+    sl.pending = true;
+    ctx->next_slot = si ^ 1u;
+    if (out_slot) *out_slot = si;
+    return RT_OK;
+}
+
+int rt_wait_frame(RtContext* ctx, uint32_t slot) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (slot > 1) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_wait_frame: slot is 0 or 1");
+    CK_DEV(ctx);
+    RtContext::FrameSlot& sl = ctx->slots[slot];
+    if (sl.pending) {
+        CK(cudaEventSynchronize(sl.copied));
+        sl.pending = false;
+    }
+    return RT_OK;
+}
+
 int rt_readback(RtContext* ctx, void* host_rgba8, size_t capacity_bytes) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     if (!host_rgba8) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_readback: NULL destination");
@@ -647,6 +711,8 @@ int rt_sync(RtContext* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     CK_DEV(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+    for (auto& sl : ctx->slots) sl.pending = false;
     return RT_OK;
 }
 

@@ -19,7 +19,8 @@ _LIB = None
 # every symbol include/b200rt.h declares
 EXPORTS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_push_image", "rt_create_model", "rt_build_tlas",
-    "rt_update_instances", "rt_update_instances_device", "rt_update_tlas", "rt_render", "rt_render_device", "rt_readback",
+    "rt_update_instances", "rt_update_instances_device", "rt_update_tlas", "rt_render", "rt_render_device", "rt_render_async",
+    "rt_wait_frame", "rt_readback",
     "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_kernel_launches", "rt_version",
 ]
 
@@ -46,6 +47,8 @@ def load():
     lib.rt_set_stream.argtypes = [p, p]
     lib.rt_update_instances_device.argtypes = [p, u32, u32, p]
     lib.rt_render_device.argtypes = [p, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams), C.POINTER(abi.RtFrameOutputs)]
+    lib.rt_render_async.argtypes = [p, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams), C.POINTER(abi.RtFrameOutputs), C.POINTER(u32)]
+    lib.rt_wait_frame.argtypes = [p, u32]
     lib.rt_readback.argtypes = [p, p, C.c_size_t]
     lib.rt_sync.argtypes = [p]
     lib.rt_get_stats.argtypes = [p, C.POINTER(abi.RtStats)]
@@ -91,6 +94,16 @@ class Renderer(CApiBackend):
         """`rt_render` with caller-owned HOST buffers (pinned memory makes the copy asynchronous-capable)."""
         out = abi.RtFrameOutputs(host_rgba8_ptr or None, None, None, ray_counts_ptr or None)
         self._check(self.lib.rt_render(self.ctx, C.byref(uniforms), C.byref(params), C.byref(out)), "render")
+
+    def render_async(self, uniforms, params, host_rgba8_ptr: int, ray_counts_ptr: int = 0) -> int:
+        """`rt_render_async`: two frames in flight; returns the frame slot to pass to `wait_frame`."""
+        out = abi.RtFrameOutputs(host_rgba8_ptr or None, None, None, ray_counts_ptr or None)
+        slot = C.c_uint32()
+        self._check(self.lib.rt_render_async(self.ctx, C.byref(uniforms), C.byref(params), C.byref(out), C.byref(slot)), "render_async")
+        return slot.value
+
+    def wait_frame(self, slot: int):
+        self._check(self.lib.rt_wait_frame(self.ctx, slot), "wait_frame")
 
     def readback(self, rows: int, width: int) -> np.ndarray:
         img = np.zeros((rows, width, 4), np.uint8)

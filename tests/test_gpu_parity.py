@@ -284,3 +284,36 @@ def test_device_output_path_and_readback():
     assert np.array_equal(rad.cpu().numpy().view(np.uint32), host["radiance"].view(np.uint32))
     assert rays.cpu().numpy().astype(np.uint64).tolist() == host["ray_counts"].tolist()
     gpu.close()
+
+
+def test_two_frames_in_flight_match_blocking_renders():
+    """rt_render_async / rt_wait_frame (the reference's two PerFrameResources + fences, src/main.rs:917-928):
+    frames rendered through the two slots, copies overlapped with the next render, equal the blocking rt_render frames."""
+    import torch
+
+    gpu = make_renderer()
+    s = build_scene(gpu, "c2", 480, 270)
+    want = [gpu.render(s.uniforms(frame_index=1 + i), s.params(), want=("rgba8", "ray_counts")) for i in range(5)]
+    fbs = [torch.zeros((270, 480, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    rcs = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(2)]
+    pending = []
+
+    def consume():
+        slot, b, i = pending.pop(0)
+        gpu.wait_frame(slot)
+        assert np.array_equal(fbs[b].numpy(), want[i]["rgba8"]), f"frame {i}"
+        assert rcs[b].numpy().astype(np.uint64).tolist() == want[i]["ray_counts"].tolist()
+
+    for i in range(5):
+        b = i & 1
+        if len(pending) == 2:
+            consume()  # the host buffer of slot b is free again
+        slot = gpu.render_async(s.uniforms(frame_index=1 + i), s.params(), fbs[b].data_ptr(), rcs[b].data_ptr())
+        assert slot == b
+        pending.append((slot, b, i))
+    while pending:
+        consume()
+    with pytest.raises(RtError):
+        gpu.wait_frame(2)
+    gpu.sync()
+    gpu.close()
