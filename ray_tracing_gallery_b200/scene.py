@@ -75,6 +75,8 @@ def make_instance(transform, model_id: int, blas_handle: int, hit_shader: int, d
 # ----------------------------------------------------------------------------- camera / sun / uniforms
 @dataclass
 class Camera:
+    """FirstPersonCamera (src/main.rs:1206-1231); positive pitch looks up."""
+
     eye: Tuple[float, float, float] = (0.0, 2.0, -5.0)
     pitch: float = 0.0
     yaw: float = math.pi
@@ -310,7 +312,7 @@ def build_scene(backend, config: str, width: Optional[int] = None, height: Optio
         kind = np.where(gi % 2 == 0, abi.RT_HIT_TEXTURED, abi.RT_HIT_MIRROR)
         tori = instances_from_trs(pos, rot, scale, tid, th, kind)
         inst = np.concatenate([np.stack([make_instance(mat_scale(60.0), pid, ph, abi.RT_HIT_TEXTURED)]), tori])
-        s = SceneSetup("c4", inst, Camera(eye=(0.0, 14.0, -62.0), pitch=0.28), Sun(), width or 3840, height or 2160,
+        s = SceneSetup("c4", inst, Camera(eye=(0.0, 14.0, -62.0), pitch=-0.28), Sun(), width or 3840, height or 2160,
                        shadow_rays=2, sun_radius=0.05, dynamic=True, base_rot=rot, base_pos=pos, base_scale=scale,
                        description="10k instanced tori, all transforms updated every frame (TLAS rebuild/refit)")
     elif config == "c5":
@@ -323,7 +325,7 @@ def build_scene(backend, config: str, width: Optional[int] = None, height: Optio
         scale = (hash_uniform(5, 4, n) * 0.09 + 0.01).astype(F)
         tori = instances_from_trs(pos, rot, scale, tid, th, abi.RT_HIT_TEXTURED)
         inst = np.concatenate([np.stack([make_instance(mat_scale(80.0), pid, ph, abi.RT_HIT_TEXTURED)]), tori])
-        s = SceneSetup("c5", inst, Camera(eye=(0.0, 16.0, -70.0), pitch=0.3), Sun(), width or 3840, height or 2160,
+        s = SceneSetup("c5", inst, Camera(eye=(0.0, 16.0, -70.0), pitch=-0.3), Sun(), width or 3840, height or 2160,
                        shadow_rays=16, sun_radius=0.05,
                        description="1M-instance synthetic scene, 16 soft-shadow rays/px")
     elif config == "default":

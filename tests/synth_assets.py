@@ -1,0 +1,138 @@
+"""Synthetic GLB models for the loader / shading paths that none of the reference's bundled assets exercises
+(SURVEY.md 8f item 1): several materials in one model (one geometry per material, src/util_structs.rs:1079-1137),
+a normal map (shaders/closest_hit_textured.glsl:141-157), a NEAREST magFilter (src/util_structs.rs:954-955),
+non-power-of-two images, uvs outside [0,1] (REPEAT), u16 and u32 indices, un-normalised vertex normals, an
+alpha-masked material next to an opaque one.  Everything is generated from a fixed seed."""
+import io
+import json
+import struct
+
+import numpy as np
+
+
+def _png(rgba: np.ndarray) -> bytes:
+    from PIL import Image
+
+    buf = io.BytesIO()
+    Image.fromarray(rgba, "RGBA").save(buf, format="PNG")
+    return buf.getvalue()
+
+
+def _pad4(b: bytes, fill=b"\x00") -> bytes:
+    return b + fill * ((4 - len(b) % 4) % 4)
+
+
+def bumpy_two_material_glb(seed: int = 7, n: int = 10) -> bytes:
+    """An n x n quad grid over [-1,1]^2 in xz with a height field; the quads are dealt to two materials in a
+    checkerboard (primitive 0: u16 indices, material 1; primitive 1: u32 indices, material 0)."""
+    rng = np.random.default_rng(seed)
+    g = np.linspace(-1.0, 1.0, n + 1, dtype=np.float32)
+    xx, zz = np.meshgrid(g, g, indexing="xy")
+    yy = (0.15 * np.sin(3.0 * xx) * np.cos(2.0 * zz)).astype(np.float32)
+    pos = np.stack([xx, yy, zz], axis=-1).reshape(-1, 3).astype(np.float32)
+    # analytic normals, deliberately NOT unit length (the shaders normalise after the transform)
+    dydx = 0.45 * np.cos(3.0 * xx) * np.cos(2.0 * zz)
+    dydz = -0.30 * np.sin(3.0 * xx) * np.sin(2.0 * zz)
+    nrm = np.stack([-dydx, np.ones_like(xx), -dydz], axis=-1).reshape(-1, 3).astype(np.float32) * np.float32(1.7)
+    uv = np.stack([(xx + 1.0) * 1.3 - 0.4, (zz + 1.0) * 0.9 - 0.3], axis=-1).reshape(-1, 2).astype(np.float32)  # leaves [0,1]
+
+    def quad(ix, iz):
+        a = iz * (n + 1) + ix
+        return [a, a + n + 1, a + 1, a + 1, a + n + 1, a + n + 2]
+
+    idx0, idx1 = [], []
+    for iz in range(n):
+        for ix in range(n):
+            (idx0 if (ix + iz) % 2 == 0 else idx1).extend(quad(ix, iz))
+    idx0 = np.asarray(idx0, np.uint16)
+    idx1 = np.asarray(idx1, np.uint32)
+
+    # images: 0 = base colour of material 0 (20x12, NEAREST), 1 = metallic-roughness (8x8, LINEAR),
+    #         2 = normal map (32x24, LINEAR), 3 = base colour + alpha mask of material 1 (16x16, LINEAR)
+    img0 = rng.integers(40, 255, (12, 20, 4), dtype=np.uint8); img0[..., 3] = 255
+    img1 = rng.integers(0, 255, (8, 8, 4), dtype=np.uint8); img1[..., 3] = 255
+    ny, nx = np.meshgrid(np.linspace(0, 4 * np.pi, 24), np.linspace(0, 6 * np.pi, 32), indexing="ij")
+    nvec = np.stack([0.35 * np.sin(nx), 0.35 * np.cos(ny), np.ones_like(nx)], axis=-1)
+    nvec /= np.linalg.norm(nvec, axis=-1, keepdims=True)
+    img2 = np.concatenate([np.round((nvec * 0.5 + 0.5) * 255), np.full(nx.shape + (1,), 255.0)], axis=-1).astype(np.uint8)
+    img3 = rng.integers(30, 255, (16, 16, 4), dtype=np.uint8)
+    cy, cx = np.meshgrid(np.arange(16), np.arange(16), indexing="ij")
+    img3[..., 3] = np.where(((cx // 4) + (cy // 4)) % 2 == 0, 255, 20)  # MASK: coarse checker of holes
+    pngs = [_png(img0), _png(img1), _png(img2), _png(img3)]
+
+    chunks, views = [], []
+
+    def add_view(b: bytes, target=None):
+        off = sum(len(c) for c in chunks)
+        chunks.append(_pad4(b))
+        v = {"buffer": 0, "byteOffset": off, "byteLength": len(b)}
+        if target:
+            v["target"] = target
+        views.append(v)
+        return len(views) - 1
+
+    v_pos, v_nrm, v_uv = add_view(pos.tobytes(), 34962), add_view(nrm.tobytes(), 34962), add_view(uv.tobytes(), 34962)
+    v_i0, v_i1 = add_view(idx0.tobytes(), 34963), add_view(idx1.tobytes(), 34963)
+    v_img = [add_view(p) for p in pngs]
+    nv = len(pos)
+    accessors = [
+        {"bufferView": v_pos, "componentType": 5126, "count": nv, "type": "VEC3", "min": pos.min(0).tolist(), "max": pos.max(0).tolist()},
+        {"bufferView": v_nrm, "componentType": 5126, "count": nv, "type": "VEC3"},
+        {"bufferView": v_uv, "componentType": 5126, "count": nv, "type": "VEC2"},
+        {"bufferView": v_i0, "componentType": 5123, "count": len(idx0), "type": "SCALAR"},
+        {"bufferView": v_i1, "componentType": 5125, "count": len(idx1), "type": "SCALAR"},
+    ]
+    doc = {
+        "asset": {"version": "2.0", "generator": "tests/synth_assets.py"},
+        "buffers": [{"byteLength": sum(len(c) for c in chunks)}],
+        "bufferViews": views,
+        "accessors": accessors,
+        "images": [{"bufferView": v, "mimeType": "image/png"} for v in v_img],
+        "samplers": [{"magFilter": 9728, "minFilter": 9728}, {"magFilter": 9729, "minFilter": 9729}],
+        "textures": [{"source": 0, "sampler": 0}, {"source": 1, "sampler": 1}, {"source": 2, "sampler": 1}, {"source": 3}],
+        "materials": [
+            {"name": "opaque_normal_mapped", "pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 1}},
+             "normalTexture": {"index": 2}},
+            {"name": "masked", "alphaMode": "MASK", "alphaCutoff": 0.5, "doubleSided": True,
+             "pbrMetallicRoughness": {"baseColorTexture": {"index": 3}, "metallicFactor": 0.25, "roughnessFactor": 0.6}},
+        ],
+        "meshes": [{"primitives": [
+            {"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 3, "material": 1},
+            {"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 4, "material": 0},
+        ]}],
+        "nodes": [{"mesh": 0, "scale": [3.0, 3.0, 3.0]}],  # node transforms are ignored by the loader (:1113)
+        "scenes": [{"nodes": [0]}],
+        "scene": 0,
+    }
+    js = _pad4(json.dumps(doc).encode("utf-8"), b" ")
+    blob = b"".join(chunks)
+    total = 12 + 8 + len(js) + 8 + len(blob)
+    return struct.pack("<III", 0x46546C67, 2, total) + struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(blob), 0x004E4942) + blob
+
+
+def build_bumpy_scene(backend, width=640, height=360, shadow_rays=2):
+    """plane + two instances of the synthetic model (one non-uniformly scaled and rotated) + a mirror torus."""
+    import numpy as np
+
+    from ray_tracing_gallery_b200 import abi
+    from ray_tracing_gallery_b200.gltf import load_gltf
+    from ray_tracing_gallery_b200.scene import (Camera, SceneSetup, Sun, load_model, make_instance, mat_rotation_y, mat_scale,
+                                                mat_translation, push_builtin_images)
+
+    push_builtin_images(backend)
+    pid, ph, _ = load_model(backend, "plane.glb", 0)
+    tid, th, _ = load_model(backend, "tori.glb", 1)
+    arrays = load_gltf(bumpy_two_material_glb(), "bumpy", 1, backend.push_image)
+    bid, bh = backend.create_model(arrays)
+    squash = np.diag([1.6, 0.8, 1.1, 1.0]).astype(np.float32)
+    inst = np.stack([
+        make_instance(mat_scale(10.0), pid, ph, abi.RT_HIT_TEXTURED),
+        make_instance(mat_translation(-1.2, 0.8, 0.5) @ mat_rotation_y(0.4) @ squash, bid, bh, abi.RT_HIT_TEXTURED, True),
+        make_instance(mat_translation(1.6, 1.4, 1.5) @ mat_rotation_y(-0.9), bid, bh, abi.RT_HIT_TEXTURED, True),
+        make_instance(mat_translation(0.5, 1.0, 4.0) @ mat_rotation_y(1.1), tid, th, abi.RT_HIT_MIRROR),
+    ])
+    s = SceneSetup("bumpy", inst, Camera(eye=(0.0, 3.0, -4.5), pitch=-0.3), Sun(), width, height, shadow_rays=shadow_rays, sun_radius=0.05,
+                   description="synthetic two-material normal-mapped model")
+    s.models = {"bumpy": (bid, bh, arrays)}
+    backend.build_tlas(s.instances)
+    return s

@@ -142,3 +142,28 @@ def test_large_configs_have_the_advertised_instance_counts(cfg, n):
         moved = s.animate(3)
         assert not np.array_equal(moved["transform"][1:], s.instances["transform"][1:])
         assert np.array_equal(moved["transform"][0], s.instances["transform"][0])
+
+
+def test_synthetic_multi_material_model():
+    """one geometry per material, images in material order (diffuse, metal-rough, [normal]), sampler choice,
+    u16/u32 indices rebased per primitive, primitive -> geometry by material index, node transform ignored."""
+    from synth_assets import bumpy_two_material_glb
+
+    log = ImageLog()
+    m = load_gltf(bumpy_two_material_glb(), "bumpy", 1, log)
+    n = 10
+    assert m.positions.shape == (2 * (n + 1) ** 2, 3)          # the two primitives each append the shared vertex block
+    assert np.abs(m.positions).max() <= 1.0 + 1e-6              # node scale 3 ignored (src/util_structs.rs:1113)
+    g0, g1 = m.geometries
+    assert g0.opaque and not g1.opaque
+    assert (g0.diffuse_image_index, g0.metallic_roughness_image_index, g0.normal_map_image_index) == (4, 5, 6)
+    assert (g1.diffuse_image_index, g1.metallic_roughness_image_index, g1.normal_map_image_index) == (7, 8, -1)
+    fmts = [(im[0], im[2], im[3]) for im in log.images]
+    assert fmts[0] == ((12, 20, 4), abi.RT_FORMAT_RGBA8_SRGB, False)     # magFilter NEAREST
+    assert fmts[1] == ((8, 8, 4), abi.RT_FORMAT_RGBA8_SRGB, True)        # metal-rough is sRGB too (reference quirk)
+    assert fmts[2] == ((24, 32, 4), abi.RT_FORMAT_RGBA8_UNORM, True)     # normal map UNORM
+    assert fmts[3] == ((16, 16, 4), abi.RT_FORMAT_RGBA8_SRGB, True)      # texture without sampler -> linear
+    assert fmts[4][1] == abi.RT_FORMAT_RGBA32_SFLOAT and log.images[4][4].reshape(4).tolist() == [1.0, np.float32(0.6), 0.25, 1.0]
+    # primitive 0 (material 1) came first: its indices are not rebased, primitive 1 (material 0) is rebased by (n+1)^2
+    assert len(g0.indices) + len(g1.indices) == n * n * 6
+    assert g1.indices.max() < (n + 1) ** 2 <= g0.indices.min()

@@ -308,3 +308,44 @@ def test_golden_fixture(cfg):
     want = np.asarray(Image.open(os.path.join(GOLDEN, f"{cfg}.png")))
     assert np.abs(r["rgba8"].astype(int) - want.astype(int)).max() <= 1
     o.close()
+
+
+def test_synthetic_model_exercises_normal_map_nearest_and_multi_material():
+    """SURVEY 8f-1 paths on the oracle: both geometries of the two-material model are hit, the masked one runs the
+    any-hit (rays pass through its holes), the normal map changes the shading, NEAREST differs from LINEAR."""
+    import synth_assets
+    from oracle.binding import Oracle
+
+    o = Oracle()
+    s = synth_assets.build_bumpy_scene(o, 320, 180)
+    r = o.render(s.uniforms(), s.params())
+    assert np.isfinite(r["radiance"]).all()
+    ids = r["hit_ids"][:, :, 0, :]
+    on_model = (ids[..., 0] == 1) | (ids[..., 0] == 2)
+    assert on_model.sum() > 1500
+    assert set(np.unique(ids[on_model][:, 1]).tolist()) == {0, 1}           # gl_GeometryIndexEXT: one geometry per material
+    g1 = on_model & (ids[..., 1] == 1)
+    g0 = on_model & (ids[..., 1] == 0)
+    assert 0.25 < g1.sum() / max(g0.sum(), 1) < 0.9                          # holes of the masked checker let rays through
+    # without the normal map the opaque geometry shades differently
+    arrays = s.models["bumpy"][2]
+    o2 = Oracle()
+    import ray_tracing_gallery_b200.gltf as gltf
+    orig = gltf.load_gltf
+
+    def no_normal_map(*a, **k):
+        m = orig(*a, **k)
+        m.geometries[0].normal_map_image_index = -1
+        return m
+
+    gltf.load_gltf = no_normal_map
+    try:
+        s2 = synth_assets.build_bumpy_scene(o2, 320, 180)
+    finally:
+        gltf.load_gltf = orig
+    r2 = o2.render(s2.uniforms(), s2.params())
+    assert np.array_equal(r2["hit_ids"], r["hit_ids"])
+    d = np.abs(r2["radiance"] - r["radiance"]).max(axis=2)
+    assert d[g0].mean() > 1e-3 and d[g1].max() == 0.0
+    assert arrays.geometries[0].normal_map_image_index >= 0
+    o.close(); o2.close()
