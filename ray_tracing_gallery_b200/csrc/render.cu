@@ -66,16 +66,21 @@ __device__ __forceinline__ void write_hit_ids(const FrameDev& F, uint32_t pixel,
     p[0] = h.instance_id; p[1] = h.geom; p[2] = h.prim;
 }
 
-// one atomicAdd per warp; every lane of the warp must call this
-__device__ __forceinline__ uint32_t warp_push(unsigned int* counter, bool pred) {
-    uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
-    if (mask == 0) return 0;
-    uint32_t leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane_id() == leader) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    return base + __popc(mask & ((1u << lane_id()) - 1u));
-}
+// Queue push: one atomicAdd per warp (ballot + popc prefix); every lane of the warp must call both halves.
+// Two halves, so that independent work can run while the atomic is in flight:
+// reserve() issues it (leader lane), slot() reads the result.
+struct WarpPush {
+    uint32_t mask, base;
+    __device__ __forceinline__ void reserve(unsigned int* counter, bool pred) {
+        mask = __ballot_sync(0xFFFFFFFFu, pred);
+        base = 0;
+        if (mask && lane_id() == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(counter, __popc(mask));
+    }
+    __device__ __forceinline__ uint32_t slot() const {
+        if (mask == 0) return 0;
+        return __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1) + __popc(mask & ((1u << lane_id()) - 1u));
+    }
+};
 
 __device__ __forceinline__ void warp_add(unsigned long long* counter, uint32_t v) {
     v = __reduce_add_sync(0xFFFFFFFFu, v);
@@ -135,22 +140,18 @@ enum { K_TRACE = 0, K_PREP = 1, K_SHADOW = 2, K_RESOLVE = 3, K_MEGA = 4, K_TAIL 
 
 __device__ __forceinline__ SegCounters* seg_counters(const FrameDev& F, uint32_t seg) { return &F.counters->seg[seg & (RT_SEG_SLOTS - 1u)]; }
 
-// Warp-wide work distribution: a warp owns a chunk [next, end) of RT_CHUNK items taken from the
-// device-side cursor with one atomic.  All members are warp-uniform.
+// Warp-wide work distribution: a warp takes RT_CHUNK items at a time from the device-side cursor with
+// one atomic.  The atomic for the NEXT batch is issued before the current batch is traced and its
+// result is only read (shuffled) when that batch starts, so the round trip to L2 (about 20 % of
+// k_trace0's stall samples in profiles/r01g) hides behind the traversal.
 struct WarpChunk {
-    uint32_t next, end;
-    bool exhausted;
-    __device__ __forceinline__ void init() { next = end = 0; exhausted = false; }
-    // make sure the chunk is non-empty; returns false when the queue has run dry
-    __device__ __forceinline__ bool ensure(unsigned int* cursor, uint32_t total) {
-        if (next < end) return true;
-        if (exhausted) return false;
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(cursor, RT_CHUNK);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= total) { exhausted = true; return false; }
-        next = base;
-        end = min(base + RT_CHUNK, total);
+    uint32_t pending;  // lane 0: base of the next batch, possibly still in flight
+    __device__ __forceinline__ void init(unsigned int* cursor) { pending = lane_id() == 0 ? atomicAdd(cursor, RT_CHUNK) : 0u; }
+    // base of the next batch into `base`; false when the queue has run dry
+    __device__ __forceinline__ bool next(unsigned int* cursor, uint32_t total, uint32_t& base) {
+        base = __shfl_sync(0xFFFFFFFFu, pending, 0);
+        if (base >= total) return false;
+        if (lane_id() == 0) pending = atomicAdd(cursor, RT_CHUNK);
         return true;
     }
 };
@@ -165,10 +166,10 @@ __device__ __forceinline__ void trace_phase(const SceneDev& S, const FrameDev& F
     RayRec* __restrict__ out_q = F.ray_q[seg & 1u];
     SegCounters* sc = seg_counters(F, seg);
     WarpChunk wc;
-    wc.init();
-    while (wc.ensure(&sc->work_next[K_TRACE], total)) {
-        uint32_t item = wc.next + lane_id();
-        wc.next += 32u;
+    wc.init(&sc->work_next[K_TRACE]);
+    uint32_t batch;
+    while (wc.next(&sc->work_next[K_TRACE], total, batch)) {
+        uint32_t item = batch + lane_id();
         bool active = false;
         uint32_t pixel = 0;
         V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
@@ -209,22 +210,25 @@ __device__ __forceinline__ void trace_phase(const SceneDev& S, const FrameDev& F
             if (bounce && ndir.x == 0.0f && ndir.y == 0.0f && ndir.z == 0.0f) bounce = false;
             if (bounce && seg + 1u >= F.max_segments) bounce = false;  // loop bound reached: colour stays 0
         }
-        if (active && !textured && !bounce) {
+        WarpPush hp, rp;
+        hp.reserve(&sc->hit_count, textured);   // the two queue reservations are in flight ...
+        rp.reserve(&sc->ray_count, bounce);
+        if (active && !textured && !bounce) {    // ... while the finished pixels are encoded and stored
             V3 c = got ? v3(0.f, 0.f, 0.f) : miss_colour(F.uniforms, F.cos_sun_radius, d);
             write_pixel(F, pixel, c);
         }
-        uint32_t hslot = warp_push(&sc->hit_count, textured);
+        uint32_t hslot = hp.slot();
         if (textured) {
             HitRec* hr = F.hit_q + hslot;
             reinterpret_cast<uint4*>(hr)[0] = make_uint4(pixel, h.inst_pos, h.geom, h.prim);
             reinterpret_cast<float4*>(hr)[1] = make_float4(h.u, h.v, h.t, 0.f);
             reinterpret_cast<float4*>(hr)[2] = make_float4(d.x, d.y, d.z, 0.f);
         }
-        uint32_t rslot = warp_push(&sc->ray_count, bounce);
+        uint32_t rslot = rp.slot();
         if (bounce) {
-            float4* rp = reinterpret_cast<float4*>(out_q + rslot);
-            rp[0] = make_float4(no.x, no.y, no.z, __uint_as_float(pixel));
-            rp[1] = make_float4(ndir.x, ndir.y, ndir.z, 0.f);
+            float4* rq = reinterpret_cast<float4*>(out_q + rslot);
+            rq[0] = make_float4(no.x, no.y, no.z, __uint_as_float(pixel));
+            rq[1] = make_float4(ndir.x, ndir.y, ndir.z, 0.f);
         }
     }
     flush_ray_counters(F, n_primary, 0, 0);
@@ -282,10 +286,10 @@ __device__ __forceinline__ void shadow_phase(const SceneDev& S, const FrameDev& 
     const SunFrame sun = make_sun_frame(F.uniforms);
     uint32_t n_shadow = 0;
     WarpChunk wc;
-    wc.init();
-    while (wc.ensure(&sc->work_next[K_SHADOW], total)) {
-        uint32_t item = wc.next + lane_id();
-        wc.next += 32u;
+    wc.init(&sc->work_next[K_SHADOW]);
+    uint32_t batch;
+    while (wc.next(&sc->work_next[K_SHADOW], total, batch)) {
+        uint32_t item = batch + lane_id();
         if (item < total) {
             uint32_t hi = item / n, i = item - hi * n;
             HitRec* hr = F.hit_q + hi;
