@@ -115,6 +115,8 @@ struct RtContext {
     size_t fb_rgba8_cap = 0, fb_radiance_cap = 0, fb_hit_ids_cap = 0;
     size_t last_rows = 0, last_tw = 0;
     uint64_t* d_ray_counts = nullptr;
+    float4* d_sun_dirs = nullptr;
+    size_t sun_dirs_cap = 0;
 
     // two frames in flight (rt_render_async)
     struct FrameSlot {
@@ -260,6 +262,15 @@ int render_common(RtContext* ctx, const RtUniforms* u, const RtRenderParams* p, 
     F.counters = ctx->d_counters;
     F.ray_q[0] = ctx->d_ray_q[0]; F.ray_q[1] = ctx->d_ray_q[1];
     F.hit_q = ctx->d_hit_q;
+    // per-frame shadow-direction table: only for the 64x64 nearest-filtered blue-noise image the shaders assume
+    F.sun_dirs = nullptr;
+    if (u->blue_noise_texture_index < ctx->tex_host.size()) {
+        const TexEntry& bn = ctx->tex_host[u->blue_noise_texture_index];
+        if (bn.obj != 0 && bn.w == 64 && bn.h == 64 && !bn.linear && p->shadow_rays <= 64) {
+            CK(grow(ctx->d_sun_dirs, ctx->sun_dirs_cap, (size_t)4096 * p->shadow_rays));
+            F.sun_dirs = ctx->d_sun_dirs;
+        }
+    }
     CK(cudaMemcpyAsync(ctx->d_uniforms, u, sizeof(RtUniforms), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     FrameTiming* timing = nullptr;
@@ -358,7 +369,7 @@ void rt_destroy(RtContext* ctx) {
     cudaFree(ctx->d_instances); cudaFree(ctx->d_inst_unsorted); cudaFree(ctx->d_inst_rt); cudaFree(ctx->d_inst_boxes);
     cudaFree(ctx->d_leaf_order); cudaFree(ctx->d_tlas_nodes); cudaFree(ctx->d_tlas_node_count); cudaFree(ctx->d_ray_counts);
     cudaFree(ctx->d_ray_q[0]); cudaFree(ctx->d_ray_q[1]); cudaFree(ctx->d_hit_q);
-    cudaFree(ctx->d_fb_rgba8); cudaFree(ctx->d_fb_radiance); cudaFree(ctx->d_fb_hit_ids);
+    cudaFree(ctx->d_fb_rgba8); cudaFree(ctx->d_fb_radiance); cudaFree(ctx->d_fb_hit_ids); cudaFree(ctx->d_sun_dirs);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->timing_ready)
@@ -528,7 +539,7 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     M.positions = m.positions; M.indices = d_index_ptrs; M.geom_start = d_geom_start; M.geom_opaque = d_geom_opaque;
     M.num_geoms = ng; M.num_tris = nt; M.num_vertices = nv;
     CKT(launch_triangle_boxes(M, d_boxes, st));
-    CKT(ctx->builder.build(d_boxes, nt, 4, ctx->blas_nodes.ptr, node_offset, prim_offset, d_leaf_order, d_count, false, st));
+    CKT(ctx->builder.build(d_boxes, nt, RT_BLAS_LEAF_TRIS, ctx->blas_nodes.ptr, node_offset, prim_offset, d_leaf_order, d_count, false, st));
     CKT(launch_gather_triangles(M, d_leaf_order, ctx->tris.ptr + prim_offset, st));
     uint32_t node_count = 0;
     Node8 root;

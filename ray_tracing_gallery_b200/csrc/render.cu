@@ -111,8 +111,14 @@ __device__ __forceinline__ void flush_ray_counters(const FrameDev& F, uint32_t n
 template <bool COUNT>
 __device__ __forceinline__ bool shadow_sample_lit(const SceneDev& S, const FrameDev& F, const SunFrame& sun, uint32_t px, uint32_t py,
                                                   uint32_t i, V3 origin, TraceCounters& tc) {
-    V2 xi = blue_noise_xi(S, F.uniforms.blue_noise_texture_index, px, py, i, F.uniforms.frame_index);
-    V3 dir = sample_directional_light(xi, sun, F.uniforms.sun_radius);
+    V3 dir;
+    if (F.sun_dirs) {
+        float4 t = __ldg(F.sun_dirs + ((size_t)(((py & 63u) << 6) | (px & 63u)) * F.shadow_rays + i));
+        dir = v3(t.x, t.y, t.z);
+    } else {
+        V2 xi = blue_noise_xi(S, F.uniforms.blue_noise_texture_index, px, py, i, F.uniforms.frame_index);
+        dir = sample_directional_light(xi, sun, F.uniforms.sun_radius);
+    }
     Hit sh;
     return !trace_ray<true, COUNT>(S, origin, dir, 0.001f, 10000.0f, sh, tc);
 }
@@ -192,7 +198,7 @@ __device__ __forceinline__ void trace_phase(const SceneDev& S, const FrameDev& F
         Hit h;
         bool got = false;
         if (active) {
-            got = trace_ray<false, COUNT>(S, o, d, 0.01f, 10000.0f, h, tc);  // lib.rs:151-163
+            got = trace_ray<false, COUNT, SEG0>(S, o, d, 0.01f, 10000.0f, h, tc);  // lib.rs:151-163
             n_primary++;
         }
         uint32_t kind = got ? (h.custom_sbt >> 24) : 0xFFFFFFFFu;  // hit group = instance sbt offset (main.rs:289-305)
@@ -430,6 +436,18 @@ __global__ void __launch_bounds__(128) k_mega(SceneDev S, FrameDev F, uint32_t t
     flush_trace_counters<COUNT>(F, 1, tcs);
 }
 
+// sample_directional_light(animated_blue_noise(..)) for every (pixel mod 64, sample) of the frame
+__global__ void __launch_bounds__(128) k_sun_dirs(SceneDev S, FrameDev F, float4* out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = F.shadow_rays;
+    if (t >= 4096u * n) return;
+    uint32_t cell = t / n, i = t - cell * n;
+    const SunFrame sun = make_sun_frame(F.uniforms);
+    V2 xi = blue_noise_xi(S, F.uniforms.blue_noise_texture_index, cell & 63u, cell >> 6, i, F.uniforms.frame_index);
+    V3 d = sample_directional_light(xi, sun, F.uniforms.sun_radius);
+    out[t] = make_float4(d.x, d.y, d.z, 0.f);
+}
+
 __global__ void k_export_counts(const FrameCounters* c, uint64_t* out) {
     out[0] = c->primary_rays;
     out[1] = c->shadow_rays;
@@ -466,6 +484,10 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
     if (total == 0 || F.max_segments == 0) {
         if (d_ray_counts) { k_export_counts<<<1, 1, 0, stream>>>(F.counters, d_ray_counts); note_launch(); }
         return cudaGetLastError();
+    }
+    if (F.sun_dirs) {
+        k_sun_dirs<<<(4096u * F.shadow_rays + 127u) / 128u, 128, 0, stream>>>(S, F, const_cast<float4*>(F.sun_dirs));
+        note_launch();
     }
     if (pipeline == RT_PIPELINE_MEGAKERNEL) {
         if (count) k_mega<true><<<(total + 127) / 128, 128, 0, stream>>>(S, F, total);

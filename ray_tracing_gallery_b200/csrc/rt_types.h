@@ -51,6 +51,9 @@ static_assert(sizeof(TriRec) == 48, "TriRec is 48 bytes");
 // A BLAS of at most this many triangles (ground planes, quads, billboards) is tested directly on instance entry:
 // its single node would cost more than the triangles it culls.
 #define RT_TINY_BLAS_TRIS 4u
+// Triangles per BLAS leaf slot.  Measured on C2/C4 with 2/4/6/7: a triangle test costs about a third of a node
+// visit and culls nothing, so small leaves win (profiles/r01_notes.md).
+#define RT_BLAS_LEAF_TRIS 2u
 
 // Per-instance traversal record in TLAS leaf order: four float4.
 struct __align__(16) InstRT {
@@ -149,6 +152,10 @@ struct FrameDev {
     FrameCounters* counters;
     RayRec*   ray_q[2];
     HitRec*   hit_q;
+    // Shadow-ray directions of this frame, [64][64][shadow_rays] float4 indexed by (py & 63, px & 63, sample): the
+    // blue-noise sample depends on the pixel only through (px, py) mod 64 (closest_hit_textured.glsl:99-111), so the
+    // 4096 * N distinct directions are computed once per frame (k_sun_dirs).  nullptr: compute per ray.
+    const float4* sun_dirs;
 };
 
 }  // namespace b200rt

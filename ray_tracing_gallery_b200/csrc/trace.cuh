@@ -43,10 +43,14 @@ struct TraceCounters {
     uint32_t nodes, instances, tris, anyhits, overflow;
 };
 
+// 1/x for the slab tests only (never for hit distances): one MUFU.RCP.  Its relative error (2^-23) moves every
+// plane parameter by |t|*2^-23 <= (|b| + 255|a|)*2^-23, well inside the outward padding p of the box test.
 __device__ __forceinline__ float safe_rcp(float x) {
     float ax = fabsf(x);
     if (!(ax >= 1e-12f)) x = copysignf(1e-12f, x);
-    return __frcp_rn(x);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // 8-bit mask of non-zero bytes of (lo, hi)
@@ -102,6 +106,20 @@ struct Traverser {
     }
 
     __device__ __forceinline__ bool found() const { return hit.inst_pos != RT_NONE; }
+
+    // Call right after begin(): false when the ray cannot touch the scene at all (slab test against the exact
+    // bounds of the TLAS root, padded for the approximate reciprocals).  Saves the 8-child test of the root
+    // for sky rays; only worth its ~20 instructions for rays that start outside the scene (primary rays).
+    __device__ __forceinline__ bool touches_scene(const SceneDev& S) const {
+        const float4* rb = reinterpret_cast<const float4*>(S.tlas_nodes) + 5;  // bytes 80..111: lo[3], hi[3], parent, slot
+        float4 a = __ldg(rb), b = __ldg(rb + 1);
+        float x0 = (a.x - o.x) * idx, x1 = (a.w - o.x) * idx;
+        float y0 = (a.y - o.y) * idy, y1 = (b.x - o.y) * idy;
+        float z0 = (a.z - o.z) * idz, z1 = (b.y - o.z) * idz;
+        float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+        float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+        return !(tn > tf + 4e-6f * (fabsf(tn) + fabsf(tf)) + 1e-30f);  // NaN (empty scene bounds) -> traverse
+    }
 
     __device__ __forceinline__ void push(uint2* stack, uint32_t x, uint32_t y, TraceCounters& tc) {
         if (sp < RT_STACK_SIZE) stack[sp++] = make_uint2(x, y);
@@ -267,11 +285,12 @@ struct Traverser {
 };
 
 // Run one ray to completion (megakernel path, tests).
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool OUTSIDE_START = false>
 __device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float tmin, float tmax, Hit& hit, TraceCounters& tc) {
     uint2 stack[RT_STACK_SIZE];
     Traverser<ANY, COUNT> T;
     T.begin(o, d, tmin, tmax);
+    if (OUTSIDE_START && !T.touches_scene(S)) { hit = T.hit; return false; }
     while (!T.step(S, stack, tc)) {}
     hit = T.hit;
     return T.found();
