@@ -193,7 +193,7 @@ int build_tlas_now(RtContext* ctx, uint32_t mode) {
     } else {
         CK(launch_prepare_instances(ctx->d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), nullptr,
                                     ctx->d_inst_unsorted, ctx->d_inst_boxes, st));
-        CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, ctx->d_tlas_nodes, 0, 0, ctx->d_leaf_order, ctx->d_tlas_node_count, true, st));
+        CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, ctx->d_tlas_nodes, 0, 0, ctx->d_leaf_order, ctx->d_tlas_node_count, true, /*sah_collapse=*/true, st));
         CK(launch_gather_instances(ctx->d_inst_unsorted, ctx->d_leaf_order, n, ctx->d_inst_rt, st));
     }
     CK(cudaEventRecord(ctx->ev[3], st));
@@ -539,7 +539,7 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     M.positions = m.positions; M.indices = d_index_ptrs; M.geom_start = d_geom_start; M.geom_opaque = d_geom_opaque;
     M.num_geoms = ng; M.num_tris = nt; M.num_vertices = nv;
     CKT(launch_triangle_boxes(M, d_boxes, st));
-    CKT(ctx->builder.build(d_boxes, nt, RT_BLAS_LEAF_TRIS, ctx->blas_nodes.ptr, node_offset, prim_offset, d_leaf_order, d_count, false, st));
+    CKT(ctx->builder.build(d_boxes, nt, RT_BLAS_LEAF_TRIS, ctx->blas_nodes.ptr, node_offset, prim_offset, d_leaf_order, d_count, false, /*sah_collapse=*/false, st));
     CKT(launch_gather_triangles(M, d_leaf_order, ctx->tris.ptr + prim_offset, st));
     uint32_t node_count = 0;
     Node8 root;

@@ -5,10 +5,14 @@
 //   3. radix sort                 cub::DeviceRadixSort::SortPairs (64-bit key, 32-bit payload)
 //   4. binary radix tree          k_hierarchy          (Karras 2012, index tie-break for duplicates)
 //   5. bottom-up AABB fit         k_fit                (one atomic flag per internal node)
+//      + in the same pass: SAH-optimal collapse table per binary node (dynamic programme of
+//        Ylitie et al. 2017, "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide
+//        BVHs", sec. 3.1): cost[n][i] = cheapest way to hand subtree n to a parent that can spare
+//        i slots, i = 1..7, with the decisions that achieve it
 //   6. collapse to 8-wide nodes   k_collapse_coop      (breadth-first, one cooperative launch:
 //                                                      task index == wide-node index, so the BFS
 //                                                      queue IS the node array; grid.sync per level)
-//      - children chosen by greedy largest-surface-area expansion of the binary tree
+//      - children of a wide node: the 8-slot cut of the binary tree the table says is cheapest
 //      - slots assigned by child-centre octant => front-to-back order is (slot XOR ray octant)
 //      - boxes quantised to 8 bits on an exactly representable power-of-two grid
 //   7. refit (TLAS update)        k_refit              (bottom-up over wide nodes)
@@ -163,6 +167,12 @@ struct Tree2 {
     uint32_t* flags;
     const Aabb* boxes;      // input boxes (by input primitive)
     int n;
+    // SAH collapse table, per internal node
+    float* dp_cost;         // [n][7]: cost with i+1 slots
+    uint8_t* dp_dec;        // [n][8]: [0] 0 = leaf / 1 = internal node when given ONE slot; [i] (i = 1..6) left child's share of i+1
+                            //         slots, 0 = no better than i slots; [7] left child's share of this node's own 8 slots
+    uint32_t max_leaf;
+    float c_node, c_prim;   // cost of visiting a wide node / of processing one leaf primitive, per unit of box area
 };
 
 __device__ __forceinline__ int delta(const uint64_t* __restrict__ k, int n, int i, int j) {
@@ -210,6 +220,18 @@ __device__ __forceinline__ Aabb ref_box_cg(const Tree2& T, int ref) {
     return ldcg_box(&T.ibox[ref]);
 }
 
+// cost[1..7] of handing child `ref` i slots (a single primitive costs the same whatever it is given)
+__device__ __forceinline__ void child_costs(const Tree2& T, int ref, float* c /* [8], index 1..7 */) {
+    if (ref < 0) {
+        float a = box_area(T.boxes[T.vals[~ref]]) * T.c_prim;
+#pragma unroll
+        for (int i = 1; i <= 7; i++) c[i] = a;
+    } else {
+#pragma unroll
+        for (int i = 1; i <= 7; i++) c[i] = __ldcg(T.dp_cost + (size_t)ref * 7 + (i - 1));
+    }
+}
+
 __global__ void k_fit(Tree2 T) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= T.n) return;
@@ -218,15 +240,56 @@ __global__ void k_fit(Tree2 T) {
         __threadfence();
         unsigned old = atomicAdd(&T.flags[cur], 1u);
         if (old == 0) return;
+        __threadfence();
         Aabb b = box_empty();
-        box_grow(b, ref_box_cg(T, T.left[cur]));
-        box_grow(b, ref_box_cg(T, T.right[cur]));
+        int L = T.left[cur], R = T.right[cur];
+        box_grow(b, ref_box_cg(T, L));
+        box_grow(b, ref_box_cg(T, R));
         float* f = reinterpret_cast<float*>(&T.ibox[cur]);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             __stcg(f + k, b.lo[k]);
             __stcg(f + 3 + k, b.hi[k]);
         }
+        if (T.dp_cost == nullptr) { cur = T.parent_int[cur]; continue; }
+        // ---- collapse table
+        float cl[8], cr[8], cost[8];
+        child_costs(T, L, cl);
+        child_costs(T, R, cr);
+        float area = box_area(b);
+        float best = CUDART_INF_F;
+        int bk = 1;
+#pragma unroll
+        for (int k = 1; k <= 7; k++) {
+            float c = cl[k] + cr[8 - k];
+            if (c < best) { best = c; bk = k; }
+        }
+        uint8_t dec[8];
+        dec[7] = (uint8_t)bk;
+        cost[1] = area * T.c_node + best;
+        dec[0] = 1;
+        uint32_t count = T.last[cur] - T.first[cur] + 1u;
+        if (count <= T.max_leaf) {
+            float lc = area * (float)count * T.c_prim;
+            if (lc <= cost[1]) { cost[1] = lc; dec[0] = 0; }
+        }
+#pragma unroll
+        for (int i = 2; i <= 7; i++) {
+            float bi = cost[i - 1];
+            int d = 0;
+            for (int k = 1; k < i; k++) {
+                float c = cl[k] + cr[i - k];
+                if (c < bi) { bi = c; d = k; }
+            }
+            cost[i] = bi;
+            dec[i - 1] = (uint8_t)d;
+        }
+#pragma unroll
+        for (int i = 1; i <= 7; i++) __stcg(T.dp_cost + (size_t)cur * 7 + (i - 1), cost[i]);
+        uint2 dw;
+        dw.x = dec[0] | (dec[1] << 8) | (dec[2] << 16) | ((uint32_t)dec[3] << 24);
+        dw.y = dec[4] | (dec[5] << 8) | (dec[6] << 16) | ((uint32_t)dec[7] << 24);
+        __stcg(reinterpret_cast<uint2*>(T.dp_dec + (size_t)cur * 8), dw);
         cur = T.parent_int[cur];
     }
 }
@@ -304,6 +367,7 @@ struct CollapseArgs {
     uint32_t node_offset, prim_offset, max_leaf;
     uint32_t* leaf_order;
     uint32_t* node_count_out;  // optional: receives the number of wide nodes written
+    bool greedy;               // children by greedy largest-area expansion instead of the SAH table
 };
 
 __device__ __forceinline__ uint32_t ref_count(const Tree2& T, int r) { return r < 0 ? 1u : T.last[r] - T.first[r] + 1u; }
@@ -312,27 +376,47 @@ __device__ __forceinline__ Aabb ref_box(const Tree2& T, int r) { return r < 0 ? 
 
 __device__ void collapse_task(const CollapseArgs& A, uint32_t w) {
     const Tree2& T = A.T;
-    int ch[8];
-    int cnt;
+    int ch[8];            // children of this wide node: binary subtree refs
+    bool internal[8];     //   true: becomes a wide node of its own; false: leaf slot holding the subtree's primitives
+    int cnt = 0;
     int r = A.task_node[w];
-    if (r < 0) { ch[0] = r; cnt = 1; }
-    else { ch[0] = T.left[r]; ch[1] = T.right[r]; cnt = 2; }
-    // greedy expansion by surface area: first only subtrees too big to be a leaf, then any subtree
-    for (int pass = 0; pass < 2; pass++) {
-        while (cnt < 8) {
-            int best = -1;
-            float best_area = -1.0f;
-            for (int j = 0; j < cnt; j++) {
-                int c = ch[j];
-                if (c < 0) continue;
-                if (pass == 0 && ref_count(T, c) <= A.max_leaf) continue;
-                float a = box_area(T.ibox[c]);
-                if (a > best_area) { best_area = a; best = j; }
+    if (r < 0) { ch[0] = r; internal[0] = false; cnt = 1; }
+    else if (A.greedy) {
+        // greedy expansion by surface area: first only subtrees too big to be a leaf, then any subtree
+        ch[0] = T.left[r]; ch[1] = T.right[r]; cnt = 2;
+        for (int pass = 0; pass < 2; pass++) {
+            while (cnt < 8) {
+                int best = -1;
+                float best_area = -1.0f;
+                for (int j = 0; j < cnt; j++) {
+                    int c = ch[j];
+                    if (c < 0) continue;
+                    if (pass == 0 && ref_count(T, c) <= A.max_leaf) continue;
+                    float a = box_area(T.ibox[c]);
+                    if (a > best_area) { best_area = a; best = j; }
+                }
+                if (best < 0) break;
+                int c = ch[best];
+                ch[best] = T.left[c];
+                ch[cnt++] = T.right[c];
             }
-            if (best < 0) break;
-            int c = ch[best];
-            ch[best] = T.left[c];
-            ch[cnt++] = T.right[c];
+        }
+        for (int j = 0; j < cnt; j++) internal[j] = ch[j] >= 0 && ref_count(T, ch[j]) > A.max_leaf;
+    } else {
+        // walk the cheapest 8-slot cut recorded by k_fit
+        int st_node[8], st_slots[8], sp = 0;
+        int k = T.dp_dec[(size_t)r * 8 + 7];
+        st_node[sp] = T.right[r]; st_slots[sp++] = 8 - k;
+        st_node[sp] = T.left[r]; st_slots[sp++] = k;
+        while (sp > 0) {
+            int n = st_node[--sp], i = st_slots[sp];
+            if (n < 0) { ch[cnt] = n; internal[cnt++] = false; continue; }
+            const uint8_t* dec = T.dp_dec + (size_t)n * 8;
+            int d = 0;
+            while (i >= 2 && (d = dec[i - 1]) == 0) i--;  // i slots are no better than i-1
+            if (i == 1) { ch[cnt] = n; internal[cnt++] = dec[0] != 0; continue; }
+            st_node[sp] = T.right[n]; st_slots[sp++] = i - d;
+            st_node[sp] = T.left[n]; st_slots[sp++] = d;
         }
     }
     Aabb cb[8];
@@ -362,9 +446,8 @@ __device__ void collapse_task(const CollapseArgs& A, uint32_t w) {
     }
     uint32_t k_int = 0, total_prims = 0;
     for (int j = 0; j < cnt; j++) {
-        uint32_t c = ref_count(T, ch[j]);
-        if (ch[j] >= 0 && c > A.max_leaf) k_int++;
-        else total_prims += c;
+        if (internal[j]) k_int++;
+        else total_prims += ref_count(T, ch[j]);
     }
     uint32_t base = k_int ? atomicAdd(&A.state[ST_WIDE_COUNT], k_int) : 0u;
     uint32_t pbase = total_prims ? atomicAdd(&A.state[ST_PRIM_CURSOR], total_prims) : 0u;
@@ -379,7 +462,7 @@ __device__ void collapse_task(const CollapseArgs& A, uint32_t w) {
         present |= 1u << s;
         sb[s] = cb[j];
         uint32_t c = ref_count(T, ch[j]);
-        if (ch[j] >= 0 && c > A.max_leaf) {
+        if (internal[j]) {
             imask |= 1u << s;
             nd.meta[s] = 0xFF;
             A.task_node[base + rank] = ch[j];
@@ -511,6 +594,8 @@ struct Scratch {
     int *left, *right, *parent_int, *parent_leaf;
     uint32_t *first, *last, *flags;
     Aabb* ibox;
+    float* dp_cost;
+    uint8_t* dp_dec;
     int* task_node;
     uint32_t* task_parent;
     uint32_t* refit_counters;
@@ -534,6 +619,8 @@ size_t layout(char* base, uint32_t n, size_t cub_bytes, Scratch& s) {
     s.last = carve<uint32_t>(p, n);
     s.flags = carve<uint32_t>(p, n);
     s.ibox = carve<Aabb>(p, n);
+    s.dp_cost = carve<float>(p, (size_t)n * 7);
+    s.dp_dec = carve<uint8_t>(p, (size_t)n * 8);
     s.task_node = carve<int>(p, maxw);
     s.task_parent = carve<uint32_t>(p, maxw);
     s.refit_counters = carve<uint32_t>(p, maxw);
@@ -578,7 +665,7 @@ cudaError_t BvhBuilder::reserve(uint32_t n) {
 }
 
 cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
-                              uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, cudaStream_t stream) {
+                              uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, bool sah_collapse, cudaStream_t stream) {
     cudaError_t e = reserve(n);
     if (e != cudaSuccess) return e;
     Scratch s;
@@ -610,6 +697,11 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
     T.left = s.left; T.right = s.right; T.parent_int = s.parent_int; T.parent_leaf = s.parent_leaf;
     T.first = s.first; T.last = s.last; T.ibox = s.ibox; T.flags = s.flags;
     T.boxes = d_boxes; T.n = (int)n;
+    T.dp_cost = sah_collapse ? s.dp_cost : nullptr; T.dp_dec = s.dp_dec;
+    T.max_leaf = max_leaf;
+    // one node visit costs about three triangle tests (220 vs 70 instructions, profiles/r01_notes.md); entering an
+    // instance (TLAS leaves, max_leaf == 1) is a constant per primitive and does not influence the cut
+    T.c_node = 3.0f; T.c_prim = 1.0f;
     if (n >= 2) {
         cudaMemsetAsync(s.flags, 0, sizeof(uint32_t) * n, stream);
         k_hierarchy<<<blocks, TB, 0, stream>>>(T);
@@ -621,6 +713,7 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
     A.nodes = nodes_pool; A.node_offset = node_offset; A.prim_offset = prim_offset; A.max_leaf = max_leaf;
     A.leaf_order = d_leaf_order;
     A.node_count_out = d_node_count;
+    A.greedy = !sah_collapse;
     bool done = false;
     bool count_written = false;
     if (coop_ok_) {

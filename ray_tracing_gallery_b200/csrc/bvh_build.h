@@ -7,9 +7,9 @@
 
 namespace b200rt {
 
-// Upper bound on wide nodes for n primitives: every non-bottom node absorbs 7 binary nodes,
-// every bottom node holds >= 2 primitives.
-inline uint32_t max_wide_nodes(uint32_t n) { return n / 2 + n / 7 + 8; }
+// Upper bound on wide nodes for n primitives: every wide node is rooted at its own binary internal node
+// (n - 1 of them) and the cost-driven cut gives no tighter guarantee.
+inline uint32_t max_wide_nodes(uint32_t n) { return n + 8; }
 
 class BvhBuilder {
 public:
@@ -26,10 +26,11 @@ public:
     // child indices are absolute pool indices, prim_base values are prim_offset + position in
     // leaf order.  d_leaf_order[i] = index of the input primitive stored at leaf position i.
     // d_node_count (device, optional) receives the number of wide nodes written.
+    // sah_collapse: children of each wide node from the SAH-optimal cut table (else greedy largest-area expansion).
     // fast_sort: Morton keys keep only as many bits as n needs (fewer radix passes; per-frame TLAS rebuilds).
     // Everything is enqueued on `stream`; no host synchronisation.
     cudaError_t build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
-                      uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, cudaStream_t stream);
+                      uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, bool sah_collapse, cudaStream_t stream);
 
     // Refit in place: recompute boxes bottom-up for a tree built by build() whose leaf order is
     // unchanged.  d_boxes_leaf_order[i] = new box of the primitive at leaf position i.

@@ -32,6 +32,7 @@ gpu.render(s.uniforms(), s.params(pipeline=pipe, flags=abi.RT_RENDER_COUNTERS), 
 st = gpu.stats()
 rays = st.primary_rays + st.shadow_rays
 print(f"[{a.workload}] {s.width}x{s.height} instances {len(s.instances)} tlas_nodes {st.tlas_nodes} blas_nodes {st.blas_nodes} tris {st.num_triangles}")
+print(f"  TLAS build {st.last_tlas_ms:.3f} ms")
 print(f"  rays: primary {st.primary_rays} shadow {st.shadow_rays} textured hits {st.textured_hits}")
 for k, nm in enumerate(("closest-hit", "shadow")):
     n = (st.primary_rays, st.shadow_rays)[k] or 1
@@ -52,4 +53,13 @@ for i in range(a.frames):
     tot += st.last_render_ms
 print("  kernel ms/frame:", {n: round(float(v) / a.frames, 4) for n, v in zip(names, acc)}, "render ms", round(tot / a.frames, 4),
       "Mrays/s", round(rays / (tot / a.frames) / 1e3, 1))
+if a.workload in ("c4", "c5"):
+    import time
+    for mode, name in ((abi.RT_UPDATE_REFIT, "refit"), (abi.RT_UPDATE_REBUILD, "rebuild")):
+        ms = []
+        for i in range(5):
+            gpu.update_instances(0, s.instances)
+            gpu.update_tlas(mode)
+            ms.append(gpu.stats().last_tlas_ms)
+        print(f"  TLAS {name}: {min(ms):.3f} ms (best of 5, CUDA events)")
 gpu.close()
