@@ -142,6 +142,12 @@ __device__ __forceinline__ V3 shade_textured(const SceneDev& S, const FrameDev& 
 // ------------------------------------------------------------------------------------ wavefront
 enum { K_TRACE = 0, K_PREP = 1, K_SHADOW = 2, K_RESOLVE = 3, K_MEGA = 4, K_TAIL = 5 };
 
+#ifndef RT_TRACE_MINB
+#define RT_TRACE_MINB 5
+#endif
+#ifndef RT_SHADOW_MINB
+#define RT_SHADOW_MINB 7
+#endif
 #define RT_CHUNK 32u   // work items a warp takes from a queue cursor per atomic (128 measured slower: coarser tail)
 
 __device__ __forceinline__ SegCounters* seg_counters(const FrameDev& F, uint32_t seg) { return &F.counters->seg[seg & (RT_SEG_SLOTS - 1u)]; }
@@ -333,7 +339,7 @@ __device__ __forceinline__ void resolve_phase(const FrameDev& F, uint32_t seg) {
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace0(SceneDev S, FrameDev F, uint32_t total) { trace_phase<true, COUNT>(S, F, 0, total); }
+__global__ void __launch_bounds__(128, RT_TRACE_MINB) k_trace0(SceneDev S, FrameDev F, uint32_t total) { trace_phase<true, COUNT>(S, F, 0, total); }
 // bounce segment as its own launch (RT_RENDER_SPLIT_TAIL): the ray count is read on the device
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_n(SceneDev S, FrameDev F, uint32_t seg) {
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(128) k_trace_n(SceneDev S, FrameDev F, uint32_
 }
 __global__ void __launch_bounds__(128) k_prep(SceneDev S, FrameDev F, uint32_t seg) { prep_phase(S, F, seg); }
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow(SceneDev S, FrameDev F, uint32_t seg) { shadow_phase<COUNT>(S, F, seg); }
+__global__ void __launch_bounds__(128, RT_SHADOW_MINB) k_shadow(SceneDev S, FrameDev F, uint32_t seg) { shadow_phase<COUNT>(S, F, seg); }
 __global__ void __launch_bounds__(128) k_resolve(FrameDev F, uint32_t seg) { resolve_phase(F, seg); }
 
 // segments >= RT_SEG_SLOTS reuse a counter slot (split-tail path)
