@@ -73,6 +73,16 @@ def f_barrier(i):
     dist.barrier()
 
 
+# correctness: the gathered, de-interleaved frame equals the frame one GPU renders alone
+render(0)
+dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
+torch.cuda.synchronize()
+if rank == 0:
+    full = torch.zeros((s.height, s.width, 4), dtype=torch.uint8, device=dev)
+    gpu.render_device(s.uniforms(frame_index=1), s.params(), rgba8=full.data_ptr(), ray_counts=rays.data_ptr())
+    torch.cuda.synchronize()
+    same = bool(torch.equal(full, deinterleave(gathered, part)))
+    print(f"[{wl}] world {world}: gathered frame == single-GPU frame: {same}", flush=True)
 res = {}
 for name, fn in [("render", f_render), ("all_gather only", f_gather), ("render+gather", f_render_gather), ("full", f_full)]:
     res[name] = timeit(fn)
