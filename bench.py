@@ -207,7 +207,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from ray_tracing_gallery_b200 import abi, native
-    from ray_tracing_gallery_b200.dist import Partition, broadcast_instances, deinterleave
+    from ray_tracing_gallery_b200.dist import Partition, broadcast_instances, deinterleave, deinterleave_into
     from ray_tracing_gallery_b200.scene import build_scene
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,6 +237,7 @@ def run_ours(args):
 
     fb = torch.zeros((rows, W, 4), dtype=torch.uint8, device=dev)
     gathered = torch.zeros((world, rows, W, 4), dtype=torch.uint8, device=dev) if world > 1 else None
+    final_dev = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
     rays_dev = torch.zeros(2, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     inst_dev = torch.zeros(len(s.instances) * 64, dtype=torch.uint8, device=dev) if s.dynamic else None
@@ -277,7 +278,7 @@ def run_ours(args):
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
             if rank == 0:
-                deinterleave(gathered, part)
+                deinterleave_into(final_dev, gathered, part)
 
     # ---- one instrumented frame: deterministic traversal counters for the roofline accounting
     step_device(0, abi.RT_RENDER_COUNTERS)
@@ -336,8 +337,13 @@ def run_ours(args):
     #      N = 1: rt_render_async, two frames in flight like the reference (src/main.rs:917-928): every step copies its
     #      uniforms (and instance records) H2D and its finished frame + ray counts D2H into pinned host memory; the copy
     #      of frame i overlaps the rendering of frame i+1; the step's result is consumed after rt_wait_frame.
-    host_fbs = [host_fb, torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()] if world == 1 else [host_fb]
+    host_fbs = [host_fb, torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()] if (world == 1 or rank == 0) else [host_fb, host_fb]
     host_rays2 = [host_rays, torch.zeros(2, dtype=torch.int64).pin_memory()]
+    copy_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    mg_final = [torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    mg_rays = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(2)]
+    mg_done = [torch.cuda.Event(), torch.cuda.Event()]
+    mg_copied = [None, None]
 
     def e2e_run(first, count):
         rays, pending = 0, []
@@ -358,13 +364,31 @@ def run_ours(args):
                     gpu.wait_frame(sl)
                     rays += int(host_rays2[pb].sum().item())
             else:
-                gpu.render_device(frame_inputs(i), params(), rgba8=fb.data_ptr(), ray_counts=rays_dev.data_ptr())
+                # N > 1, the same two-frames-in-flight scheme with torch streams: render + all-gather (+ de-interleave on
+                # rank 0) on the main stream into device slot b, D2H copies of slot b on the copy stream
+                b = k & 1
+                if mg_copied[b] is not None:       # slot b's previous frame: its fence, then consume its result
+                    mg_copied[b].synchronize()
+                    rays += int(host_rays2[b].sum().item())
+                gpu.render_device(frame_inputs(i), params(), rgba8=fb.data_ptr(), ray_counts=mg_rays[b].data_ptr())
                 dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
                 if rank == 0:
-                    host_fb.copy_(deinterleave(gathered, part), non_blocking=True)
-                host_rays.copy_(rays_dev, non_blocking=True)
-                torch.cuda.synchronize()
-                rays += int(host_rays.sum().item())
+                    deinterleave_into(mg_final[b], gathered, part)
+                mg_done[b].record(stream)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(mg_done[b])
+                    if rank == 0:
+                        host_fbs[b].copy_(mg_final[b], non_blocking=True)
+                    host_rays2[b].copy_(mg_rays[b], non_blocking=True)
+                    mg_copied[b] = torch.cuda.Event()
+                    mg_copied[b].record(copy_stream)
+        if world > 1:
+            order = [(count & 1), ((count + 1) & 1)] if count >= 2 else [0]
+            for b in order:
+                if mg_copied[b] is not None:
+                    mg_copied[b].synchronize()
+                    rays += int(host_rays2[b].sum().item())
+                    mg_copied[b] = None
         for sl, pb in pending:
             gpu.wait_frame(sl)
             rays += int(host_rays2[pb].sum().item())
@@ -439,7 +463,8 @@ def run_ours(args):
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / args.steps * 1e3,
-                    "path": "rt_render_async (pinned host buffers, two frames in flight) + rt_wait_frame" if world == 1 else "rt_render_device + NCCL all-gather + D2H on rank 0"},
+                    "path": "rt_render_async (pinned host buffers, two frames in flight) + rt_wait_frame" if world == 1
+                    else "rt_render_device + NCCL all-gather + D2H to pinned memory on rank 0 (copy stream, two frames in flight)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

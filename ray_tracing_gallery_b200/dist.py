@@ -74,6 +74,18 @@ def deinterleave(gathered, part: Partition):
     return g.permute(1, 0, 2, 3, 4).contiguous().view(part.height, part.width, -1)
 
 
+def deinterleave_into(out, gathered, part: Partition):
+    """Same as `deinterleave`, written into a preallocated [H, W, C] torch tensor with ONE strided copy."""
+    w, sh = part.world, part.strip_height
+    c = gathered.shape[-1]
+    if w == 1:
+        out.copy_(gathered.reshape(part.height, part.width, c))
+        return out
+    j = part.local_rows // sh
+    out.view(j, w, sh, part.width, c).copy_(gathered.view(w, j, sh, part.width, c).permute(1, 0, 2, 3, 4))
+    return out
+
+
 def gather_frame(local_rgba8, part: Partition, out=None):
     """All ranks contribute their [local_rows, W, 4] slab; returns the de-interleaved [H, W, 4] frame
     (meaningful on every rank; rank 0 is the consumer)."""

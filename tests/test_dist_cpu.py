@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from ray_tracing_gallery_b200 import abi
-from ray_tracing_gallery_b200.dist import Partition, choose_strip_height, deinterleave
+from ray_tracing_gallery_b200.dist import Partition, choose_strip_height, deinterleave, deinterleave_into
 
 
 def test_strip_height_choice():
@@ -28,6 +28,14 @@ def test_deinterleave_inverts_the_partition():
     assert np.array_equal(deinterleave(slabs, parts[0]), img)
     rows = np.concatenate([p.global_rows() for p in parts])
     assert sorted(rows.tolist()) == list(range(H))
+    import torch
+
+    out = torch.zeros((H, W, 4), dtype=torch.int64)
+    deinterleave_into(out, torch.from_numpy(slabs.astype(np.int64)), parts[0])
+    assert np.array_equal(out.numpy(), img)
+    one = Partition.make(W, H, 1, 0)
+    deinterleave_into(out, torch.from_numpy(img.astype(np.int64)[None]), one)
+    assert np.array_equal(out.numpy(), img)
 
 
 def _worker(rank, world, port, tmp):
