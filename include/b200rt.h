@@ -78,7 +78,8 @@ typedef enum RtPipeline {
 enum {
     RT_RENDER_COUNTERS = 1u,    /* also count nodes/instances/triangles visited (slower; for the roofline audit) */
     RT_RENDER_TIMING = 2u,      /* CUDA events around every kernel of the frame -> RtStats.kernel_ms */
-    RT_RENDER_SPLIT_TAIL = 4u   /* bounce segments as four launches each instead of the one cooperative k_tail (A/B) */
+    RT_RENDER_SPLIT_TAIL = 4u,  /* bounce segments as four launches each instead of the one cooperative k_tail (A/B) */
+    RT_RENDER_NO_PDL = 8u       /* plain stream-ordered launches instead of programmatic dependent launches (A/B) */
 };
 
 /* What `cmd_trace_rays(width, height, 1)` + the hard-coded shader constants

@@ -145,6 +145,7 @@ RT_PIPELINE_WAVEFRONT, RT_PIPELINE_MEGAKERNEL = 0, 1
 RT_RENDER_COUNTERS = 1
 RT_RENDER_TIMING = 2
 RT_RENDER_SPLIT_TAIL = 4
+RT_RENDER_NO_PDL = 8
 RT_INSTANCE_TRIANGLE_FACING_CULL_DISABLE = 1
 MISS_ID = 0xFFFFFFFF
 

@@ -282,7 +282,7 @@ int render_common(RtContext* ctx, const RtUniforms* u, const RtRenderParams* p, 
         timing = &ctx->timing;
     }
     ctx->timing_valid = timing != nullptr;
-    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, (p->flags & RT_RENDER_SPLIT_TAIL) != 0, ctx->sms, d_ray_counts, timing, ctx->stream));
+    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, (p->flags & RT_RENDER_SPLIT_TAIL) != 0, (p->flags & RT_RENDER_NO_PDL) != 0, ctx->sms, d_ray_counts, timing, ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->render_timed = true;
     ctx->last_rows = f.rows;

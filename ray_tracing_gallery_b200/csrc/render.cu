@@ -29,6 +29,14 @@ namespace {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialisation attribute may
+// be scheduled while its predecessor in the stream is still draining; pdl_wait() blocks until the predecessor
+// has completed and its writes are visible, pdl_release() lets the successor start being scheduled.  Both are
+// no-ops for plain launches.  Used so that launch latency and block scheduling of the next stage hide behind
+// the tail of the current one.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // compact local row -> global y (strips dealt round-robin to ranks)
 __device__ __forceinline__ uint32_t global_y(const FrameDev& F, uint32_t ly) {
     if (F.strip_count > 1 && F.strip_height > 0) {
@@ -339,15 +347,27 @@ __device__ __forceinline__ void resolve_phase(const FrameDev& F, uint32_t seg) {
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, RT_TRACE_MINB) k_trace0(SceneDev S, FrameDev F, uint32_t total) { trace_phase<true, COUNT>(S, F, 0, total); }
+__global__ void __launch_bounds__(128, RT_TRACE_MINB) k_trace0(SceneDev S, FrameDev F, uint32_t total) {
+    pdl_release();
+    pdl_wait();
+    trace_phase<true, COUNT>(S, F, 0, total);
+}
 // bounce segment as its own launch (RT_RENDER_SPLIT_TAIL): the ray count is read on the device
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_n(SceneDev S, FrameDev F, uint32_t seg) {
     trace_phase<false, COUNT>(S, F, seg, *((volatile unsigned int*)&seg_counters(F, seg - 1u)->ray_count));
 }
-__global__ void __launch_bounds__(128) k_prep(SceneDev S, FrameDev F, uint32_t seg) { prep_phase(S, F, seg); }
+__global__ void __launch_bounds__(128) k_prep(SceneDev S, FrameDev F, uint32_t seg) {
+    pdl_release();
+    pdl_wait();
+    prep_phase(S, F, seg);
+}
 template <bool COUNT>
-__global__ void __launch_bounds__(128, RT_SHADOW_MINB) k_shadow(SceneDev S, FrameDev F, uint32_t seg) { shadow_phase<COUNT>(S, F, seg); }
+__global__ void __launch_bounds__(128, RT_SHADOW_MINB) k_shadow(SceneDev S, FrameDev F, uint32_t seg) {
+    pdl_release();
+    pdl_wait();
+    shadow_phase<COUNT>(S, F, seg);
+}
 __global__ void __launch_bounds__(128) k_resolve(FrameDev F, uint32_t seg) { resolve_phase(F, seg); }
 
 // segments >= RT_SEG_SLOTS reuse a counter slot (split-tail path)
@@ -444,6 +464,7 @@ __global__ void __launch_bounds__(128) k_mega(SceneDev S, FrameDev F, uint32_t t
 
 // sample_directional_light(animated_blue_noise(..)) for every (pixel mod 64, sample) of the frame
 __global__ void __launch_bounds__(128) k_sun_dirs(SceneDev S, FrameDev F, float4* out) {
+    pdl_release();
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = F.shadow_rays;
     if (t >= 4096u * n) return;
@@ -461,6 +482,21 @@ __global__ void k_export_counts(const FrameCounters* c, uint64_t* out) {
 
 }  // namespace
 
+// Launch with the programmatic-stream-serialisation attribute (see pdl_wait); plain launch when `pdl` is false.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename K>
 static int persistent_grid(K kernel, int sms) {
     int per_sm = 0;
@@ -469,7 +505,8 @@ static int persistent_grid(K kernel, int sms) {
     return sms * per_sm;
 }
 
-cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, int sms, uint64_t* d_ray_counts,
+cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, bool no_pdl, int sms,
+                         uint64_t* d_ray_counts,
                          FrameTiming* timing, cudaStream_t stream) {
     cudaMemsetAsync(F.counters, 0, sizeof(FrameCounters), stream);
     if (F.hit_ids) cudaMemsetAsync(F.hit_ids, 0xFF, (size_t)F.rows * F.tw * F.max_segments * 3 * sizeof(uint32_t), stream);
@@ -511,13 +548,20 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
         }
         int cap = (int)((total + 127) / 128);  // no more blocks than there could be work
         auto fit = [&](int g, uint32_t per_item) { long long c = (long long)cap * per_item; return (int)(c < g ? c : g); };
-        if (count) k_trace0<true><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, total);
-        else k_trace0<false><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, total);
+        // stage-to-stage launches overlap the predecessor's tail (programmatic dependent launch); not when
+        // per-kernel timing events sit between them
+        const bool pdl = timing == nullptr && !no_pdl;
+        cudaError_t le;
+        if (count) le = launch_pdl(k_trace0<true>, fit(g_trace0[ci], 1), stream, pdl && F.sun_dirs != nullptr, S, F, total);
+        else le = launch_pdl(k_trace0<false>, fit(g_trace0[ci], 1), stream, pdl && F.sun_dirs != nullptr, S, F, total);
+        if (le != cudaSuccess) return le;
         mark(K_TRACE);
-        k_prep<<<fit(g_prep, 1), 128, 0, stream>>>(S, F, 0);
+        le = launch_pdl(k_prep, fit(g_prep, 1), stream, pdl, S, F, 0u);
+        if (le != cudaSuccess) return le;
         mark(K_PREP);
-        if (count) k_shadow<true><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, 0);
-        else k_shadow<false><<<fit(g_shadow[ci], F.shadow_rays), 128, 0, stream>>>(S, F, 0);
+        if (count) le = launch_pdl(k_shadow<true>, fit(g_shadow[ci], F.shadow_rays), stream, pdl, S, F, 0u);
+        else le = launch_pdl(k_shadow<false>, fit(g_shadow[ci], F.shadow_rays), stream, pdl, S, F, 0u);
+        if (le != cudaSuccess) return le;
         mark(K_SHADOW);
         if (F.max_segments == 1 || split_tail) {
             k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, 0);

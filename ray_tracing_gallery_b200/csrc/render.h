@@ -14,7 +14,8 @@ struct FrameTiming {
 };
 
 // Enqueue one frame on `stream`.  d_ray_counts (device, optional) receives {ray-gen segments, shadow rays}.
-cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, int sms, uint64_t* d_ray_counts,
+cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, bool no_pdl, int sms,
+                         uint64_t* d_ray_counts,
                          FrameTiming* timing, cudaStream_t stream);
 
 // BLAS input: per flattened triangle (geometry-major) the padded AABB.

@@ -53,6 +53,13 @@ for i in range(a.frames):
     tot += st.last_render_ms
 print("  kernel ms/frame:", {n: round(float(v) / a.frames, 4) for n, v in zip(names, acc)}, "render ms", round(tot / a.frames, 4),
       "Mrays/s", round(rays / (tot / a.frames) / 1e3, 1))
+# whole-frame A/B without per-kernel events: programmatic dependent launches on / off
+for name, fl in (("pdl", 0), ("no-pdl", abi.RT_RENDER_NO_PDL), ("pdl", 0), ("no-pdl", abi.RT_RENDER_NO_PDL)):
+    ms = []
+    for i in range(max(a.frames, 20)):
+        gpu.render(s.uniforms(frame_index=2 + i), part.apply(s.params(pipeline=pipe, flags=fl, **tile)), want=("rgba8",))
+        ms.append(gpu.stats().last_render_ms)
+    print(f"  frame ms ({name}): median {np.median(ms):.4f} min {min(ms):.4f}")
 if a.workload in ("c4", "c5"):
     import time
     for mode, name in ((abi.RT_UPDATE_REFIT, "refit"), (abi.RT_UPDATE_REBUILD, "rebuild")):
