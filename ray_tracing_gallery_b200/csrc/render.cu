@@ -56,6 +56,10 @@ __device__ __forceinline__ bool item_to_pixel(const FrameDev& F, uint32_t item, 
     return lx < F.tw && ly < F.rows;
 }
 
+__device__ __forceinline__ uint32_t encode_rgba8(V3 c) {
+    uint32_t r = unorm8(linear_to_srgb1(c.x)), g = unorm8(linear_to_srgb1(c.y)), b = unorm8(linear_to_srgb1(c.z));
+    return r | (g << 8) | (b << 16) | 0xFF000000u;
+}
 __device__ __forceinline__ void write_pixel(const FrameDev& F, uint32_t pixel, V3 c) {
     if (F.radiance) {
         F.radiance[3 * (size_t)pixel] = c.x;
@@ -63,9 +67,18 @@ __device__ __forceinline__ void write_pixel(const FrameDev& F, uint32_t pixel, V
         F.radiance[3 * (size_t)pixel + 2] = c.z;
     }
     if (F.rgba8) {
-        uint32_t r = unorm8(linear_to_srgb1(c.x)), g = unorm8(linear_to_srgb1(c.y)), b = unorm8(linear_to_srgb1(c.z));
-        reinterpret_cast<uint32_t*>(F.rgba8)[pixel] = r | (g << 8) | (b << 16) | 0xFF000000u;
+        reinterpret_cast<uint32_t*>(F.rgba8)[pixel] = encode_rgba8(c);
     }
+}
+
+// same store with the sRGB encode already done (the two miss colours are constants of the frame)
+__device__ __forceinline__ void write_pixel_encoded(const FrameDev& F, uint32_t pixel, V3 c, uint32_t rgba) {
+    if (F.radiance) {
+        F.radiance[3 * (size_t)pixel] = c.x;
+        F.radiance[3 * (size_t)pixel + 1] = c.y;
+        F.radiance[3 * (size_t)pixel + 2] = c.z;
+    }
+    if (F.rgba8) reinterpret_cast<uint32_t*>(F.rgba8)[pixel] = rgba;
 }
 
 __device__ __forceinline__ void write_hit_ids(const FrameDev& F, uint32_t pixel, uint32_t seg, const Hit& h) {
@@ -185,6 +198,7 @@ __device__ __forceinline__ void trace_phase(const SceneDev& S, const FrameDev& F
     const RayRec* __restrict__ in_q = F.ray_q[(seg + 1u) & 1u];
     RayRec* __restrict__ out_q = F.ray_q[seg & 1u];
     SegCounters* sc = seg_counters(F, seg);
+    const uint32_t rgba_sky = encode_rgba8(v3(0.0f, 0.0f, 0.05f)), rgba_sun = encode_rgba8(v3(1.0f, 1.0f, 1.0f));
     WarpChunk wc;
     wc.init(&sc->work_next[K_TRACE]);
     uint32_t batch;
@@ -234,8 +248,12 @@ __device__ __forceinline__ void trace_phase(const SceneDev& S, const FrameDev& F
         hp.reserve(&sc->hit_count, textured);   // the two queue reservations are in flight ...
         rp.reserve(&sc->ray_count, bounce);
         if (active && !textured && !bounce) {    // ... while the finished pixels are encoded and stored
-            V3 c = got ? v3(0.f, 0.f, 0.f) : miss_colour(F.uniforms, F.cos_sun_radius, d);
-            write_pixel(F, pixel, c);
+            if (got) {
+                write_pixel_encoded(F, pixel, v3(0.f, 0.f, 0.f), 0xFF000000u);  // segment budget used up: colour stays 0
+            } else {
+                V3 c = miss_colour(F.uniforms, F.cos_sun_radius, d);  // primary_ray_miss: sun disc or SKY_COLOUR (lib.rs:38-51)
+                write_pixel_encoded(F, pixel, c, c.x == 1.0f ? rgba_sun : rgba_sky);
+            }
         }
         uint32_t hslot = hp.slot();
         if (textured) {

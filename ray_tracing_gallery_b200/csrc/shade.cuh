@@ -147,7 +147,9 @@ struct DotParams { float NoH, NoV, NoL, LoH, roughness; };
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float pdot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ float compute_f90(const DotParams& p) { return 0.5f + 2.0f * p.roughness * p.LoH * p.LoH; }
-__device__ __forceinline__ float schlick1(float u, float f0, float f90) { return f0 + (f90 - f0) * powf(1.0f - u, 5.0f); }
+// pow(x, 5.0) of pbr.glsl:70 for x in [0,1]: three multiplications (within 2 ulp of powf; BRDF terms carry the 1e-3 tolerance)
+__device__ __forceinline__ float pow5(float x) { float x2 = x * x; return x2 * x2 * x; }
+__device__ __forceinline__ float schlick1(float u, float f0, float f90) { return f0 + (f90 - f0) * pow5(1.0f - u); }
 
 // pbr.glsl:174-211.  The result is light_intensity * NoL * (diffuse + specular) (:200-210); the
 // light-independent part is returned so that the wavefront can finish the product after its shadow
@@ -176,7 +178,7 @@ __device__ __forceinline__ BrdfTerms brdf_terms(V3 normal, V3 view, V3 light, V3
     float f0y = dielectric_f0 * (1.0f - metallic) + base.y * metallic;
     float f0z = dielectric_f0 * (1.0f - metallic) + base.z * metallic;
     float f90 = compute_f90(p);
-    float fw = powf(1.0f - p.LoH, 5.0f);
+    float fw = pow5(1.0f - p.LoH);
     float Fx = f0x + (f90 - f0x) * fw, Fy = f0y + (f90 - f0y) * fw, Fz = f0z + (f90 - f0z) * fw;
     // V_SmithGGXCorrelated, :56-65
     float a2 = p.roughness * p.roughness;
