@@ -232,11 +232,12 @@ def run_ours(args):
     part = Partition.make(W, H, world, rank)
     pipeline = abi.RT_PIPELINE_MEGAKERNEL if args.pipeline == "mega" else abi.RT_PIPELINE_WAVEFRONT
     update_mode = abi.RT_UPDATE_REFIT if args.update_mode == "refit" else abi.RT_UPDATE_REBUILD
-    rows = part.local_rows
+    rows = part.local_rows      # rows this rank renders
+    slab_rows = part.max_rows   # common slab size of the all-gather (shares differ by at most one strip)
     pixels = rows * W
 
-    fb = torch.zeros((rows, W, 4), dtype=torch.uint8, device=dev)
-    gathered = torch.zeros((world, rows, W, 4), dtype=torch.uint8, device=dev) if world > 1 else None
+    fb = torch.zeros((slab_rows, W, 4), dtype=torch.uint8, device=dev)
+    gathered = torch.zeros((world, slab_rows, W, 4), dtype=torch.uint8, device=dev) if world > 1 else None
     final_dev = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
     rays_dev = torch.zeros(2, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2

@@ -93,7 +93,8 @@ typedef struct RtRenderParams {
     uint32_t tile_w, tile_h;    /*   tile_w == 0 => full image */
     uint32_t strip_height;      /* >0: rows of the tile are dealt to `strip_count` ranks in strips */
     uint32_t strip_count;       /*   of this height, round-robin; this call renders strips with */
-    uint32_t strip_index;       /*   (strip % strip_count) == strip_index.  0 => no interleave */
+    uint32_t strip_index;       /*   (strip % strip_count) == strip_index (the last strip may be partial, */
+                                /*   shares may differ by one strip).  0 => no interleave */
     uint32_t pipeline;          /* RtPipeline */
     uint32_t flags;             /* RT_RENDER_* */
     uint32_t _reserved[3];

@@ -217,9 +217,11 @@ int plan_frame(RtContext* ctx, const RtRenderParams* p, FramePlan& f) {
     f.rows = f.th;
     if (p->strip_height && p->strip_count > 1) {
         if (p->strip_index >= p->strip_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: strip_index >= strip_count");
-        if (f.th % (p->strip_height * p->strip_count) != 0)
-            return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: tile height must be a multiple of strip_height * strip_count");
-        f.rows = f.th / p->strip_count;
+        // strips s = 0.. of strip_height rows (the last one may be partial); this call owns s % strip_count == strip_index
+        uint32_t strips = (f.th + p->strip_height - 1) / p->strip_height;
+        uint32_t own = strips / p->strip_count + (p->strip_index < strips % p->strip_count ? 1u : 0u);
+        f.rows = own * p->strip_height;
+        if (strips && (strips - 1) % p->strip_count == p->strip_index) f.rows -= strips * p->strip_height - f.th;
     }
     if ((uint64_t)f.rows * f.tw > 0x7FFFFFFFull) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_render: too many pixels");
     return RT_OK;

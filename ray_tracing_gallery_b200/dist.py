@@ -4,13 +4,15 @@ The reference is single-GPU; the path shards because pixels are independent
 (no inter-pixel dependency in `ray_generation`, blue noise is indexed by the
 global pixel coordinate: shaders/closest_hit_textured.glsl:100).  Layout:
 
-  * rows are dealt to ranks in strips of `strip_height` rows, round-robin, so
-    sky and geometry are spread evenly (RtRenderParams.strip_*);
+  * rows are dealt to ranks in strips of 8 rows, round-robin, so sky and
+    geometry are spread evenly (RtRenderParams.strip_*); the last strip may be
+    partial and ranks may own different numbers of rows;
   * every rank holds the full scene (replicated at load);
   * on a TLAS change rank 0 broadcasts the 64-byte instance records
     (`broadcast_instances`), every rank rebuilds its replica;
   * per frame the RGBA8 strips are gathered (`all_gather_into_tensor` over
-    equal-sized slabs) and rank 0 de-interleaves them into the final image.
+    slabs padded to the largest share) and rank 0 de-interleaves them into the
+    final image with one row-gather.
 
 torch.distributed is the plumbing (NCCL on GPUs, gloo in the CPU tests); the
 collectives carry finished bytes only, there is no reduction.
@@ -20,11 +22,13 @@ from dataclasses import dataclass
 import numpy as np
 
 
-def choose_strip_height(height: int, world: int, preferred=(8, 4, 2, 1)) -> int:
-    for sh in preferred:
-        if height % (sh * world) == 0:
-            return sh
-    raise ValueError(f"image height {height} cannot be dealt to {world} ranks in equal strips")
+STRIP_HEIGHT = 8  # rows per strip: two 8x4 warp tiles high, so a rank's warps trace the same compact tiles one GPU would
+
+
+def choose_strip_height(height: int, world: int) -> int:
+    """Strips of 8 rows whatever the image height (the last strip may be partial and ranks may own
+    different numbers of rows); measured on C2 at 8 ranks: 1-row strips cost a rank 14 % (profiles/r01_notes.md)."""
+    return STRIP_HEIGHT if world > 1 else 0
 
 
 @dataclass
@@ -37,11 +41,28 @@ class Partition:
 
     @classmethod
     def make(cls, width, height, world, rank):
-        return cls(width, height, world, rank, choose_strip_height(height, world) if world > 1 else 0)
+        return cls(width, height, world, rank, choose_strip_height(height, world))
+
+    def global_rows(self, rank=None) -> np.ndarray:
+        """Global y of each compact local row of `rank`, ascending."""
+        rank = self.rank if rank is None else rank
+        y = np.arange(self.height)
+        if self.world == 1:
+            return y
+        return y[(y // self.strip_height) % self.world == rank]
+
+    def rows_of(self, rank) -> int:
+        return len(self.global_rows(rank))
 
     @property
     def local_rows(self) -> int:
-        return self.height // self.world
+        """Rows this rank renders (rt_render's compact output has exactly this many)."""
+        return self.rows_of(self.rank)
+
+    @property
+    def max_rows(self) -> int:
+        """Rows of the largest share: the slab size of the equal-sized all-gather."""
+        return max(self.rows_of(r) for r in range(self.world))
 
     def apply(self, params):
         """Fill the strip fields of an RtRenderParams for this rank."""
@@ -51,52 +72,66 @@ class Partition:
             params.strip_index = self.rank
         return params
 
-    def global_rows(self, rank=None) -> np.ndarray:
-        """Global y of each compact local row of `rank`."""
-        rank = self.rank if rank is None else rank
-        if self.world == 1:
-            return np.arange(self.height)
-        sh = self.strip_height
-        j = np.arange(self.local_rows) // sh
-        r = np.arange(self.local_rows) % sh
-        return (j * self.world + rank) * sh + r
+    def source_rows(self) -> np.ndarray:
+        """For every global row y: its row in the gathered [world * max_rows] slab stack."""
+        src = np.zeros(self.height, np.int64)
+        m = self.max_rows
+        for r in range(self.world):
+            g = self.global_rows(r)
+            src[g] = r * m + np.arange(len(g))
+        return src
 
 
 def deinterleave(gathered, part: Partition):
-    """[world, local_rows, W, C] slabs -> [H, W, C] image.  Works on torch tensors and numpy arrays."""
-    w, sh = part.world, part.strip_height
-    if w == 1:
-        return gathered.reshape(part.height, part.width, gathered.shape[-1])
-    j = part.local_rows // sh
-    g = gathered.reshape(w, j, sh, part.width, gathered.shape[-1])
-    if isinstance(g, np.ndarray):
-        return np.ascontiguousarray(g.transpose(1, 0, 2, 3, 4)).reshape(part.height, part.width, -1)
-    return g.permute(1, 0, 2, 3, 4).contiguous().view(part.height, part.width, -1)
+    """[world, max_rows, W, C] slabs (rows beyond a rank's share are padding) -> [H, W, C] image.
+    Works on torch tensors and numpy arrays."""
+    c = gathered.shape[-1]
+    if part.world == 1:
+        return gathered.reshape(part.height, part.width, c)
+    flat = gathered.reshape(part.world * gathered.shape[1], part.width, c)
+    src = part.source_rows()
+    if isinstance(flat, np.ndarray):
+        return flat[src]
+    import torch
+
+    return flat.index_select(0, torch.as_tensor(src, device=flat.device))
+
+
+_INDEX_CACHE = {}
 
 
 def deinterleave_into(out, gathered, part: Partition):
-    """Same as `deinterleave`, written into a preallocated [H, W, C] torch tensor with ONE strided copy."""
-    w, sh = part.world, part.strip_height
+    """Same as `deinterleave`, written into a preallocated [H, W, C] torch tensor with ONE gather kernel."""
+    import torch
+
     c = gathered.shape[-1]
-    if w == 1:
+    if part.world == 1:
         out.copy_(gathered.reshape(part.height, part.width, c))
         return out
-    j = part.local_rows // sh
-    out.view(j, w, sh, part.width, c).copy_(gathered.view(w, j, sh, part.width, c).permute(1, 0, 2, 3, 4))
+    key = (part.width, part.height, part.world, part.strip_height, gathered.shape[1], str(gathered.device))
+    idx = _INDEX_CACHE.get(key)
+    if idx is None:
+        idx = _INDEX_CACHE[key] = torch.as_tensor(part.source_rows(), device=gathered.device)
+    torch.index_select(gathered.reshape(part.world * gathered.shape[1], part.width * c), 0, idx, out=out.view(part.height, part.width * c))
     return out
 
 
 def gather_frame(local_rgba8, part: Partition, out=None):
-    """All ranks contribute their [local_rows, W, 4] slab; returns the de-interleaved [H, W, 4] frame
+    """All ranks contribute their [local_rows, W, 4] rows; returns the de-interleaved [H, W, 4] frame
     (meaningful on every rank; rank 0 is the consumer)."""
     import torch
     import torch.distributed as dist
 
     if part.world == 1:
         return local_rgba8
+    m = part.max_rows
+    slab = local_rgba8
+    if slab.shape[0] != m:  # pad to the common slab size
+        slab = torch.zeros((m,) + tuple(local_rgba8.shape[1:]), dtype=local_rgba8.dtype, device=local_rgba8.device)
+        slab[: local_rgba8.shape[0]] = local_rgba8
     if out is None:
-        out = torch.empty((part.world,) + tuple(local_rgba8.shape), dtype=local_rgba8.dtype, device=local_rgba8.device)
-    dist.all_gather_into_tensor(out.view(-1), local_rgba8.reshape(-1))
+        out = torch.empty((part.world,) + tuple(slab.shape), dtype=slab.dtype, device=slab.device)
+    dist.all_gather_into_tensor(out.view(-1), slab.reshape(-1))
     return deinterleave(out, part)
 
 

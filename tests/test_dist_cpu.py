@@ -10,21 +10,23 @@ from ray_tracing_gallery_b200 import abi
 from ray_tracing_gallery_b200.dist import Partition, choose_strip_height, deinterleave, deinterleave_into
 
 
-def test_strip_height_choice():
-    assert choose_strip_height(1080, 1) == 8
-    assert choose_strip_height(1080, 2) == 4
-    assert choose_strip_height(1080, 8) == 1
-    assert choose_strip_height(2160, 8) == 2
-    assert choose_strip_height(2160, 4) == 4
-    with pytest.raises(ValueError):
-        choose_strip_height(1081, 2)
+def test_strips_are_eight_rows_and_shares_may_be_ragged():
+    assert choose_strip_height(1080, 1) == 0 and choose_strip_height(1080, 8) == 8
+    parts = [Partition.make(1920, 1080, 8, r) for r in range(8)]   # 135 strips of 8 rows over 8 ranks: 17 or 16 strips each
+    rows = [p.local_rows for p in parts]
+    assert rows == [136] * 7 + [128] and sum(rows) == 1080 and parts[0].max_rows == 136
+    parts = [Partition.make(64, 36, 4, r) for r in range(4)]       # the last strip is partial (4 rows) and belongs to rank 0
+    assert [p.local_rows for p in parts] == [12, 8, 8, 8]
+    assert parts[0].global_rows().tolist() == list(range(0, 8)) + list(range(32, 36))
 
 
 def test_deinterleave_inverts_the_partition():
-    H, W, world = 48, 5, 4
+    H, W, world = 52, 5, 4   # 7 strips: shares of 16, 16, 12 (8 + the partial 4), 8 rows
     img = np.arange(H * W * 4, dtype=np.uint32).reshape(H, W, 4)
     parts = [Partition.make(W, H, world, r) for r in range(world)]
-    slabs = np.stack([img[p.global_rows()] for p in parts])
+    slabs = np.zeros((world, parts[0].max_rows, W, 4), np.uint32)
+    for r, p in enumerate(parts):
+        slabs[r, : p.local_rows] = img[p.global_rows()]
     assert np.array_equal(deinterleave(slabs, parts[0]), img)
     rows = np.concatenate([p.global_rows() for p in parts])
     assert sorted(rows.tolist()) == list(range(H))
@@ -49,7 +51,7 @@ def _worker(rank, world, port, tmp):
     from ray_tracing_gallery_b200.dist import broadcast_instances, gather_frame
     from ray_tracing_gallery_b200.scene import build_scene
 
-    W, H = 64, 32
+    W, H = 64, 36   # ragged: rank 0 renders 20 rows, rank 1 16
     o = Oracle(threads=2)
     s = build_scene(o, "c3", W, H, num_instances=8)
     # rank 0 owns the authoritative instance records; the others start from garbage

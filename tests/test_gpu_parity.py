@@ -147,16 +147,29 @@ def test_tiles_and_strips_reassemble_the_full_frame():
     tile = gpu.render(s.uniforms(), s.params(tile_x0=40, tile_y0=64, tile_w=120, tile_h=72))
     assert np.array_equal(tile["rgba8"], full["rgba8"][64:136, 40:160])
     assert np.array_equal(tile["hit_ids"], full["hit_ids"][64:136, 40:160])
-    for world in (2, 4, 8):
+    for world in (2, 4, 5, 8):   # 24 strips of 8 rows: even shares for 2/4/8, ragged for 5
         parts = [Partition.make(W, H, world, r) for r in range(world)]
-        slabs, rays = [], np.zeros(2, np.uint64)
-        for part in parts:
+        slabs, rays = np.zeros((world, parts[0].max_rows, W, 4), np.uint8), np.zeros(2, np.uint64)
+        for r, part in enumerate(parts):
             out = gpu.render(s.uniforms(), part.apply(s.params()))
-            assert out["rgba8"].shape == (H // world, W, 4)
-            slabs.append(out["rgba8"])
+            assert out["rgba8"].shape == (part.local_rows, W, 4)
+            slabs[r, : part.local_rows] = out["rgba8"]
             rays += out["ray_counts"]
-        assert np.array_equal(deinterleave(np.stack(slabs), parts[0]), full["rgba8"])
+        assert np.array_equal(deinterleave(slabs, parts[0]), full["rgba8"])
         assert np.array_equal(rays, full["ray_counts"])
+    gpu.close()
+    # a frame height that is no multiple of the strip height: the last strip is partial (100 = 12 * 8 + 4)
+    gpu = make_renderer()
+    s2 = build_scene(gpu, "c1", 200, 100)
+    full = gpu.render(s2.uniforms(), s2.params())
+    parts = [Partition.make(200, 100, 3, r) for r in range(3)]
+    assert [p.local_rows for p in parts] == [36, 32, 32]
+    slabs = np.zeros((3, 36, 200, 4), np.uint8)
+    for r, part in enumerate(parts):
+        out = gpu.render(s2.uniforms(), part.apply(s2.params()))
+        assert out["rgba8"].shape == (part.local_rows, 200, 4)
+        slabs[r, : part.local_rows] = out["rgba8"]
+    assert np.array_equal(deinterleave(slabs, parts[0]), full["rgba8"])
     gpu.close()
 
 

@@ -21,7 +21,7 @@ torch.cuda.set_stream(stream)
 gpu.set_stream(stream.cuda_stream)
 s = build_scene(gpu, wl)
 part = Partition.make(s.width, s.height, world, rank)
-rows = part.local_rows
+rows = part.max_rows
 fb = torch.zeros((rows, s.width, 4), dtype=torch.uint8, device=dev)
 gathered = torch.zeros((world, rows, s.width, 4), dtype=torch.uint8, device=dev)
 rays = torch.zeros(2, dtype=torch.int64, device=dev)
