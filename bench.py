@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--update-mode", default="refit", choices=["rebuild", "refit"],
                     help="dynamic scenes: refit = the reference's in-place UPDATE (src/util_structs.rs:309), rebuild = full LBVH build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"], help="N > 1: how the frame reaches rank 0")
     return ap.parse_args()
 
 
@@ -207,7 +208,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from ray_tracing_gallery_b200 import abi, native
-    from ray_tracing_gallery_b200.dist import Partition, broadcast_instances, deinterleave, deinterleave_into
+    from ray_tracing_gallery_b200.dist import Partition, SharedFrame, broadcast_instances, deinterleave_into
     from ray_tracing_gallery_b200.scene import build_scene
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -238,7 +239,7 @@ def run_ours(args):
 
     fb = torch.zeros((slab_rows, W, 4), dtype=torch.uint8, device=dev)
     gathered = torch.zeros((world, slab_rows, W, 4), dtype=torch.uint8, device=dev) if world > 1 else None
-    final_dev = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    mg_final = [torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
     rays_dev = torch.zeros(2, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     inst_dev = torch.zeros(len(s.instances) * 64, dtype=torch.uint8, device=dev) if s.dynamic else None
@@ -272,14 +273,41 @@ def run_ours(args):
 
     rays_steps = torch.zeros((args.steps, 2), dtype=torch.int64, device=dev)  # per timed step {ray-gen segments, shadow rays}
 
-    def step_device(i, flags=0, counts=None):
-        if s.dynamic:
-            update_scene_device(i)
-        gpu.render_device(frame_inputs(i), params(flags), rgba8=fb.data_ptr(), ray_counts=(rays_dev if counts is None else counts).data_ptr())
+    # N > 1: how the frame reaches rank 0.  "peer": every rank's render kernels store their rows straight into rank 0's
+    # frame through NVLink peer memory (torch symmetric memory + RT_RENDER_OUTPUT_IMAGE_ROWS), then one cross-rank
+    # barrier.  "nccl": compact slabs, all_gather_into_tensor, de-interleave on rank 0.
+    shared, gather_path = None, "none"
+    if world > 1:
+        gather_path = "nccl all-gather + de-interleave"
+        if args.gather in ("auto", "peer"):
+            try:
+                shared = SharedFrame(W, H, dev)
+                gather_path = "peer stores into rank 0's frame (NVLink symmetric memory) + barrier"
+            except Exception as e:  # noqa: BLE001 - any failure of the optional path falls back to NCCL
+                if args.gather == "peer":
+                    raise
+                print(f"[bench] SharedFrame unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+
+    def render_and_collect(i, flags, counts, slot, before_barrier=None):
+        """One frame on this rank + whatever brings it to rank 0 (device side only)."""
+        if shared is not None:
+            gpu.render_device(frame_inputs(i), params(flags | abi.RT_RENDER_OUTPUT_IMAGE_ROWS), rgba8=shared.target_ptr(slot),
+                              ray_counts=counts.data_ptr())
+            if before_barrier is not None:
+                stream.wait_event(before_barrier)
+            shared.barrier()
+            return shared.frame(slot) if rank == 0 else None
+        gpu.render_device(frame_inputs(i), params(flags), rgba8=fb.data_ptr(), ray_counts=counts.data_ptr())
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
             if rank == 0:
-                deinterleave_into(final_dev, gathered, part)
+                return deinterleave_into(mg_final[slot & 1], gathered, part)
+        return None
+
+    def step_device(i, flags=0, counts=None):
+        if s.dynamic:
+            update_scene_device(i)
+        render_and_collect(i, flags, rays_dev if counts is None else counts, i & 1)
 
     # ---- one instrumented frame: deterministic traversal counters for the roofline accounting
     step_device(0, abi.RT_RENDER_COUNTERS)
@@ -341,7 +369,6 @@ def run_ours(args):
     host_fbs = [host_fb, torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()] if (world == 1 or rank == 0) else [host_fb, host_fb]
     host_rays2 = [host_rays, torch.zeros(2, dtype=torch.int64).pin_memory()]
     copy_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    mg_final = [torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
     mg_rays = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(2)]
     mg_done = [torch.cuda.Event(), torch.cuda.Event()]
     mg_copied = [None, None]
@@ -371,15 +398,14 @@ def run_ours(args):
                 if mg_copied[b] is not None:       # slot b's previous frame: its fence, then consume its result
                     mg_copied[b].synchronize()
                     rays += int(host_rays2[b].sum().item())
-                gpu.render_device(frame_inputs(i), params(), rgba8=fb.data_ptr(), ray_counts=mg_rays[b].data_ptr())
-                dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
-                if rank == 0:
-                    deinterleave_into(mg_final[b], gathered, part)
+                # peer path: ranks may start storing frame i+1 (slot b^1) once they pass this frame's barrier, so rank 0 does
+                # not enter the barrier before its copy of the previous frame in that slot has finished
+                frame = render_and_collect(i, 0, mg_rays[b], b, before_barrier=mg_copied[b ^ 1])
                 mg_done[b].record(stream)
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(mg_done[b])
                     if rank == 0:
-                        host_fbs[b].copy_(mg_final[b], non_blocking=True)
+                        host_fbs[b].copy_(frame, non_blocking=True)
                     host_rays2[b].copy_(mg_rays[b], non_blocking=True)
                     mg_copied[b] = torch.cuda.Event()
                     mg_copied[b].record(copy_stream)
@@ -460,12 +486,12 @@ def run_ours(args):
             "config": workload_config(s, args, {
                 "pipeline": args.pipeline, "partition": f"{world} rank(s), row strips of {part.strip_height or H} rows, round-robin",
                 "l2": "flushed between timed steps (256 MiB device write)", "tlas_update": (args.update_mode if s.dynamic else "static"),
-                "rays_per_frame": rays_frame if world == 1 else None}),
+                "rays_per_frame": rays_frame if world == 1 else None, "gather": gather_path}),
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "path": "rt_render_async (pinned host buffers, two frames in flight) + rt_wait_frame" if world == 1
-                    else "rt_render_device + NCCL all-gather + D2H to pinned memory on rank 0 (copy stream, two frames in flight)"},
+                    else f"rt_render_device + {gather_path} + D2H to pinned memory on rank 0 (copy stream, two frames in flight)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -260,6 +260,7 @@ int render_common(RtContext* ctx, const RtUniforms* u, const RtRenderParams* p, 
     F.x0 = f.x0; F.y0 = f.y0; F.tw = f.tw; F.rows = f.rows; F.tile_h = f.th;
     F.strip_height = p->strip_height; F.strip_count = p->strip_count; F.strip_index = p->strip_index;
     F.cos_sun_radius = cosf(u->sun_radius);
+    F.image_rows = (p->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) ? 1u : 0u;
     F.rgba8 = d_rgba8; F.radiance = d_radiance; F.hit_ids = d_hit_ids;
     F.counters = ctx->d_counters;
     F.ray_q[0] = ctx->d_ray_q[0]; F.ray_q[1] = ctx->d_ray_q[1];
@@ -631,6 +632,8 @@ int rt_render_device(RtContext* ctx, const RtUniforms* uniforms, const RtRenderP
     FramePlan f;
     int rc = plan_frame(ctx, params, f);
     if (rc) return rc;
+    if ((params->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) && out && out->hit_ids)
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_device: RT_RENDER_OUTPUT_IMAGE_ROWS supports rgba8 and radiance only");
     return render_common(ctx, uniforms, params, f, out ? out->rgba8 : nullptr, out ? out->radiance : nullptr, out ? out->hit_ids : nullptr,
                          out ? out->ray_counts : nullptr);
 }
@@ -638,6 +641,7 @@ int rt_render_device(RtContext* ctx, const RtUniforms* uniforms, const RtRenderP
 int rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params, const RtFrameOutputs* out) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     if (!uniforms || !params) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: NULL argument");
+    if (params->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: RT_RENDER_OUTPUT_IMAGE_ROWS is for rt_render_device");
     CK_DEV(ctx);
     FramePlan f;
     int rc = plan_frame(ctx, params, f);
@@ -665,6 +669,7 @@ int rt_render_async(RtContext* ctx, const RtUniforms* uniforms, const RtRenderPa
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     if (!uniforms || !params) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_async: NULL argument");
     if (out && (out->radiance || out->hit_ids)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_async: only rgba8 and ray_counts outputs");
+    if (params->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_async: RT_RENDER_OUTPUT_IMAGE_ROWS is for rt_render_device");
     CK_DEV(ctx);
     FramePlan f;
     int rc = plan_frame(ctx, params, f);

@@ -60,11 +60,21 @@ __device__ __forceinline__ uint32_t encode_rgba8(V3 c) {
     uint32_t r = unorm8(linear_to_srgb1(c.x)), g = unorm8(linear_to_srgb1(c.y)), b = unorm8(linear_to_srgb1(c.z));
     return r | (g << 8) | (b << 16) | 0xFF000000u;
 }
-__device__ __forceinline__ void write_pixel(const FrameDev& F, uint32_t pixel, V3 c) {
+// Output index of compact pixel `pixel`.  Default: the compact index itself (outputs hold the rendered rows only).
+// RT_RENDER_OUTPUT_IMAGE_ROWS: outputs are whole tile images and this call fills its own rows in place, so that
+// several ranks can store into ONE frame (e.g. rank 0's, through NVLink peer memory) with no gather afterwards.
+__device__ __forceinline__ size_t out_index(const FrameDev& F, uint32_t pixel) {
+    if (!F.image_rows) return pixel;
+    uint32_t ly = pixel / F.tw, lx = pixel - ly * F.tw;
+    return (size_t)(global_y(F, ly) - F.y0) * F.tw + lx;
+}
+
+__device__ __forceinline__ void write_pixel(const FrameDev& F, uint32_t cpixel, V3 c) {
+    const size_t pixel = out_index(F, cpixel);
     if (F.radiance) {
-        F.radiance[3 * (size_t)pixel] = c.x;
-        F.radiance[3 * (size_t)pixel + 1] = c.y;
-        F.radiance[3 * (size_t)pixel + 2] = c.z;
+        F.radiance[3 * pixel] = c.x;
+        F.radiance[3 * pixel + 1] = c.y;
+        F.radiance[3 * pixel + 2] = c.z;
     }
     if (F.rgba8) {
         reinterpret_cast<uint32_t*>(F.rgba8)[pixel] = encode_rgba8(c);
@@ -72,11 +82,12 @@ __device__ __forceinline__ void write_pixel(const FrameDev& F, uint32_t pixel, V
 }
 
 // same store with the sRGB encode already done (the two miss colours are constants of the frame)
-__device__ __forceinline__ void write_pixel_encoded(const FrameDev& F, uint32_t pixel, V3 c, uint32_t rgba) {
+__device__ __forceinline__ void write_pixel_encoded(const FrameDev& F, uint32_t cpixel, V3 c, uint32_t rgba) {
+    const size_t pixel = out_index(F, cpixel);
     if (F.radiance) {
-        F.radiance[3 * (size_t)pixel] = c.x;
-        F.radiance[3 * (size_t)pixel + 1] = c.y;
-        F.radiance[3 * (size_t)pixel + 2] = c.z;
+        F.radiance[3 * pixel] = c.x;
+        F.radiance[3 * pixel + 1] = c.y;
+        F.radiance[3 * pixel + 2] = c.z;
     }
     if (F.rgba8) reinterpret_cast<uint32_t*>(F.rgba8)[pixel] = rgba;
 }

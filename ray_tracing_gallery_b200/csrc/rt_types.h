@@ -146,6 +146,7 @@ struct FrameDev {
     uint32_t tile_h;
     uint32_t strip_height, strip_count, strip_index;
     float    cos_sun_radius;
+    uint32_t image_rows;            // RT_RENDER_OUTPUT_IMAGE_ROWS: rgba8 / radiance are whole tile images, rows stored in place
     uint8_t*  rgba8;
     float*    radiance;
     uint32_t* hit_ids;

@@ -135,6 +135,44 @@ def gather_frame(local_rgba8, part: Partition, out=None):
     return deinterleave(out, part)
 
 
+class SharedFrame:
+    """The fused form of render + gather: every rank's render kernels store their rows straight into rank 0's
+    frame through NVLink peer memory (RT_RENDER_OUTPUT_IMAGE_ROWS), so the frame needs no all-gather and no
+    de-interleave — only a cross-rank barrier before rank 0 reads it.
+
+    Built on torch's symmetric memory (`torch.distributed._symmetric_memory`): `slots` frames of [H, W, 4] bytes
+    are allocated symmetrically on every rank; only rank 0's copies are written.  Raises if the platform cannot
+    provide peer-mapped memory; callers fall back to `gather_frame`."""
+
+    def __init__(self, width: int, height: int, device, group=None, slots: int = 2):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.width, self.height, self.slots = width, height, slots
+        self.buf = symm_mem.empty((slots, height, width, 4), dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.rank = self.hdl.rank
+        self.frame_bytes = height * width * 4
+        self.root_ptr = int(self.hdl.buffer_ptrs[0])  # rank 0's buffer as seen from this rank
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)
+
+    def target_ptr(self, slot: int) -> int:
+        """Device pointer to pass as RtFrameOutputs.rgba8: frame `slot` of rank 0."""
+        return self.root_ptr + (slot % self.slots) * self.frame_bytes
+
+    def barrier(self, channel: int = 0):
+        """All ranks' stores of the frame are complete and visible once this returns on the current stream."""
+        self.hdl.barrier(channel=channel)
+
+    def frame(self, slot: int):
+        """Rank 0: the finished [H, W, 4] frame (valid after `barrier`)."""
+        return self.buf[slot % self.slots]
+
+
 def broadcast_instances(records_tensor, src: int = 0):
     """NCCL/gloo broadcast of the instance records (uint8 view of N x 64 bytes) from rank `src`."""
     import torch.distributed as dist

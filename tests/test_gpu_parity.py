@@ -346,3 +346,39 @@ def test_two_frames_in_flight_match_blocking_renders():
         gpu.wait_frame(2)
     gpu.sync()
     gpu.close()
+
+
+def test_image_rows_output_lets_ranks_share_one_frame():
+    """RT_RENDER_OUTPUT_IMAGE_ROWS: each strip share stores its rows in place into ONE [H][W] frame (what the ranks of a
+    multi-GPU frame do into rank 0's peer-mapped frame, dist.SharedFrame); no gather, no de-interleave."""
+    import torch
+
+    gpu = make_renderer()
+    gpu.set_stream(torch.cuda.current_stream().cuda_stream)
+    W, H = 200, 100   # 13 strips, the last one partial
+    s = build_scene(gpu, "default", W, H)
+    full = gpu.render(s.uniforms(), s.params(), want=("rgba8", "radiance", "ray_counts"))
+    frame = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    rad = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+    rays = torch.zeros(2, dtype=torch.int64, device="cuda")
+    total = np.zeros(2, np.uint64)
+    for r in range(3):
+        part = Partition.make(W, H, 3, r)
+        gpu.render_device(s.uniforms(), part.apply(s.params(flags=abi.RT_RENDER_OUTPUT_IMAGE_ROWS)), rgba8=frame.data_ptr(),
+                          radiance=rad.data_ptr(), ray_counts=rays.data_ptr())
+        torch.cuda.synchronize()
+        total += rays.cpu().numpy().astype(np.uint64)
+    assert np.array_equal(frame.cpu().numpy(), full["rgba8"])
+    assert np.array_equal(rad.cpu().numpy().view(np.uint32), full["radiance"].view(np.uint32))
+    assert np.array_equal(total, full["ray_counts"])
+    # a tile with an origin: rows are relative to the tile
+    tile = torch.zeros((40, 64, 4), dtype=torch.uint8, device="cuda")
+    for r in range(2):
+        part = Partition.make(W, H, 2, r)
+        gpu.render_device(s.uniforms(), part.apply(s.params(flags=abi.RT_RENDER_OUTPUT_IMAGE_ROWS, tile_x0=30, tile_y0=20, tile_w=64, tile_h=40)),
+                          rgba8=tile.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(tile.cpu().numpy(), full["rgba8"][20:60, 30:94])
+    with pytest.raises(RtError):
+        gpu.render(s.uniforms(), s.params(flags=abi.RT_RENDER_OUTPUT_IMAGE_ROWS))
+    gpu.close()

@@ -77,13 +77,38 @@ def f_barrier(i):
 render(0)
 dist.all_gather_into_tensor(gathered.view(-1), fb.view(-1))
 torch.cuda.synchronize()
+full = None
 if rank == 0:
     full = torch.zeros((s.height, s.width, 4), dtype=torch.uint8, device=dev)
     gpu.render_device(s.uniforms(frame_index=1), s.params(), rgba8=full.data_ptr(), ray_counts=rays.data_ptr())
     torch.cuda.synchronize()
     same = bool(torch.equal(full, deinterleave(gathered, part)))
     print(f"[{wl}] world {world}: gathered frame == single-GPU frame: {same}", flush=True)
+# fused variant: every rank stores its rows into rank 0's frame over NVLink peer memory
+shared = None
+try:
+    from ray_tracing_gallery_b200.dist import SharedFrame
+    shared = SharedFrame(s.width, s.height, dev)
+except Exception as e:  # noqa: BLE001
+    if rank == 0:
+        print(f"[{wl}] SharedFrame unavailable: {type(e).__name__}: {e}", flush=True)
+if shared is not None:
+    def f_shared(i):
+        b = i & 1
+        p = part.apply(s.params(flags=abi.RT_RENDER_OUTPUT_IMAGE_ROWS))
+        gpu.render_device(s.uniforms(frame_index=1 + i), p, rgba8=shared.target_ptr(b), ray_counts=rays.data_ptr())
+        shared.barrier()
+
+    f_shared(0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        print(f"[{wl}] world {world}: shared frame == single-GPU frame: {bool(torch.equal(full, shared.frame(0)))}", flush=True)
+
 res = {}
+if shared is not None:
+    res["render+peer stores+barrier"] = timeit(f_shared)
+    res["render+peer stores+barrier (no flush)"] = timeit(f_shared, do_flush=False)
 for name, fn in [("render", f_render), ("all_gather only", f_gather), ("render+gather", f_render_gather), ("full", f_full)]:
     res[name] = timeit(fn)
     res[name + " (no flush)"] = timeit(fn, do_flush=False)
