@@ -224,6 +224,7 @@ int plan_frame(RtContext* ctx, const RtRenderParams* p, FramePlan& f) {
         if (strips && (strips - 1) % p->strip_count == p->strip_index) f.rows -= strips * p->strip_height - f.th;
     }
     if ((uint64_t)f.rows * f.tw > 0x7FFFFFFFull) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_render: too many pixels");
+    if (p->width > 65536u || p->height > 32768u) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_render: launch size above 65536 x 32768");
     return RT_OK;
 }
 

@@ -270,8 +270,8 @@ __device__ __forceinline__ void trace_phase(const SceneDev& S, const FrameDev& F
         if (textured) {
             HitRec* hr = F.hit_q + hslot;
             reinterpret_cast<uint4*>(hr)[0] = make_uint4(pixel, h.inst_pos, h.geom, h.prim);
-            reinterpret_cast<float4*>(hr)[1] = make_float4(h.u, h.v, h.t, 0.f);
-            reinterpret_cast<float4*>(hr)[2] = make_float4(d.x, d.y, d.z, 0.f);
+            reinterpret_cast<float4*>(hr)[1] = make_float4(h.u, h.v, __uint_as_float(h.custom_sbt & 0xFFFFFFu), 0.f);
+            reinterpret_cast<float4*>(hr)[2] = make_float4(d.x, d.y, d.z, __uint_as_float(h.instance_id));
         }
         uint32_t rslot = rp.slot();
         if (bounce) {
@@ -300,6 +300,7 @@ __device__ __forceinline__ void prep_phase(const SceneDev& S, const FrameDev& F,
         th.px = F.x0 + lx; th.py = global_y(F, ly);
         th.inst_pos = a.y; th.geom = a.z; th.prim = a.w;
         th.u = b.x; th.v = b.y;
+        th.custom_index = __float_as_uint(b.z); th.instance_id = __float_as_uint(c.w);
         th.dir = v3(c.x, c.y, c.z);
         ShadeCtx ctx;
         float4 r0 = make_float4(__uint_as_float(a.x), 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, 0.f), r2 = r1, r3 = r1;
@@ -310,7 +311,8 @@ __device__ __forceinline__ void prep_phase(const SceneDev& S, const FrameDev& F,
             r0.y = bt.NoL;
             r1 = make_float4(bt.comb.x, bt.comb.y, bt.comb.z, 0.f);  // .w: lit = 0
             r2 = make_float4(base.x, base.y, base.z, 0.f);
-            r3 = make_float4(so.x, so.y, so.z, __uint_as_float(1u));
+            // .w: valid bit | gl_LaunchIDEXT.x << 1 | gl_LaunchIDEXT.y << 17 (k_shadow's blue-noise cell without a division)
+            r3 = make_float4(so.x, so.y, so.z, __uint_as_float(1u | (th.px << 1) | (th.py << 17)));
         }
         reinterpret_cast<float4*>(hr)[0] = r0;
         reinterpret_cast<float4*>(hr)[1] = r1;
@@ -333,6 +335,8 @@ __device__ __forceinline__ void shadow_phase(const SceneDev& S, const FrameDev& 
     const uint32_t n = F.shadow_rays;
     const uint32_t total = *((volatile unsigned int*)&sc->hit_count) * n;
     const SunFrame sun = make_sun_frame(F.uniforms);
+    const bool pow2 = (n & (n - 1u)) == 0u;
+    const uint32_t shift = 31u - __clz(n);
     uint32_t n_shadow = 0;
     WarpChunk wc;
     wc.init(&sc->work_next[K_SHADOW]);
@@ -340,13 +344,12 @@ __device__ __forceinline__ void shadow_phase(const SceneDev& S, const FrameDev& 
     while (wc.next(&sc->work_next[K_SHADOW], total, batch)) {
         uint32_t item = batch + lane_id();
         if (item < total) {
-            uint32_t hi = item / n, i = item - hi * n;
+            uint32_t hi = pow2 ? item >> shift : item / n, i = item - hi * n;
             HitRec* hr = F.hit_q + hi;
-            uint32_t pixel = __ldg(&hr->pixel);
             float4 so = __ldg(reinterpret_cast<const float4*>(hr) + 3);
-            if (__float_as_uint(so.w)) {
-                uint32_t ly = pixel / F.tw, lx = pixel - ly * F.tw;
-                bool lit = shadow_sample_lit<COUNT>(S, F, sun, F.x0 + lx, global_y(F, ly), i, v3(so.x, so.y, so.z), tc);
+            const uint32_t w = __float_as_uint(so.w);
+            if (w & 1u) {
+                bool lit = shadow_sample_lit<COUNT>(S, F, sun, (w >> 1) & 0xFFFFu, w >> 17, i, v3(so.x, so.y, so.z), tc);
                 if (lit) atomicAdd(&hr->lit, 1u);  // shadow_ray_miss: shadowed = false (lib.rs:33-36)
                 n_shadow++;
             }
@@ -365,7 +368,7 @@ __device__ __forceinline__ void resolve_phase(const FrameDev& F, uint32_t seg) {
         float4 r0 = __ldcg(reinterpret_cast<const float4*>(hr));
         float4 r1 = __ldcg(reinterpret_cast<const float4*>(hr) + 1);
         float4 r2 = __ldcg(reinterpret_cast<const float4*>(hr) + 2);
-        uint32_t valid = __ldcg(&hr->shadow_valid);
+        uint32_t valid = __ldcg(&hr->shadow_valid) & 1u;
         V3 col = v3(0.f, 0.f, 0.f);
         if (valid) {
             float sun_factor = div_((float)__float_as_uint(r1.w), (float)F.shadow_rays);
@@ -468,6 +471,7 @@ __global__ void __launch_bounds__(128) k_mega(SceneDev S, FrameDev F, uint32_t t
             if (kind == RT_HIT_TEXTURED) {
                 TexturedHit th;
                 th.px = px; th.py = py; th.inst_pos = h.inst_pos; th.geom = h.geom; th.prim = h.prim;
+                th.custom_index = h.custom_sbt & 0xFFFFFFu; th.instance_id = h.instance_id;
                 th.u = h.u; th.v = h.v; th.dir = d;
                 colour = shade_textured<COUNT>(S, F, th, n_shadow, tcs);
                 n_textured++;

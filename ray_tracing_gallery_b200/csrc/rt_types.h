@@ -98,9 +98,9 @@ struct __align__(16) RayRec {   // 32 B: a ray-gen segment waiting to be traced
 // k_trace writes the hit (words 0..11); k_prep replaces it in place by what the later stages need.
 struct __align__(16) HitRec {
     uint32_t pixel; uint32_t a1, a2, a3;  // k_trace: inst_pos, geom, prim       k_prep: NoL, -, -
-    float    b0, b1, b2; uint32_t lit;    // k_trace: u, v, t                    k_prep: comb.xyz; lit = unshadowed rays (k_shadow, atomic)
-    float    c0, c1, c2; uint32_t _pad;   // k_trace: gl_WorldRayDirectionEXT    k_prep: base colour
-    float    sox, soy, soz; uint32_t shadow_valid;  // k_prep: shadow-ray origin; 0 = triangle not resolvable
+    float    b0, b1, b2; uint32_t lit;    // k_trace: u, v, custom index         k_prep: comb.xyz; lit = unshadowed rays (k_shadow, atomic)
+    float    c0, c1, c2; uint32_t c3;     // k_trace: gl_WorldRayDirectionEXT, gl_InstanceID      k_prep: base colour
+    float    sox, soy, soz; uint32_t shadow_valid;  // k_prep: shadow-ray origin; bit 0: triangle resolved, bits 1..16 px, 17..31 py
 };
 static_assert(sizeof(HitRec) == 64, "HitRec is 64 bytes");
 

@@ -255,6 +255,8 @@ __device__ __forceinline__ V3 sample_directional_light(V2 rng, const SunFrame& f
 struct TexturedHit {       // what the textured closest-hit needs after traversal
     uint32_t px, py;       // gl_LaunchIDEXT.xy
     uint32_t inst_pos;     // TLAS leaf position (-> InstRT)
+    uint32_t custom_index; // gl_InstanceCustomIndexEXT and gl_InstanceID, carried from the traversal so that the
+    uint32_t instance_id;  //   ModelInfo fetch does not have to wait for an InstRT read
     uint32_t geom, prim;
     float u, v;
     V3 dir;                // gl_WorldRayDirectionEXT
@@ -271,11 +273,9 @@ struct ShadeCtx {          // state kept between the shadow-ray phase and the BR
 
 // closest_hit_textured main(), part 1: ModelInfo -> GeometryInfo -> load_triangle -> interpolate (:175-188)
 __device__ __forceinline__ bool shade_textured_load(const SceneDev& S, const TexturedHit& h, ShadeCtx& c) {
-    const InstRT* ir = S.inst_rt + h.inst_pos;
-    uint32_t custom = __ldg(&ir->custom_sbt) & 0xFFFFFFu;
-    c.instance_id = __ldg(&ir->instance_id);
+    c.instance_id = h.instance_id;
     RtModelInfo mi;
-    if (!load_geometry(S, custom, h.geom, mi, c.gi)) return false;
+    if (!load_geometry(S, h.custom_index, h.geom, mi, c.gi)) return false;
     uint32_t ia, ib, ic;
     load_indices(c.gi, h.prim, ia, ib, ic);
     const float* pos = reinterpret_cast<const float*>(mi.position_buffer_address);
