@@ -413,7 +413,7 @@ __global__ void k_reset_segment(FrameCounters* c, uint32_t seg) {
 // then the ray-count export.  Most frames have few or no bounce rays; the kernel leaves as soon as a
 // segment's ray queue is empty, so such frames pay one launch instead of four per segment plus two.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_tail(SceneDev S, FrameDev F, uint64_t* ray_counts_out) {
+__global__ void __launch_bounds__(128, 5) k_tail(SceneDev S, FrameDev F, uint64_t* ray_counts_out) {
     cg::grid_group grid = cg::this_grid();
     resolve_phase(F, 0);
     bool traced = false;
