@@ -207,9 +207,15 @@ class SceneSetup:
         return p
 
     def animate(self, tick: int) -> np.ndarray:
-        """C4: every instance gets rotation_y += 0.05 per tick (cf. src/scene.rs:163-165)."""
+        """The instance records after `tick` updates.
+        default: DefaultScene::update + write_resources (src/scene.rs:162-181): lain's rotation += 0.05 per tick, its
+                 48-byte transform rewritten at instance 2, everything else untouched;
+        C4:      every torus gets rotation_y += 0.05 per tick."""
         assert self.dynamic
         rec = self.instances.copy()
+        if self.name == "default":
+            rec["transform"][LAIN_INSTANCE] = lain_transform(tick)
+            return rec
         moved = instances_from_trs(self.base_pos, self.base_rot + F(0.05) * F(tick), self.base_scale, 0, 0, 0)
         n = len(moved)
         rec["transform"][-n:] = moved["transform"]
@@ -344,13 +350,16 @@ def build_scene(backend, config: str, width: Optional[int] = None, height: Optio
         ])
         field_inst, _, _, _ = _mirror_field(0xD5CE, num_instances or 100, tid, th)
         inst = np.concatenate([head, field_inst])
-        s = SceneSetup("default", inst, Camera(), Sun(), width or 1280, height or 720, shadow_rays=2, sun_radius=0.05,
-                       description="reference DefaultScene (seeded tori)")
+        s = SceneSetup("default", inst, Camera(), Sun(), width or 1280, height or 720, shadow_rays=2, sun_radius=0.05, dynamic=True,
+                       description="reference DefaultScene (seeded tori), lain rotating: one instance record + TLAS update per frame")
     else:
         raise ValueError(f"unknown config {config!r}")
     s.models = models
     backend.build_tlas(s.instances)
     return s
+
+
+LAIN_INSTANCE = 2  # `lain_instance_offset` of DefaultScene (src/scene.rs:115-120): the record the per-frame update rewrites
 
 
 def lain_transform(tick: int) -> np.ndarray:

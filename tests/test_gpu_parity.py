@@ -193,6 +193,39 @@ def test_tlas_update_parity(mode):
     orc.close(); gpu.close()
 
 
+def test_default_scene_animation_loop():
+    """SURVEY 8f-2, the reference's per-frame loop (src/scene.rs:162-204, src/main.rs:917-948): rotate lain, rewrite ONE
+    64-byte instance record, TLAS UPDATE in place (refit), frame_index + 1, render with two frames in flight.  Every
+    frame must equal the oracle's frame after the same update (the oracle rebuilds from scratch)."""
+    import torch
+
+    from ray_tracing_gallery_b200.scene import LAIN_INSTANCE
+
+    orc, so, gpu, sg = both("default", 640, 360)
+    fbs = [torch.zeros((360, 640, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    pending, want = [], {}
+    for tick in range(1, 6):
+        rec = sg.animate(tick)
+        assert not np.array_equal(rec[LAIN_INSTANCE], sg.instances[LAIN_INSTANCE]) and np.array_equal(rec[:2], sg.instances[:2])
+        gpu.update_instances(LAIN_INSTANCE, rec[LAIN_INSTANCE:LAIN_INSTANCE + 1])
+        gpu.update_tlas(abi.RT_UPDATE_REFIT)
+        orc.update_instances(LAIN_INSTANCE, so.animate(tick)[LAIN_INSTANCE:LAIN_INSTANCE + 1])
+        orc.update_tlas(abi.RT_UPDATE_REBUILD)
+        want[tick] = orc.render(so.uniforms(frame_index=1 + tick), so.params(), want=("rgba8",))["rgba8"]
+        if len(pending) == 2:
+            slot, b, t = pending.pop(0)
+            gpu.wait_frame(slot)
+            assert np.mean(np.abs(fbs[b].numpy().astype(int) - want[t].astype(int)).max(axis=2) <= 1) >= 0.999, f"tick {t}"
+        b = tick & 1
+        pending.append((gpu.render_async(sg.uniforms(frame_index=1 + tick), sg.params(), fbs[b].data_ptr()), b, tick))
+    for slot, b, t in pending:
+        gpu.wait_frame(slot)
+        assert np.mean(np.abs(fbs[b].numpy().astype(int) - want[t].astype(int)).max(axis=2) <= 1) >= 0.999, f"tick {t}"
+    # and the full per-pixel bar on the last state
+    check_parity(gpu.render(sg.uniforms(frame_index=6), sg.params()), orc.render(so.uniforms(frame_index=6), so.params()), strict_ids=False)
+    orc.close(); gpu.close()
+
+
 def test_many_instances_tile_parity():
     """C5 in small (50k instances, 16 soft-shadow rays): a tile of the 4K launch against the oracle."""
     orc, so, gpu, sg = both("c5", 3840, 2160, num_instances=50000)

@@ -100,6 +100,9 @@ def test_default_scene_texture_indices():
     assert (geo["lain"].diffuse_image_index, geo["lain"].metallic_roughness_image_index) == (6, 7)
     assert (geo["fence"].diffuse_image_index, geo["fence"].metallic_roughness_image_index) == (8, 9)
     assert len(s.instances) == 105  # src/scene.rs:95-156
+    moved = s.animate(3)  # DefaultScene::update x3: only lain's 48 transform bytes change (src/scene.rs:173-181)
+    diff = [i for i in range(105) if moved[i].tobytes() != s.instances[i].tobytes()]
+    assert diff == [2] and moved[2]["blas"] == s.instances[2]["blas"]
     kinds = s.instances["sbt_offset_and_flags"] & 0xFFFFFF
     assert kinds[3] == abi.RT_HIT_PORTAL and set(kinds[5:].tolist()) == {abi.RT_HIT_TEXTURED, abi.RT_HIT_MIRROR}
 
