@@ -89,7 +89,8 @@ struct RtContext {
     DevVec<RtModelInfo> d_model_info;
     DevVec<BlasInfo> d_blas_info;
     DevVec<Node8> blas_nodes;
-    DevVec<TriRec> tris;
+    DevVec<TriRec> tris;          // BVH leaf order; a tiny BLAS is followed by one bounds record
+    uint32_t num_triangles = 0;
 
     // instances / TLAS
     uint32_t num_instances = 0, inst_cap = 0;
@@ -510,7 +511,7 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     // ---- BLAS
     uint32_t node_offset = (uint32_t)ctx->blas_nodes.size, prim_offset = (uint32_t)ctx->tris.size;
     CKM(ctx->blas_nodes.reserve(ctx->blas_nodes.size + max_wide_nodes(nt), st));
-    CKM(ctx->tris.reserve(ctx->tris.size + (nt ? nt : 1), st));
+    CKM(ctx->tris.reserve(ctx->tris.size + (nt ? nt : 1) + 1, st));  // + the bounds record of a tiny BLAS
     uint32_t** d_index_ptrs = nullptr;
     uint32_t* d_geom_start = nullptr;
     uint8_t* d_geom_opaque = nullptr;
@@ -553,6 +554,16 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     cleanup_tmp();
     ctx->blas_nodes.size += node_count;
     ctx->tris.size += nt;
+    ctx->num_triangles += nt;
+    if (nt > 0 && nt <= RT_TINY_BLAS_TRIS) {
+        // tiny BLAS (tested without its node, trace.cuh): exact object-space bounds in the record after its triangles
+        TriRec box;
+        memset(&box, 0, sizeof(box));
+        for (int k = 0; k < 3; k++) { box.v0[k] = root.lo[k]; box.e1[k] = root.hi[k]; }
+        CKM(cudaMemcpyAsync(ctx->tris.ptr + prim_offset + nt, &box, sizeof(box), cudaMemcpyHostToDevice, st));
+        CKM(cudaStreamSynchronize(st));
+        ctx->tris.size += 1;
+    }
     m.blas.root = node_offset;
     m.blas.num_tris = nt;
     m.blas.tri_first = prim_offset;
@@ -770,7 +781,7 @@ int rt_get_stats(RtContext* ctx, RtStats* out) {
     if (ctx->tlas_built) CK(cudaMemcpy(&out->tlas_nodes, ctx->d_tlas_node_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     out->blas_nodes = (uint32_t)ctx->blas_nodes.size;
     out->num_instances = ctx->num_instances;
-    out->num_triangles = (uint32_t)ctx->tris.size;
+    out->num_triangles = ctx->num_triangles;
     return RT_OK;
 }
 

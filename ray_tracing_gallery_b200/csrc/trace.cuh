@@ -251,8 +251,19 @@ struct Traverser {
                 float inv[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
                 const uint32_t tiny = (mw >> 8) & 0xFFu;
                 if (tiny) {
-                    // tiny BLAS: its triangles are tested right here, traversal stays in the TLAS
+                    // tiny BLAS: its triangles are tested right here, traversal stays in the TLAS.  First the exact
+                    // object-space bounds (the record after the triangles): the TLAS slot box is quantised to the
+                    // root's grid, far too coarse to reject e.g. a shadow ray leaving the ground plane it starts on.
                     V3 oo = xform_point(inv, o), od = xform_vec(inv, d);
+                    const float4* bp = reinterpret_cast<const float4*>(S.tris + root + tiny);
+                    float4 blo = __ldg(bp), bhi = __ldg(bp + 1);
+                    float ix = safe_rcp(od.x), iy = safe_rcp(od.y), iz = safe_rcp(od.z);
+                    float x0 = (blo.x - oo.x) * ix, x1 = (bhi.x - oo.x) * ix;
+                    float y0 = (blo.y - oo.y) * iy, y1 = (bhi.y - oo.y) * iy;
+                    float z0 = (blo.z - oo.z) * iz, z1 = (bhi.z - oo.z) * iz;
+                    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+                    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), hit.t));
+                    if (tn > tf + 4e-6f * (fabsf(tn) + fabsf(tf)) + 1e-30f) return false;
                     for (uint32_t k = 0; k < tiny; k++)
                         if (test_triangle(S, root + k, oo, od, pos, __float_as_uint(r3.y), __float_as_uint(r3.z), tc) && ANY) return true;
                     return false;
