@@ -154,8 +154,10 @@ def run_reference(args):
         holder["s"] = build_scene(backend, args.workload, args.width or None, args.height or None, num_instances=args.instances or None)
         return holder["s"]
 
-    steps = max(1, min(args.steps, 5))
-    warm = max(0, min(args.warmup, 1))
+    # each step is one frame on all host threads; the step count is bounded so that the arm ends within a few minutes
+    cap = 60 if args.workload in ("c1", "c2", "c3", "default") else 2
+    steps = max(1, min(args.steps, cap))
+    warm = max(0, min(args.warmup, 2))
     value, info = oracle_sample(args, builder, steps=steps, warmup=warm)
     s = holder["s"]
     line = {
@@ -193,9 +195,9 @@ def algorithmic_bytes(st, setup, pixels):
     # k_prep: hit record 48 B in, ModelInfo 32 + GeometryInfo 24 + indices 12 + 3 vertices x 32, instance transform 48 + inverse 64,
     #         two bilinear taps (4 texels x 4 B each), 64 B record out
     prep_b = hits * (48 + 32 + 24 + 12 + 96 + 48 + 64 + 2 * 16 + 64)
-    # k_shadow: per ray 20 B of the hit record (pixel + origin), two blue-noise texels, 4 B atomic on `lit`
-    shadow_b = trav[1] + st.shadow_rays * (20 + 8 + 4)
-    # k_resolve: 52 B of the record, 4 B framebuffer
+    # k_shadow: per ray 16 B of the hit record (origin + launch id), 16 B of the direction table, 4 B atomic on `lit`
+    shadow_b = trav[1] + st.shadow_rays * (16 + 16 + 4)
+    # resolve phase (in k_tail): 52 B of the record, 4 B framebuffer
     resolve_b = hits * (52 + 4)
     mega_b = trav[0] + trav[1] + 112 * bounces + hits * (32 + 24 + 12 + 96 + 48 + 64 + 2 * 16 + 8 * n) + 4 * pixels
     return {"trace": int(trace_b), "prep": int(prep_b), "shadow": int(shadow_b), "resolve": int(resolve_b), "mega": int(mega_b),
@@ -471,13 +473,14 @@ def run_ours(args):
                         "bytes": float(bytes_frame["mega"] if args.pipeline == "mega" else sum(bytes_frame[k] for k in KERNELS[:4])) / rays_frame},
             "note": "achieved = algorithmic bytes (per-ray node/instance/triangle fetches + queue records, DESIGN.md 3) / kernel time; the working "
                     "set of C1-C4 is cache resident (traffic = DRAM bytes of one ncu capture, far below the algorithmic bytes), the kernel is "
-                    "issue-bound (profiles/r01i_summary.md: 70 % issue slots busy, 19.7 of 32 lanes active)",
+                    "issue-bound (profiles/r01j_summary.md: 70 % issue slots busy, 19 of 32 lanes active)",
         }
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             def builder(backend):
                 return build_scene(backend, args.workload, args.width or None, args.height or None, num_instances=args.instances or None)
-            v, info = oracle_sample(args, builder, steps=3 if args.workload in ("c1", "c2", "c3", "default") else 1, warmup=0)
+            # bounded sample, about 10 s of CPU work on the box's host cores
+            v, info = oracle_sample(args, builder, steps=60 if args.workload in ("c1", "c2", "c3", "default") else 1, warmup=1)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
