@@ -64,6 +64,23 @@ struct TexRes {
 
 }  // namespace
 
+// What one frame in flight owns: the stream its kernels run on and every buffer they write besides the outputs.
+// The scene (models, BLASes, TLAS, images) is shared and read-only while frames render.
+struct FrameResources {
+    cudaStream_t stream = nullptr;
+    FrameCounters* d_counters = nullptr;
+    RayRec* d_ray_q[2] = {nullptr, nullptr};
+    HitRec* d_hit_q = nullptr;
+    size_t queue_cap = 0;
+    float4* d_sun_dirs = nullptr;
+    size_t sun_dirs_cap = 0;
+    void release() {
+        cudaFree(d_counters); cudaFree(d_ray_q[0]); cudaFree(d_ray_q[1]); cudaFree(d_hit_q); cudaFree(d_sun_dirs);
+        d_counters = nullptr; d_ray_q[0] = d_ray_q[1] = nullptr; d_hit_q = nullptr; d_sun_dirs = nullptr;
+        queue_cap = sun_dirs_cap = 0;
+    }
+};
+
 struct RtContext {
     int device = 0;
     int sms = 0;
@@ -106,26 +123,25 @@ struct RtContext {
 
     // frame
     RtUniforms* d_uniforms = nullptr;  // copy kept for the push-constant parity view
-    FrameCounters* d_counters = nullptr;
-    RayRec* d_ray_q[2] = {nullptr, nullptr};
-    HitRec* d_hit_q = nullptr;
-    size_t queue_cap = 0;
+    FrameResources main;               // rt_render / rt_render_device (main.stream == stream)
+    FrameResources* last_res = nullptr;  // resources of the most recent frame (rt_get_stats)
     uint8_t* d_fb_rgba8 = nullptr;
     float* d_fb_radiance = nullptr;
     uint32_t* d_fb_hit_ids = nullptr;
     size_t fb_rgba8_cap = 0, fb_radiance_cap = 0, fb_hit_ids_cap = 0;
     size_t last_rows = 0, last_tw = 0;
     uint64_t* d_ray_counts = nullptr;
-    float4* d_sun_dirs = nullptr;
-    size_t sun_dirs_cap = 0;
 
-    // two frames in flight (rt_render_async)
+    // two frames in flight (rt_render_async): each slot renders on its own stream with its own queues, so consecutive
+    // frames overlap on the GPU wherever one frame alone leaves it idle (kernel tails, stage boundaries)
     struct FrameSlot {
+        FrameResources res;
         uint8_t* d_rgba8 = nullptr;
         size_t cap = 0;
         uint64_t* d_ray_counts = nullptr;
-        cudaEvent_t rendered = nullptr, copied = nullptr;
-        bool pending = false;
+        cudaEvent_t scene_ready = nullptr, rendered = nullptr, copied = nullptr;
+        bool pending = false;       // host has not waited for `copied` yet
+        bool rendering = false;     // `rendered` may not have fired yet: scene changes must wait for it
     } slots[2];
     cudaStream_t copy_stream = nullptr;
     uint32_t next_slot = 0;
@@ -203,6 +219,17 @@ int build_tlas_now(RtContext* ctx, uint32_t mode) {
     return RT_OK;
 }
 
+// A scene change (instance write, TLAS build/update, new model or image) enqueued on the context's stream must not
+// overtake frames still rendering on the slot streams of rt_render_async.
+int wait_for_frames_in_flight(RtContext* ctx) {
+    for (auto& sl : ctx->slots)
+        if (sl.rendering) {
+            CK(cudaStreamWaitEvent(ctx->stream, sl.rendered, 0));
+            sl.rendering = false;
+        }
+    return RT_OK;
+}
+
 struct FramePlan {
     uint32_t x0, y0, tw, th, rows;
 };
@@ -229,16 +256,20 @@ int plan_frame(RtContext* ctx, const RtRenderParams* p, FramePlan& f) {
     return RT_OK;
 }
 
-int render_common(RtContext* ctx, const RtUniforms* u, const RtRenderParams* p, const FramePlan& f, uint8_t* d_rgba8, float* d_radiance,
-                  uint32_t* d_hit_ids, uint64_t* d_ray_counts) {
+int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const RtRenderParams* p, const FramePlan& f, uint8_t* d_rgba8,
+                  float* d_radiance, uint32_t* d_hit_ids, uint64_t* d_ray_counts) {
     if (!ctx->tlas_built) return fail(ctx, RT_ERR_NOT_BUILT, "rt_render before rt_build_tlas");
     size_t pixels = (size_t)f.rows * f.tw;
-    if (pixels > ctx->queue_cap) {
+    if (!R.d_counters) {
+        CK(cudaMalloc(&R.d_counters, sizeof(FrameCounters)));
+        CK(cudaMemsetAsync(R.d_counters, 0, sizeof(FrameCounters), R.stream));
+    }
+    if (pixels > R.queue_cap) {
         size_t cap = 0;
-        for (int i = 0; i < 2; i++) { cap = ctx->queue_cap; CK(grow(ctx->d_ray_q[i], cap, pixels)); }
-        cap = ctx->queue_cap;
-        CK(grow(ctx->d_hit_q, cap, pixels));
-        ctx->queue_cap = pixels;
+        for (int i = 0; i < 2; i++) { cap = R.queue_cap; CK(grow(R.d_ray_q[i], cap, pixels)); }
+        cap = R.queue_cap;
+        CK(grow(R.d_hit_q, cap, pixels));
+        R.queue_cap = pixels;
     }
     SceneDev S;
     S.tlas_nodes = ctx->d_tlas_nodes;
@@ -264,20 +295,20 @@ int render_common(RtContext* ctx, const RtUniforms* u, const RtRenderParams* p, 
     F.cos_sun_radius = cosf(u->sun_radius);
     F.image_rows = (p->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) ? 1u : 0u;
     F.rgba8 = d_rgba8; F.radiance = d_radiance; F.hit_ids = d_hit_ids;
-    F.counters = ctx->d_counters;
-    F.ray_q[0] = ctx->d_ray_q[0]; F.ray_q[1] = ctx->d_ray_q[1];
-    F.hit_q = ctx->d_hit_q;
+    F.counters = R.d_counters;
+    F.ray_q[0] = R.d_ray_q[0]; F.ray_q[1] = R.d_ray_q[1];
+    F.hit_q = R.d_hit_q;
     // per-frame shadow-direction table: only for the 64x64 nearest-filtered blue-noise image the shaders assume
     F.sun_dirs = nullptr;
     if (u->blue_noise_texture_index < ctx->tex_host.size()) {
         const TexEntry& bn = ctx->tex_host[u->blue_noise_texture_index];
         if (bn.obj != 0 && bn.w == 64 && bn.h == 64 && !bn.linear && p->shadow_rays <= 64) {
-            CK(grow(ctx->d_sun_dirs, ctx->sun_dirs_cap, (size_t)4096 * p->shadow_rays));
-            F.sun_dirs = ctx->d_sun_dirs;
+            CK(grow(R.d_sun_dirs, R.sun_dirs_cap, (size_t)4096 * p->shadow_rays));
+            F.sun_dirs = R.d_sun_dirs;
         }
     }
-    CK(cudaMemcpyAsync(ctx->d_uniforms, u, sizeof(RtUniforms), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (&R == &ctx->main) CK(cudaMemcpyAsync(ctx->d_uniforms, u, sizeof(RtUniforms), cudaMemcpyHostToDevice, R.stream));
+    CK(cudaEventRecord(ctx->ev[0], R.stream));
     FrameTiming* timing = nullptr;
     if (p->flags & RT_RENDER_TIMING) {
         if (!ctx->timing_ready) {
@@ -287,9 +318,10 @@ int render_common(RtContext* ctx, const RtUniforms* u, const RtRenderParams* p, 
         timing = &ctx->timing;
     }
     ctx->timing_valid = timing != nullptr;
-    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, (p->flags & RT_RENDER_SPLIT_TAIL) != 0, (p->flags & RT_RENDER_NO_PDL) != 0, ctx->sms, d_ray_counts, timing, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, (p->flags & RT_RENDER_SPLIT_TAIL) != 0, (p->flags & RT_RENDER_NO_PDL) != 0, ctx->sms, d_ray_counts, timing, R.stream));
+    CK(cudaEventRecord(ctx->ev[1], R.stream));
     ctx->render_timed = true;
+    ctx->last_res = &R;
     ctx->last_rows = f.rows;
     ctx->last_tw = f.tw;
     return RT_OK;
@@ -336,7 +368,9 @@ int rt_create(int cuda_device, RtContext** out) {
     if ((e = cudaMalloc(&c->d_real_textures, sizeof(uint32_t) * RT_MAX_BOUND_IMAGES)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_srgb_lut, sizeof(float) * 512)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_uniforms, sizeof(RtUniforms))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&c->d_counters, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMalloc");
+    c->main.stream = c->stream;
+    if ((e = cudaMalloc(&c->main.d_counters, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMalloc");
+    c->last_res = &c->main;
     if ((e = cudaMalloc(&c->d_tlas_node_count, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_ray_counts, sizeof(uint64_t) * 2)) != cudaSuccess) return bail(e, "cudaMalloc");
     // sRGB EOTF table (exact per 8-bit code, decode happens before filtering)
@@ -346,7 +380,7 @@ int rt_create(int cuda_device, RtContext** out) {
         c->srgb_lut[256 + i] = v;  // UNORM8 decode: code / 255, correctly rounded
     }
     if ((e = cudaMemcpy(c->d_srgb_lut, c->srgb_lut, sizeof(c->srgb_lut), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
-    if ((e = cudaMemset(c->d_counters, 0, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMemset(c->main.d_counters, 0, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMemset");
     *out = c;
     return RT_OK;
 }
@@ -357,7 +391,10 @@ void rt_destroy(RtContext* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (auto& sl : ctx->slots) {
+        if (sl.res.stream) { cudaStreamSynchronize(sl.res.stream); cudaStreamDestroy(sl.res.stream); }
+        sl.res.release();
         cudaFree(sl.d_rgba8); cudaFree(sl.d_ray_counts);
+        if (sl.scene_ready) cudaEventDestroy(sl.scene_ready);
         if (sl.rendered) cudaEventDestroy(sl.rendered);
         if (sl.copied) cudaEventDestroy(sl.copied);
     }
@@ -370,11 +407,11 @@ void rt_destroy(RtContext* ctx) {
         for (auto* p : m.index_bufs) cudaFree(p);
     }
     ctx->d_model_info.release(); ctx->d_blas_info.release(); ctx->blas_nodes.release(); ctx->tris.release();
-    cudaFree(ctx->d_textures); cudaFree(ctx->d_real_textures); cudaFree(ctx->d_srgb_lut); cudaFree(ctx->d_uniforms); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_textures); cudaFree(ctx->d_real_textures); cudaFree(ctx->d_srgb_lut); cudaFree(ctx->d_uniforms);
+    ctx->main.release();
     cudaFree(ctx->d_instances); cudaFree(ctx->d_inst_unsorted); cudaFree(ctx->d_inst_rt); cudaFree(ctx->d_inst_boxes);
     cudaFree(ctx->d_leaf_order); cudaFree(ctx->d_tlas_nodes); cudaFree(ctx->d_tlas_node_count); cudaFree(ctx->d_ray_counts);
-    cudaFree(ctx->d_ray_q[0]); cudaFree(ctx->d_ray_q[1]); cudaFree(ctx->d_hit_q);
-    cudaFree(ctx->d_fb_rgba8); cudaFree(ctx->d_fb_radiance); cudaFree(ctx->d_fb_hit_ids); cudaFree(ctx->d_sun_dirs);
+    cudaFree(ctx->d_fb_rgba8); cudaFree(ctx->d_fb_radiance); cudaFree(ctx->d_fb_hit_ids);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->timing_ready)
@@ -390,6 +427,7 @@ int rt_set_stream(RtContext* ctx, void* cuda_stream) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;  // NULL names the legacy default stream, as in the CUDA runtime
+    ctx->main.stream = ctx->stream;
     ctx->own_stream = false;
     ctx->render_timed = ctx->tlas_timed = false;
     ctx->timing_valid = false;
@@ -402,6 +440,7 @@ int rt_push_image(RtContext* ctx, const void* texels, uint32_t width, uint32_t h
     if (!texels || !width || !height || format > RT_FORMAT_RGBA32_SFLOAT) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_push_image: bad argument");
     if (ctx->tex_host.size() >= RT_MAX_BOUND_IMAGES) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_push_image: image table full (128)");
     CK_DEV(ctx);
+    { int w = wait_for_frames_in_flight(ctx); if (w) return w; }
     TexEntry te;
     memset(&te, 0, sizeof(te));
     te.w = width; te.h = height; te.format = format; te.linear = linear_filter ? 1u : 0u;
@@ -458,6 +497,7 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     if (!desc || (desc->num_vertices && (!desc->positions || !desc->normals || !desc->uvs)) || (desc->num_geometries && !desc->geometries))
         return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_create_model: bad argument");
     CK_DEV(ctx);
+    { int w = wait_for_frames_in_flight(ctx); if (w) return w; }
     cudaStream_t st = ctx->stream;
     uint32_t nv = desc->num_vertices, ng = desc->num_geometries;
     std::vector<uint32_t> geom_start(ng + 1, 0);
@@ -596,6 +636,7 @@ int rt_build_tlas(RtContext* ctx, const RtInstance* instances, uint32_t count) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     if (count && !instances) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_build_tlas: instances is NULL");
     CK_DEV(ctx);
+    { int w = wait_for_frames_in_flight(ctx); if (w) return w; }
     int rc = ensure_instance_capacity(ctx, count);
     if (rc) return rc;
     ctx->num_instances = count;
@@ -612,6 +653,7 @@ int rt_update_instances(RtContext* ctx, uint32_t first, uint32_t count, const Rt
     if ((uint64_t)first + count > ctx->num_instances) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_update_instances: range outside the instance buffer");
     if (count && !host_records) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_instances: records is NULL");
     CK_DEV(ctx);
+    { int w = wait_for_frames_in_flight(ctx); if (w) return w; }
     if (count) {
         CK(cudaMemcpyAsync(ctx->d_instances + first, host_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));  // pageable source: the caller owns it again on return
@@ -624,6 +666,7 @@ int rt_update_instances_device(RtContext* ctx, uint32_t first, uint32_t count, c
     if ((uint64_t)first + count > ctx->num_instances) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_update_instances_device: range outside the instance buffer");
     if (count && !device_records) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_instances_device: records is NULL");
     CK_DEV(ctx);
+    { int w = wait_for_frames_in_flight(ctx); if (w) return w; }
     if (count) CK(cudaMemcpyAsync(ctx->d_instances + first, device_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyDeviceToDevice, ctx->stream));
     return RT_OK;
 }
@@ -633,6 +676,7 @@ int rt_update_tlas(RtContext* ctx, uint32_t mode) {
     if (mode > RT_UPDATE_REBUILD) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_tlas: unknown mode");
     if (!ctx->tlas_built) return fail(ctx, RT_ERR_NOT_BUILT, "rt_update_tlas before rt_build_tlas");
     CK_DEV(ctx);
+    { int w = wait_for_frames_in_flight(ctx); if (w) return w; }
     if (mode == RT_UPDATE_AUTO) mode = RT_UPDATE_REBUILD;
     return build_tlas_now(ctx, mode);
 }
@@ -646,7 +690,7 @@ int rt_render_device(RtContext* ctx, const RtUniforms* uniforms, const RtRenderP
     if (rc) return rc;
     if ((params->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) && out && out->hit_ids)
         return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_device: RT_RENDER_OUTPUT_IMAGE_ROWS supports rgba8 and radiance only");
-    return render_common(ctx, uniforms, params, f, out ? out->rgba8 : nullptr, out ? out->radiance : nullptr, out ? out->hit_ids : nullptr,
+    return render_common(ctx, ctx->main, uniforms, params, f, out ? out->rgba8 : nullptr, out ? out->radiance : nullptr, out ? out->hit_ids : nullptr,
                          out ? out->ray_counts : nullptr);
 }
 
@@ -663,7 +707,7 @@ int rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* 
     CK(grow(ctx->d_fb_rgba8, ctx->fb_rgba8_cap, pixels * 4 + 16));
     if (want_rad) CK(grow(ctx->d_fb_radiance, ctx->fb_radiance_cap, pixels * 3 + 4));
     if (want_ids) CK(grow(ctx->d_fb_hit_ids, ctx->fb_hit_ids_cap, pixels * 3 * params->max_segments + 4));
-    rc = render_common(ctx, uniforms, params, f, ctx->d_fb_rgba8, want_rad ? ctx->d_fb_radiance : nullptr,
+    rc = render_common(ctx, ctx->main, uniforms, params, f, ctx->d_fb_rgba8, want_rad ? ctx->d_fb_radiance : nullptr,
                        want_ids ? ctx->d_fb_hit_ids : nullptr, ctx->d_ray_counts);
     if (rc) return rc;
     if (out) {
@@ -691,6 +735,8 @@ int rt_render_async(RtContext* ctx, const RtUniforms* uniforms, const RtRenderPa
     RtContext::FrameSlot& sl = ctx->slots[si];
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (!sl.rendered) {
+        CK(cudaStreamCreateWithFlags(&sl.res.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&sl.scene_ready, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&sl.rendered, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
         CK(cudaMalloc(&sl.d_ray_counts, 16));
@@ -700,9 +746,13 @@ int rt_render_async(RtContext* ctx, const RtUniforms* uniforms, const RtRenderPa
         sl.pending = false;
     }
     CK(grow(sl.d_rgba8, sl.cap, pixels * 4 + 16));
-    rc = render_common(ctx, uniforms, params, f, sl.d_rgba8, nullptr, nullptr, sl.d_ray_counts);
+    // the frame sees every scene change enqueued so far on the context's stream, then runs on the slot's own stream
+    CK(cudaEventRecord(sl.scene_ready, ctx->stream));
+    CK(cudaStreamWaitEvent(sl.res.stream, sl.scene_ready, 0));
+    rc = render_common(ctx, sl.res, uniforms, params, f, sl.d_rgba8, nullptr, nullptr, sl.d_ray_counts);
     if (rc) return rc;
-    CK(cudaEventRecord(sl.rendered, ctx->stream));
+    CK(cudaEventRecord(sl.rendered, sl.res.stream));
+    sl.rendering = true;
     CK(cudaStreamWaitEvent(ctx->copy_stream, sl.rendered, 0));
     if (out && out->rgba8) CK(cudaMemcpyAsync(out->rgba8, sl.d_rgba8, pixels * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
     if (out && out->ray_counts) CK(cudaMemcpyAsync(out->ray_counts, sl.d_ray_counts, 16, cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -741,8 +791,10 @@ int rt_sync(RtContext* ctx) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     CK_DEV(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& sl : ctx->slots)
+        if (sl.res.stream) CK(cudaStreamSynchronize(sl.res.stream));
     if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
-    for (auto& sl : ctx->slots) sl.pending = false;
+    for (auto& sl : ctx->slots) sl.pending = sl.rendering = false;
     return RT_OK;
 }
 
@@ -751,8 +803,10 @@ int rt_get_stats(RtContext* ctx, RtStats* out) {
     if (!out) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_get_stats: NULL");
     CK_DEV(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
+    FrameResources* lr = ctx->last_res ? ctx->last_res : &ctx->main;
+    if (lr->stream != ctx->stream) CK(cudaStreamSynchronize(lr->stream));
     FrameCounters fc;
-    CK(cudaMemcpy(&fc, ctx->d_counters, sizeof(fc), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&fc, lr->d_counters, sizeof(fc), cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof(*out));
     out->primary_rays = fc.primary_rays;
     out->shadow_rays = fc.shadow_rays;
