@@ -194,6 +194,13 @@ int  rt_render_device(RtContext* ctx, const RtUniforms* uniforms, const RtRender
 int  rt_render_async(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params,
                      const RtFrameOutputs* out, uint32_t* out_slot);
 int  rt_wait_frame(RtContext* ctx, uint32_t slot);
+/* The device-output form of the same idea, for hosts that own the streams (e.g. one process per GPU with the frame
+ * going to another rank): render into caller-owned DEVICE outputs on the caller's cudaStream_t using the private
+ * queues of frame slot 0 or 1, so that two frames on two streams overlap.  Frames that use the same slot must be
+ * ordered by the caller (same stream, or events).  Scene changes made through this context are ordered before and
+ * after the frame by the library. */
+int  rt_render_device_slot(RtContext* ctx, uint32_t slot, void* cuda_stream, const RtUniforms* uniforms,
+                           const RtRenderParams* params, const RtFrameOutputs* out);
 /* Storage-image copy / present (src/command_buffer_recording.rs:165-179): copy the
  * RGBA8 rows of the last rt_render(…, NULL) / rt_render frame to host memory (blocking). */
 int  rt_readback(RtContext* ctx, void* host_rgba8, size_t capacity_bytes);

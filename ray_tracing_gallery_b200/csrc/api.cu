@@ -145,6 +145,13 @@ struct RtContext {
     } slots[2];
     cudaStream_t copy_stream = nullptr;
     uint32_t next_slot = 0;
+
+    // rt_render_device_slot: the same per-frame resources for caller-owned streams and device outputs
+    struct DeviceSlot {
+        FrameResources res;
+        cudaEvent_t scene_ready = nullptr, rendered = nullptr;
+        bool rendering = false;
+    } dev_slots[2];
 };
 
 namespace {
@@ -223,6 +230,11 @@ int build_tlas_now(RtContext* ctx, uint32_t mode) {
 // overtake frames still rendering on the slot streams of rt_render_async.
 int wait_for_frames_in_flight(RtContext* ctx) {
     for (auto& sl : ctx->slots)
+        if (sl.rendering) {
+            CK(cudaStreamWaitEvent(ctx->stream, sl.rendered, 0));
+            sl.rendering = false;
+        }
+    for (auto& sl : ctx->dev_slots)
         if (sl.rendering) {
             CK(cudaStreamWaitEvent(ctx->stream, sl.rendered, 0));
             sl.rendering = false;
@@ -390,6 +402,12 @@ void rt_destroy(RtContext* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (auto& sl : ctx->dev_slots) {
+        if (sl.rendering && sl.rendered) cudaEventSynchronize(sl.rendered);
+        sl.res.release();
+        if (sl.scene_ready) cudaEventDestroy(sl.scene_ready);
+        if (sl.rendered) cudaEventDestroy(sl.rendered);
+    }
     for (auto& sl : ctx->slots) {
         if (sl.res.stream) { cudaStreamSynchronize(sl.res.stream); cudaStreamDestroy(sl.res.stream); }
         sl.res.release();
@@ -763,6 +781,33 @@ int rt_render_async(RtContext* ctx, const RtUniforms* uniforms, const RtRenderPa
     return RT_OK;
 }
 
+int rt_render_device_slot(RtContext* ctx, uint32_t slot, void* cuda_stream, const RtUniforms* uniforms, const RtRenderParams* params,
+                          const RtFrameOutputs* out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!uniforms || !params) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_device_slot: NULL argument");
+    if (slot > 1) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_render_device_slot: slot is 0 or 1");
+    if ((params->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) && out && out->hit_ids)
+        return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_device_slot: RT_RENDER_OUTPUT_IMAGE_ROWS supports rgba8 and radiance only");
+    CK_DEV(ctx);
+    FramePlan f;
+    int rc = plan_frame(ctx, params, f);
+    if (rc) return rc;
+    RtContext::DeviceSlot& sl = ctx->dev_slots[slot];
+    if (!sl.rendered) {
+        CK(cudaEventCreateWithFlags(&sl.scene_ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.rendered, cudaEventDisableTiming));
+    }
+    sl.res.stream = (cudaStream_t)cuda_stream;
+    CK(cudaEventRecord(sl.scene_ready, ctx->stream));             // scene changes enqueued so far ...
+    CK(cudaStreamWaitEvent(sl.res.stream, sl.scene_ready, 0));    // ... happen before this frame
+    rc = render_common(ctx, sl.res, uniforms, params, f, out ? out->rgba8 : nullptr, out ? out->radiance : nullptr,
+                       out ? out->hit_ids : nullptr, out ? out->ray_counts : nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(sl.rendered, sl.res.stream));
+    sl.rendering = true;
+    return RT_OK;
+}
+
 int rt_wait_frame(RtContext* ctx, uint32_t slot) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     if (slot > 1) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_wait_frame: slot is 0 or 1");
@@ -795,6 +840,8 @@ int rt_sync(RtContext* ctx) {
         if (sl.res.stream) CK(cudaStreamSynchronize(sl.res.stream));
     if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
     for (auto& sl : ctx->slots) sl.pending = sl.rendering = false;
+    for (auto& sl : ctx->dev_slots)
+        if (sl.rendering) { CK(cudaEventSynchronize(sl.rendered)); sl.rendering = false; }
     return RT_OK;
 }
 

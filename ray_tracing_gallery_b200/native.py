@@ -20,7 +20,7 @@ _LIB = None
 EXPORTS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_push_image", "rt_create_model", "rt_build_tlas",
     "rt_update_instances", "rt_update_instances_device", "rt_update_tlas", "rt_render", "rt_render_device", "rt_render_async",
-    "rt_wait_frame", "rt_readback",
+    "rt_wait_frame", "rt_render_device_slot", "rt_readback",
     "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_kernel_launches", "rt_version",
 ]
 
@@ -49,6 +49,7 @@ def load():
     lib.rt_render_device.argtypes = [p, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams), C.POINTER(abi.RtFrameOutputs)]
     lib.rt_render_async.argtypes = [p, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams), C.POINTER(abi.RtFrameOutputs), C.POINTER(u32)]
     lib.rt_wait_frame.argtypes = [p, u32]
+    lib.rt_render_device_slot.argtypes = [p, u32, p, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams), C.POINTER(abi.RtFrameOutputs)]
     lib.rt_readback.argtypes = [p, p, C.c_size_t]
     lib.rt_sync.argtypes = [p]
     lib.rt_get_stats.argtypes = [p, C.POINTER(abi.RtStats)]
@@ -89,6 +90,11 @@ class Renderer(CApiBackend):
         """Enqueue a frame whose outputs are caller-owned device buffers (raw pointers)."""
         out = abi.RtFrameOutputs(rgba8 or None, radiance or None, hit_ids or None, ray_counts or None)
         self._check(self.lib.rt_render_device(self.ctx, C.byref(uniforms), C.byref(params), C.byref(out)), "render_device")
+
+    def render_device_slot(self, slot: int, cuda_stream: int, uniforms, params, rgba8=0, radiance=0, hit_ids=0, ray_counts=0):
+        """`rt_render_device_slot`: a frame on the caller's stream with the private queues of frame slot 0/1."""
+        out = abi.RtFrameOutputs(rgba8 or None, radiance or None, hit_ids or None, ray_counts or None)
+        self._check(self.lib.rt_render_device_slot(self.ctx, slot, cuda_stream, C.byref(uniforms), C.byref(params), C.byref(out)), "render_device_slot")
 
     def render_to_host(self, uniforms, params, host_rgba8_ptr: int, ray_counts_ptr: int = 0):
         """`rt_render` with caller-owned HOST buffers (pinned memory makes the copy asynchronous-capable)."""

@@ -415,3 +415,30 @@ def test_image_rows_output_lets_ranks_share_one_frame():
     with pytest.raises(RtError):
         gpu.render(s.uniforms(), s.params(flags=abi.RT_RENDER_OUTPUT_IMAGE_ROWS))
     gpu.close()
+
+
+def test_device_slots_render_concurrently_on_caller_streams():
+    """rt_render_device_slot: two frames on two caller-owned streams, each with the private queues of its slot, equal
+    the frames rendered one after the other; a TLAS update issued afterwards waits for both."""
+    import torch
+
+    gpu = make_renderer()
+    s = build_scene(gpu, "c3", 480, 270)
+    want = [gpu.render(s.uniforms(frame_index=1 + i), s.params(), want=("rgba8", "ray_counts")) for i in range(4)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    fbs = [torch.zeros((270, 480, 4), dtype=torch.uint8, device="cuda") for _ in range(4)]
+    rcs = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(4)]
+    for i in range(4):  # frames 0,2 on slot/stream 0, frames 1,3 on slot/stream 1: same-slot frames are ordered by their stream
+        gpu.render_device_slot(i & 1, streams[i & 1].cuda_stream, s.uniforms(frame_index=1 + i), s.params(), rgba8=fbs[i].data_ptr(),
+                               ray_counts=rcs[i].data_ptr())
+    gpu.update_instances(0, s.instances)        # ordered after the four frames by the library
+    gpu.update_tlas(abi.RT_UPDATE_REBUILD)
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert np.array_equal(fbs[i].cpu().numpy(), want[i]["rgba8"]), f"frame {i}"
+        assert rcs[i].cpu().numpy().astype(np.uint64).tolist() == want[i]["ray_counts"].tolist()
+    after = gpu.render(s.uniforms(frame_index=1), s.params(), want=("rgba8",))
+    assert np.array_equal(after["rgba8"], want[0]["rgba8"])
+    with pytest.raises(RtError):
+        gpu.render_device_slot(2, 0, s.uniforms(), s.params())
+    gpu.close()
