@@ -295,18 +295,25 @@ __global__ void k_fit(Tree2 T) {
 }
 
 // ------------------------------------------------------------------------------------ quantisation
+// Exact power-of-two helpers: the builder scales by 2^e with one multiplication (exact for the clamped
+// exponents used here) instead of ldexpf/frexpf, which dominated the per-node cost of collapse and refit.
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((e + 127) << 23); }  // -126 <= e <= 127
+__device__ __forceinline__ int frexp_exponent(float x) {  // x > 0: x = m * 2^e with m in [0.5, 1)
+    int b = (__float_as_int(x) >> 23) & 0xFF;
+    return b == 0 ? -126 : b - 126;  // denormals count as 2^-126 (every caller clamps the result to >= -100)
+}
+
 // Choose the grid (origin, exponent) of one axis so that lo..hi spans <= 254 cells (one cell of
 // slack for the outward rounding fix-up) and every plane origin + q*2^e is exactly representable.
 __device__ __forceinline__ void axis_grid(float lo, float hi, float& origin, int& e) {
     float s = (hi - lo) / 253.0f;
-    int es = -126, em = -126;
-    if (s > 0.0f) frexpf(s, &es);  // s = m * 2^es, m in [0.5,1)  =>  2^es > s
+    int es = s > 0.0f ? frexp_exponent(s) : -126;  // 2^es > s
     float mx = fmaxf(fabsf(lo), fabsf(hi));
-    if (mx > 0.0f) frexpf(mx, &em);  // mx < 2^em
+    int em = mx > 0.0f ? frexp_exponent(mx) : -126;  // mx < 2^em
     e = max(max(es, em - 22), -100);
     for (;;) {
-        origin = ldexpf(floorf(ldexpf(lo, -e)), e);
-        float top = ceilf(ldexpf(hi - origin, -e));
+        origin = floorf(lo * pow2i(-e)) * pow2i(e);
+        float top = ceilf((hi - origin) * pow2i(-e));
         if (top <= 254.0f || e >= 120) break;
         e++;
     }
@@ -323,24 +330,26 @@ __device__ void quantise_node(Node8& nd, const Aabb* cb, uint32_t present) {
     if (any) {
         for (int k = 0; k < 3; k++) axis_grid(nb.lo[k], nb.hi[k], org[k], ex[k]);
     }
+    float cell[3], inv[3];
     for (int k = 0; k < 3; k++) {
         nd.origin[k] = org[k];
         nd.exp[k] = (int8_t)ex[k];
         nd.lo[k] = nb.lo[k];
         nd.hi[k] = nb.hi[k];
+        cell[k] = pow2i(ex[k]);
+        inv[k] = pow2i(-ex[k]);
     }
     for (int s = 0; s < 8; s++) {
         bool ok = (present >> s & 1) && box_valid(cb[s]);
         for (int k = 0; k < 3; k++) {
             uint8_t ql = 255, qh = 0;
             if (ok) {
-                float cell = ldexpf(1.0f, ex[k]);
-                float a = floorf(ldexpf(cb[s].lo[k] - org[k], -ex[k]));
+                float a = floorf((cb[s].lo[k] - org[k]) * inv[k]);
                 a = fminf(fmaxf(a, 0.0f), 255.0f);
-                while (a > 0.0f && fmaf(a, cell, org[k]) > cb[s].lo[k]) a -= 1.0f;
-                float b = ceilf(ldexpf(cb[s].hi[k] - org[k], -ex[k]));
+                while (a > 0.0f && fmaf(a, cell[k], org[k]) > cb[s].lo[k]) a -= 1.0f;
+                float b = ceilf((cb[s].hi[k] - org[k]) * inv[k]);
                 b = fminf(fmaxf(b, 0.0f), 255.0f);
-                while (b < 255.0f && fmaf(b, cell, org[k]) < cb[s].hi[k]) b += 1.0f;
+                while (b < 255.0f && fmaf(b, cell[k], org[k]) < cb[s].hi[k]) b += 1.0f;
                 ql = (uint8_t)a;
                 qh = (uint8_t)b;
             }
