@@ -105,7 +105,8 @@ typedef struct RtRenderParams {
 } RtRenderParams;
 
 /* Output arrays are compact over the rendered rows (ascending global y), row
- * pitch = tile_w pixels.  Any pointer may be NULL. */
+ * pitch = tile_w pixels — or, with RT_RENDER_OUTPUT_IMAGE_ROWS (rt_render_device*), whole
+ * [tile_h][tile_w] images of which the call stores its own rows.  Any pointer may be NULL. */
 typedef struct RtFrameOutputs {
     uint8_t*  rgba8;        /* [rows][tile_w][4]  linear_to_srgb + UNORM8 store, alpha 255 (lib.rs:188-190) */
     float*    radiance;     /* [rows][tile_w][3]  payload.colour before the sRGB encode */
@@ -126,7 +127,8 @@ typedef struct RtStats {
     uint64_t anyhit_calls[2];
     float    last_render_ms;    /* CUDA-event time of the last rt_render*, valid after rt_sync */
     float    last_tlas_ms;      /* CUDA-event time of the last rt_build_tlas / rt_update_tlas */
-    float    kernel_ms[6];      /* with RT_RENDER_TIMING: {k_trace0, k_prep, k_shadow, k_resolve (segment 0), k_mega, k_tail (segments >= 1)} */
+    float    kernel_ms[6];      /* with RT_RENDER_TIMING: {trace kernels, k_prep, k_shadow, k_resolve (split-tail path only),
+                                   k_mega, k_tail (resolve + bounce segments + ray-count export)} */
     uint32_t kernel_launches[6];/* launches behind kernel_ms */
     uint32_t tlas_nodes;        /* 128-byte wide nodes in the current TLAS */
     uint32_t blas_nodes;        /* over all models */

@@ -1,20 +1,23 @@
 // render.cu — the frame: what one vkCmdTraceRaysKHR(width, height, 1) does in the reference
 // (src/command_buffer_recording.rs:116-126 -> ray_generation, shaders/ray-tracing/src/lib.rs:94-191).
 //
-// Wavefront pipeline (default), per ray-gen segment s = 0 .. max_segments-1:
-//   k_trace<s>   ray generation (s = 0) or ray-queue read (s > 0) + closest-hit traversal;
-//                miss -> sky colour to the framebuffer; mirror/portal -> next ray pushed to the
-//                compacted ray queue; textured hit -> HitRec pushed to the compacted hit queue
-//                (warp ballot + one atomic per warp).
+// Wavefront pipeline (default).  One frame = counter memset + five launches:
+//   k_sun_dirs   the frame's 4096 x N shadow-ray directions (blue noise repeats every 64 pixels).
+//   k_trace0     ray generation + closest-hit traversal; miss -> sky colour to the framebuffer;
+//                mirror/portal -> next ray pushed to the compacted ray queue; textured hit ->
+//                HitRec pushed to the compacted hit queue (warp ballot + one atomic per warp).
 //   k_prep       one thread per queued textured hit: triangle fetch, shadow-terminator origin,
 //                textures, normal, BRDF terms; the HitRec is rewritten in place.
-//   k_shadow     one thread per shadow ray (hit x sample): blue-noise direction + first-hit
-//                traversal; unshadowed rays are counted into HitRec.lit.
-//   k_resolve    one thread per hit: sun_factor, final colour, sRGB encode, framebuffer write.
+//   k_shadow     one thread per shadow ray (hit x sample): first-hit traversal; unshadowed rays
+//                are counted into HitRec.lit.
+//   k_tail       cooperative: segment 0's resolve phase (sun_factor, final colour, sRGB encode,
+//                framebuffer store), then ray-gen segments >= 1 (bounce rays) as trace / prep /
+//                shadow / resolve phases separated by grid barriers, then the ray-count export.
+//                k_trace_n / k_resolve are the same phases as separate launches (RT_RENDER_SPLIT_TAIL).
 // Small kernels on purpose: the one-pass shade kernel of the first version was instruction-fetch
 // bound (profiles/r01a_shade_details.txt: 31 % of issue stalls "no instruction", 128 registers).
-// All are persistent kernels: warps pull 32-item batches from a device-side cursor, so a launch
-// never needs a queue length on the host.
+// Traversal kernels are persistent: warps pull 32-item batches from a device-side cursor, so a launch
+// never needs a queue length on the host; stages chain with programmatic dependent launches.
 // Megakernel (A/B baseline): one thread per pixel runs the whole segment loop.
 #include <cooperative_groups.h>
 
