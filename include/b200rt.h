@@ -209,6 +209,11 @@ int  rt_readback(RtContext* ctx, void* host_rgba8, size_t capacity_bytes);
 /* Fence wait (src/main.rs:919-923). */
 int  rt_sync(RtContext* ctx);
 
+/* Page-locked host memory for frame read-back and instance uploads (what the reference gets from its host-visible
+ * `Buffer`s, src/util_structs.rs:17-120): copies to/from it are asynchronous, so rt_render_async really overlaps. */
+int  rt_host_alloc(RtContext* ctx, size_t bytes, void** out);
+int  rt_host_free(RtContext* ctx, void* ptr);
+
 int  rt_get_stats(RtContext* ctx, RtStats* out);
 /* The three device addresses the reference pushes as push constants
  * (ModelInfo[] table, Uniforms copy, TLAS root) — exposed for layout parity checks. */

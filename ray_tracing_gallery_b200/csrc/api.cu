@@ -845,6 +845,22 @@ int rt_sync(RtContext* ctx) {
     return RT_OK;
 }
 
+int rt_host_alloc(RtContext* ctx, size_t bytes, void** out) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!out) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_host_alloc: out is NULL");
+    *out = nullptr;
+    CK_DEV(ctx);
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return RT_OK;
+}
+
+int rt_host_free(RtContext* ctx, void* ptr) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    CK_DEV(ctx);
+    if (ptr) CK(cudaFreeHost(ptr));
+    return RT_OK;
+}
+
 int rt_get_stats(RtContext* ctx, RtStats* out) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     if (!out) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_get_stats: NULL");

@@ -20,7 +20,7 @@ _LIB = None
 EXPORTS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_push_image", "rt_create_model", "rt_build_tlas",
     "rt_update_instances", "rt_update_instances_device", "rt_update_tlas", "rt_render", "rt_render_device", "rt_render_async",
-    "rt_wait_frame", "rt_render_device_slot", "rt_readback",
+    "rt_wait_frame", "rt_render_device_slot", "rt_host_alloc", "rt_host_free", "rt_readback",
     "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_kernel_launches", "rt_version",
 ]
 
@@ -50,6 +50,8 @@ def load():
     lib.rt_render_async.argtypes = [p, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams), C.POINTER(abi.RtFrameOutputs), C.POINTER(u32)]
     lib.rt_wait_frame.argtypes = [p, u32]
     lib.rt_render_device_slot.argtypes = [p, u32, p, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams), C.POINTER(abi.RtFrameOutputs)]
+    lib.rt_host_alloc.argtypes = [p, C.c_size_t, C.POINTER(p)]
+    lib.rt_host_free.argtypes = [p, p]
     lib.rt_readback.argtypes = [p, p, C.c_size_t]
     lib.rt_sync.argtypes = [p]
     lib.rt_get_stats.argtypes = [p, C.POINTER(abi.RtStats)]

@@ -1,0 +1,177 @@
+"""The C++ host side (ray_tracing_gallery_b200/host_cpp) against the Python host: same GLB -> same arrays, same images in
+the same order with the same formats and samplers; same scene recipes -> same instance records and uniforms.
+CPU only: `host_dump` runs the C++ loader / recipes against a recording backend."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from ray_tracing_gallery_b200 import abi
+from ray_tracing_gallery_b200.gltf import load_gltf
+from ray_tracing_gallery_b200.scene import ASSET_DIR, build_scene
+
+HOST_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ray_tracing_gallery_b200", "host_cpp")
+
+
+@pytest.fixture(scope="module")
+def host_dump():
+    subprocess.check_call(["make", "-C", HOST_DIR, "host_dump", "rt_demo"], stdout=subprocess.DEVNULL)
+    return os.path.join(HOST_DIR, "host_dump")
+
+
+def read_sections(path):
+    out, data, p = {}, open(path, "rb").read(), 0
+    while p < len(data):
+        tag, n = struct.unpack_from("<IQ", data, p)
+        out[tag] = data[p + 12 : p + 12 + n]
+        p += 12 + n
+    return out
+
+
+class ImageLog:
+    def __init__(self, start):
+        self.images, self.start = [], start
+
+    def __call__(self, texels, fmt, linear):
+        self.images.append((np.ascontiguousarray(texels), fmt, bool(linear)))
+        return self.start + len(self.images) - 1
+
+
+def compare_model(host_dump, tmp_path, glb_path, name, fallback):
+    out = str(tmp_path / (name + ".bin"))
+    subprocess.check_call([host_dump, "model", glb_path, str(fallback), "4", out])
+    sec = read_sections(out)
+    log = ImageLog(4)
+    with open(glb_path, "rb") as f:
+        m = load_gltf(f.read(), name, fallback, log)
+    assert sec[1] == m.positions.tobytes() and sec[2] == m.normals.tobytes() and sec[3] == m.uvs.tobytes()
+    for g, geo in enumerate(m.geometries):
+        hdr = struct.unpack("<4i", sec[100 + g])
+        assert hdr == (int(geo.opaque), geo.diffuse_image_index, geo.metallic_roughness_image_index, geo.normal_map_image_index)
+        assert sec[200 + g] == geo.indices.tobytes()
+    assert 100 + len(m.geometries) not in sec
+    for i, (texels, fmt, linear) in enumerate(log.images):
+        w, h, f, lin = struct.unpack("<4I", sec[1000 + 4 + i])
+        assert (h, w) == texels.shape[:2] and f == fmt and bool(lin) == linear, (name, i)
+        assert sec[2000 + 4 + i] == texels.tobytes(), (name, i)  # PNG decode incl. the 16-bit narrowing, byte for byte
+    assert 1000 + 4 + len(log.images) not in sec
+    return m
+
+
+@pytest.mark.parametrize("name,fallback", [("plane.glb", 0), ("tori.glb", 1), ("lain.glb", 1), ("fence.glb", 0)])
+def test_cpp_loader_equals_python_loader_on_the_reference_assets(host_dump, tmp_path, name, fallback):
+    compare_model(host_dump, tmp_path, os.path.join(ASSET_DIR, name), name, fallback)
+
+
+def test_cpp_loader_on_the_synthetic_multi_material_model(host_dump, tmp_path):
+    from synth_assets import bumpy_two_material_glb
+
+    p = tmp_path / "bumpy.glb"
+    p.write_bytes(bumpy_two_material_glb())
+    m = compare_model(host_dump, tmp_path, str(p), "bumpy", 1)
+    assert len(m.geometries) == 2 and m.geometries[0].normal_map_image_index >= 0
+
+
+def test_cpp_png_decoder_on_the_builtin_images(host_dump, tmp_path):
+    """The four built-ins (8-bit RGB, 16-bit grey, 8-bit RGBA) come out of build_scene's push_builtin_images."""
+    out = str(tmp_path / "scene.bin")
+    subprocess.check_call([host_dump, "scene", "c1", ASSET_DIR, out])
+    sec = read_sections(out)
+    from ray_tracing_gallery_b200.gltf import load_png_file_rgba8
+
+    for i, (f, fmt, lin) in enumerate([("green.png", abi.RT_FORMAT_RGBA8_SRGB, 0), ("pink.png", abi.RT_FORMAT_RGBA8_SRGB, 0),
+                                       ("blue_noise_64x64.png", abi.RT_FORMAT_RGBA8_UNORM, 0), ("flipped_ggx_lut.png", abi.RT_FORMAT_RGBA8_UNORM, 1)]):
+        img = load_png_file_rgba8(os.path.join(ASSET_DIR, f))
+        assert struct.unpack("<4I", sec[1000 + i]) == (img.shape[1], img.shape[0], fmt, lin)
+        assert sec[2000 + i] == img.tobytes(), f
+
+
+class Recorder:
+    """The Python twin of host_dump's recording backend."""
+
+    def __init__(self):
+        self.n = self.m = 0
+
+    def push_image(self, *a):
+        self.n += 1
+        return self.n - 1
+
+    def create_model(self, m):
+        self.m += 1
+        return self.m - 1, 1000 + self.m - 1
+
+    def build_tlas(self, inst):
+        self.inst = inst
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "default"])
+def test_cpp_scene_recipes_equal_python_recipes(host_dump, tmp_path, cfg):
+    out = str(tmp_path / "scene.bin")
+    subprocess.check_call([host_dump, "scene", cfg, ASSET_DIR, out])
+    sec = read_sections(out)
+    s = build_scene(Recorder(), cfg)
+    got = np.frombuffer(sec[5000], abi.INSTANCE_DTYPE)
+    assert len(got) == len(s.instances)
+    for k in ("custom_index_and_mask", "sbt_offset_and_flags", "blas"):
+        assert np.array_equal(got[k], s.instances[k]), k
+    # transforms: float32 on both sides; numpy's vectorised cos/sin and matmul may differ from libm in the last bits
+    assert np.allclose(got["transform"], s.instances["transform"], rtol=2e-6, atol=2e-6)
+    u = abi.RtUniforms.from_buffer_copy(sec[5001])
+    w = s.uniforms()
+    for field in ("view_inverse", "proj_inverse", "sun_dir"):
+        assert np.allclose(list(getattr(u, field)), list(getattr(w, field)), rtol=1e-6, atol=1e-6), field
+    assert (u.sun_radius, u.blue_noise_texture_index, u.ggx_lut_texture_index, u.frame_index) == (w.sun_radius, 2, 3, 1)
+    assert struct.unpack("<4I", sec[5002]) == (s.width, s.height, s.shadow_rays, s.max_segments)
+
+
+# ----------------------------------------------------------------------------------------------- on the GPU
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "ray_tracing_gallery_b200", "csrc", "libb200rt.so")
+
+
+@pytest.fixture(scope="module")
+def host_parity(host_dump):
+    exe = os.path.join(ROOT, "tests", "cpp", "host_parity")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "host_parity.cpp"), "-ldl", "-lz"])
+    from oracle import binding
+
+    return exe, binding.build()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,size", [("c1", (640, 360)), ("c3", (640, 360)), ("default", (640, 360)), ("c2", (960, 540))])
+def test_cpp_host_parity_against_the_oracle(host_parity, cfg, size):
+    """The parity bars, with both the CUDA path and the oracle driven from the C++ host through the C ABI."""
+    import json
+
+    exe, liborc = host_parity
+    r = subprocess.run([exe, LIB, liborc, ASSET_DIR, cfg, str(size[0]), str(size[1])], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["ray_counts_equal"] and out["hit_id_agreement"] >= 0.9999
+
+
+@pytest.mark.gpu
+def test_rt_demo_frame_loop(host_dump, tmp_path):
+    """rt_demo: the reference's headless frame loop from C++ (two frames in flight); its last frame equals the frame the
+    Python host renders for the same frame index (scene floats agree to the last bits, so allow a handful of edge pixels)."""
+    import json
+
+    from conftest import make_renderer
+
+    ppm = str(tmp_path / "c1.ppm")
+    r = subprocess.run([os.path.join(HOST_DIR, "rt_demo"), "--config", "c1", "--width", "640", "--height", "360", "--frames", "6", "--out", ppm],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["frames"] == 6 and line["rays"] > 6 * 640 * 360 and line["mrays_per_s"] > 0
+    data = open(ppm, "rb").read()
+    assert data.startswith(b"P6\n640 360\n255\n")
+    img = np.frombuffer(data[len(b"P6\n640 360\n255\n"):], np.uint8).reshape(360, 640, 3)
+    gpu = make_renderer()
+    s = build_scene(gpu, "c1", 640, 360)
+    want = gpu.render(s.uniforms(frame_index=6), s.params(), want=("rgba8",))["rgba8"][..., :3]
+    gpu.close()
+    assert np.mean(np.abs(img.astype(int) - want.astype(int)).max(axis=2) <= 1) >= 0.999
