@@ -82,6 +82,22 @@ def test_library_exports_every_declared_symbol():
     assert lib.rt_version() >> 16 == 1
 
 
+def test_rust_binding_file_declares_every_export_and_matches_the_layouts():
+    """bindings/b200rt_ffi.rs is not compiled here (no Rust toolchain); keep it in step with the header mechanically."""
+    rs = open(os.path.join(ROOT, "bindings", "b200rt_ffi.rs")).read()
+    declared = sorted(set(re.findall(r"pub fn (rt_[a-z_0-9]+)\s*\(", rs)))
+    assert declared == declared_functions()
+    # struct field order of the plain-data structs must equal the ctypes mirrors (which tests above tie to rt_abi.h / b200rt.h)
+    for name, cls in (("RtRenderParams", abi.RtRenderParams), ("RtFrameOutputs", abi.RtFrameOutputs), ("RtStats", abi.RtStats)):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, rs, flags=re.S).group(1)
+        fields = re.findall(r"pub ([a-z_0-9]+):", body)
+        assert fields == [f[0] for f in cls._fields_], name
+    for const in ("RT_RENDER_COUNTERS", "RT_RENDER_TIMING", "RT_RENDER_SPLIT_TAIL", "RT_RENDER_NO_PDL", "RT_RENDER_OUTPUT_IMAGE_ROWS",
+                  "RT_UPDATE_AUTO", "RT_UPDATE_REFIT", "RT_UPDATE_REBUILD", "RT_FORMAT_RGBA8_UNORM", "RT_FORMAT_RGBA8_SRGB", "RT_FORMAT_RGBA32_SFLOAT"):
+        m = re.search(r"pub const %s: u32 = (\d+);" % const, rs)
+        assert m and int(m.group(1)) == getattr(abi, const), const
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
 
