@@ -3,6 +3,7 @@
 // tests/test_host_cpp.py can compare it with the Python host byte for byte.
 //   host_dump model <file.glb> <fallback_index> <first_image_index> <out.bin>
 //   host_dump scene <config> <assets_dir> <out.bin> [width height]
+//   host_dump png <file.png> <out.bin>
 // Section = u32 tag, u64 byte count, payload.  Tags: 1 positions, 2 normals, 3 uvs, 100+g geometry header
 // {opaque, diffuse, metal-rough, normal map}, 200+g indices, 1000+i image header {w, h, format, linear}, 2000+i texels,
 // 5000 instances (64 B each), 5001 uniforms (176 B), 5002 {width, height, shadow_rays, max_segments}.
@@ -64,6 +65,13 @@ int main(int argc, char** argv) {
                 section(100 + (uint32_t)g, hdr, sizeof(hdr));
                 section(200 + (uint32_t)g, ge.indices.data(), ge.indices.size() * 4);
             }
+        } else if (argc >= 4 && std::string(argv[1]) == "png") {
+            g_out = std::fopen(argv[3], "wb");
+            std::vector<uint8_t> bytes = read_file(argv[2]);
+            ImageRgba8 im = decode_png_rgba8(bytes.data(), bytes.size());
+            uint32_t hdr[4] = {im.width, im.height, 0, 0};
+            section(1000, hdr, sizeof(hdr));
+            section(2000, im.texels.data(), im.texels.size());
         } else if (argc >= 5 && std::string(argv[1]) == "scene") {
             g_out = std::fopen(argv[4], "wb");
             Backend be;

@@ -88,6 +88,35 @@ def test_cpp_png_decoder_on_the_builtin_images(host_dump, tmp_path):
         assert sec[2000 + i] == img.tobytes(), f
 
 
+@pytest.mark.parametrize("mode,depth16", [("L", False), ("LA", False), ("RGB", False), ("RGBA", False), ("P", False), ("1", False), ("I;16", True)])
+def test_cpp_png_decoder_colour_types(host_dump, tmp_path, mode, depth16):
+    """Every PNG colour type the `image` crate would hand to `to_rgba8()`: the C++ decoder against the Python host's decoder."""
+    from PIL import Image
+
+    from ray_tracing_gallery_b200.gltf import decode_png_rgba8
+
+    rng = np.random.default_rng(3)
+    w, h = 37, 23  # odd sizes: sub-byte rows end mid-byte
+    if mode == "I;16":
+        img = Image.fromarray(rng.integers(0, 65535, (h, w), dtype=np.uint16))
+    elif mode == "1":
+        img = Image.fromarray((rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)).convert("1")
+    elif mode == "P":
+        img = Image.fromarray(rng.integers(0, 255, (h, w, 3), dtype=np.uint8), "RGB").convert("P", palette=Image.ADAPTIVE, colors=17)
+    else:
+        ch = {"L": 1, "LA": 2, "RGB": 3, "RGBA": 4}[mode]
+        a = rng.integers(0, 255, (h, w, ch), dtype=np.uint8)
+        img = Image.fromarray(a[..., 0] if ch == 1 else a, mode)
+    p = tmp_path / "t.png"
+    img.save(p, format="PNG")
+    out = str(tmp_path / "t.bin")
+    subprocess.check_call([host_dump, "png", str(p), out])
+    sec = read_sections(out)
+    want = decode_png_rgba8(p.read_bytes())
+    assert struct.unpack("<4I", sec[1000])[:2] == (w, h)
+    assert sec[2000] == want.tobytes()
+
+
 class Recorder:
     """The Python twin of host_dump's recording backend."""
 
