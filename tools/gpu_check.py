@@ -37,9 +37,9 @@ def main():
     for cfg in cfgs:
         size = {"c1": (640, 360), "c2": (480, 270), "c3": (640, 360), "default": (640, 360), "c4": (480, 270), "c5": (480, 270)}[cfg]
         kw = {}
-        if cfg == "c4":
+        if cfg == "c4" and not os.environ.get("FULL_SCALE"):
             kw["num_instances"] = 2000
-        if cfg == "c5":
+        if cfg == "c5" and not os.environ.get("FULL_SCALE"):
             kw["num_instances"] = 20000
         orc = Oracle()
         so = build_scene(orc, cfg, *size, **kw)
@@ -57,8 +57,8 @@ def main():
             nm = f"{cfg}/{'mega' if pipeline else 'wave'}"
             eq = compare(nm, ra, rb, p.max_segments)
             rays = st.primary_rays + st.shadow_rays
-            print(f"    render {st.last_render_ms:.3f} ms (cpu oracle {t_cpu*1e3:.0f} ms)  tlas {st.last_tlas_ms:.3f} ms  nodes/ray {st.nodes_visited/max(rays,1):.1f} "
-                  f"inst/ray {st.instances_entered/max(rays,1):.2f} tris/ray {st.triangles_tested/max(rays,1):.1f} anyhit {st.anyhit_calls} "
+            print(f"    render {st.last_render_ms:.3f} ms (cpu oracle {t_cpu*1e3:.0f} ms)  tlas {st.last_tlas_ms:.3f} ms  nodes/ray {sum(st.nodes_visited)/max(rays,1):.1f} "
+                  f"inst/ray {sum(st.instances_entered)/max(rays,1):.2f} tris/ray {sum(st.triangles_tested)/max(rays,1):.1f} anyhit {sum(st.anyhit_calls)} "
                   f"tlas_nodes {st.tlas_nodes} blas_nodes {st.blas_nodes} tris {st.num_triangles}", flush=True)
             Image.fromarray(ra["rgba8"]).save(f"gpurun_out/{cfg}_{'mega' if pipeline else 'wave'}.png")
             if not eq.all():
