@@ -136,3 +136,68 @@ def build_bumpy_scene(backend, width=640, height=360, shadow_rays=2):
     s.models = {"bumpy": (bid, bh, arrays)}
     backend.build_tlas(s.instances)
     return s
+
+
+def build_random_scene(backend, seed: int, width=256, height=144):
+    """Seeded random stress scene for the traversal semantics: a triangle soup in two geometries (one alpha-masked with a
+    random NEAREST texture), a second model with exactly coincident duplicate triangles (exact t ties: lowest ids must win),
+    instances with arbitrary rotations, non-uniform and NEGATIVE scales, mirror / portal / textured hit groups, one
+    degenerate (zero-area) triangle, a camera orbiting the origin."""
+    from ray_tracing_gallery_b200 import abi
+    from ray_tracing_gallery_b200.gltf import Geometry, ModelArrays
+    from ray_tracing_gallery_b200.scene import Camera, SceneSetup, Sun, load_model, make_instance, mat_scale, push_builtin_images
+
+    rng = np.random.default_rng(seed)
+    push_builtin_images(backend)
+    pid, ph, _ = load_model(backend, "plane.glb", 0)
+
+    def soup(n_tris, spread, size):
+        c = rng.uniform(-spread, spread, (n_tris, 1, 3))
+        v = c + rng.uniform(-size, size, (n_tris, 3, 3))
+        pos = v.reshape(-1, 3).astype(np.float32)
+        nrm = np.repeat(np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]), 3, axis=0).astype(np.float32)
+        nrm[np.all(nrm == 0, axis=1)] = (0, 1, 0)
+        uv = rng.uniform(-1.5, 2.5, (n_tris * 3, 2)).astype(np.float32)
+        return pos, nrm, uv
+
+    # model A: soup, geometry 0 opaque with a random linear sRGB texture, geometry 1 alpha-masked with a NEAREST one
+    pos, nrm, uv = soup(160, 1.0, 0.35)
+    pos[9:12] = pos[9]  # a degenerate triangle (three equal vertices): never hit
+    tex_a = rng.integers(0, 255, (9, 13, 4), dtype=np.uint8); tex_a[..., 3] = 255
+    tex_b = rng.integers(0, 255, (8, 8, 4), dtype=np.uint8)
+    ia = backend.push_image(tex_a, abi.RT_FORMAT_RGBA8_SRGB, True)
+    ib = backend.push_image(tex_b, abi.RT_FORMAT_RGBA8_SRGB, False)
+    mr = backend.push_image(np.asarray([1.0, 0.45, 0.3, 1.0], np.float32).reshape(1, 1, 4), abi.RT_FORMAT_RGBA32_SFLOAT, False)
+    idx = np.arange(160 * 3, dtype=np.uint32)
+    model_a = ModelArrays("soup", pos, nrm, uv, [Geometry(idx[: 100 * 3], True, ia, mr, -1), Geometry(idx[100 * 3 :], False, ib, mr, -1)])
+    aid, ah = backend.create_model(model_a)
+    # model B: 12 triangles, every one stored twice (exactly coincident): the tie rule decides which primitive id is reported
+    pos, nrm, uv = soup(12, 0.6, 0.5)
+    pos2, nrm2, uv2 = np.concatenate([pos, pos]), np.concatenate([nrm, nrm]), np.concatenate([uv, uv])
+    model_b = ModelArrays("twins", pos2, nrm2, uv2, [Geometry(np.arange(72, dtype=np.uint32), True, 1, mr, -1)])
+    bid, bh = backend.create_model(model_b)
+
+    def random_transform():
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        w, x, y, z = q
+        rot = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        sc = rng.uniform(0.4, 1.6, 3) * rng.choice([1.0, 1.0, 1.0, -1.0], 3)  # some axes mirrored: negative determinants
+        m = np.eye(4, dtype=np.float32)
+        m[:3, :3] = (rot * sc).astype(np.float32)
+        m[:3, 3] = rng.uniform(-3.0, 3.0, 3).astype(np.float32) + np.float32([0, 2.0, 0])
+        return m
+
+    inst = [make_instance(mat_scale(10.0), pid, ph, abi.RT_HIT_TEXTURED)]
+    for k in range(14):
+        model, handle = ((aid, ah), (bid, bh))[k % 3 == 2]
+        kind = (abi.RT_HIT_TEXTURED, abi.RT_HIT_TEXTURED, abi.RT_HIT_MIRROR, abi.RT_HIT_PORTAL)[int(rng.integers(0, 4))]
+        inst.append(make_instance(random_transform(), model, handle, kind, True))
+    inst.append(inst[3].copy())  # an exact duplicate INSTANCE: every hit on it ties with instance 3, the lower gl_InstanceID wins
+    ang = rng.uniform(0, 2 * np.pi)
+    cam = Camera(eye=(float(9 * np.sin(ang)), float(rng.uniform(2.5, 5.0)), float(-9 * np.cos(ang))), pitch=-0.25, yaw=float(np.pi - ang))
+    s = SceneSetup(f"random{seed}", np.stack(inst), cam, Sun(pitch=float(rng.uniform(0.3, 1.2)), yaw=float(rng.uniform(0, 6.28))), width, height,
+                   shadow_rays=int(rng.integers(1, 6)), sun_radius=float(rng.uniform(0.0, 0.08)), description="seeded random stress scene")
+    backend.build_tlas(s.instances)
+    return s

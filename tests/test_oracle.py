@@ -349,3 +349,20 @@ def test_synthetic_model_exercises_normal_map_nearest_and_multi_material():
     assert d[g0].mean() > 1e-3 and d[g1].max() == 0.0
     assert arrays.geometries[0].normal_map_image_index >= 0
     o.close(); o2.close()
+
+
+def test_random_stress_scene_tie_rules_on_the_oracle():
+    """Exact ties by construction: a duplicated instance and twin triangles.  Lowest (instance, geometry, primitive) wins."""
+    import synth_assets
+    from oracle.binding import Oracle
+
+    o = Oracle()
+    s = synth_assets.build_random_scene(o, 1)
+    r = o.render(s.uniforms(), s.params())
+    ids = r["hit_ids"].reshape(-1, 3)
+    hit = ids[ids[:, 0] != 0xFFFFFFFF]
+    assert 15 not in set(hit[:, 0].tolist()) and 3 in set(hit[:, 0].tolist())      # instance 15 is an exact copy of instance 3
+    twins = hit[np.isin(hit[:, 0], [i for i in range(1, 15) if (i - 1) % 3 == 2])]      # instances of the twin-triangle model
+    assert len(twins) > 0 and twins[:, 2].max() < 12                                    # the second copy (prims 12..23) never wins
+    assert np.isfinite(r["radiance"]).all()
+    o.close()
