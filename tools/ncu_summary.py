@@ -41,6 +41,16 @@ def main():
                 if key in k and label:
                     u, v = k[key]
                     print(f"- {label}: {v} {u}".rstrip())
+            try:  # L2 traffic (SURVEY 8d asks for achieved L2 GB/s next to HBM GB/s): sectors are 32 B
+                sectors = float(k["lts__t_sectors.sum"][1])
+                unit, dur = k["gpu__time_duration.sum"]
+                sec = float(dur) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}[unit]
+                dr, dw = k["dram__bytes_read.sum"], k["dram__bytes_write.sum"]
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                dram = float(dr[1]) * scale[dr[0]] + float(dw[1]) * scale[dw[0]]
+                print(f"- L2 traffic: {sectors * 32 / 1e6:.1f} MB = {sectors * 32 / sec / 1e9:.0f} GB/s;  DRAM traffic: {dram / 1e6:.1f} MB = {dram / sec / 1e9:.0f} GB/s")
+            except (KeyError, ValueError):
+                pass
             stalls = []
             for key, (u, v) in k.items():
                 if key.startswith("smsp__average_warps_issue_stalled_") and key.endswith("_per_issue_active.ratio") and "not_issued" not in key:
