@@ -474,12 +474,14 @@ def run_ours(args):
         bytes_per_launch = bytes_frame[names[dom]] / max(launches_per_frame, 1)
         achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         rays_frame = max(int(st_count.primary_rays + st_count.shadow_rays), 1)
+        ncu_note = None
         traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload only)
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath) and world == 1:
             tj = json.load(open(tpath))
             if tj.get("workload") == s.name and not (args.width or args.height or args.instances):
                 traffic = tj.get(names[dom])
+                ncu_note = tj.get("ncu", {}).get(names[dom])
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "kernel": KERNEL_DESC[names[dom]],
@@ -488,6 +490,7 @@ def run_ours(args):
             "kernel_share_of_step": float((kernel_ms[dom] / ksteps) / (total_ms / args.steps)) if world == 1 else None,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "launches_per_frame": float(launches_per_frame),
+            "ncu": ncu_note,  # from the committed capture of the same kernel (profiles/r01j_summary.md): what actually limits it
             "per_ray": {"nodes": float(sum(st_count.nodes_visited)) / rays_frame, "instances": float(sum(st_count.instances_entered)) / rays_frame,
                         "triangles": float(sum(st_count.triangles_tested)) / rays_frame,
                         "bytes": float(bytes_frame["mega"] if args.pipeline == "mega" else sum(bytes_frame[k] for k in KERNELS[:4])) / rays_frame},
