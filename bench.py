@@ -39,8 +39,8 @@ UNIT = "Mrays/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "default"])
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "mega"])
@@ -74,16 +74,27 @@ def workload_config(setup, args, extra=None):
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(gpu_index), "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(gpu_index), "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+
+    def wait_first_sample(self, timeout=3.0):
+        """nvidia-smi needs a moment to start; the frames are short, so wait until it is sampling before loading the GPU."""
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -94,7 +105,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, busy = [], [], set(), []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
@@ -104,6 +115,10 @@ class ClockSampler:
                     sm.append(float(f[1])); smax.append(float(f[2]))
                 except ValueError:
                     continue
+                try:
+                    busy.append(float(f[9]) > 0)
+                except (ValueError, IndexError):
+                    busy.append(True)
                 for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
@@ -111,7 +126,8 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+            loaded = [c for c, b in zip(sm, busy) if b] or sm  # median over the samples taken under load
+            out.update(sm_mhz=float(np.median(loaded)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
         return out
 
 
@@ -319,6 +335,12 @@ def run_ours(args):
     st_count = gpu.stats()
     bytes_frame = algorithmic_bytes(st_count, s, pixels)
 
+    # ---- clocks: sampled from here (warm-up, timed region, kernel-timing pass, e2e region) — the timed region alone lasts
+    #      a few tens of milliseconds, shorter than nvidia-smi's sampling period
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first_sample()
+
     # ---- warm-up
     for i in range(args.warmup):
         step_device(i)
@@ -330,7 +352,6 @@ def run_ours(args):
     # ---- timed region: K steps enqueued back to back (no host synchronisation inside), a CUDA-event pair per step on the
     #      launching stream with the L2 flush between steps outside the pairs; ray counts land in a per-step device slot
     launches0 = gpu.lib.rt_kernel_launches()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = np.zeros(len(KERNELS))
     kernel_launches = np.zeros(len(KERNELS), np.int64)
@@ -344,7 +365,6 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
     launches = gpu.lib.rt_kernel_launches() - launches0
     # ---- per-kernel durations (roofline): a separate pass with CUDA events around every kernel of the frame,
     #      same stream, L2 flushed between frames; kept out of the timed region because the events serialise launches
@@ -457,6 +477,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
     e2e_value = int(r.item()) / float(t.item()) / 1e6
+    clocks = sampler.stop() if sampler else None
     h2d = 176 + (len(s.instances) * 64 if s.dynamic else 0)
     d2h = (H * W * 4 if rank == 0 else 0) + 16
 
