@@ -75,7 +75,8 @@ pub struct RtRenderParams {
     pub strip_index: u32,
     pub pipeline: u32,
     pub flags: u32,
-    pub _reserved: [u32; 3],
+    pub heatmap_scale: f32, // 0 = 1_000_000.0, the `heatmap_scale` of lib.rs:179
+    pub _reserved: [u32; 2],
 }
 
 #[repr(C)]
@@ -84,6 +85,7 @@ pub struct RtFrameOutputs {
     pub radiance: *mut f32,
     pub hit_ids: *mut u32,
     pub ray_counts: *mut u64,
+    pub cost_cycles: *mut u32, // show_heatmap frames: clock ticks per pixel (lib.rs:174-177)
 }
 
 #[repr(C)]

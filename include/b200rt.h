@@ -101,7 +101,9 @@ typedef struct RtRenderParams {
                                 /*   shares may differ by one strip).  0 => no interleave */
     uint32_t pipeline;          /* RtPipeline */
     uint32_t flags;             /* RT_RENDER_* */
-    uint32_t _reserved[3];
+    float    heatmap_scale;     /* Uniforms.show_heatmap: clock ticks that map to heat 1.0; 0 => 1 000 000, the
+                                   reference's hard-coded `heatmap_scale` (lib.rs:179) */
+    uint32_t _reserved[2];
 } RtRenderParams;
 
 /* Output arrays are compact over the rendered rows (ascending global y), row
@@ -113,6 +115,8 @@ typedef struct RtFrameOutputs {
     uint32_t* hit_ids;      /* [rows][tile_w][max_segments][3] = (gl_InstanceID, gl_GeometryIndexEXT,
                                gl_PrimitiveID) per ray-gen segment; 0xFFFFFFFF x3 = miss / segment not traced */
     uint64_t* ray_counts;   /* [2] trace calls issued: {ray-gen segments, shadow rays} */
+    uint32_t* cost_cycles;  /* [rows][tile_w]  SM clock ticks the pixel's ray-gen invocation took (saturating) — the
+                               `delta_time` of lib.rs:174-177.  Only written by frames with Uniforms.show_heatmap set */
 } RtFrameOutputs;
 
 typedef struct RtStats {

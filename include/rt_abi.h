@@ -33,7 +33,7 @@ typedef struct RtUniforms {
     uint32_t blue_noise_texture_index;  /* 148  (=2, src/main.rs:595) */
     uint32_t ggx_lut_texture_index;     /* 152  (=3, src/main.rs:596; bound, never sampled) */
     uint32_t frame_index;               /* 156  first rendered frame is 1 (src/main.rs:944) */
-    uint8_t  show_heatmap;              /* 160  ignored by this library (debug viz) */
+    uint8_t  show_heatmap;              /* 160  per-pixel clock heatmap instead of the colour (lib.rs:120-124, 174-186) */
     uint8_t  _tail_padding[15];         /* 161..175 */
 } RtUniforms;
 

@@ -38,6 +38,10 @@ def load():
         lib.orc_brdf.restype = None
         lib.orc_v_smith_ggx.argtypes = [fp, fp, fp, C.c_float]
         lib.orc_v_smith_ggx.restype = C.c_float
+        lib.orc_heatmap_temperature.argtypes = [C.c_float, fp]
+        lib.orc_heatmap_temperature.restype = None
+        lib.orc_heatmap_pixel.argtypes = [C.c_uint32, C.c_float, fp, fp]
+        lib.orc_heatmap_pixel.restype = None
         lib.orc_linear_to_srgb.argtypes = [C.c_float]
         lib.orc_linear_to_srgb.restype = C.c_float
         lib.orc_unorm8.argtypes = [C.c_float]
@@ -96,6 +100,22 @@ class Oracle(CApiBackend):
 
     def v_smith_ggx(self, normal, view, light, roughness):
         return self.lib.orc_v_smith_ggx(_fp(f32(*normal)), _fp(f32(*view)), _fp(f32(*light)), roughness)
+
+    def heatmap_temperature(self, heat):
+        out = np.zeros(3, np.float32)
+        self.lib.orc_heatmap_temperature(heat, _fp(out))
+        return out
+
+    def heatmap_pixel(self, cycles, colour, scale=0.0):
+        out = np.zeros(3, np.float32)
+        self.lib.orc_heatmap_pixel(int(cycles), scale, _fp(f32(*colour)), _fp(out))
+        return out
+
+    def linear_to_srgb(self, c):
+        return self.lib.orc_linear_to_srgb(float(c))
+
+    def unorm8(self, c):
+        return self.lib.orc_unorm8(float(c))
 
     def blue_noise_xi(self, px, py, iteration, frame, tex=2):
         out = np.zeros(2, np.float32)

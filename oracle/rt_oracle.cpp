@@ -21,6 +21,7 @@
 //   primary_ray_miss        shaders/ray-tracing/src/lib.rs:40-51
 //   shadow_ray_miss         shaders/ray-tracing/src/lib.rs:33-36
 //   closest_hit_portal      shaders/ray-tracing/src/lib.rs:300-312
+//   heatmap_temperature     shaders/ray-tracing/src/heatmap.rs:5-54 (+ lib.rs:120-124, 174-186)
 //   closest_hit_textured    shaders/closest_hit_textured.glsl:13-226
 //   hit_shader_common       shaders/hit_shader_common.glsl:75-165
 //   brdf & friends          shaders/pbr.glsl:25-103, 174-211
@@ -749,6 +750,41 @@ Ray generate_primary_ray(const RtUniforms& u, uint32_t x, uint32_t y, uint32_t W
     return Ray{origin, dir, 0.01f, 10000.0f};
 }
 
+// heatmap.rs:43-54
+inline float saturate1(float x) { return std::fmin(std::fmax(x, 0.0f), 1.0f); }
+inline float smoothstep1(float e0, float e1, float x) {
+    float t = saturate1((x - e0) / (e1 - e0));
+    return (t * t) * (3.0f - 2.0f * t);
+}
+// heatmap.rs:5-41.  `colours[heat as i32]` reads one past the table at heat == 1.0 exactly (undefined in
+// SPIR-V): `cur` is clamped to the last entry, the same rule as the CUDA path.
+V3 heatmap_temperature(float heat) {
+    static const float k[10][3] = {
+        {0.0f / 255.0f, 2.0f / 255.0f, 91.0f / 255.0f},    {0.0f / 255.0f, 108.0f / 255.0f, 251.0f / 255.0f},
+        {0.0f / 255.0f, 221.0f / 255.0f, 221.0f / 255.0f}, {51.0f / 255.0f, 221.0f / 255.0f, 0.0f / 255.0f},
+        {255.0f / 255.0f, 252.0f / 255.0f, 0.0f / 255.0f}, {255.0f / 255.0f, 180.0f / 255.0f, 0.0f / 255.0f},
+        {255.0f / 255.0f, 104.0f / 255.0f, 0.0f / 255.0f}, {226.0f / 255.0f, 22.0f / 255.0f, 0.0f / 255.0f},
+        {191.0f / 255.0f, 0.0f / 255.0f, 83.0f / 255.0f},  {145.0f / 255.0f, 0.0f / 255.0f, 65.0f / 255.0f}};
+    heat = saturate1(heat) * 10.0f;
+    int idx = (int)heat;
+    int cur = std::min(idx, 9), prv = std::max(idx - 1, 0), nxt = std::min(idx + 1, 9);
+    float lo = std::floor(heat), hi = std::ceil(heat), blur = 0.8f;
+    float s_lo = smoothstep1(lo - blur, lo + blur, heat);
+    float s_hi = smoothstep1(hi - blur, hi + blur, heat);
+    float wc = s_lo * (1.0f - s_hi), wp = 1.0f - s_lo, wn = s_hi;
+    V3 r = add3(add3(scale3(v3(k[cur][0], k[cur][1], k[cur][2]), wc), scale3(v3(k[prv][0], k[prv][1], k[prv][2]), wp)),
+                scale3(v3(k[nxt][0], k[nxt][1], k[nxt][2]), wn));
+    return v3(saturate1(r.x), saturate1(r.y), saturate1(r.z));
+}
+// lib.rs:174-186
+V3 heatmap_pixel(uint32_t cycles, float scale, V3 colour) {
+    return add3(heatmap_temperature((float)cycles / scale), scale3(colour, 0.000001f));
+}
+// The oracle has no shader clock.  Its show_heatmap frames use this stand-in for `end_time - start_time`:
+// a fixed number of ticks per trace call the pixel issued (ray-gen segments + shadow rays).  The CUDA path's real
+// clock values are never compared with it — tests feed the GPU's own cost_cycles through heatmap_pixel().
+constexpr uint32_t kOracleTicksPerTrace = 20000u;
+
 struct PixelOut {
     V3 colour;
     uint32_t ids[9];
@@ -961,8 +997,15 @@ int orc_render(OrcContext* c, const RtUniforms* u, const RtRenderParams* p, cons
             if (r >= nrows) break;
             for (uint32_t i = 0; i < tw; i++) {
                 PixelOut po;
+                const uint64_t traces_before = np + ns;
                 render_pixel(*c, *u, *p, x0 + i, ys[r], po, np, ns);
                 size_t pix = (size_t)r * tw + i;
+                if (u->show_heatmap) {
+                    uint64_t ticks = (np + ns - traces_before) * kOracleTicksPerTrace;
+                    uint32_t cycles = ticks > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)ticks;
+                    if (out && out->cost_cycles) out->cost_cycles[pix] = cycles;
+                    po.colour = heatmap_pixel(cycles, p->heatmap_scale > 0.0f ? p->heatmap_scale : 1000000.0f, po.colour);
+                }
                 if (out && out->radiance) { out->radiance[pix * 3] = po.colour.x; out->radiance[pix * 3 + 1] = po.colour.y; out->radiance[pix * 3 + 2] = po.colour.z; }
                 if (out && out->rgba8) {
                     out->rgba8[pix * 4] = unorm8(linear_to_srgb1(po.colour.x));
@@ -1010,6 +1053,14 @@ float orc_v_smith_ggx(const float* normal, const float* view, const float* light
     p.NoL = clampf(plain_dot(n, l), 0.0f, 1.0f);
     p.NoH = p.LoH = 0.f;
     return V_SmithGGXCorrelated(p);
+}
+void orc_heatmap_temperature(float heat, float* out3) {
+    V3 r = heatmap_temperature(heat);
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+void orc_heatmap_pixel(uint32_t cycles, float scale, const float* colour3, float* out3) {
+    V3 r = heatmap_pixel(cycles, scale > 0.0f ? scale : 1000000.0f, v3(colour3[0], colour3[1], colour3[2]));
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
 }
 float orc_linear_to_srgb(float c) { return linear_to_srgb1(c); }
 uint8_t orc_unorm8(float c) { return unorm8(c); }

@@ -103,7 +103,8 @@ class RtRenderParams(C.Structure):
         ("strip_index", C.c_uint32),
         ("pipeline", C.c_uint32),
         ("flags", C.c_uint32),
-        ("_reserved", C.c_uint32 * 3),
+        ("heatmap_scale", C.c_float),
+        ("_reserved", C.c_uint32 * 2),
     ]
 
 
@@ -113,6 +114,7 @@ class RtFrameOutputs(C.Structure):
         ("radiance", C.c_void_p),
         ("hit_ids", C.c_void_p),
         ("ray_counts", C.c_void_p),
+        ("cost_cycles", C.c_void_p),
     ]
 
 

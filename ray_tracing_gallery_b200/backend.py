@@ -128,6 +128,9 @@ class CApiBackend:
         if "ray_counts" in want:
             res["ray_counts"] = np.zeros(2, np.uint64)
             out.ray_counts = res["ray_counts"].ctypes.data
+        if "cost_cycles" in want:  # only written by show_heatmap frames
+            res["cost_cycles"] = np.zeros((rows, tw), np.uint32)
+            out.cost_cycles = res["cost_cycles"].ctypes.data
         rc = self._fn("render")(self.ctx, C.byref(uniforms), C.byref(params), C.byref(out))
         self._check(rc, "render")
         return res

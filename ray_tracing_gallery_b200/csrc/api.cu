@@ -128,7 +128,8 @@ struct RtContext {
     uint8_t* d_fb_rgba8 = nullptr;
     float* d_fb_radiance = nullptr;
     uint32_t* d_fb_hit_ids = nullptr;
-    size_t fb_rgba8_cap = 0, fb_radiance_cap = 0, fb_hit_ids_cap = 0;
+    uint32_t* d_fb_cost = nullptr;
+    size_t fb_rgba8_cap = 0, fb_radiance_cap = 0, fb_hit_ids_cap = 0, fb_cost_cap = 0;
     size_t last_rows = 0, last_tw = 0;
     uint64_t* d_ray_counts = nullptr;
 
@@ -269,7 +270,7 @@ int plan_frame(RtContext* ctx, const RtRenderParams* p, FramePlan& f) {
 }
 
 int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const RtRenderParams* p, const FramePlan& f, uint8_t* d_rgba8,
-                  float* d_radiance, uint32_t* d_hit_ids, uint64_t* d_ray_counts) {
+                  float* d_radiance, uint32_t* d_hit_ids, uint64_t* d_ray_counts, uint32_t* d_cost = nullptr) {
     if (!ctx->tlas_built) return fail(ctx, RT_ERR_NOT_BUILT, "rt_render before rt_build_tlas");
     size_t pixels = (size_t)f.rows * f.tw;
     if (!R.d_counters) {
@@ -307,6 +308,8 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
     F.cos_sun_radius = cosf(u->sun_radius);
     F.image_rows = (p->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) ? 1u : 0u;
     F.rgba8 = d_rgba8; F.radiance = d_radiance; F.hit_ids = d_hit_ids;
+    F.cost = u->show_heatmap ? d_cost : nullptr;
+    F.heatmap_scale = p->heatmap_scale > 0.0f ? p->heatmap_scale : 1000000.0f;  // lib.rs:179
     F.counters = R.d_counters;
     F.ray_q[0] = R.d_ray_q[0]; F.ray_q[1] = R.d_ray_q[1];
     F.hit_q = R.d_hit_q;
@@ -429,7 +432,7 @@ void rt_destroy(RtContext* ctx) {
     ctx->main.release();
     cudaFree(ctx->d_instances); cudaFree(ctx->d_inst_unsorted); cudaFree(ctx->d_inst_rt); cudaFree(ctx->d_inst_boxes);
     cudaFree(ctx->d_leaf_order); cudaFree(ctx->d_tlas_nodes); cudaFree(ctx->d_tlas_node_count); cudaFree(ctx->d_ray_counts);
-    cudaFree(ctx->d_fb_rgba8); cudaFree(ctx->d_fb_radiance); cudaFree(ctx->d_fb_hit_ids);
+    cudaFree(ctx->d_fb_rgba8); cudaFree(ctx->d_fb_radiance); cudaFree(ctx->d_fb_hit_ids); cudaFree(ctx->d_fb_cost);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->timing_ready)
@@ -709,7 +712,7 @@ int rt_render_device(RtContext* ctx, const RtUniforms* uniforms, const RtRenderP
     if ((params->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) && out && out->hit_ids)
         return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_device: RT_RENDER_OUTPUT_IMAGE_ROWS supports rgba8 and radiance only");
     return render_common(ctx, ctx->main, uniforms, params, f, out ? out->rgba8 : nullptr, out ? out->radiance : nullptr, out ? out->hit_ids : nullptr,
-                         out ? out->ray_counts : nullptr);
+                         out ? out->ray_counts : nullptr, out ? out->cost_cycles : nullptr);
 }
 
 int rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params, const RtFrameOutputs* out) {
@@ -722,11 +725,13 @@ int rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* 
     if (rc) return rc;
     size_t pixels = (size_t)f.rows * f.tw;
     bool want_rad = out && out->radiance, want_ids = out && out->hit_ids;
+    bool want_cost = out && out->cost_cycles && uniforms->show_heatmap;
     CK(grow(ctx->d_fb_rgba8, ctx->fb_rgba8_cap, pixels * 4 + 16));
     if (want_rad) CK(grow(ctx->d_fb_radiance, ctx->fb_radiance_cap, pixels * 3 + 4));
     if (want_ids) CK(grow(ctx->d_fb_hit_ids, ctx->fb_hit_ids_cap, pixels * 3 * params->max_segments + 4));
+    if (want_cost) CK(grow(ctx->d_fb_cost, ctx->fb_cost_cap, pixels + 4));
     rc = render_common(ctx, ctx->main, uniforms, params, f, ctx->d_fb_rgba8, want_rad ? ctx->d_fb_radiance : nullptr,
-                       want_ids ? ctx->d_fb_hit_ids : nullptr, ctx->d_ray_counts);
+                       want_ids ? ctx->d_fb_hit_ids : nullptr, ctx->d_ray_counts, want_cost ? ctx->d_fb_cost : nullptr);
     if (rc) return rc;
     if (out) {
         cudaStream_t st = ctx->stream;
@@ -734,6 +739,7 @@ int rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* 
         if (want_rad) CK(cudaMemcpyAsync(out->radiance, ctx->d_fb_radiance, pixels * 12, cudaMemcpyDeviceToHost, st));
         if (want_ids) CK(cudaMemcpyAsync(out->hit_ids, ctx->d_fb_hit_ids, pixels * 12 * params->max_segments, cudaMemcpyDeviceToHost, st));
         if (out->ray_counts) CK(cudaMemcpyAsync(out->ray_counts, ctx->d_ray_counts, 16, cudaMemcpyDeviceToHost, st));
+        if (want_cost) CK(cudaMemcpyAsync(out->cost_cycles, ctx->d_fb_cost, pixels * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
     return RT_OK;
@@ -742,7 +748,7 @@ int rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* 
 int rt_render_async(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params, const RtFrameOutputs* out, uint32_t* out_slot) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     if (!uniforms || !params) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_async: NULL argument");
-    if (out && (out->radiance || out->hit_ids)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_async: only rgba8 and ray_counts outputs");
+    if (out && (out->radiance || out->hit_ids || out->cost_cycles)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_async: only rgba8 and ray_counts outputs");
     if (params->flags & RT_RENDER_OUTPUT_IMAGE_ROWS) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render_async: RT_RENDER_OUTPUT_IMAGE_ROWS is for rt_render_device");
     CK_DEV(ctx);
     FramePlan f;
@@ -801,7 +807,7 @@ int rt_render_device_slot(RtContext* ctx, uint32_t slot, void* cuda_stream, cons
     CK(cudaEventRecord(sl.scene_ready, ctx->stream));             // scene changes enqueued so far ...
     CK(cudaStreamWaitEvent(sl.res.stream, sl.scene_ready, 0));    // ... happen before this frame
     rc = render_common(ctx, sl.res, uniforms, params, f, out ? out->rgba8 : nullptr, out ? out->radiance : nullptr,
-                       out ? out->hit_ids : nullptr, out ? out->ray_counts : nullptr);
+                       out ? out->hit_ids : nullptr, out ? out->ray_counts : nullptr, out ? out->cost_cycles : nullptr);
     if (rc) return rc;
     CK(cudaEventRecord(sl.rendered, sl.res.stream));
     sl.rendering = true;

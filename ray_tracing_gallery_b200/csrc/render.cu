@@ -450,7 +450,10 @@ __global__ void __launch_bounds__(128, 5) k_tail(SceneDev S, FrameDev F, uint64_
 }
 
 // ------------------------------------------------------------------------------------ megakernel
-template <bool COUNT>
+// HEAT = Uniforms.show_heatmap (lib.rs:120-124, 174-186): the pixel shows how many clock ticks its ray-gen
+// invocation took instead of its colour.  The reference's definition is per invocation (read_clock_khr before
+// and after the segment loop), so heatmap frames always run this one-thread-per-pixel kernel.
+template <bool COUNT, bool HEAT>
 __global__ void __launch_bounds__(128) k_mega(SceneDev S, FrameDev F, uint32_t total) {
     TraceCounters tc = {0, 0, 0, 0, 0}, tcs = {0, 0, 0, 0, 0};
     uint32_t n_primary = 0, n_shadow = 0, n_textured = 0;
@@ -458,6 +461,7 @@ __global__ void __launch_bounds__(128) k_mega(SceneDev S, FrameDev F, uint32_t t
     uint32_t lx, ly;
     bool active = item < total && item_to_pixel(F, item, lx, ly);
     if (active) {
+        const long long start_time = HEAT ? clock64() : 0ll;
         uint32_t pixel = ly * F.tw + lx;
         uint32_t px = F.x0 + lx, py = global_y(F, ly);
         V3 o, d;
@@ -490,6 +494,12 @@ __global__ void __launch_bounds__(128) k_mega(SceneDev S, FrameDev F, uint32_t t
             }
             if (nd.x == 0.0f && nd.y == 0.0f && nd.z == 0.0f) break;
             o = no; d = nd;
+        }
+        if (HEAT) {
+            const unsigned long long delta_time = (unsigned long long)(clock64() - start_time);
+            const uint32_t cycles = delta_time > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)delta_time;
+            if (F.cost) F.cost[out_index(F, pixel)] = cycles;
+            colour = heatmap_pixel(cycles, F.heatmap_scale, colour);
         }
         write_pixel(F, pixel, colour);
     }
@@ -568,9 +578,16 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
         k_sun_dirs<<<(4096u * F.shadow_rays + 127u) / 128u, 128, 0, stream>>>(S, F, const_cast<float4*>(F.sun_dirs));
         note_launch();
     }
-    if (pipeline == RT_PIPELINE_MEGAKERNEL) {
-        if (count) k_mega<true><<<(total + 127) / 128, 128, 0, stream>>>(S, F, total);
-        else k_mega<false><<<(total + 127) / 128, 128, 0, stream>>>(S, F, total);
+    const bool heat = F.uniforms.show_heatmap != 0;
+    if (pipeline == RT_PIPELINE_MEGAKERNEL || heat) {
+        const unsigned g = (total + 127) / 128;
+        if (heat) {
+            if (count) k_mega<true, true><<<g, 128, 0, stream>>>(S, F, total);
+            else k_mega<false, true><<<g, 128, 0, stream>>>(S, F, total);
+        } else {
+            if (count) k_mega<true, false><<<g, 128, 0, stream>>>(S, F, total);
+            else k_mega<false, false><<<g, 128, 0, stream>>>(S, F, total);
+        }
         mark(K_MEGA);
     } else {
         static int g_trace0[2] = {0, 0}, g_shadow[2] = {0, 0}, g_tail[2] = {0, 0}, g_prep = 0, g_resolve = 0;

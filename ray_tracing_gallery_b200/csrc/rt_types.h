@@ -150,6 +150,8 @@ struct FrameDev {
     uint8_t*  rgba8;
     float*    radiance;
     uint32_t* hit_ids;
+    uint32_t* cost;                 // show_heatmap frames: clock ticks per pixel (optional)
+    float     heatmap_scale;        // ticks that map to heat 1.0
     FrameCounters* counters;
     RayRec*   ray_q[2];
     HitRec*   hit_q;

@@ -383,6 +383,37 @@ __device__ __forceinline__ uint32_t unorm8(float c) {
     return (uint32_t)floorf(c * 255.0f + 0.5f);
 }
 
+// heatmap.rs:5-54 — `heatmap_temperature`, every operation rounded once (contract arithmetic, no fusing).
+// The reference indexes `colours[heat as i32]`, which is one past the table at heat == 1.0 exactly
+// (undefined in SPIR-V); `cur` is clamped to the last entry here and in the oracle.
+__device__ __forceinline__ float saturate1(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+__device__ __forceinline__ float smoothstep1(float e0, float e1, float x) {
+    float t = saturate1(div_(sub_(x, e0), sub_(e1, e0)));
+    return mul_(mul_(t, t), sub_(3.0f, mul_(2.0f, t)));
+}
+__device__ __forceinline__ V3 heatmap_temperature(float heat) {
+    const float k[10][3] = {
+        {0.0f / 255.0f, 2.0f / 255.0f, 91.0f / 255.0f},    {0.0f / 255.0f, 108.0f / 255.0f, 251.0f / 255.0f},
+        {0.0f / 255.0f, 221.0f / 255.0f, 221.0f / 255.0f}, {51.0f / 255.0f, 221.0f / 255.0f, 0.0f / 255.0f},
+        {255.0f / 255.0f, 252.0f / 255.0f, 0.0f / 255.0f}, {255.0f / 255.0f, 180.0f / 255.0f, 0.0f / 255.0f},
+        {255.0f / 255.0f, 104.0f / 255.0f, 0.0f / 255.0f}, {226.0f / 255.0f, 22.0f / 255.0f, 0.0f / 255.0f},
+        {191.0f / 255.0f, 0.0f / 255.0f, 83.0f / 255.0f},  {145.0f / 255.0f, 0.0f / 255.0f, 65.0f / 255.0f}};
+    heat = mul_(saturate1(heat), 10.0f);
+    const int idx = (int)heat;
+    const int cur = min(idx, 9), prv = max(idx - 1, 0), nxt = min(idx + 1, 9);
+    const float lo = floorf(heat), hi = ceilf(heat), blur = 0.8f;
+    const float s_lo = smoothstep1(sub_(lo, blur), add_(lo, blur), heat);
+    const float s_hi = smoothstep1(sub_(hi, blur), add_(hi, blur), heat);
+    const float wc = mul_(s_lo, sub_(1.0f, s_hi)), wp = sub_(1.0f, s_lo), wn = s_hi;
+    V3 r = add3(add3(scale3(v3(k[cur][0], k[cur][1], k[cur][2]), wc), scale3(v3(k[prv][0], k[prv][1], k[prv][2]), wp)),
+                scale3(v3(k[nxt][0], k[nxt][1], k[nxt][2]), wn));
+    return v3(saturate1(r.x), saturate1(r.y), saturate1(r.z));
+}
+// lib.rs:174-186: `heatmap_temperature(delta_time as f32 / heatmap_scale) + payload.colour * 0.000001`
+__device__ __forceinline__ V3 heatmap_pixel(uint32_t cycles, float scale, V3 colour) {
+    return add3(heatmap_temperature(div_((float)cycles, scale)), scale3(colour, 0.000001f));
+}
+
 // lib.rs:126-142
 __device__ __forceinline__ void primary_ray(const RtUniforms& U, uint32_t x, uint32_t y, uint32_t W, uint32_t H, V3& o, V3& d) {
     float pcx = add_((float)x, 0.5f), pcy = add_((float)y, 0.5f);

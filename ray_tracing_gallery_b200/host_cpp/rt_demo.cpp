@@ -1,7 +1,7 @@
 // rt_demo — headless frame loop of the reference on libb200rt, driven from C++ (the reference's
 // `main.rs` loop without the window: load assets, build the scene, render frames with two in flight).
 //   rt_demo [--config c1|c2|c3|default] [--width W] [--height H] [--frames N] [--device D]
-//           [--lib path/to/libb200rt.so] [--assets dir] [--out frame.ppm]
+//           [--lib path/to/libb200rt.so] [--assets dir] [--out frame.ppm] [--heatmap]
 // Prints one JSON line (rays, ms/frame, Mrays/s).  No CPU fallback: fails without a CUDA device.
 #include <chrono>
 #include <cstdio>
@@ -22,6 +22,7 @@ int main(int argc, char** argv) {
     std::string lib = self + "/../csrc/libb200rt.so", assets = self + "/../../assets", config = "c2", out;
     uint32_t width = 0, height = 0, frames = 20;
     int device = 0;
+    bool heatmap = false;  // the `H` key of the reference (src/main.rs:820)
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string {
@@ -36,6 +37,7 @@ int main(int argc, char** argv) {
         else if (a == "--lib") lib = next();
         else if (a == "--assets") assets = next();
         else if (a == "--out") out = next();
+        else if (a == "--heatmap") heatmap = true;
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
     Backend be;
@@ -67,6 +69,7 @@ int main(int argc, char** argv) {
                 rays += counts[b][0] + counts[b][1];
             }
             RtUniforms u = s.uniforms(1 + k);
+            u.show_heatmap = heatmap ? 1 : 0;
             RtFrameOutputs o = {fb[b], nullptr, nullptr, counts[b]};
             be.check(be.render_async(be.ctx, &u, &p, &o, &slot_of[b]), "render_async");
         }

@@ -256,6 +256,37 @@ def test_many_instances_tile_parity():
     orc.close(); gpu.close()
 
 
+def test_show_heatmap_frame():
+    """SURVEY 8f-3, Uniforms.show_heatmap (lib.rs:120-124, 174-186; heatmap.rs): the frame shows
+    heatmap_temperature(clock ticks of the pixel's ray-gen invocation / heatmap_scale) + 1e-6 * colour.  The clock is the
+    GPU's own, so the check feeds the exported cost_cycles through the oracle's heatmap_pixel; ray work is unchanged."""
+    orc, gpu = make_oracle(), make_renderer()
+    s = build_scene(gpu, "default", 320, 180)
+    plain = gpu.render(s.uniforms(), s.params())
+    u = s.uniforms()
+    u.show_heatmap = 1
+    want_all = ("rgba8", "radiance", "hit_ids", "ray_counts", "cost_cycles")
+    for pipeline, scale in ((abi.RT_PIPELINE_WAVEFRONT, 0.0), (abi.RT_PIPELINE_MEGAKERNEL, 200000.0)):
+        p = s.params(pipeline=pipeline)
+        p.heatmap_scale = scale
+        heat = gpu.render(u, p, want=want_all)
+        gpu.stats()
+        assert np.array_equal(heat["hit_ids"], plain["hit_ids"]) and np.array_equal(heat["ray_counts"], plain["ray_counts"])
+        cost = heat["cost_cycles"]
+        assert cost.min() > 0
+        hit = plain["hit_ids"][:, :, 0, 0] != abi.MISS_ID
+        assert cost[hit].mean() > 1.5 * cost[~hit].mean()  # shaded pixels also run the hit shader and its shadow rays
+        ys, xs = np.meshgrid(np.arange(0, 180, 7), np.arange(0, 320, 11), indexing="ij")
+        for y, x in zip(ys.ravel(), xs.ravel()):
+            want = orc.heatmap_pixel(cost[y, x], plain["radiance"][y, x], scale)
+            assert np.array_equal(heat["radiance"][y, x], want), (y, x, cost[y, x])
+            enc = [orc.unorm8(orc.linear_to_srgb(c)) for c in want]
+            assert np.abs(heat["rgba8"][y, x][:3].astype(int) - np.asarray(enc)).max() <= 1 and heat["rgba8"][y, x][3] == 255
+    # a plain frame does not touch the cost output
+    assert not np.any(gpu.render(s.uniforms(), s.params(), want=("cost_cycles",))["cost_cycles"])
+    orc.close(); gpu.close()
+
+
 def test_device_tables_keep_the_reference_layout():
     gpu = make_renderer()
     s = build_scene(gpu, "default", 64, 36)

@@ -294,6 +294,80 @@ def test_alpha_clip_anyhit_lets_rays_through_the_fence():
     o.close()
 
 
+# ---------------------------------------------------------------- show_heatmap (heatmap.rs, lib.rs:120-124, 174-186)
+HEAT_COLOURS = np.array([(0, 2, 91), (0, 108, 251), (0, 221, 221), (51, 221, 0), (255, 252, 0), (255, 180, 0), (255, 104, 0),
+                         (226, 22, 0), (191, 0, 83), (145, 0, 65)], np.float64) / 255.0
+
+
+def heatmap64(heat):
+    """float64 re-derivation of heatmap.rs:5-54 (with `cur` clamped to the table, see the oracle)."""
+    def sat(x):
+        return min(max(x, 0.0), 1.0)
+
+    def smooth(e0, e1, x):
+        t = sat((x - e0) / (e1 - e0))
+        return t * t * (3.0 - 2.0 * t)
+
+    # the function jumps where heat * 10 crosses an integer (exact integers take the floor == ceil branch), so the
+    # product is rounded to f32 like the shader's; everything after it is float64
+    h = float(np.float32(sat(heat)) * np.float32(10.0))
+    idx = int(h)
+    cur, prv, nxt = min(idx, 9), max(idx - 1, 0), min(idx + 1, 9)
+    lo, hi = math.floor(h), math.ceil(h)
+    s_lo, s_hi = smooth(lo - 0.8, lo + 0.8, h), smooth(hi - 0.8, hi + 0.8, h)
+    r = s_lo * (1.0 - s_hi) * HEAT_COLOURS[cur] + (1.0 - s_lo) * HEAT_COLOURS[prv] + s_hi * HEAT_COLOURS[nxt]
+    return np.clip(r, 0.0, 1.0)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/shaders/ray_generation.spv"), reason="reference tree not present")
+def test_shipped_ray_generation_spirv_holds_the_heatmap_constants():
+    floats, ints = _spv_constants("/root/reference/shaders/ray_generation.spv")
+    f32s = np.asarray(floats, np.float32)
+    for want in (1_000_000.0, 0.000001, 0.8, 10.0, 3.0, 2.0, 0.01, 10000.0, 0.0031308, 12.92, 1.055, 0.055):
+        assert np.any(f32s == np.float32(want)), want
+    for c in sorted({int(v) for v in (HEAT_COLOURS * 255.0).round().ravel()} - {0, 255}):
+        assert np.any(f32s == np.float32(c) / np.float32(255.0)), c  # the table entries, bit-exact f32 quotients
+    assert 9 in ints and 10 in ints
+
+
+def test_heatmap_temperature_against_float64(orc):
+    heats = np.concatenate([np.linspace(-0.2, 1.2, 1401), np.arange(0, 11) / 10.0, [0.05, 0.149999, 0.150001, 0.999999]])
+    for h in heats:
+        got = orc.heatmap_temperature(float(np.float32(h)))
+        want = heatmap64(float(np.float32(h)))
+        assert np.all(np.abs(got - want) <= 2e-6), (h, got, want)
+    # cold end: heat 0 -> floor == ceil == 0: s_lo = s_hi = 0.5 -> 0.25*c0 + 0.5*c0 + 0.5*c1
+    assert np.allclose(orc.heatmap_temperature(0.0), 0.75 * HEAT_COLOURS[0] + 0.5 * HEAT_COLOURS[1], atol=1e-6)
+    # hot end: one past the table in the reference; clamped here -> 1.25 * c9, clamped to [0, 1]
+    assert np.allclose(orc.heatmap_temperature(1.0), np.clip(1.25 * HEAT_COLOURS[9], 0, 1), atol=1e-6)
+    assert np.array_equal(orc.heatmap_temperature(7.0), orc.heatmap_temperature(1.0))  # saturate
+    # lib.rs:182: the payload colour only tints the heat by 1e-6
+    base = orc.heatmap_pixel(250_000, (0.0, 0.0, 0.0))
+    assert np.array_equal(base, orc.heatmap_temperature(0.25))
+    assert np.allclose(orc.heatmap_pixel(250_000, (1.0, 0.5, 0.25)) - base, (1e-6, 0.5e-6, 0.25e-6), atol=1e-7)
+    assert np.array_equal(orc.heatmap_pixel(500, (0, 0, 0), scale=1000.0), orc.heatmap_temperature(0.5))
+
+
+def test_oracle_heatmap_frame_uses_the_stand_in_clock():
+    o = make_oracle()
+    s = build_scene(o, "c1", 96, 54)
+    plain = o.render(s.uniforms(), s.params())
+    u = s.uniforms()
+    u.show_heatmap = 1
+    heat = o.render(u, s.params(), want=("rgba8", "radiance", "hit_ids", "ray_counts", "cost_cycles"))
+    assert np.array_equal(heat["hit_ids"], plain["hit_ids"]) and np.array_equal(heat["ray_counts"], plain["ray_counts"])
+    hit = plain["hit_ids"][:, :, 0, 0] != abi.MISS_ID
+    assert np.all(heat["cost_cycles"][~hit] == 20000) and np.all(heat["cost_cycles"][hit] == 20000 * (1 + s.shadow_rays))
+    assert int(heat["cost_cycles"].sum()) == 20000 * int(plain["ray_counts"].sum())
+    for (y, x) in ((0, 0), (53, 95), (40, 48), (27, 48)):
+        want = o.heatmap_pixel(heat["cost_cycles"][y, x], plain["radiance"][y, x])
+        assert np.array_equal(heat["radiance"][y, x], want)
+        assert tuple(heat["rgba8"][y, x][:3]) == tuple(o.unorm8(o.linear_to_srgb(c)) for c in want)
+    # without show_heatmap the cost output is left alone
+    assert not np.any(o.render(s.uniforms(), s.params(), want=("cost_cycles",))["cost_cycles"])
+    o.close()
+
+
 # ---------------------------------------------------------------- committed golden fixtures
 @pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "default"])
 def test_golden_fixture(cfg):
