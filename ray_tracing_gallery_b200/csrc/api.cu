@@ -109,16 +109,24 @@ struct RtContext {
     DevVec<TriRec> tris;          // BVH leaf order; a tiny BLAS is followed by one bounds record
     uint32_t num_triangles = 0;
 
-    // instances / TLAS
+    // instances / TLAS.  Two sets, like the reference's PerFrameResources (instance buffer + TLAS per frame in flight,
+    // src/command_buffer_recording.rs:22-30): frames read set `cur`; instance writes and the TLAS update that follows go
+    // to the other set and `cur` flips when the update is enqueued, so updating the scene for frame i+1 only waits for the
+    // frames that still read the set being written (frame i-1), not for frame i.
+    struct TlasSet {
+        RtInstance* d_instances = nullptr;   // the caller's 64-byte records, by gl_InstanceID
+        InstRT* d_inst_rt = nullptr;         // traversal records, TLAS leaf order
+        uint32_t* d_leaf_order = nullptr;
+        Node8* d_tlas_nodes = nullptr;
+        uint32_t* d_node_count = nullptr;
+    } sets[2];
+    uint32_t cur = 0;
+    bool staged = false;                     // set cur^1 holds the records of `cur` plus the writes since the last flip
     uint32_t num_instances = 0, inst_cap = 0;
     bool tlas_built = false;
-    RtInstance* d_instances = nullptr;
-    InstRT *d_inst_unsorted = nullptr, *d_inst_rt = nullptr;
+    InstRT* d_inst_unsorted = nullptr;       // builder inputs: only touched on the context's stream
     Aabb* d_inst_boxes = nullptr;
-    uint32_t* d_leaf_order = nullptr;
-    Node8* d_tlas_nodes = nullptr;
     uint32_t tlas_node_cap = 0;
-    uint32_t* d_tlas_node_count = nullptr;
     BvhBuilder builder;
 
     // frame
@@ -143,6 +151,7 @@ struct RtContext {
         cudaEvent_t scene_ready = nullptr, rendered = nullptr, copied = nullptr;
         bool pending = false;       // host has not waited for `copied` yet
         bool rendering = false;     // `rendered` may not have fired yet: scene changes must wait for it
+        uint32_t reads_set = 0;     // the TLAS set the frame renders from
     } slots[2];
     cudaStream_t copy_stream = nullptr;
     uint32_t next_slot = 0;
@@ -152,6 +161,7 @@ struct RtContext {
         FrameResources res;
         cudaEvent_t scene_ready = nullptr, rendered = nullptr;
         bool rendering = false;
+        uint32_t reads_set = 0;
     } dev_slots[2];
 };
 
@@ -183,43 +193,56 @@ cudaError_t grow(T*& p, size_t& cap, size_t want) {
     return e;
 }
 
-int ensure_instance_capacity(RtContext* ctx, uint32_t n) {
-    if (n <= ctx->inst_cap && ctx->d_instances) return RT_OK;
-    uint32_t cap = n + n / 8 + 16;
-    if (ctx->d_instances) cudaFree(ctx->d_instances);
-    if (ctx->d_inst_unsorted) cudaFree(ctx->d_inst_unsorted);
-    if (ctx->d_inst_rt) cudaFree(ctx->d_inst_rt);
-    if (ctx->d_inst_boxes) cudaFree(ctx->d_inst_boxes);
-    if (ctx->d_leaf_order) cudaFree(ctx->d_leaf_order);
-    if (ctx->d_tlas_nodes) cudaFree(ctx->d_tlas_nodes);
-    ctx->d_instances = nullptr; ctx->d_inst_unsorted = nullptr; ctx->d_inst_rt = nullptr;
-    ctx->d_inst_boxes = nullptr; ctx->d_leaf_order = nullptr; ctx->d_tlas_nodes = nullptr;
+void free_instance_buffers(RtContext* ctx) {
+    for (auto& s : ctx->sets) {
+        cudaFree(s.d_instances); cudaFree(s.d_inst_rt); cudaFree(s.d_leaf_order); cudaFree(s.d_tlas_nodes);
+        s.d_instances = nullptr; s.d_inst_rt = nullptr; s.d_leaf_order = nullptr; s.d_tlas_nodes = nullptr;
+    }
+    cudaFree(ctx->d_inst_unsorted); cudaFree(ctx->d_inst_boxes);
+    ctx->d_inst_unsorted = nullptr; ctx->d_inst_boxes = nullptr;
     ctx->inst_cap = 0;
-    CK(cudaMalloc(&ctx->d_instances, sizeof(RtInstance) * cap));
-    CK(cudaMalloc(&ctx->d_inst_unsorted, sizeof(InstRT) * cap));
-    CK(cudaMalloc(&ctx->d_inst_rt, sizeof(InstRT) * cap));
-    CK(cudaMalloc(&ctx->d_inst_boxes, sizeof(Aabb) * cap));
-    CK(cudaMalloc(&ctx->d_leaf_order, sizeof(uint32_t) * cap));
+}
+
+int ensure_instance_capacity(RtContext* ctx, uint32_t n) {
+    if (n <= ctx->inst_cap && ctx->sets[0].d_instances) return RT_OK;
+    uint32_t cap = n + n / 8 + 16;
+    free_instance_buffers(ctx);
     ctx->tlas_node_cap = max_wide_nodes(cap);
-    CK(cudaMalloc(&ctx->d_tlas_nodes, sizeof(Node8) * ctx->tlas_node_cap));
+    for (auto& s : ctx->sets) {
+        CK(cudaMalloc(&s.d_instances, sizeof(RtInstance) * cap));
+        CK(cudaMalloc(&s.d_inst_rt, sizeof(InstRT) * cap));
+        CK(cudaMalloc(&s.d_leaf_order, sizeof(uint32_t) * cap));
+        CK(cudaMalloc(&s.d_tlas_nodes, sizeof(Node8) * ctx->tlas_node_cap));
+    }
+    CK(cudaMalloc(&ctx->d_inst_unsorted, sizeof(InstRT) * cap));
+    CK(cudaMalloc(&ctx->d_inst_boxes, sizeof(Aabb) * cap));
     ctx->inst_cap = cap;
     return RT_OK;
 }
 
-int build_tlas_now(RtContext* ctx, uint32_t mode) {
+// Build (or refit) the TLAS of set `dst` from dst's instance records.  A refit keeps the topology of set `src`
+// (VK mode UPDATE with src == dst in the reference, src/util_structs.rs:309-319; here src may be the other set, whose
+// nodes, leaf order and node count are copied over first).
+int build_tlas_now(RtContext* ctx, uint32_t mode, uint32_t src, uint32_t dst) {
     uint32_t n = ctx->num_instances;
     cudaStream_t st = ctx->stream;
+    RtContext::TlasSet& D = ctx->sets[dst];
     CK(cudaEventRecord(ctx->ev[2], st));
     if (mode == RT_UPDATE_REFIT && ctx->tlas_built) {
+        if (src != dst) {
+            const RtContext::TlasSet& S = ctx->sets[src];
+            CK(launch_copy_tlas(S.d_tlas_nodes, D.d_tlas_nodes, S.d_node_count, D.d_node_count, S.d_leaf_order, D.d_leaf_order, n,
+                                ctx->tlas_node_cap, ctx->sms, st));
+        }
         // keep topology: records and boxes are produced directly in leaf order
-        CK(launch_prepare_instances(ctx->d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), ctx->d_leaf_order,
-                                    ctx->d_inst_rt, ctx->d_inst_boxes, st));
-        CK(ctx->builder.refit(ctx->d_inst_boxes, n, ctx->d_tlas_nodes, 0, 0, ctx->d_tlas_node_count, ctx->tlas_node_cap, st));
+        CK(launch_prepare_instances(D.d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), D.d_leaf_order,
+                                    D.d_inst_rt, ctx->d_inst_boxes, st));
+        CK(ctx->builder.refit(ctx->d_inst_boxes, n, D.d_tlas_nodes, 0, 0, D.d_node_count, ctx->tlas_node_cap, st));
     } else {
-        CK(launch_prepare_instances(ctx->d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), nullptr,
+        CK(launch_prepare_instances(D.d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), nullptr,
                                     ctx->d_inst_unsorted, ctx->d_inst_boxes, st));
-        CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, ctx->d_tlas_nodes, 0, 0, ctx->d_leaf_order, ctx->d_tlas_node_count, true, /*sah_collapse=*/true, st));
-        CK(launch_gather_instances(ctx->d_inst_unsorted, ctx->d_leaf_order, n, ctx->d_inst_rt, st));
+        CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, D.d_tlas_nodes, 0, 0, D.d_leaf_order, D.d_node_count, true, /*sah_collapse=*/true, st));
+        CK(launch_gather_instances(ctx->d_inst_unsorted, D.d_leaf_order, n, D.d_inst_rt, st));
     }
     CK(cudaEventRecord(ctx->ev[3], st));
     ctx->tlas_timed = true;
@@ -227,8 +250,38 @@ int build_tlas_now(RtContext* ctx, uint32_t mode) {
     return RT_OK;
 }
 
-// A scene change (instance write, TLAS build/update, new model or image) enqueued on the context's stream must not
-// overtake frames still rendering on the slot streams of rt_render_async.
+// Writes into TLAS set `set` (enqueued on the context's stream) must not overtake frames that still render from it on the
+// slot streams of rt_render_async / rt_render_device_slot.  Frames reading the other set keep running.
+int wait_for_readers(RtContext* ctx, uint32_t set) {
+    for (auto& sl : ctx->slots)
+        if (sl.rendering && sl.reads_set == set) {
+            CK(cudaStreamWaitEvent(ctx->stream, sl.rendered, 0));
+            sl.rendering = false;
+        }
+    for (auto& sl : ctx->dev_slots)
+        if (sl.rendering && sl.reads_set == set) {
+            CK(cudaStreamWaitEvent(ctx->stream, sl.rendered, 0));
+            sl.rendering = false;
+        }
+    return RT_OK;
+}
+
+// First write after a flip: the other set takes over the current records (skipped when the write that follows replaces
+// the whole buffer anyway, like C4's per-frame update of every transform).
+int begin_staging(RtContext* ctx, bool whole_buffer_follows) {
+    if (ctx->staged) return RT_OK;
+    const uint32_t w = ctx->cur ^ 1u;
+    int rc = wait_for_readers(ctx, w);
+    if (rc) return rc;
+    if (!whole_buffer_follows && ctx->num_instances)
+        CK(cudaMemcpyAsync(ctx->sets[w].d_instances, ctx->sets[ctx->cur].d_instances, sizeof(RtInstance) * (size_t)ctx->num_instances,
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->staged = true;
+    return RT_OK;
+}
+
+// A scene change that touches what every frame reads (new model or image, full TLAS build) enqueued on the context's
+// stream must not overtake any frame still rendering on the slot streams.
 int wait_for_frames_in_flight(RtContext* ctx) {
     for (auto& sl : ctx->slots)
         if (sl.rendering) {
@@ -285,9 +338,10 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
         R.queue_cap = pixels;
     }
     SceneDev S;
-    S.tlas_nodes = ctx->d_tlas_nodes;
-    S.inst_rt = ctx->d_inst_rt;
-    S.instances = ctx->d_instances;
+    const RtContext::TlasSet& T = ctx->sets[ctx->cur];
+    S.tlas_nodes = T.d_tlas_nodes;
+    S.inst_rt = T.d_inst_rt;
+    S.instances = T.d_instances;
     S.blas_nodes = ctx->blas_nodes.ptr;
     S.tris = ctx->tris.ptr;
     S.model_info = ctx->d_model_info.ptr;
@@ -386,7 +440,10 @@ int rt_create(int cuda_device, RtContext** out) {
     c->main.stream = c->stream;
     if ((e = cudaMalloc(&c->main.d_counters, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMalloc");
     c->last_res = &c->main;
-    if ((e = cudaMalloc(&c->d_tlas_node_count, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    for (auto& s : c->sets) {
+        if ((e = cudaMalloc(&s.d_node_count, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+        if ((e = cudaMemset(s.d_node_count, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
+    }
     if ((e = cudaMalloc(&c->d_ray_counts, sizeof(uint64_t) * 2)) != cudaSuccess) return bail(e, "cudaMalloc");
     // sRGB EOTF table (exact per 8-bit code, decode happens before filtering)
     for (int i = 0; i < 256; i++) {
@@ -430,8 +487,9 @@ void rt_destroy(RtContext* ctx) {
     ctx->d_model_info.release(); ctx->d_blas_info.release(); ctx->blas_nodes.release(); ctx->tris.release();
     cudaFree(ctx->d_textures); cudaFree(ctx->d_real_textures); cudaFree(ctx->d_srgb_lut); cudaFree(ctx->d_uniforms);
     ctx->main.release();
-    cudaFree(ctx->d_instances); cudaFree(ctx->d_inst_unsorted); cudaFree(ctx->d_inst_rt); cudaFree(ctx->d_inst_boxes);
-    cudaFree(ctx->d_leaf_order); cudaFree(ctx->d_tlas_nodes); cudaFree(ctx->d_tlas_node_count); cudaFree(ctx->d_ray_counts);
+    free_instance_buffers(ctx);
+    for (auto& s : ctx->sets) cudaFree(s.d_node_count);
+    cudaFree(ctx->d_ray_counts);
     cudaFree(ctx->d_fb_rgba8); cudaFree(ctx->d_fb_radiance); cudaFree(ctx->d_fb_hit_ids); cudaFree(ctx->d_fb_cost);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -662,8 +720,9 @@ int rt_build_tlas(RtContext* ctx, const RtInstance* instances, uint32_t count) {
     if (rc) return rc;
     ctx->num_instances = count;
     ctx->tlas_built = false;
-    if (count) CK(cudaMemcpyAsync(ctx->d_instances, instances, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-    rc = build_tlas_now(ctx, RT_UPDATE_REBUILD);
+    ctx->staged = false;
+    if (count) CK(cudaMemcpyAsync(ctx->sets[ctx->cur].d_instances, instances, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    rc = build_tlas_now(ctx, RT_UPDATE_REBUILD, ctx->cur, ctx->cur);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));  // the caller may free `instances` now
     return RT_OK;
@@ -674,9 +733,9 @@ int rt_update_instances(RtContext* ctx, uint32_t first, uint32_t count, const Rt
     if ((uint64_t)first + count > ctx->num_instances) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_update_instances: range outside the instance buffer");
     if (count && !host_records) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_instances: records is NULL");
     CK_DEV(ctx);
-    { int w = wait_for_frames_in_flight(ctx); if (w) return w; }
     if (count) {
-        CK(cudaMemcpyAsync(ctx->d_instances + first, host_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+        { int w = begin_staging(ctx, first == 0 && count == ctx->num_instances); if (w) return w; }
+        CK(cudaMemcpyAsync(ctx->sets[ctx->cur ^ 1u].d_instances + first, host_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));  // pageable source: the caller owns it again on return
     }
     return RT_OK;
@@ -687,8 +746,10 @@ int rt_update_instances_device(RtContext* ctx, uint32_t first, uint32_t count, c
     if ((uint64_t)first + count > ctx->num_instances) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_update_instances_device: range outside the instance buffer");
     if (count && !device_records) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_instances_device: records is NULL");
     CK_DEV(ctx);
-    { int w = wait_for_frames_in_flight(ctx); if (w) return w; }
-    if (count) CK(cudaMemcpyAsync(ctx->d_instances + first, device_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (count) {
+        { int w = begin_staging(ctx, first == 0 && count == ctx->num_instances); if (w) return w; }
+        CK(cudaMemcpyAsync(ctx->sets[ctx->cur ^ 1u].d_instances + first, device_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     return RT_OK;
 }
 
@@ -697,9 +758,14 @@ int rt_update_tlas(RtContext* ctx, uint32_t mode) {
     if (mode > RT_UPDATE_REBUILD) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_tlas: unknown mode");
     if (!ctx->tlas_built) return fail(ctx, RT_ERR_NOT_BUILT, "rt_update_tlas before rt_build_tlas");
     CK_DEV(ctx);
-    { int w = wait_for_frames_in_flight(ctx); if (w) return w; }
+    { int w = begin_staging(ctx, false); if (w) return w; }  // an update without instance writes still builds into the other set
     if (mode == RT_UPDATE_AUTO) mode = RT_UPDATE_REBUILD;
-    return build_tlas_now(ctx, mode);
+    const uint32_t w = ctx->cur ^ 1u;
+    int rc = build_tlas_now(ctx, mode, ctx->cur, w);
+    if (rc) return rc;
+    ctx->cur = w;  // frames enqueued from now on render from the updated set
+    ctx->staged = false;
+    return RT_OK;
 }
 
 int rt_render_device(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* params, const RtFrameOutputs* out) {
@@ -777,6 +843,7 @@ int rt_render_async(RtContext* ctx, const RtUniforms* uniforms, const RtRenderPa
     if (rc) return rc;
     CK(cudaEventRecord(sl.rendered, sl.res.stream));
     sl.rendering = true;
+    sl.reads_set = ctx->cur;
     CK(cudaStreamWaitEvent(ctx->copy_stream, sl.rendered, 0));
     if (out && out->rgba8) CK(cudaMemcpyAsync(out->rgba8, sl.d_rgba8, pixels * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
     if (out && out->ray_counts) CK(cudaMemcpyAsync(out->ray_counts, sl.d_ray_counts, 16, cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -811,6 +878,7 @@ int rt_render_device_slot(RtContext* ctx, uint32_t slot, void* cuda_stream, cons
     if (rc) return rc;
     CK(cudaEventRecord(sl.rendered, sl.res.stream));
     sl.rendering = true;
+    sl.reads_set = ctx->cur;
     return RT_OK;
 }
 
@@ -901,7 +969,7 @@ int rt_get_stats(RtContext* ctx, RtStats* out) {
     if (fc.stack_overflow) return fail(ctx, RT_ERR_OUT_OF_RANGE, "traversal stack overflow in the last frame");
     if (ctx->render_timed) CK(cudaEventElapsedTime(&out->last_render_ms, ctx->ev[0], ctx->ev[1]));
     if (ctx->tlas_timed) CK(cudaEventElapsedTime(&out->last_tlas_ms, ctx->ev[2], ctx->ev[3]));
-    if (ctx->tlas_built) CK(cudaMemcpy(&out->tlas_nodes, ctx->d_tlas_node_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (ctx->tlas_built) CK(cudaMemcpy(&out->tlas_nodes, ctx->sets[ctx->cur].d_node_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     out->blas_nodes = (uint32_t)ctx->blas_nodes.size;
     out->num_instances = ctx->num_instances;
     out->num_triangles = ctx->num_triangles;
@@ -913,7 +981,7 @@ int rt_get_push_constants(RtContext* ctx, RtPushConstantBufferAddresses* out) {
     if (!out) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_get_push_constants: NULL");
     out->model_info = (uint64_t)(uintptr_t)ctx->d_model_info.ptr;
     out->uniforms = (uint64_t)(uintptr_t)ctx->d_uniforms;
-    out->acceleration_structure = (uint64_t)(uintptr_t)ctx->d_tlas_nodes;
+    out->acceleration_structure = (uint64_t)(uintptr_t)ctx->sets[ctx->cur].d_tlas_nodes;
     return RT_OK;
 }
 

@@ -34,5 +34,8 @@ cudaError_t launch_gather_triangles(const ModelGeomDev& M, const uint32_t* leaf_
 cudaError_t launch_prepare_instances(const RtInstance* instances, uint32_t n, const BlasInfo* blas, uint32_t num_models,
                                      const uint32_t* leaf_order, InstRT* out_rt, Aabb* out_boxes, cudaStream_t stream);
 cudaError_t launch_gather_instances(const InstRT* in, const uint32_t* leaf_order, uint32_t n, InstRT* out, cudaStream_t stream);
+// Copy the topology of one TLAS set to the other (wide nodes in use, leaf order, node count) before a refit of the copy.
+cudaError_t launch_copy_tlas(const Node8* src_nodes, Node8* dst_nodes, const uint32_t* src_count, uint32_t* dst_count,
+                             const uint32_t* src_order, uint32_t* dst_order, uint32_t n, uint32_t node_cap, int sms, cudaStream_t stream);
 
 }  // namespace b200rt

@@ -4,6 +4,7 @@
 // src/util_structs.rs:285-357).
 #include <math_constants.h>
 
+#include "bvh_build.h"
 #include "contract.cuh"
 #include "launch_count.h"
 #include "render.h"
@@ -148,7 +149,35 @@ __global__ void k_gather_instances(const InstRT* __restrict__ in, const uint32_t
     d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
 }
 
+// Topology hand-over between the two TLAS sets (refit of the set that is not being rendered from): the wide nodes in
+// use, the leaf order and the node count, all sized by the device-side count (no host read-back on the update path).
+__global__ void __launch_bounds__(256) k_copy_tlas(const Node8* __restrict__ src_nodes, Node8* __restrict__ dst_nodes,
+                                                   const uint32_t* __restrict__ src_count, uint32_t* __restrict__ dst_count,
+                                                   const uint32_t* __restrict__ src_order, uint32_t* __restrict__ dst_order, uint32_t n,
+                                                   uint32_t node_cap) {
+    uint32_t count = *src_count;
+    if (count > node_cap) count = node_cap;
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4* s = reinterpret_cast<const uint4*>(src_nodes);
+    uint4* d = reinterpret_cast<uint4*>(dst_nodes);
+    const size_t quads = (size_t)count * (sizeof(Node8) / sizeof(uint4));
+    for (size_t i = t0; i < quads; i += stride) d[i] = __ldg(s + i);
+    for (uint32_t i = t0; i < n; i += stride) dst_order[i] = __ldg(src_order + i);
+    if (t0 == 0) *dst_count = count;
+}
+
 }  // namespace
+
+cudaError_t launch_copy_tlas(const Node8* src_nodes, Node8* dst_nodes, const uint32_t* src_count, uint32_t* dst_count,
+                             const uint32_t* src_order, uint32_t* dst_order, uint32_t n, uint32_t node_cap, int sms, cudaStream_t stream) {
+    // the node count is only known on the device: enough blocks for the largest TLAS, grid-stride inside
+    uint32_t want = (max_wide_nodes(n) * 8u + 255u) / 256u;
+    uint32_t cap = (uint32_t)(sms > 0 ? sms : 1) * 8u;
+    uint32_t grid = want < cap ? (want ? want : 1u) : cap;
+    k_copy_tlas<<<grid, 256, 0, stream>>>(src_nodes, dst_nodes, src_count, dst_count, src_order, dst_order, n, node_cap);
+    note_launch();
+    return cudaGetLastError();
+}
 
 cudaError_t launch_triangle_boxes(const ModelGeomDev& M, Aabb* boxes, cudaStream_t stream) {
     if (M.num_tris) { k_triangle_boxes<<<(M.num_tris + 255) / 256, 256, 0, stream>>>(M, boxes); note_launch(); }

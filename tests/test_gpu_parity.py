@@ -245,6 +245,56 @@ def test_default_scene_animation_loop():
     orc.close(); gpu.close()
 
 
+def test_double_buffered_tlas_updates_with_frames_in_flight():
+    """SURVEY 8b (threading row): instance buffer + TLAS are double-buffered like the reference's PerFrameResources
+    (src/command_buffer_recording.rs:22-30).  Updates for frame i+1 are enqueued while frame i is still in flight and go to
+    the other set; every frame must show exactly the state it was enqueued with, whatever mix of full / partial writes,
+    refit / rebuild, and updates without writes came before it."""
+    import torch
+
+    orc, so, gpu, sg = both("c4", 320, 180, num_instances=600)
+    n = len(sg.instances)
+    fbs = [torch.zeros((180, 320, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    steps = [  # (tick, first, count, mode)
+        (1, 0, n, abi.RT_UPDATE_REFIT), (2, 0, n, abi.RT_UPDATE_REFIT), (3, n - 40, 40, abi.RT_UPDATE_REFIT), (4, 0, n, abi.RT_UPDATE_REBUILD),
+        (5, n - 300, 7, abi.RT_UPDATE_REFIT), (5, 0, 0, abi.RT_UPDATE_REFIT), (6, n - 300, 150, abi.RT_UPDATE_REBUILD), (7, 0, n, abi.RT_UPDATE_AUTO),
+    ]
+    state_o = so.instances.copy()
+    pending, want = [], []
+
+    def consume():
+        slot, b, k = pending.pop(0)
+        gpu.wait_frame(slot)
+        assert np.mean(np.abs(fbs[b].numpy().astype(int) - want[k].astype(int)).max(axis=2) <= 1) >= 0.999, f"step {k}"
+
+    for k, (tick, first, count, mode) in enumerate(steps):
+        rec = sg.animate(tick)
+        if count:
+            gpu.update_instances(first, rec[first:first + count])
+            state_o[first:first + count] = so.animate(tick)[first:first + count]
+            orc.update_instances(0, state_o)
+        gpu.update_tlas(mode)
+        orc.update_tlas(abi.RT_UPDATE_REBUILD)
+        want.append(orc.render(so.uniforms(frame_index=1 + k), so.params(), want=("rgba8",))["rgba8"])
+        if len(pending) == 2:
+            consume()
+        b = k & 1
+        pending.append((gpu.render_async(sg.uniforms(frame_index=1 + k), sg.params(), fbs[b].data_ptr()), b, k))
+    while pending:
+        consume()
+    # records written without a TLAS update stay invisible (the acceleration structure keeps its own copy of the transforms)
+    before = gpu.render(sg.uniforms(frame_index=9), sg.params())
+    gpu.update_instances(0, sg.animate(40))
+    after = gpu.render(sg.uniforms(frame_index=9), sg.params())
+    for key in ("rgba8", "hit_ids", "ray_counts"):
+        assert np.array_equal(before[key], after[key])
+    gpu.update_tlas(abi.RT_UPDATE_REFIT)
+    orc.update_instances(0, so.animate(40)); orc.update_tlas(abi.RT_UPDATE_REBUILD)
+    check_parity(gpu.render(sg.uniforms(frame_index=9), sg.params()), orc.render(so.uniforms(frame_index=9), so.params()))
+    gpu.stats()
+    orc.close(); gpu.close()
+
+
 def test_many_instances_tile_parity():
     """C5 in small (50k instances, 16 soft-shadow rays): a tile of the 4K launch against the oracle."""
     orc, so, gpu, sg = both("c5", 3840, 2160, num_instances=50000)
