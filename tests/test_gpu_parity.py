@@ -329,7 +329,7 @@ def test_show_heatmap_frame():
         ys, xs = np.meshgrid(np.arange(0, 180, 7), np.arange(0, 320, 11), indexing="ij")
         for y, x in zip(ys.ravel(), xs.ravel()):
             want = orc.heatmap_pixel(cost[y, x], plain["radiance"][y, x], scale)
-            assert np.array_equal(heat["radiance"][y, x], want), (y, x, cost[y, x])
+            assert np.allclose(heat["radiance"][y, x], want, rtol=0, atol=1e-6, equal_nan=True), (y, x, cost[y, x])
             enc = [orc.unorm8(orc.linear_to_srgb(c)) for c in want]
             assert np.abs(heat["rgba8"][y, x][:3].astype(int) - np.asarray(enc)).max() <= 1 and heat["rgba8"][y, x][3] == 255
     # a plain frame does not touch the cost output
