@@ -63,6 +63,46 @@ def test_shipped_spirv_constants_match_the_restatement():
         assert any(abs(f - want) <= 1e-6 * max(1.0, abs(want)) for f in floats), want
 
 
+def _spv_opcounts(path):
+    words = np.frombuffer(open(path, "rb").read(), dtype="<u4")
+    i, ops = 5, {}
+    while i < len(words):
+        wc, op = int(words[i]) >> 16, int(words[i]) & 0xFFFF
+        ops[op] = ops.get(op, 0) + 1
+        i += max(wc, 1)
+    return ops
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/shaders/any_hit_alpha_clip.spv"), reason="reference tree not present")
+def test_shipped_spirv_stage_structure_matches_the_restatement():
+    """The other shipped stages: what they sample, trace, ignore and which constants they carry — the facts the oracle's
+    stages (and the CUDA ones) are written to."""
+    OP_SAMPLE_IMPLICIT, OP_SAMPLE_EXPLICIT, OP_TRACE_RAY, OP_IGNORE, OP_READ_CLOCK = 87, 88, 4445, 4448, 5056
+    sh = "/root/reference/shaders/"
+    # any-hit: ONE explicit-LOD texture tap, ignoreIntersection, threshold 0.5 (any_hit_alpha_clip.glsl:24-27)
+    ops = _spv_opcounts(sh + "any_hit_alpha_clip.spv")
+    assert ops.get(OP_SAMPLE_EXPLICIT) == 1 and ops.get(OP_IGNORE) == 1 and OP_SAMPLE_IMPLICIT not in ops
+    assert 0.5 in _spv_constants(sh + "any_hit_alpha_clip.spv")[0]
+    # textured closest-hit: blue noise x2 + diffuse + metal-rough + normal map = 5 taps, all LOD 0; one trace call site (the shadow ray)
+    ops = _spv_opcounts(sh + "closest_hit_textured.spv")
+    assert ops.get(OP_SAMPLE_EXPLICIT) == 5 and OP_SAMPLE_IMPLICIT not in ops and ops.get(OP_TRACE_RAY) == 1
+    floats, ints = _spv_constants(sh + "closest_hit_textured.spv")
+    assert 12 in ints  # gl_RayFlagsTerminateOnFirstHitEXT (4) | gl_RayFlagsSkipClosestHitShaderEXT (8)
+    assert np.float32(1.0 / 64.0) in np.asarray(floats, np.float32)  # blue-noise texel size
+    # mirror: no texture, no trace; portal: +5 on y; miss: the sky's 0.05 blue and the sun's 1.0
+    ops = _spv_opcounts(sh + "closest_hit_mirror.spv")
+    assert OP_SAMPLE_EXPLICIT not in ops and OP_TRACE_RAY not in ops
+    def real(path):  # 32-bit constants that are not small integers read as denormals
+        return sorted({float(np.float32(f)) for f in _spv_constants(path)[0] if abs(f) > 1e-30})
+
+    assert real(sh + "closest_hit_portal.spv") == [5.0]
+    assert real(sh + "primary_ray_miss.spv") == [float(np.float32(0.05)), 1.0]
+    assert real(sh + "shadow_ray_miss.spv") == []
+    # ray generation: one trace call site inside the segment loop, the clock read twice (show_heatmap)
+    ops = _spv_opcounts(sh + "ray_generation.spv")
+    assert ops.get(OP_TRACE_RAY) == 1 and ops.get(OP_READ_CLOCK) == 2
+
+
 # ---------------------------------------------------------------- shading formulas in float64
 def brdf64(n, v, l, base, pr, m, sun):
     n, v, l, base = (np.asarray(x, np.float64) for x in (n, v, l, base))
