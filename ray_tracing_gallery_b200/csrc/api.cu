@@ -352,6 +352,7 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
     S.num_real_textures = (uint32_t)ctx->real_tex_host.size();
     S.real_textures = ctx->d_real_textures;
     S.srgb_lut = ctx->d_srgb_lut;
+    S.one_bits = 0x3F800000u;
     FrameDev F;
     memset(&F, 0, sizeof(F));
     F.uniforms = *u;

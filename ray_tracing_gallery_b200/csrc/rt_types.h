@@ -136,6 +136,11 @@ struct SceneDev {
     uint32_t          num_real_textures;  // images that need a TEX fetch (not 1x1 constants)
     const uint32_t*   real_textures;      // their indices, ascending
     const float*      srgb_lut;      // 512 floats: sRGB EOTF per 8-bit code, then code / 255
+    // The bits of 1.0f as a kernel parameter.  The box test merges plane bytes into this word with PRMT; SASS PRMT has one
+    // immediate slot, and when ptxas knows the word is a constant it spends the slot on it and re-materialises the four byte
+    // selectors into registers before most of the 48 PRMTs of a node visit.  Coming from the constant bank, the word is
+    // a plain operand and the selectors stay immediates (A/B: -DRT_PRMT_CONST_ONE).
+    uint32_t          one_bits;
 };
 
 struct FrameDev {

@@ -68,11 +68,22 @@ __device__ __forceinline__ uint32_t permute_by_octant(uint32_t m, uint32_t oct) 
     return m;
 }
 
-// byte `SEL` of w placed in the mantissa of 1.0f: 1 + q * 2^-15
+// byte `SEL` of w placed in the mantissa of 1.0f: 1 + q * 2^-15.  `one` = the bits of 1.0f (SceneDev::one_bits).
 template <int SEL>
-__device__ __forceinline__ float byte_m(uint32_t w) {
-    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (SEL << 4)));
+__device__ __forceinline__ float byte_m(uint32_t w, uint32_t one) {
+#ifdef RT_PRMT_CONST_ONE
+    one = 0x3F800000u;
+#endif
+    return __uint_as_float(__byte_perm(w, one, 0x7604u | (SEL << 4)));
 }
+
+// Shadow rays stop at the first accepted hit, whatever its distance: their children need no front-to-back order, so
+// the octant permutation of the pending mask is skipped for them (A/B: -DRT_ANY_ORDERED keeps it).
+#ifdef RT_ANY_ORDERED
+#define RT_UNORDERED(ANY) false
+#else
+#define RT_UNORDERED(ANY) (ANY)
+#endif
 
 template <bool ANY, bool COUNT>
 struct Traverser {
@@ -102,7 +113,7 @@ struct Traverser {
         cur_inst_pos = cur_instance_id = cur_custom_sbt = 0;
         enter_inst = RT_NONE;
         ng_base = 0;                       // TLAS root = slot 0 of a virtual parent
-        ng_bits = (1u << oct) | (1u << 8);
+        ng_bits = (RT_UNORDERED(ANY) ? 1u : (1u << oct)) | (1u << 8);
     }
 
     __device__ __forceinline__ bool found() const { return hit.inst_pos != RT_NONE; }
@@ -157,13 +168,29 @@ struct Traverser {
         return true;
     }
 
-    // One traversal step.  Returns true when the ray is finished (then found() tells hit or miss).
+    // One traversal step: pop (when the current group is exhausted), node visit, instance entry — in this order, so
+    // that a popped group is visited and a popped or freshly found instance is entered in the same step, and the warp
+    // runs as few passes over the three blocks as its longest ray needs.  Returns true when the ray is finished (then
+    // found() tells hit or miss).
     __device__ __forceinline__ bool step(const SceneDev& S, uint2* stack, TraceCounters& tc) {
+#ifndef RT_STEP_POP_LAST
+        if ((ng_bits & 0xFFu) == 0u) {
+            // ---- current group exhausted: pop
+            if (inst_sp >= 0 && sp == inst_sp) {
+                inst_sp = -1;
+                set_space(o, d);
+            }
+            if (sp == 0) return true;
+            uint2 e = stack[--sp];
+            if (e.y & 0x80000000u) enter_inst = e.x;
+            else { ng_base = e.x; ng_bits = e.y; }
+        }
+#endif
         if (ng_bits & 0xFFu) {
             // ---- visit the nearest pending child of the current group
             uint32_t i = __ffs(ng_bits & 0xFFu) - 1;
             ng_bits &= ~(1u << i);
-            uint32_t slot = i ^ oct;
+            uint32_t slot = RT_UNORDERED(ANY) ? i : (i ^ oct);
             uint32_t child = ng_base + __popc((ng_bits >> 8) & ((1u << slot) - 1u));
             if (ng_bits & 0xFFu) push(stack, ng_base, ng_bits, tc);
             const Node8* nodes = inst_sp >= 0 ? S.blas_nodes : S.tlas_nodes;
@@ -190,13 +217,14 @@ struct Traverser {
             if (oct & 2u) { ny0 = n4.x; ny1 = n4.y; fy0 = n2.z; fy1 = n2.w; } else { ny0 = n2.z; ny1 = n2.w; fy0 = n4.x; fy1 = n4.y; }
             if (oct & 4u) { nz0 = n4.z; nz1 = n4.w; fz0 = n3.x; fz1 = n3.y; } else { nz0 = n3.x; nz1 = n3.y; fz0 = n4.z; fz1 = n4.w; }
             float tlimit = hit.t;
+            const uint32_t one = S.one_bits;
             uint32_t h = 0;
 #define RT_BOX(SLOT, SEL, WNX, WNY, WNZ, WFX, WFY, WFZ)                                                   \
     {                                                                                                    \
-        float tn = fmaxf(fmaxf(fmaf(byte_m<SEL>(WNX), Ax, Bnx), fmaf(byte_m<SEL>(WNY), Ay, Bny)),          \
-                         fmaxf(fmaf(byte_m<SEL>(WNZ), Az, Bnz), tmin));                                  \
-        float tf = fminf(fminf(fmaf(byte_m<SEL>(WFX), Ax, Bfx), fmaf(byte_m<SEL>(WFY), Ay, Bfy)),          \
-                         fminf(fmaf(byte_m<SEL>(WFZ), Az, Bfz), tlimit));                                \
+        float tn = fmaxf(fmaxf(fmaf(byte_m<SEL>(WNX, one), Ax, Bnx), fmaf(byte_m<SEL>(WNY, one), Ay, Bny)),          \
+                         fmaxf(fmaf(byte_m<SEL>(WNZ, one), Az, Bnz), tmin));                                  \
+        float tf = fminf(fminf(fmaf(byte_m<SEL>(WFX, one), Ax, Bfx), fmaf(byte_m<SEL>(WFY, one), Ay, Bfy)),          \
+                         fminf(fmaf(byte_m<SEL>(WFZ, one), Az, Bfz), tlimit));                                \
         if (tn <= tf) h |= 1u << SLOT;                                                                   \
     }
             RT_BOX(0, 0, nx0, ny0, nz0, fx0, fy0, fz0)
@@ -212,7 +240,7 @@ struct Traverser {
             h &= nonzero_bytes(n1.z, n1.w);
             uint32_t hl = h & ~imask;
             ng_base = n1.x;
-            ng_bits = permute_by_octant(h & imask, oct) | (imask << 8);
+            ng_bits = (RT_UNORDERED(ANY) ? (h & imask) : permute_by_octant(h & imask, oct)) | (imask << 8);
 
             // ---- leaves of this node
             uint64_t meta = ((uint64_t)n1.w << 32) | n1.z;
@@ -263,25 +291,29 @@ struct Traverser {
                     float z0 = (blo.z - oo.z) * iz, z1 = (bhi.z - oo.z) * iz;
                     float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
                     float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), hit.t));
-                    if (tn > tf + 4e-6f * (fabsf(tn) + fabsf(tf)) + 1e-30f) return false;
-                    for (uint32_t k = 0; k < tiny; k++)
-                        if (test_triangle(S, root + k, oo, od, pos, __float_as_uint(r3.y), __float_as_uint(r3.z), tc) && ANY) return true;
-                    return false;
+                    if (!(tn > tf + 4e-6f * (fabsf(tn) + fabsf(tf)) + 1e-30f)) {
+                        for (uint32_t k = 0; k < tiny; k++)
+                            if (test_triangle(S, root + k, oo, od, pos, __float_as_uint(r3.y), __float_as_uint(r3.z), tc) && ANY) return true;
+                    }
+                } else {
+                    if (ng_bits & 0xFFu) push(stack, ng_base, ng_bits, tc);
+                    set_space(xform_point(inv, o), xform_vec(inv, d));
+                    cur_inst_pos = pos;
+                    cur_instance_id = __float_as_uint(r3.y);
+                    cur_custom_sbt = __float_as_uint(r3.z);
+                    ng_base = root;
+                    ng_bits = (RT_UNORDERED(ANY) ? 1u : (1u << oct)) | (1u << 8);
+                    inst_sp = sp;
                 }
-                if (ng_bits & 0xFFu) push(stack, ng_base, ng_bits, tc);
-                set_space(xform_point(inv, o), xform_vec(inv, d));
-                cur_inst_pos = pos;
-                cur_instance_id = __float_as_uint(r3.y);
-                cur_custom_sbt = __float_as_uint(r3.z);
-                ng_base = root;
-                ng_bits = (1u << oct) | (1u << 8);
-                inst_sp = sp;
             }
+#ifdef RT_STEP_POP_LAST
             return false;
+#endif
         }
 
+#ifdef RT_STEP_POP_LAST
         if ((ng_bits & 0xFFu) == 0u) {
-            // ---- current group exhausted: pop
+            // ---- current group exhausted: pop (the order of the first version, kept for A/B)
             if (inst_sp >= 0 && sp == inst_sp) {
                 inst_sp = -1;
                 set_space(o, d);
@@ -292,6 +324,10 @@ struct Traverser {
             else { ng_base = e.x; ng_bits = e.y; }
         }
         return false;
+#else
+        // nothing pending and nothing stacked: finished (saves the pass that would only find the stack empty)
+        return (ng_bits & 0xFFu) == 0u && sp == 0;
+#endif
     }
 };
 

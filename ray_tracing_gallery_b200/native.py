@@ -13,7 +13,8 @@ from . import abi
 from .backend import CApiBackend, RtError
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(_CSRC, "libb200rt.so")
+# B200RT_LIB: an A/B build of the same library (csrc/Makefile `variant`); still the CUDA product, never a fallback
+LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(_CSRC, "libb200rt.so")
 _LIB = None
 
 # every symbol include/b200rt.h declares
