@@ -333,7 +333,7 @@ __device__ void quantise_node(Node8& nd, const Aabb* cb, uint32_t present) {
     float cell[3], inv[3];
     for (int k = 0; k < 3; k++) {
         nd.origin[k] = org[k];
-        nd.exp[k] = (int8_t)ex[k];
+        nd.exp[k] = (uint8_t)(ex[k] + 127);  // -100 <= ex <= 120: the byte is the fp32 exponent field of the cell size
         nd.lo[k] = nb.lo[k];
         nd.hi[k] = nb.hi[k];
         cell[k] = pow2i(ex[k]);

@@ -12,7 +12,7 @@ namespace b200rt {
 // Traversal reads bytes 0..79 as five ld.global.nc.v4; bytes 80..127 are build/refit state.
 //
 // Child boxes are quantised to 8 bits per plane on a power-of-two grid anchored at `origin`:
-//     plane = origin[k] + q * 2^exp[k]
+//     plane = origin[k] + q * 2^(exp[k] - 127)
 // The origin is snapped onto that grid and exp is clamped so that every plane is exactly
 // representable in fp32 (builder: quantise_node).  lo planes are rounded down, hi planes up.
 // Slots are assigned by the octant of the child centre relative to the node centre, so that
@@ -23,7 +23,7 @@ namespace b200rt {
 // slot, 0xFF for an internal slot, 0 for an empty slot (which also has qlo = 255, qhi = 0).
 struct __align__(128) Node8 {
     float    origin[3];   //  0
-    int8_t   exp[3];      // 12
+    uint8_t  exp[3];      // 12  biased like an fp32 exponent field: cell size = 2^(exp - 127)
     uint8_t  imask;       // 15  bit s: slot s is an internal child
     uint32_t child_base;  // 16
     uint32_t prim_base;   // 20

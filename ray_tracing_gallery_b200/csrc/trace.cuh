@@ -199,9 +199,10 @@ struct Traverser {
             if (COUNT) tc.nodes++;
 
             // per-axis: A = 2^15 * 2^e / d, B = (origin - o)/d - A, padded outwards by p
-            float ax = __uint_as_float((uint32_t)((int)(int8_t)(n0.w & 0xFFu) + 127) << 23) * idx;
-            float ay = __uint_as_float((uint32_t)((int)(int8_t)((n0.w >> 8) & 0xFFu) + 127) << 23) * idy;
-            float az = __uint_as_float((uint32_t)((int)(int8_t)((n0.w >> 16) & 0xFFu) + 127) << 23) * idz;
+            // (the exponent bytes are stored biased: shifted into place they ARE the cell sizes 2^e)
+            float ax = __uint_as_float((n0.w << 23) & 0x7F800000u) * idx;
+            float ay = __uint_as_float((n0.w << 15) & 0x7F800000u) * idy;
+            float az = __uint_as_float((n0.w << 7) & 0x7F800000u) * idz;
             float bx = (__uint_as_float(n0.x) - co.x) * idx;
             float by = (__uint_as_float(n0.y) - co.y) * idy;
             float bz = (__uint_as_float(n0.z) - co.z) * idz;
@@ -216,6 +217,8 @@ struct Traverser {
             if (oct & 1u) { nx0 = n3.z; nx1 = n3.w; fx0 = n2.x; fx1 = n2.y; } else { nx0 = n2.x; nx1 = n2.y; fx0 = n3.z; fx1 = n3.w; }
             if (oct & 2u) { ny0 = n4.x; ny1 = n4.y; fy0 = n2.z; fy1 = n2.w; } else { ny0 = n2.z; ny1 = n2.w; fy0 = n4.x; fy1 = n4.y; }
             if (oct & 4u) { nz0 = n4.z; nz1 = n4.w; fz0 = n3.x; fz1 = n3.y; } else { nz0 = n3.x; nz1 = n3.y; fz0 = n4.z; fz1 = n4.w; }
+            // closest-hit rays cull children beyond the committed hit; first-hit rays keep tmax for the triangles only
+            // (a child box beyond tmax = 10 000 scene units is visited in vain, never wrongly accepted)
             float tlimit = hit.t;
             const uint32_t one = S.one_bits;
             uint32_t h = 0;
@@ -223,8 +226,9 @@ struct Traverser {
     {                                                                                                    \
         float tn = fmaxf(fmaxf(fmaf(byte_m<SEL>(WNX, one), Ax, Bnx), fmaf(byte_m<SEL>(WNY, one), Ay, Bny)),          \
                          fmaxf(fmaf(byte_m<SEL>(WNZ, one), Az, Bnz), tmin));                                  \
-        float tf = fminf(fminf(fmaf(byte_m<SEL>(WFX, one), Ax, Bfx), fmaf(byte_m<SEL>(WFY, one), Ay, Bfy)),          \
-                         fminf(fmaf(byte_m<SEL>(WFZ, one), Az, Bfz), tlimit));                                \
+        float tfz = fmaf(byte_m<SEL>(WFZ, one), Az, Bfz);                                                \
+        if (!ANY) tfz = fminf(tfz, tlimit);                                                              \
+        float tf = fminf(fminf(fmaf(byte_m<SEL>(WFX, one), Ax, Bfx), fmaf(byte_m<SEL>(WFY, one), Ay, Bfy)), tfz); \
         if (tn <= tf) h |= 1u << SLOT;                                                                   \
     }
             RT_BOX(0, 0, nx0, ny0, nz0, fx0, fy0, fz0)
