@@ -38,6 +38,7 @@ pub const RT_RENDER_TIMING: u32 = 2;
 pub const RT_RENDER_SPLIT_TAIL: u32 = 4;
 pub const RT_RENDER_NO_PDL: u32 = 8;
 pub const RT_RENDER_OUTPUT_IMAGE_ROWS: u32 = 16;
+pub const RT_RENDER_COOP_TAIL: u32 = 32;
 
 #[repr(C)]
 pub struct RtGeometryDesc {

@@ -78,8 +78,11 @@ typedef enum RtPipeline {
 enum {
     RT_RENDER_COUNTERS = 1u,    /* also count nodes/instances/triangles visited (slower; for the roofline audit) */
     RT_RENDER_TIMING = 2u,      /* CUDA events around every kernel of the frame -> RtStats.kernel_ms */
-    RT_RENDER_SPLIT_TAIL = 4u,  /* bounce segments as four launches each instead of the one cooperative k_tail (A/B) */
+    RT_RENDER_SPLIT_TAIL = 4u,  /* bounce segments as four launches each instead of the one cooperative k_tail.  Without this
+                                   flag (and without RT_RENDER_COOP_TAIL) the library picks per frame from the bounce-ray
+                                   count of the latest finished frame; the frames are identical either way */
     RT_RENDER_NO_PDL = 8u,      /* plain stream-ordered launches instead of programmatic dependent launches (A/B) */
+    RT_RENDER_COOP_TAIL = 32u,  /* always the one cooperative k_tail (A/B) */
     RT_RENDER_OUTPUT_IMAGE_ROWS = 16u /* rt_render_device: out->rgba8 / out->radiance are whole [tile_h][tile_w] images and the call
                                    stores its own rows in place (strip partition).  All ranks of a multi-GPU frame can then
                                    store into ONE frame — rank 0's, mapped through NVLink peer memory — instead of

@@ -149,6 +149,7 @@ RT_RENDER_TIMING = 2
 RT_RENDER_SPLIT_TAIL = 4
 RT_RENDER_NO_PDL = 8
 RT_RENDER_OUTPUT_IMAGE_ROWS = 16
+RT_RENDER_COOP_TAIL = 32
 RT_INSTANCE_TRIANGLE_FACING_CULL_DISABLE = 1
 MISS_ID = 0xFFFFFFFF
 

@@ -90,6 +90,14 @@ struct RtContext {
     bool render_timed = false, tlas_timed = false;
     FrameTiming timing;
     bool timing_ready = false, timing_valid = false;
+    // Tail policy.  Bounce segments run either inside the one cooperative k_tail (one launch; best when there are few or no
+    // bounce rays: C2 0.453 against 0.505 ms) or as separate launches at each kernel's own occupancy (better when a frame
+    // bounces a lot: C3 0.927 -> 0.903 ms, C4 8.76 -> 8.55 ms, and consecutive frames overlap better: C3 e2e +10 %).  Frames
+    // are coherent, so the choice follows the bounce-ray count of the latest finished frame, which the frame kernels leave
+    // in a host-mapped word (no copy, no synchronisation).  B200RT_SPLIT_TAIL=0 / 1 pins the choice (A/B).
+    int tail_policy = -1;                    // -1 adaptive, 0 always cooperative, 1 always split
+    volatile unsigned int* h_bounce = nullptr;  // cudaHostAllocMapped
+    unsigned int* d_bounce = nullptr;           // its device alias
     std::string err;
 
     // images
@@ -296,6 +304,9 @@ int wait_for_frames_in_flight(RtContext* ctx) {
     return RT_OK;
 }
 
+// bounce rays in the latest frame from which the next frame runs its bounce segments as separate launches
+#define RT_SPLIT_TAIL_BOUNCE_RAYS 131072u
+
 struct FramePlan {
     uint32_t x0, y0, tw, th, rows;
 };
@@ -378,6 +389,12 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
         }
     }
     if (&R == &ctx->main) CK(cudaMemcpyAsync(ctx->d_uniforms, u, sizeof(RtUniforms), cudaMemcpyHostToDevice, R.stream));
+    F.bounce_hint = ctx->d_bounce;
+    bool split_tail = (p->flags & RT_RENDER_SPLIT_TAIL) != 0;
+    if (!split_tail && !(p->flags & RT_RENDER_COOP_TAIL)) {
+        if (ctx->tail_policy >= 0) split_tail = ctx->tail_policy == 1;
+        else split_tail = ctx->h_bounce && *ctx->h_bounce >= RT_SPLIT_TAIL_BOUNCE_RAYS;
+    }
     CK(cudaEventRecord(ctx->ev[0], R.stream));
     FrameTiming* timing = nullptr;
     if (p->flags & RT_RENDER_TIMING) {
@@ -388,7 +405,7 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
         timing = &ctx->timing;
     }
     ctx->timing_valid = timing != nullptr;
-    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, (p->flags & RT_RENDER_SPLIT_TAIL) != 0, (p->flags & RT_RENDER_NO_PDL) != 0, ctx->sms, d_ray_counts, timing, R.stream));
+    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, split_tail, (p->flags & RT_RENDER_NO_PDL) != 0, ctx->sms, d_ray_counts, timing, R.stream));
     CK(cudaEventRecord(ctx->ev[1], R.stream));
     ctx->render_timed = true;
     ctx->last_res = &R;
@@ -438,6 +455,16 @@ int rt_create(int cuda_device, RtContext** out) {
     if ((e = cudaMalloc(&c->d_real_textures, sizeof(uint32_t) * RT_MAX_BOUND_IMAGES)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_srgb_lut, sizeof(float) * 512)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_uniforms, sizeof(RtUniforms))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if (const char* v = getenv("B200RT_SPLIT_TAIL")) c->tail_policy = atoi(v) != 0 ? 1 : 0;
+    {
+        void* hp = nullptr;
+        if ((e = cudaHostAlloc(&hp, sizeof(unsigned int), cudaHostAllocMapped)) != cudaSuccess) return bail(e, "cudaHostAlloc");
+        c->h_bounce = static_cast<volatile unsigned int*>(hp);
+        *c->h_bounce = 0u;
+        void* dp = nullptr;
+        if ((e = cudaHostGetDevicePointer(&dp, hp, 0)) != cudaSuccess) return bail(e, "cudaHostGetDevicePointer");
+        c->d_bounce = static_cast<unsigned int*>(dp);
+    }
     c->main.stream = c->stream;
     if ((e = cudaMalloc(&c->main.d_counters, sizeof(FrameCounters))) != cudaSuccess) return bail(e, "cudaMalloc");
     c->last_res = &c->main;
@@ -490,6 +517,7 @@ void rt_destroy(RtContext* ctx) {
     ctx->main.release();
     free_instance_buffers(ctx);
     for (auto& s : ctx->sets) cudaFree(s.d_node_count);
+    if (ctx->h_bounce) cudaFreeHost(const_cast<unsigned int*>(ctx->h_bounce));
     cudaFree(ctx->d_ray_counts);
     cudaFree(ctx->d_fb_rgba8); cudaFree(ctx->d_fb_radiance); cudaFree(ctx->d_fb_hit_ids); cudaFree(ctx->d_fb_cost);
     for (int i = 0; i < 4; i++)

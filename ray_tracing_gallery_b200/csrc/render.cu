@@ -403,7 +403,16 @@ __global__ void __launch_bounds__(128, RT_SHADOW_MINB) k_shadow(SceneDev S, Fram
     pdl_wait();
     shadow_phase<COUNT>(S, F, seg);
 }
-__global__ void __launch_bounds__(128) k_resolve(FrameDev F, uint32_t seg) { resolve_phase(F, seg); }
+// How many bounce rays segment 0 queued: the host's hint for the tail policy of the frames that follow (host-mapped
+// word: no copy, no synchronisation).  Called by the first kernel after segment 0's shadow rays, before any counter slot
+// can be reused.
+__device__ __forceinline__ void export_bounce_hint(const FrameDev& F) {
+    if (F.bounce_hint && blockIdx.x == 0 && threadIdx.x == 0) *F.bounce_hint = *((volatile unsigned int*)&seg_counters(F, 0)->ray_count);
+}
+__global__ void __launch_bounds__(128) k_resolve(FrameDev F, uint32_t seg) {
+    if (seg == 0) export_bounce_hint(F);
+    resolve_phase(F, seg);
+}
 
 // segments >= RT_SEG_SLOTS reuse a counter slot (split-tail path)
 __global__ void k_reset_segment(FrameCounters* c, uint32_t seg) {
@@ -418,6 +427,7 @@ __global__ void k_reset_segment(FrameCounters* c, uint32_t seg) {
 template <bool COUNT>
 __global__ void __launch_bounds__(128, 5) k_tail(SceneDev S, FrameDev F, uint64_t* ray_counts_out) {
     cg::grid_group grid = cg::this_grid();
+    export_bounce_hint(F);
     resolve_phase(F, 0);
     bool traced = false;
     for (uint32_t seg = 1; seg < F.max_segments; seg++) {

@@ -158,6 +158,7 @@ struct FrameDev {
     uint32_t* cost;                 // show_heatmap frames: clock ticks per pixel (optional)
     float     heatmap_scale;        // ticks that map to heat 1.0
     FrameCounters* counters;
+    unsigned int* bounce_hint;      // host-mapped word: bounce rays queued by segment 0 of the latest wavefront frame (optional)
     RayRec*   ray_q[2];
     HitRec*   hit_q;
     // Shadow-ray directions of this frame, [64][64][shadow_rays] float4 indexed by (py & 63, px & 63, sample): the

@@ -118,7 +118,7 @@ def test_bounce_segments_cooperative_tail_equals_split_launches():
     gpu = make_renderer()
     s = build_scene(gpu, "c3", 640, 360)
     for segs in (1, 3, 10):
-        a = gpu.render(s.uniforms(), s.params(max_segments=segs))
+        a = gpu.render(s.uniforms(), s.params(max_segments=segs, flags=abi.RT_RENDER_COOP_TAIL))
         if segs == 3:
             assert gpu.stats().segment_rays[0] > 0, "the config must have bounce rays for this test to mean anything"
         b = gpu.render(s.uniforms(), s.params(max_segments=segs, flags=abi.RT_RENDER_SPLIT_TAIL))
@@ -127,6 +127,31 @@ def test_bounce_segments_cooperative_tail_equals_split_launches():
             assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], m[k]), (segs, k)
         assert np.array_equal(a["radiance"].view(np.uint32), b["radiance"].view(np.uint32))
     gpu.close()
+
+
+def test_tail_policy_follows_the_bounce_rays_of_the_latest_frame():
+    """Without RT_RENDER_SPLIT_TAIL / RT_RENDER_COOP_TAIL the library picks the tail per frame: the cooperative k_tail while
+    frames bounce little, separate launches once the latest frame queued many bounce rays (the count reaches the host
+    through a host-mapped word, no synchronisation).  Whatever it picks, the frame is the same."""
+    gpu = make_renderer()
+    s = build_scene(gpu, "c3", 1920, 1080)
+    timing = abi.RT_RENDER_TIMING
+    ref = gpu.render(s.uniforms(), s.params(flags=abi.RT_RENDER_COOP_TAIL | timing))
+    st = gpu.stats()
+    assert st.kernel_launches[5] == 1 and st.kernel_launches[3] == 0  # K_TAIL, K_RESOLVE
+    assert st.segment_rays[0] >= 131072, "C3 at 1080p must bounce enough for the policy to switch"
+    b = gpu.render(s.uniforms(), s.params(flags=timing))  # the frame before this one bounced a lot -> separate launches
+    st = gpu.stats()
+    assert st.kernel_launches[5] == 0 and st.kernel_launches[3] == 3, list(st.kernel_launches)
+    for k in ("hit_ids", "rgba8", "ray_counts"):
+        assert np.array_equal(ref[k], b[k]), k
+    assert np.array_equal(ref["radiance"].view(np.uint32), b["radiance"].view(np.uint32))
+    # a scene without bounce rays goes back to the cooperative tail after one frame
+    gpu2 = make_renderer()
+    s2 = build_scene(gpu2, "c1", 640, 360)
+    gpu2.render(s2.uniforms(), s2.params(flags=timing))
+    assert gpu2.stats().kernel_launches[5] == 1
+    gpu.close(); gpu2.close()
 
 
 def test_blue_noise_sequence_over_frames():

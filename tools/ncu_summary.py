@@ -51,6 +51,16 @@ def main():
                 print(f"- L2 traffic: {sectors * 32 / 1e6:.1f} MB = {sectors * 32 / sec / 1e9:.0f} GB/s;  DRAM traffic: {dram / 1e6:.1f} MB = {dram / sec / 1e9:.0f} GB/s")
             except (KeyError, ValueError):
                 pass
+            pipes = []
+            for key, (u, v) in k.items():  # which execution pipe is the busiest (alu: PRMT/FMNMX/LOP3/SEL, fma: FFMA/FMUL/IMAD)
+                if key.startswith("sm__inst_executed_pipe_") and key.endswith(".avg.pct_of_peak_sustained_active"):
+                    try:
+                        pipes.append((float(v), key[len("sm__inst_executed_pipe_"):-len(".avg.pct_of_peak_sustained_active")]))
+                    except ValueError:
+                        pass
+            pipes.sort(reverse=True)
+            if pipes:
+                print("- pipe utilisation (% of peak, instructions executed): " + ", ".join(f"{n} {p:.1f}" for p, n in pipes[:6]))
             stalls = []
             for key, (u, v) in k.items():
                 if key.startswith("smsp__average_warps_issue_stalled_") and key.endswith("_per_issue_active.ratio") and "not_issued" not in key:
