@@ -511,13 +511,13 @@ def run_ours(args):
             "kernel_share_of_step": float((kernel_ms[dom] / ksteps) / (total_ms / args.steps)) if world == 1 else None,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "launches_per_frame": float(launches_per_frame),
-            "ncu": ncu_note,  # from the committed capture of the same kernel (profiles/r01j_summary.md): what actually limits it
+            "ncu": ncu_note,  # from the committed capture of the same kernel (profiles/r01r_summary.md): what actually limits it
             "per_ray": {"nodes": float(sum(st_count.nodes_visited)) / rays_frame, "instances": float(sum(st_count.instances_entered)) / rays_frame,
                         "triangles": float(sum(st_count.triangles_tested)) / rays_frame,
                         "bytes": float(bytes_frame["mega"] if args.pipeline == "mega" else sum(bytes_frame[k] for k in KERNELS[:4])) / rays_frame},
             "note": "achieved = algorithmic bytes (per-ray node/instance/triangle fetches + queue records, DESIGN.md 3) / kernel time; the working "
                     "set of C1-C4 is cache resident (traffic = DRAM bytes of one ncu capture, far below the algorithmic bytes), the kernel is "
-                    "issue-bound (profiles/r01j_summary.md: 70 % issue slots busy, 19 of 32 lanes active)",
+                    "limited by instruction issue and load latency at about half SIMD width (profiles/r01r_summary.md: 64 % issue slots busy, 18.5 of 32 lanes active, alu pipe 54 %, top stall long_scoreboard 25 %)",
         }
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
