@@ -145,6 +145,14 @@ typedef struct RtStats {
     uint32_t segment_hits[8];   /* wavefront: textured hits queued by ray-gen segment s */
 } RtStats;
 
+#if defined(__cplusplus)
+static_assert(sizeof(RtRenderParams) == 64, "RtRenderParams is 64 bytes");
+static_assert(sizeof(RtFrameOutputs) == 5 * sizeof(void*), "RtFrameOutputs is five pointers");
+#else
+_Static_assert(sizeof(RtRenderParams) == 64, "RtRenderParams is 64 bytes");
+_Static_assert(sizeof(RtFrameOutputs) == 5 * sizeof(void*), "RtFrameOutputs is five pointers");
+#endif
+
 /* Device/allocator creation: src/main.rs:157-204,337.  One context per GPU. */
 int  rt_create(int cuda_device, RtContext** out);
 /* Explicit teardown, like the reference's cleanup() chain, src/main.rs:997-1023. */

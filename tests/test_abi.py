@@ -66,6 +66,32 @@ def test_headers_compile_as_c_and_cxx(tmp_path):
         assert subprocess.call([str(tmp_path / "t")]) == 0
 
 
+def test_ctypes_mirrors_match_the_headers_field_by_field(tmp_path):
+    """Compile a C program that prints sizeof / offsetof of every field the ctypes mirrors declare and compare: ties
+    abi.py (and through test_rust_binding... the Rust file) to include/*.h mechanically."""
+    structs = ["RtUniforms", "RtModelInfo", "RtGeometryImages", "RtGeometryInfo", "RtPushConstantBufferAddresses", "RtInstance",
+               "RtGeometryDesc", "RtModelDesc", "RtRenderParams", "RtFrameOutputs", "RtStats"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200rt.h"', "int main(void){"]
+    for name in structs:
+        cls = getattr(abi, name)
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines.append("return 0;}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name in structs:
+        cls = getattr(abi, name)
+        assert int(got[name]) == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
+    assert C.sizeof(abi.RtRenderParams) == 64 and abi.RtRenderParams.heatmap_scale.offset == 52
+    assert C.sizeof(abi.RtFrameOutputs) == 40 and abi.RtFrameOutputs.cost_cycles.offset == 32
+
+
 def declared_functions():
     text = open(os.path.join(ROOT, "include", "b200rt.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
