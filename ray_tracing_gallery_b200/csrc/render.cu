@@ -191,9 +191,10 @@ __device__ __forceinline__ SegCounters* seg_counters(const FrameDev& F, uint32_t
 // one atomic.  The atomic for the NEXT batch is issued before the current batch is traced and its
 // result is only read (shuffled) when that batch starts, so the round trip to L2 (about 20 % of
 // k_trace0's stall samples in profiles/r01g) hides behind the traversal.
+#ifndef RT_STATIC_SHARE
 struct WarpChunk {
     uint32_t pending;  // lane 0: base of the next batch, possibly still in flight
-    __device__ __forceinline__ void init(unsigned int* cursor) { pending = lane_id() == 0 ? atomicAdd(cursor, RT_CHUNK) : 0u; }
+    __device__ __forceinline__ void init(unsigned int* cursor, uint32_t /*total*/) { pending = lane_id() == 0 ? atomicAdd(cursor, RT_CHUNK) : 0u; }
     // base of the next batch into `base`; false when the queue has run dry
     __device__ __forceinline__ bool next(unsigned int* cursor, uint32_t total, uint32_t& base) {
         base = __shfl_sync(0xFFFFFFFFu, pending, 0);
@@ -202,6 +203,37 @@ struct WarpChunk {
         return true;
     }
 };
+#else
+// Prepared A/B variant (not measured yet).  profiles/r01r: a fifth of k_trace0's stall samples sit on its atomics — every warp
+// of the grid takes every batch from ONE cursor (65 k same-address atomics in 140 us, about the rate one L2 address
+// sustains).  Here the first RT_STATIC_SHARE / 8 of the batches are dealt statically (warp w takes batches w, w + W, ...;
+// a batch is one 8x4 tile or 32 queue items, so a warp's share is spread over the whole frame) and only the rest goes
+// through the cursor, which still evens out the tail.
+struct WarpChunk {
+    uint32_t pending;      // lane 0: base of the next dynamic batch, possibly still in flight
+    uint32_t next_static;  // next statically assigned batch of this warp
+    uint32_t static_end;   // batches [0, static_end) are static, the cursor deals the rest
+    uint32_t warps;
+    __device__ __forceinline__ void init(unsigned int* cursor, uint32_t total) {
+        warps = gridDim.x * (blockDim.x >> 5);
+        const uint32_t batches = (total + RT_CHUNK - 1u) / RT_CHUNK;
+        static_end = ((uint32_t)(((unsigned long long)batches * RT_STATIC_SHARE) >> 3) / warps) * warps;  // whole rounds only
+        next_static = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        pending = lane_id() == 0 ? atomicAdd(cursor, RT_CHUNK) : 0u;
+    }
+    __device__ __forceinline__ bool next(unsigned int* cursor, uint32_t total, uint32_t& base) {
+        if (next_static < static_end) {
+            base = next_static * RT_CHUNK;
+            next_static += warps;
+            return true;
+        }
+        base = static_end * RT_CHUNK + __shfl_sync(0xFFFFFFFFu, pending, 0);
+        if (base >= total) return false;
+        if (lane_id() == 0) pending = atomicAdd(cursor, RT_CHUNK);
+        return true;
+    }
+};
+#endif
 
 // Ray generation (segment 0) or ray-queue read, closest-hit traversal, miss / mirror / portal shaders,
 // textured hits -> hit queue.
@@ -214,7 +246,7 @@ __device__ __forceinline__ void trace_phase(const SceneDev& S, const FrameDev& F
     SegCounters* sc = seg_counters(F, seg);
     const uint32_t rgba_sky = encode_rgba8(v3(0.0f, 0.0f, 0.05f)), rgba_sun = encode_rgba8(v3(1.0f, 1.0f, 1.0f));
     WarpChunk wc;
-    wc.init(&sc->work_next[K_TRACE]);
+    wc.init(&sc->work_next[K_TRACE], total);
     uint32_t batch;
     while (wc.next(&sc->work_next[K_TRACE], total, batch)) {
         uint32_t item = batch + lane_id();
@@ -342,7 +374,7 @@ __device__ __forceinline__ void shadow_phase(const SceneDev& S, const FrameDev& 
     const uint32_t shift = 31u - __clz(n);
     uint32_t n_shadow = 0;
     WarpChunk wc;
-    wc.init(&sc->work_next[K_SHADOW]);
+    wc.init(&sc->work_next[K_SHADOW], total);
     uint32_t batch;
     while (wc.next(&sc->work_next[K_SHADOW], total, batch)) {
         uint32_t item = batch + lane_id();
