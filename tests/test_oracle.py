@@ -334,6 +334,92 @@ def test_alpha_clip_anyhit_lets_rays_through_the_fence():
     o.close()
 
 
+def test_frame_against_an_independent_float64_brute_force():
+    """A second, independent statement of the whole segment-0 path in numpy float64 — ray generation (lib.rs:126-142), instance
+    transform, brute force over every triangle in WORLD space, exclusive interval, closest t — against the oracle's frame: hit IDs
+    must agree except on silhouette pixels (fp32 against fp64), the hard-shadow flag of C1 decides lit/unlit per pixel, and the
+    trace-call count follows from the hit mask."""
+    o = make_oracle()
+    W, H = 128, 72
+    s = build_scene(o, "c1", W, H)
+    r = o.render(s.uniforms(), s.params())
+    u = s.uniforms()
+    Vi = np.array(list(u.view_inverse), np.float64).reshape(4, 4).T   # column-major -> matrix
+    Pi = np.array(list(u.proj_inverse), np.float64).reshape(4, 4).T
+    sun = np.array(list(u.sun_dir), np.float64)
+    xs, ys = np.meshgrid(np.arange(W) + 0.5, np.arange(H) + 0.5)
+    ndc = np.stack([xs / W * 2 - 1, ys / H * 2 - 1, np.ones_like(xs), np.ones_like(xs)], axis=-1)
+    target = ndc @ Pi.T
+    ld = target[..., :3] / np.linalg.norm(target[..., :3], axis=-1, keepdims=True)
+    d = ld @ Vi[:3, :3].T
+    org = np.broadcast_to(Vi[:3, 3], d.shape)
+
+    # world-space triangles of every instance, with their (instance, geometry, primitive) ids
+    tris, ids = [], []
+    names = {mid: arrays for (mid, _, arrays) in s.models.values()}
+    for ii, rec in enumerate(s.instances):
+        m = names[int(rec["custom_index_and_mask"]) & 0xFFFFFF]
+        T = rec["transform"].astype(np.float64).reshape(3, 4)
+        P = m.positions.astype(np.float64) @ T[:, :3].T + T[:, 3]
+        for gi, g in enumerate(m.geometries):
+            idx = np.asarray(g.indices, np.int64).reshape(-1, 3)
+            tris.append(P[idx])
+            ids.append(np.stack([np.full(len(idx), ii), np.full(len(idx), gi), np.arange(len(idx))], axis=1))
+    tris, ids = np.concatenate(tris), np.concatenate(ids)
+
+    def closest(o3, d3, tmin, tmax):
+        """(N,3) rays against all triangles: index of the closest valid candidate (-1 = miss) and its t."""
+        v0, e1, e2 = tris[:, 0], tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]
+        best_t, best_i = np.full(len(o3), np.inf), np.full(len(o3), -1)
+        for a in range(0, len(tris), 256):
+            sl = slice(a, a + 256)
+            p = np.cross(d3[:, None, :], e2[None, sl])
+            det = np.einsum("ntk,tk->nt", p, e1[sl])
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inv = 1.0 / det
+                tv = o3[:, None, :] - v0[None, sl]
+                uu = np.einsum("ntk,ntk->nt", tv, p) * inv
+                q = np.cross(tv, e1[None, sl])
+                vv = np.einsum("nk,ntk->nt", d3, q) * inv
+                tt = np.einsum("ntk,tk->nt", q, e2[sl]) * inv
+            ok = (det != 0) & (uu >= 0) & (vv >= 0) & (uu + vv <= 1) & (tt > tmin) & (tt < tmax)
+            tt = np.where(ok, tt, np.inf)
+            k = tt.argmin(axis=1)
+            t_here = tt[np.arange(len(o3)), k]
+            better = t_here < best_t
+            best_t = np.where(better, t_here, best_t)
+            best_i = np.where(better, a + k, best_i)
+        return best_i, best_t
+
+    bi, bt = closest(org.reshape(-1, 3), d.reshape(-1, 3), 0.01, 10000.0)
+    want_ids = np.where(bi[:, None] >= 0, ids[np.maximum(bi, 0)], abi.MISS_ID).reshape(H, W, 3)
+    got_ids = r["hit_ids"][:, :, 0, :].astype(np.int64)
+    agree = np.all(got_ids == want_ids, axis=2)
+    assert agree.mean() >= 0.995, agree.mean()
+    assert (bi >= 0).mean() > 0.3 and (bi < 0).mean() > 0.1           # the frame shows ground, tori and sky
+    hit = (bi >= 0).reshape(H, W)
+    assert abs(int(r["ray_counts"][0]) - W * H) == 0 and abs(int(r["ray_counts"][1]) - int(hit.sum())) <= (~agree).sum()
+    # sky pixels: SKY_COLOUR or the sun disc (lib.rs:38-51); sun_radius 0 -> cos = 1 -> never the disc
+    sky = ~hit & agree
+    assert np.all(r["rgba8"][sky] == np.array([0, 0, 63, 255], np.uint8))
+    # hard shadow (sun_radius 0): a pixel whose shadow ray (from the hit point, nudged along the normal side) is blocked gets only
+    # the 0.1 * base ambient term; check the darkest / brightest split on the ground plane against the float64 shadow test
+    ground = (want_ids[..., 0] == 0) & agree
+    hp = (org.reshape(-1, 3) + d.reshape(-1, 3) * bt[:, None]).reshape(H, W, 3)
+    gidx = np.argwhere(ground)[::7]
+    so = hp[gidx[:, 0], gidx[:, 1]] + np.array([0.0, 1e-4, 0.0])
+    si, _ = closest(so, np.broadcast_to(sun, so.shape).copy(), 0.001, 10000.0)
+    lum = r["radiance"][gidx[:, 0], gidx[:, 1]].sum(axis=1)
+    shadowed, lit = lum[si >= 0], lum[si < 0]
+    assert len(shadowed) > 20 and len(lit) > 20
+    # allow the few samples on the shadow edge to fall on either side
+    thresh = 0.5 * (np.median(shadowed) + np.median(lit))
+    assert np.median(lit) > 2 * np.median(shadowed)
+    assert np.isclose(np.median(shadowed), lum.min(), rtol=1e-6)  # blocked -> exactly the 0.1 * base ambient term (glsl:222-225)
+    assert (shadowed < thresh).mean() > 0.97 and (lit > thresh).mean() > 0.97
+    o.close()
+
+
 # ---------------------------------------------------------------- show_heatmap (heatmap.rs, lib.rs:120-124, 174-186)
 HEAT_COLOURS = np.array([(0, 2, 91), (0, 108, 251), (0, 221, 221), (51, 221, 0), (255, 252, 0), (255, 180, 0), (255, 104, 0),
                          (226, 22, 0), (191, 0, 83), (145, 0, 65)], np.float64) / 255.0
