@@ -420,6 +420,117 @@ def test_frame_against_an_independent_float64_brute_force():
     o.close()
 
 
+def test_mirror_bounce_and_alpha_clip_against_an_independent_float64_brute_force():
+    """Same idea for the rest of the trace semantics, on a small C3: the alpha-clip any-hit (any_hit_alpha_clip.glsl:11-28: a
+    candidate on non-opaque geometry counts only if the bilinear alpha at its uv is >= 0.5), closest_hit_mirror
+    (closest_hit_mirror.glsl:11-29: n = normalize(inverse-transpose * interpolated normal), reflect, origin = o + d t) and the
+    second ray-gen segment — restated in numpy float64 over world-space triangles, with raw texels recorded at push_image."""
+    o = make_oracle()
+    images = []
+    push = o.push_image
+
+    def recording_push(texels, fmt, linear):
+        images.append(np.array(texels))
+        return push(texels, fmt, linear)
+
+    o.push_image = recording_push
+    W, H = 64, 36
+    s = build_scene(o, "c3", W, H, num_instances=12)
+    r = o.render(s.uniforms(), s.params())
+    u = s.uniforms()
+    Vi = np.array(list(u.view_inverse), np.float64).reshape(4, 4).T
+    Pi = np.array(list(u.proj_inverse), np.float64).reshape(4, 4).T
+    xs, ys = np.meshgrid(np.arange(W) + 0.5, np.arange(H) + 0.5)
+    target = np.stack([xs / W * 2 - 1, ys / H * 2 - 1, np.ones_like(xs), np.ones_like(xs)], axis=-1) @ Pi.T
+    ld = target[..., :3] / np.linalg.norm(target[..., :3], axis=-1, keepdims=True)
+    d0 = (ld @ Vi[:3, :3].T).reshape(-1, 3)
+    o0 = np.broadcast_to(Vi[:3, 3], d0.shape).copy()
+
+    by_id = {mid: arrays for (mid, _, arrays) in s.models.values()}
+    V0, E1, E2, IDS, NRM, UV, ALPHA_TEX, KIND, NMAT = [], [], [], [], [], [], [], [], []
+    for ii, rec in enumerate(s.instances):
+        m = by_id[int(rec["custom_index_and_mask"]) & 0xFFFFFF]
+        T = rec["transform"].astype(np.float64).reshape(3, 4)
+        P = m.positions.astype(np.float64) @ T[:, :3].T + T[:, 3]
+        nmat = np.linalg.inv(T[:, :3]).T  # mat3(gl_WorldToObject3x4EXT) * n == inverse-transpose * n
+        for gi, g in enumerate(m.geometries):
+            idx = np.asarray(g.indices, np.int64).reshape(-1, 3)
+            V0.append(P[idx[:, 0]]); E1.append(P[idx[:, 1]] - P[idx[:, 0]]); E2.append(P[idx[:, 2]] - P[idx[:, 0]])
+            IDS.append(np.stack([np.full(len(idx), ii), np.full(len(idx), gi), np.arange(len(idx))], axis=1))
+            NRM.append(m.normals.astype(np.float64)[idx]); UV.append(m.uvs.astype(np.float64)[idx])
+            ALPHA_TEX.append(np.full(len(idx), -1 if g.opaque else g.diffuse_image_index))
+            KIND.append(np.full(len(idx), int(rec["sbt_offset_and_flags"]) & 0xFFFFFF))
+            NMAT.append(np.broadcast_to(nmat, (len(idx), 3, 3)))
+    V0, E1, E2, IDS, NRM, UV, ALPHA_TEX, KIND, NMAT = (np.concatenate(a) for a in (V0, E1, E2, IDS, NRM, UV, ALPHA_TEX, KIND, NMAT))
+    assert (ALPHA_TEX >= 0).sum() >= 2  # the fence quads
+
+    def alpha_at(tex, uv):
+        a = images[tex][..., 3].astype(np.float64) / 255.0
+        h, w = a.shape
+        x, y = uv[:, 0] * w - 0.5, uv[:, 1] * h - 0.5
+        x0, y0 = np.floor(x), np.floor(y)
+        fx, fy = x - x0, y - y0
+        xi0, xi1, yi0, yi1 = (x0.astype(int) % w), ((x0.astype(int) + 1) % w), (y0.astype(int) % h), ((y0.astype(int) + 1) % h)
+        return (a[yi0, xi0] * (1 - fx) + a[yi0, xi1] * fx) * (1 - fy) + (a[yi1, xi0] * (1 - fx) + a[yi1, xi1] * fx) * fy
+
+    def closest(oo, dd):
+        n = len(oo)
+        best_t, best_i, best_u, best_v = np.full(n, np.inf), np.full(n, -1), np.zeros(n), np.zeros(n)
+        for a in range(0, len(V0), 512):
+            sl = slice(a, min(a + 512, len(V0)))
+            p = np.cross(dd[:, None, :], E2[None, sl])
+            det = np.einsum("ntk,tk->nt", p, E1[sl])
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inv = 1.0 / det
+                tv = oo[:, None, :] - V0[None, sl]
+                uu = np.einsum("ntk,ntk->nt", tv, p) * inv
+                q = np.cross(tv, E1[None, sl])
+                vv = np.einsum("nk,ntk->nt", dd, q) * inv
+                tt = np.einsum("ntk,tk->nt", q, E2[sl]) * inv
+            ok = (det != 0) & (uu >= 0) & (vv >= 0) & (uu + vv <= 1) & (tt > 0.01) & (tt < 10000.0)
+            for col in np.nonzero(ALPHA_TEX[sl] >= 0)[0]:  # any-hit: ignoreIntersection when alpha < 0.5
+                rows = np.nonzero(ok[:, col])[0]
+                if len(rows):
+                    w = np.stack([1 - uu[rows, col] - vv[rows, col], uu[rows, col], vv[rows, col]], axis=1)
+                    uv = np.einsum("nk,kc->nc", w, UV[a + col])
+                    ok[rows, col] = alpha_at(int(ALPHA_TEX[a + col]), uv) >= 0.5
+            tt = np.where(ok, tt, np.inf)
+            k = tt.argmin(axis=1)
+            rng = np.arange(n)
+            better = tt[rng, k] < best_t
+            best_t = np.where(better, tt[rng, k], best_t)
+            best_i = np.where(better, a + k, best_i)
+            best_u = np.where(better, uu[rng, k], best_u)
+            best_v = np.where(better, vv[rng, k], best_v)
+        return best_i, best_t, best_u, best_v
+
+    i0, t0, u0, v0 = closest(o0, d0)
+    want0 = np.where(i0[:, None] >= 0, IDS[np.maximum(i0, 0)], abi.MISS_ID)
+    got = r["hit_ids"].reshape(-1, 3, 3).astype(np.int64)
+    agree0 = np.all(got[:, 0] == want0, axis=1)
+    assert agree0.mean() >= 0.99, agree0.mean()
+    fence_insts = sorted(set(IDS[ALPHA_TEX >= 0][:, 0].tolist()))
+    seen_fence = np.isin(want0[:, 0], fence_insts).sum()
+    assert 0 < seen_fence < (W * H) // 2          # the fence is in view, and rays get through its holes
+
+    mirror = (i0 >= 0) & (KIND[np.maximum(i0, 0)] == abi.RT_HIT_MIRROR) & agree0
+    assert mirror.sum() > 30
+    mi = i0[mirror]
+    w = np.stack([1 - u0[mirror] - v0[mirror], u0[mirror], v0[mirror]], axis=1)
+    n_obj = np.einsum("nk,nkc->nc", w, NRM[mi])
+    n_w = np.einsum("nij,nj->ni", NMAT[mi], n_obj)
+    n_w /= np.linalg.norm(n_w, axis=1, keepdims=True)
+    d1 = d0[mirror] - 2.0 * np.einsum("nk,nk->n", n_w, d0[mirror])[:, None] * n_w
+    o1 = o0[mirror] + d0[mirror] * t0[mirror][:, None]
+    i1, _, _, _ = closest(o1, d1)
+    want1 = np.where(i1[:, None] >= 0, IDS[np.maximum(i1, 0)], abi.MISS_ID)
+    agree1 = np.all(got[mirror, 1] == want1, axis=1)
+    assert agree1.mean() >= 0.95, agree1.mean()
+    # pixels whose first hit is not a mirror / portal never trace a second segment
+    assert np.all(got[(i0 >= 0) & (KIND[np.maximum(i0, 0)] == abi.RT_HIT_TEXTURED) & agree0, 1] == abi.MISS_ID)
+    o.close()
+
+
 # ---------------------------------------------------------------- show_heatmap (heatmap.rs, lib.rs:120-124, 174-186)
 HEAT_COLOURS = np.array([(0, 2, 91), (0, 108, 251), (0, 221, 221), (51, 221, 0), (255, 252, 0), (255, 180, 0), (255, 104, 0),
                          (226, 22, 0), (191, 0, 83), (145, 0, 65)], np.float64) / 255.0
