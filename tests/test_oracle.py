@@ -417,6 +417,18 @@ def test_frame_against_an_independent_float64_brute_force():
     assert np.median(lit) > 2 * np.median(shadowed)
     assert np.isclose(np.median(shadowed), lum.min(), rtol=1e-6)  # blocked -> exactly the 0.1 * base ambient term (glsl:222-225)
     assert (shadowed < thresh).mean() > 0.97 and (lit > thresh).mean() > 0.97
+    # and the whole pixel, closest_hit_textured.glsl:174-226 for the ground: base = green.png (103, 234, 64) sRGB-decoded, material
+    # fallback roughness 1 / metallic 0 (util_structs.rs:1090-1111), n = +y, v = -d, l = sun_dir, sun_factor from the float64
+    # shadow test; colour = brdf + 0.1 * base
+    srgb = lambda c: c / 12.92 if c <= 0.04045 else ((c + 0.055) / 1.055) ** 2.4
+    base = np.array([srgb(103 / 255), srgb(234 / 255), srgb(64 / 255)])
+    dd = d[gidx[:, 0], gidx[:, 1]]
+    got_rad = r["radiance"][gidx[:, 0], gidx[:, 1]].astype(np.float64)
+    close = 0
+    for k in range(len(gidx)):
+        want = brdf64((0.0, 1.0, 0.0), -dd[k], sun, base, 1.0, 0.0, 0.0 if si[k] >= 0 else 1.0) + 0.1 * base
+        close += bool(np.all(np.abs(got_rad[k] - want) <= 1e-3 * np.maximum(np.abs(want), 1e-3)))
+    assert close >= 0.97 * len(gidx), (close, len(gidx))  # all but the samples on a shadow edge
     o.close()
 
 
