@@ -432,6 +432,90 @@ def test_frame_against_an_independent_float64_brute_force():
     o.close()
 
 
+def test_soft_shadow_samples_against_an_independent_float64_brute_force():
+    """closest_hit_textured.glsl:77-120, 159-203 end to end for the ground pixels of a C1 scene with a sun disc: blue-noise taps by
+    global pixel and sample index (raw 16-bit PNG narrowed by the host, recorded at push_image), golden-ratio animation,
+    disc -> direction, one first-hit test per sample in numpy float64, sun_factor = lit / N read back out of the oracle's radiance."""
+    o = make_oracle()
+    images = []
+    push = o.push_image
+
+    def recording_push(texels, fmt, linear):
+        images.append(np.array(texels))
+        return push(texels, fmt, linear)
+
+    o.push_image = recording_push
+    W, H, N, FRAME = 96, 54, 4, 37
+    s = build_scene(o, "c1", W, H)
+    s.shadow_rays, s.sun_radius = N, 0.08
+    r = o.render(s.uniforms(frame_index=FRAME), s.params())
+    u = s.uniforms(frame_index=FRAME)
+    noise = images[u.blue_noise_texture_index][..., 0].astype(np.float64) / 255.0
+    assert noise.shape == (64, 64)
+    Vi = np.array(list(u.view_inverse), np.float64).reshape(4, 4).T
+    Pi = np.array(list(u.proj_inverse), np.float64).reshape(4, 4).T
+    sun = np.array(list(u.sun_dir), np.float64)
+    by_id = {mid: arrays for (mid, _, arrays) in s.models.values()}
+    tris = []
+    for rec in s.instances:
+        m = by_id[int(rec["custom_index_and_mask"]) & 0xFFFFFF]
+        T = rec["transform"].astype(np.float64).reshape(3, 4)
+        P = m.positions.astype(np.float64) @ T[:, :3].T + T[:, 3]
+        for g in m.geometries:
+            tris.append(P[np.asarray(g.indices, np.int64).reshape(-1, 3)])
+    tris = np.concatenate(tris)
+    v0, e1, e2 = tris[:, 0], tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]
+
+    def any_hit(oo, dd, tmin):
+        hit = np.zeros(len(oo), bool)
+        for a in range(0, len(tris), 512):
+            sl = slice(a, a + 512)
+            p = np.cross(dd[:, None, :], e2[None, sl])
+            det = np.einsum("ntk,tk->nt", p, e1[sl])
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inv = 1.0 / det
+                tv = oo[:, None, :] - v0[None, sl]
+                uu = np.einsum("ntk,ntk->nt", tv, p) * inv
+                q = np.cross(tv, e1[None, sl])
+                vv = np.einsum("nk,ntk->nt", dd, q) * inv
+                tt = np.einsum("ntk,tk->nt", q, e2[sl]) * inv
+            hit |= np.any((det != 0) & (uu >= 0) & (vv >= 0) & (uu + vv <= 1) & (tt > tmin) & (tt < 10000.0), axis=1)
+        return hit
+
+    ground = np.argwhere(r["hit_ids"][:, :, 0, 0] == 0)[::5]          # instance 0 = the plane
+    py, px = ground[:, 0], ground[:, 1]
+    ndc = np.stack([(px + 0.5) / W * 2 - 1, (py + 0.5) / H * 2 - 1, np.ones(len(px)), np.ones(len(px))], axis=-1) @ Pi.T
+    ld = ndc[:, :3] / np.linalg.norm(ndc[:, :3], axis=1, keepdims=True)
+    d = ld @ Vi[:3, :3].T
+    t = -Vi[1, 3] / d[:, 1]                                           # the plane is y = 0
+    origin = Vi[:3, 3] + d * t[:, None]                               # flat ground: the terminator fix adds nothing
+    tangent = np.cross(sun, (0.0, 1.0, 0.0)); tangent /= np.linalg.norm(tangent)
+    bitangent = np.cross(tangent, sun); bitangent /= np.linalg.norm(bitangent)
+    lit = np.zeros(len(px))
+    for i in range(N):
+        ax, ay = (px + 2 * i * 13) % 64, (py + 2 * i * 41) % 64
+        bx, by = (px + (2 * i + 1) * 13) % 64, (py + (2 * i + 1) * 41) % 64
+        # f32 like the shader for the fract() wrap, float64 afterwards
+        shift = np.float32(FRAME % 32) * np.float32(0.618033988749)
+        xi_x = (noise[ay, ax].astype(np.float32) + shift).astype(np.float32); xi_x = (xi_x - np.floor(xi_x)).astype(np.float64)
+        xi_y = (noise[by, bx].astype(np.float32) + shift).astype(np.float32); xi_y = (xi_y - np.floor(xi_y)).astype(np.float64)
+        rad, ang = np.sqrt(xi_x), xi_y * 2.0 * math.pi
+        pt = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1) * s.sun_radius
+        sd = sun + pt[:, :1] * tangent + pt[:, 1:] * bitangent
+        sd /= np.linalg.norm(sd, axis=1, keepdims=True)
+        lit += ~any_hit(origin + np.array([0.0, 1e-5, 0.0]), sd, 0.001)
+    want_factor = lit / N
+    srgb = lambda c: c / 12.92 if c <= 0.04045 else ((c + 0.055) / 1.055) ** 2.4
+    base = np.array([srgb(103 / 255), srgb(234 / 255), srgb(64 / 255)])
+    got_rad = r["radiance"][py, px].astype(np.float64)
+    got_factor = np.array([(got_rad[k, 1] - 0.1 * base[1]) / brdf64((0.0, 1.0, 0.0), -d[k], sun, base, 1.0, 0.0, 1.0)[1] for k in range(len(px))])
+    assert np.all(np.abs(got_factor * N - np.round(got_factor * N)) < 1e-2)        # multiples of 1 / N
+    assert len(set(np.round(got_factor * N).astype(int).tolist())) >= 3              # a penumbra: several levels present
+    assert np.mean(np.abs(got_factor - want_factor) < 1e-2) >= 0.97, np.mean(np.abs(got_factor - want_factor) < 1e-2)
+    assert int(r["ray_counts"][1]) == N * int((r["hit_ids"][:, :, 0, 0] != abi.MISS_ID).sum())
+    o.close()
+
+
 def test_mirror_bounce_and_alpha_clip_against_an_independent_float64_brute_force():
     """Same idea for the rest of the trace semantics, on a small C3: the alpha-clip any-hit (any_hit_alpha_clip.glsl:11-28: a
     candidate on non-opaque geometry counts only if the bilinear alpha at its uv is >= 0.5), closest_hit_mirror
