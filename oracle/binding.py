@@ -59,6 +59,7 @@ def load():
         lib.orc_primary_ray.restype = None
         lib.orc_terminator_origin.argtypes = [fp, fp, fp, fp, fp]
         lib.orc_terminator_origin.restype = None
+        lib.orc_anyhit_accepts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float]
         lib.orc_trace.argtypes = [C.c_void_p, fp, fp, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_uint32), fp]
         _LIB = lib
     return _LIB
@@ -157,3 +158,10 @@ class Oracle(CApiBackend):
         tuv = np.zeros(3, np.float32)
         hit = self.lib.orc_trace(self.ctx, _fp(f32(*o)), _fp(f32(*d)), tmin, tmax, int(any_hit), ids, _fp(tuv))
         return (hit != 0), tuple(ids), tuv
+
+    def anyhit_accepts(self, instance_id, geom, prim, u, v):
+        """any_hit_alpha_clip on one candidate: True = kept, False = ignoreIntersectionEXT."""
+        r = self.lib.orc_anyhit_accepts(self.ctx, instance_id, geom, prim, u, v)
+        if r < 0:
+            raise ValueError("no such candidate")
+        return r == 1

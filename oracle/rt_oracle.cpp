@@ -4,16 +4,19 @@
 // and bench.py's cpu_baseline / --impl reference legs may load it.  libb200rt.so
 // does not link, include or call anything in oracle/.
 //
-// PARITY STATUS: *unpinned by the reference's own tests*.  The reference
-// (Rust + Vulkan KHR ray tracing) cannot be built or run here (no rustc/cargo,
-// no Vulkan loader/ICD, no RT-capable device), it ships no golden images, and
-// its single unit test (shaders/ray-tracing/src/pbr.rs:52-69) only asserts
-// finiteness.  BVH build, traversal, ray/triangle intersection and texture
-// filtering live inside the Vulkan driver, not under /root/reference.  This
-// oracle therefore restates (a) the seven shader stages line by line and (b)
-// the VK_KHR_ray_tracing_pipeline trace semantics, and is pinned by: that KAT,
-// the constants of the shipped .spv files, the struct layouts, independent
-// float64 re-derivations in tests/, and BVH-vs-brute-force equality.
+// PARITY STATUS: shading arithmetic PINNED to the reference's own compiled shaders; traversal pinned by float64
+// brute force (the reference holds nothing for it).  The reference (Rust + Vulkan KHR ray tracing) cannot be built or
+// run here (no rustc/cargo, no Vulkan loader/ICD, no RT-capable device), it ships no golden images, and its single
+// unit test (shaders/ray-tracing/src/pbr.rs:52-69) only asserts finiteness.  What it does ship is its arithmetic as
+// SPIR-V: shaders/*.spv, all seven stages.  tests/spirv_interp.py EXECUTES those modules on the CPU
+// (tests/spirv_pipeline.py plays the driver: intersections, texture sampling and buffer loads are callbacks) and
+// tests/golden/make_spirv_golden.py stores their outputs for ~6 000 pixels of five scenes, seeded any-hit candidates
+// and heat-map deltas (tests/golden/spirv_*.npz).  tests/test_spirv_pin.py holds this oracle to those vectors at
+// <= 1e-5 relative (payload colour, sRGB store, hit IDs, trace-call counts, any-hit decisions) and the CUDA path to the
+// same vectors at the north star's 1e-3.  BVH build, traversal, ray/triangle intersection and texture filtering live
+// inside the Vulkan driver, not under /root/reference: for those the oracle restates the VK_KHR_ray_tracing_pipeline
+// semantics and is pinned by independent numpy float64 brute-force frames (tests/test_oracle.py), BVH-vs-brute-force
+// equality, the KAT above, the constants of the shipped .spv files and the struct layouts.
 //
 // What follows what (reference paths relative to /root/reference):
 //   ray_generation          shaders/ray-tracing/src/lib.rs:94-191
@@ -1107,6 +1110,19 @@ int orc_trace(OrcContext* c, const float* o, const float* d, float tmin, float t
     ids3[0] = h.inst; ids3[1] = tr.geom; ids3[2] = tr.prim;
     tuv3[0] = h.t; tuv3[1] = h.u; tuv3[2] = h.v;
     return 1;
+}
+
+// any_hit_alpha_clip.glsl:11-28 on one candidate (instance, geometry, primitive, barycentrics): 1 = the candidate is kept,
+// 0 = ignoreIntersectionEXT.  -1: no such instance / geometry / primitive.
+int orc_anyhit_accepts(OrcContext* c, uint32_t instance_id, uint32_t geom, uint32_t prim, float u, float v) {
+    if (instance_id >= c->insts.size()) return -1;
+    const Inst& in = c->insts[instance_id];
+    Tri tr{};
+    tr.geom = geom; tr.prim = prim;
+    uint32_t custom = in.rec.instance_custom_index_and_mask & 0xFFFFFFu;
+    if (custom >= c->models.size() || geom >= c->models[custom].geoms.size()) return -1;
+    if ((size_t)prim * 3 + 2 >= c->models[custom].geoms[geom].indices.size()) return -1;
+    return anyhit_accepts(*c, in, tr, u, v) ? 1 : 0;
 }
 
 }  // extern "C"
