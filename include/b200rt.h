@@ -65,7 +65,8 @@ typedef struct RtModelDesc {
 } RtModelDesc;
 
 typedef enum RtUpdateMode {
-    RT_UPDATE_AUTO = 0,     /* library picks (rebuild when many instances moved) */
+    RT_UPDATE_AUTO = 0,     /* library picks: refit, and a full rebuild once the instance records written since the last
+                               build add up to 4x the instance count (topology drift) */
     RT_UPDATE_REFIT = 1,    /* keep topology, refit boxes: VK mode UPDATE, src/util_structs.rs:309 */
     RT_UPDATE_REBUILD = 2   /* full LBVH rebuild */
 } RtUpdateMode;

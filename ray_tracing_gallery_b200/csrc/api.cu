@@ -90,13 +90,14 @@ struct RtContext {
     bool render_timed = false, tlas_timed = false;
     FrameTiming timing;
     bool timing_ready = false, timing_valid = false;
+    LaunchGeometry launch_geometry;  // grids of the persistent kernels on this context's device
     // Tail policy.  Bounce segments run either inside the one cooperative k_tail (one launch; best when there are few or no
     // bounce rays: C2 0.453 against 0.505 ms) or as separate launches at each kernel's own occupancy (better when a frame
     // bounces a lot: C3 0.927 -> 0.903 ms, C4 8.76 -> 8.55 ms, and consecutive frames overlap better: C3 e2e +10 %).  Frames
     // are coherent, so the choice follows the bounce-ray count of the latest finished frame, which the frame kernels leave
     // in a host-mapped word (no copy, no synchronisation).  B200RT_SPLIT_TAIL=0 / 1 pins the choice (A/B).
     int tail_policy = -1;                    // -1 adaptive, 0 always cooperative, 1 always split
-    volatile unsigned int* h_bounce = nullptr;  // cudaHostAllocMapped
+    volatile unsigned int* h_bounce = nullptr;  // cudaHostAllocMapped, two words: [0] bounce hint, [1] traversal-stack overflow flag
     unsigned int* d_bounce = nullptr;           // its device alias
     std::string err;
 
@@ -104,8 +105,6 @@ struct RtContext {
     std::vector<TexRes> tex_res;
     std::vector<TexEntry> tex_host;
     TexEntry* d_textures = nullptr;
-    std::vector<uint32_t> real_tex_host;
-    uint32_t* d_real_textures = nullptr;
     float* d_srgb_lut = nullptr;
     float srgb_lut[512];
 
@@ -132,6 +131,7 @@ struct RtContext {
     bool staged = false;                     // set cur^1 holds the records of `cur` plus the writes since the last flip
     uint32_t num_instances = 0, inst_cap = 0;
     bool tlas_built = false;
+    uint64_t writes_since_build = 0;         // instance records written since the last full build (RT_UPDATE_AUTO)
     InstRT* d_inst_unsorted = nullptr;       // builder inputs: only touched on the context's stream
     Aabb* d_inst_boxes = nullptr;
     uint32_t tlas_node_cap = 0;
@@ -251,6 +251,7 @@ int build_tlas_now(RtContext* ctx, uint32_t mode, uint32_t src, uint32_t dst) {
                                     ctx->d_inst_unsorted, ctx->d_inst_boxes, st));
         CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, D.d_tlas_nodes, 0, 0, D.d_leaf_order, D.d_node_count, true, /*sah_collapse=*/true, st));
         CK(launch_gather_instances(ctx->d_inst_unsorted, D.d_leaf_order, n, D.d_inst_rt, st));
+        ctx->writes_since_build = 0;
     }
     CK(cudaEventRecord(ctx->ev[3], st));
     ctx->tlas_timed = true;
@@ -304,6 +305,20 @@ int wait_for_frames_in_flight(RtContext* ctx) {
     return RT_OK;
 }
 
+// A traversal stack (RT_STACK_SIZE node groups / stacked instances per ray) that overflows drops a subtree: the frame would
+// silently miss hits or shadows.  The kernels raise a host-mapped flag; every call that hands finished results to the
+// caller (rt_render, rt_wait_frame, rt_readback, rt_sync, rt_get_stats) checks it after its synchronisation and fails.
+int check_stack_overflow(RtContext* ctx, const char* who) {
+    if (ctx->h_bounce && ctx->h_bounce[1]) {
+        ctx->h_bounce[1] = 0u;
+        return fail(ctx, RT_ERR_OUT_OF_RANGE, std::string(who) + ": a traversal stack overflowed (acceleration structure needs more than " +
+                                                  std::to_string(RT_STACK_SIZE) + " stacked entries): the frame is incomplete");
+    }
+    return RT_OK;
+}
+
+#define RT_AUTO_REBUILD_WRITES 4u
+
 // bounce rays in the latest frame from which the next frame runs its bounce segments as separate launches
 #define RT_SPLIT_TAIL_BOUNCE_RAYS 131072u
 
@@ -329,6 +344,9 @@ int plan_frame(RtContext* ctx, const RtRenderParams* p, FramePlan& f) {
         if (strips && (strips - 1) % p->strip_count == p->strip_index) f.rows -= strips * p->strip_height - f.th;
     }
     if ((uint64_t)f.rows * f.tw > 0x7FFFFFFFull) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_render: too many pixels");
+    // shadow-ray work items (hits x shadow_rays) and the cursors of the persistent kernels are 32-bit
+    if ((uint64_t)f.rows * f.tw * p->shadow_rays + 4096ull > 0xFFFFFFFFull)
+        return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_render: pixels x shadow_rays must stay below 2^32");
     if (p->width > 65536u || p->height > 32768u) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_render: launch size above 65536 x 32768");
     return RT_OK;
 }
@@ -360,8 +378,6 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
     S.num_instances = ctx->num_instances;
     S.textures = ctx->d_textures;
     S.num_textures = (uint32_t)ctx->tex_host.size();
-    S.num_real_textures = (uint32_t)ctx->real_tex_host.size();
-    S.real_textures = ctx->d_real_textures;
     S.srgb_lut = ctx->d_srgb_lut;
     S.one_bits = 0x3F800000u;
     FrameDev F;
@@ -390,6 +406,7 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
     }
     if (&R == &ctx->main) CK(cudaMemcpyAsync(ctx->d_uniforms, u, sizeof(RtUniforms), cudaMemcpyHostToDevice, R.stream));
     F.bounce_hint = ctx->d_bounce;
+    F.overflow_flag = ctx->d_bounce + 1;
     bool split_tail = (p->flags & RT_RENDER_SPLIT_TAIL) != 0;
     if (!split_tail && !(p->flags & RT_RENDER_COOP_TAIL)) {
         if (ctx->tail_policy >= 0) split_tail = ctx->tail_policy == 1;
@@ -405,7 +422,9 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
         timing = &ctx->timing;
     }
     ctx->timing_valid = timing != nullptr;
-    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, split_tail, (p->flags & RT_RENDER_NO_PDL) != 0, ctx->sms, d_ray_counts, timing, R.stream));
+    CK(init_launch_geometry(ctx->launch_geometry, ctx->sms));
+    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, split_tail, (p->flags & RT_RENDER_NO_PDL) != 0, ctx->launch_geometry,
+                    d_ray_counts, timing, R.stream));
     CK(cudaEventRecord(ctx->ev[1], R.stream));
     ctx->render_timed = true;
     ctx->last_res = &R;
@@ -452,15 +471,14 @@ int rt_create(int cuda_device, RtContext** out) {
     for (int i = 0; i < 4; i++)
         if ((e = cudaEventCreate(&c->ev[i])) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&c->d_textures, sizeof(TexEntry) * RT_MAX_BOUND_IMAGES)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&c->d_real_textures, sizeof(uint32_t) * RT_MAX_BOUND_IMAGES)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_srgb_lut, sizeof(float) * 512)) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->d_uniforms, sizeof(RtUniforms))) != cudaSuccess) return bail(e, "cudaMalloc");
     if (const char* v = getenv("B200RT_SPLIT_TAIL")) c->tail_policy = atoi(v) != 0 ? 1 : 0;
     {
         void* hp = nullptr;
-        if ((e = cudaHostAlloc(&hp, sizeof(unsigned int), cudaHostAllocMapped)) != cudaSuccess) return bail(e, "cudaHostAlloc");
+        if ((e = cudaHostAlloc(&hp, 2 * sizeof(unsigned int), cudaHostAllocMapped)) != cudaSuccess) return bail(e, "cudaHostAlloc");
         c->h_bounce = static_cast<volatile unsigned int*>(hp);
-        *c->h_bounce = 0u;
+        c->h_bounce[0] = c->h_bounce[1] = 0u;
         void* dp = nullptr;
         if ((e = cudaHostGetDevicePointer(&dp, hp, 0)) != cudaSuccess) return bail(e, "cudaHostGetDevicePointer");
         c->d_bounce = static_cast<unsigned int*>(dp);
@@ -513,7 +531,7 @@ void rt_destroy(RtContext* ctx) {
         for (auto* p : m.index_bufs) cudaFree(p);
     }
     ctx->d_model_info.release(); ctx->d_blas_info.release(); ctx->blas_nodes.release(); ctx->tris.release();
-    cudaFree(ctx->d_textures); cudaFree(ctx->d_real_textures); cudaFree(ctx->d_srgb_lut); cudaFree(ctx->d_uniforms);
+    cudaFree(ctx->d_textures); cudaFree(ctx->d_srgb_lut); cudaFree(ctx->d_uniforms);
     ctx->main.release();
     free_instance_buffers(ctx);
     for (auto& s : ctx->sets) cudaFree(s.d_node_count);
@@ -585,8 +603,6 @@ int rt_push_image(RtContext* ctx, const void* texels, uint32_t width, uint32_t h
     }
     uint32_t index = (uint32_t)ctx->tex_host.size();
     cudaError_t e = cudaMemcpyAsync(ctx->d_textures + index, &te, sizeof(te), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && tr.obj)
-        e = cudaMemcpyAsync(ctx->d_real_textures + ctx->real_tex_host.size(), &index, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         if (tr.obj) cudaDestroyTextureObject(tr.obj);
@@ -595,7 +611,6 @@ int rt_push_image(RtContext* ctx, const void* texels, uint32_t width, uint32_t h
     }
     ctx->tex_host.push_back(te);
     ctx->tex_res.push_back(tr);
-    if (tr.obj) ctx->real_tex_host.push_back(index);
     if (out_index) *out_index = index;
     return RT_OK;
 }
@@ -766,6 +781,7 @@ int rt_update_instances(RtContext* ctx, uint32_t first, uint32_t count, const Rt
         { int w = begin_staging(ctx, first == 0 && count == ctx->num_instances); if (w) return w; }
         CK(cudaMemcpyAsync(ctx->sets[ctx->cur ^ 1u].d_instances + first, host_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));  // pageable source: the caller owns it again on return
+        ctx->writes_since_build += count;
     }
     return RT_OK;
 }
@@ -778,6 +794,7 @@ int rt_update_instances_device(RtContext* ctx, uint32_t first, uint32_t count, c
     if (count) {
         { int w = begin_staging(ctx, first == 0 && count == ctx->num_instances); if (w) return w; }
         CK(cudaMemcpyAsync(ctx->sets[ctx->cur ^ 1u].d_instances + first, device_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->writes_since_build += count;
     }
     return RT_OK;
 }
@@ -788,7 +805,12 @@ int rt_update_tlas(RtContext* ctx, uint32_t mode) {
     if (!ctx->tlas_built) return fail(ctx, RT_ERR_NOT_BUILT, "rt_update_tlas before rt_build_tlas");
     CK_DEV(ctx);
     { int w = begin_staging(ctx, false); if (w) return w; }  // an update without instance writes still builds into the other set
-    if (mode == RT_UPDATE_AUTO) mode = RT_UPDATE_REBUILD;
+    // AUTO: the reference's per-frame path is an in-place UPDATE (refit, src/util_structs.rs:309); a refit keeps the topology, so
+    // its quality drifts as instances move.  Refit until the records written since the last full build add up to
+    // RT_AUTO_REBUILD_WRITES x the instance count (C4, every transform every frame: three refits, then a rebuild; the
+    // reference's one-record-per-frame animation: a rebuild every 4 N frames), then rebuild.
+    if (mode == RT_UPDATE_AUTO)
+        mode = ctx->writes_since_build >= (uint64_t)RT_AUTO_REBUILD_WRITES * (ctx->num_instances ? ctx->num_instances : 1u) ? RT_UPDATE_REBUILD : RT_UPDATE_REFIT;
     const uint32_t w = ctx->cur ^ 1u;
     int rc = build_tlas_now(ctx, mode, ctx->cur, w);
     if (rc) return rc;
@@ -836,6 +858,7 @@ int rt_render(RtContext* ctx, const RtUniforms* uniforms, const RtRenderParams* 
         if (out->ray_counts) CK(cudaMemcpyAsync(out->ray_counts, ctx->d_ray_counts, 16, cudaMemcpyDeviceToHost, st));
         if (want_cost) CK(cudaMemcpyAsync(out->cost_cycles, ctx->d_fb_cost, pixels * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        return check_stack_overflow(ctx, "rt_render");
     }
     return RT_OK;
 }
@@ -919,6 +942,7 @@ int rt_wait_frame(RtContext* ctx, uint32_t slot) {
     if (sl.pending) {
         CK(cudaEventSynchronize(sl.copied));
         sl.pending = false;
+        return check_stack_overflow(ctx, "rt_wait_frame");
     }
     return RT_OK;
 }
@@ -932,7 +956,7 @@ int rt_readback(RtContext* ctx, void* host_rgba8, size_t capacity_bytes) {
     CK_DEV(ctx);
     CK(cudaMemcpyAsync(host_rgba8, ctx->d_fb_rgba8, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return check_stack_overflow(ctx, "rt_readback");
 }
 
 int rt_sync(RtContext* ctx) {
@@ -945,7 +969,7 @@ int rt_sync(RtContext* ctx) {
     for (auto& sl : ctx->slots) sl.pending = sl.rendering = false;
     for (auto& sl : ctx->dev_slots)
         if (sl.rendering) { CK(cudaEventSynchronize(sl.rendered)); sl.rendering = false; }
-    return RT_OK;
+    return check_stack_overflow(ctx, "rt_sync");
 }
 
 int rt_host_alloc(RtContext* ctx, size_t bytes, void** out) {
@@ -995,7 +1019,10 @@ int rt_get_stats(RtContext* ctx, RtStats* out) {
             out->kernel_launches[ctx->timing.kind[i]]++;
         }
     }
-    if (fc.stack_overflow) return fail(ctx, RT_ERR_OUT_OF_RANGE, "traversal stack overflow in the last frame");
+    if (fc.stack_overflow) {
+        ctx->h_bounce[1] = 0u;
+        return fail(ctx, RT_ERR_OUT_OF_RANGE, "traversal stack overflow in the last frame");
+    }
     if (ctx->render_timed) CK(cudaEventElapsedTime(&out->last_render_ms, ctx->ev[0], ctx->ev[1]));
     if (ctx->tlas_timed) CK(cudaEventElapsedTime(&out->last_tlas_ms, ctx->ev[2], ctx->ev[3]));
     if (ctx->tlas_built) CK(cudaMemcpy(&out->tlas_nodes, ctx->sets[ctx->cur].d_node_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));

@@ -132,7 +132,10 @@ __device__ __forceinline__ void flush_trace_counters(const FrameDev& F, int phas
         warp_add(&F.counters->anyhit_calls[phase], tc.anyhits);
     }
     uint32_t ov = __reduce_add_sync(0xFFFFFFFFu, tc.overflow);
-    if (lane_id() == 0 && ov) atomicAdd(&F.counters->stack_overflow, ov);
+    if (lane_id() == 0 && ov) {
+        atomicAdd(&F.counters->stack_overflow, ov);
+        if (F.overflow_flag) *F.overflow_flag = 1u;  // a subtree was skipped: the API must not return this frame as good
+    }
 }
 
 __device__ __forceinline__ void flush_ray_counters(const FrameDev& F, uint32_t n_primary, uint32_t n_shadow, uint32_t n_textured) {
@@ -190,8 +193,9 @@ __device__ __forceinline__ SegCounters* seg_counters(const FrameDev& F, uint32_t
 // Warp-wide work distribution: a warp takes RT_CHUNK items at a time from the device-side cursor with
 // one atomic.  The atomic for the NEXT batch is issued before the current batch is traced and its
 // result is only read (shuffled) when that batch starts, so the round trip to L2 (about 20 % of
-// k_trace0's stall samples in profiles/r01g) hides behind the traversal.
-#ifndef RT_STATIC_SHARE
+// k_trace0's stall samples in profiles/r01g) hides behind the traversal.  Dealing most batches statically and
+// leaving only the tail to the cursor was measured 9 % slower (profiles/r02a_ab.txt, variant ss6): the cursor is
+// what balances rays of very different length.
 struct WarpChunk {
     uint32_t pending;  // lane 0: base of the next batch, possibly still in flight
     __device__ __forceinline__ void init(unsigned int* cursor, uint32_t /*total*/) { pending = lane_id() == 0 ? atomicAdd(cursor, RT_CHUNK) : 0u; }
@@ -203,37 +207,6 @@ struct WarpChunk {
         return true;
     }
 };
-#else
-// Prepared A/B variant (not measured yet).  profiles/r01r: a fifth of k_trace0's stall samples sit on its atomics — every warp
-// of the grid takes every batch from ONE cursor (65 k same-address atomics in 140 us, about the rate one L2 address
-// sustains).  Here the first RT_STATIC_SHARE / 8 of the batches are dealt statically (warp w takes batches w, w + W, ...;
-// a batch is one 8x4 tile or 32 queue items, so a warp's share is spread over the whole frame) and only the rest goes
-// through the cursor, which still evens out the tail.
-struct WarpChunk {
-    uint32_t pending;      // lane 0: base of the next dynamic batch, possibly still in flight
-    uint32_t next_static;  // next statically assigned batch of this warp
-    uint32_t static_end;   // batches [0, static_end) are static, the cursor deals the rest
-    uint32_t warps;
-    __device__ __forceinline__ void init(unsigned int* cursor, uint32_t total) {
-        warps = gridDim.x * (blockDim.x >> 5);
-        const uint32_t batches = (total + RT_CHUNK - 1u) / RT_CHUNK;
-        static_end = ((uint32_t)(((unsigned long long)batches * RT_STATIC_SHARE) >> 3) / warps) * warps;  // whole rounds only
-        next_static = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        pending = lane_id() == 0 ? atomicAdd(cursor, RT_CHUNK) : 0u;
-    }
-    __device__ __forceinline__ bool next(unsigned int* cursor, uint32_t total, uint32_t& base) {
-        if (next_static < static_end) {
-            base = next_static * RT_CHUNK;
-            next_static += warps;
-            return true;
-        }
-        base = static_end * RT_CHUNK + __shfl_sync(0xFFFFFFFFu, pending, 0);
-        if (base >= total) return false;
-        if (lane_id() == 0) pending = atomicAdd(cursor, RT_CHUNK);
-        return true;
-    }
-};
-#endif
 
 // Ray generation (segment 0) or ray-queue read, closest-hit traversal, miss / mirror / portal shaders,
 // textured hits -> hit queue.
@@ -593,8 +566,19 @@ static int persistent_grid(K kernel, int sms) {
     return sms * per_sm;
 }
 
-cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, bool no_pdl, int sms,
-                         uint64_t* d_ray_counts,
+cudaError_t init_launch_geometry(LaunchGeometry& g, int sms) {
+    if (g.ready) return cudaSuccess;
+    g.trace0[0] = persistent_grid(k_trace0<false>, sms); g.trace0[1] = persistent_grid(k_trace0<true>, sms);
+    g.shadow[0] = persistent_grid(k_shadow<false>, sms); g.shadow[1] = persistent_grid(k_shadow<true>, sms);
+    g.tail[0] = persistent_grid(k_tail<false>, sms);     g.tail[1] = persistent_grid(k_tail<true>, sms);
+    g.prep = persistent_grid(k_prep, sms);
+    g.resolve = persistent_grid(k_resolve, sms);
+    g.ready = true;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, bool no_pdl,
+                         const LaunchGeometry& geom, uint64_t* d_ray_counts,
                          FrameTiming* timing, cudaStream_t stream) {
     cudaMemsetAsync(F.counters, 0, sizeof(FrameCounters), stream);
     if (F.hit_ids) cudaMemsetAsync(F.hit_ids, 0xFF, (size_t)F.rows * F.tw * F.max_segments * 3 * sizeof(uint32_t), stream);
@@ -632,15 +616,9 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
         }
         mark(K_MEGA);
     } else {
-        static int g_trace0[2] = {0, 0}, g_shadow[2] = {0, 0}, g_tail[2] = {0, 0}, g_prep = 0, g_resolve = 0;
-        int ci = count ? 1 : 0;
-        if (!g_trace0[ci]) {
-            g_trace0[ci] = count ? persistent_grid(k_trace0<true>, sms) : persistent_grid(k_trace0<false>, sms);
-            g_shadow[ci] = count ? persistent_grid(k_shadow<true>, sms) : persistent_grid(k_shadow<false>, sms);
-            g_tail[ci] = count ? persistent_grid(k_tail<true>, sms) : persistent_grid(k_tail<false>, sms);
-            g_prep = persistent_grid(k_prep, sms);
-            g_resolve = persistent_grid(k_resolve, sms);
-        }
+        const int ci = count ? 1 : 0;
+        const int* g_trace0 = geom.trace0; const int* g_shadow = geom.shadow; const int* g_tail = geom.tail;
+        const int g_prep = geom.prep, g_resolve = geom.resolve;
         int cap = (int)((total + 127) / 128);  // no more blocks than there could be work
         auto fit = [&](int g, uint32_t per_item) { long long c = (long long)cap * per_item; return (int)(c < g ? c : g); };
         // stage-to-stage launches overlap the predecessor's tail (programmatic dependent launch); not when

@@ -13,9 +13,18 @@ struct FrameTiming {
     int n;
 };
 
+// Grid sizes of the persistent / cooperative frame kernels on ONE device: SMs x resident blocks from the occupancy API.
+// Owned by the context (one per GPU) and filled on its first frame, so contexts on different GPUs, or rendering from
+// different host threads, never share them.  [0] = plain kernels, [1] = the RT_RENDER_COUNTERS instantiations.
+struct LaunchGeometry {
+    bool ready = false;
+    int trace0[2] = {0, 0}, shadow[2] = {0, 0}, tail[2] = {0, 0}, prep = 0, resolve = 0;
+};
+cudaError_t init_launch_geometry(LaunchGeometry& g, int sms);
+
 // Enqueue one frame on `stream`.  d_ray_counts (device, optional) receives {ray-gen segments, shadow rays}.
-cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, bool no_pdl, int sms,
-                         uint64_t* d_ray_counts,
+cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, bool no_pdl,
+                         const LaunchGeometry& geom, uint64_t* d_ray_counts,
                          FrameTiming* timing, cudaStream_t stream);
 
 // BLAS input: per flattened triangle (geometry-major) the padded AABB.

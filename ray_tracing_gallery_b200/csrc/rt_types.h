@@ -40,6 +40,12 @@ struct __align__(128) Node8 {
 };
 static_assert(sizeof(Node8) == 128, "Node8 must be one 128-byte line");
 
+// Entries of a ray's traversal stack (trace.cuh): one per visited node that still has other hit children, one per TLAS leaf
+// found but not entered yet.  Typical depth < 10; an overflow is reported by the API (api.cu: check_stack_overflow).
+#ifndef RT_STACK_SIZE
+#define RT_STACK_SIZE 48
+#endif
+
 // Triangle record in BVH leaf order: three float4.
 struct __align__(16) TriRec {
     float v0[3];  uint32_t prim;        // gl_PrimitiveID
@@ -133,8 +139,6 @@ struct SceneDev {
     uint32_t          num_instances;
     const TexEntry*   textures;
     uint32_t          num_textures;
-    uint32_t          num_real_textures;  // images that need a TEX fetch (not 1x1 constants)
-    const uint32_t*   real_textures;      // their indices, ascending
     const float*      srgb_lut;      // 512 floats: sRGB EOTF per 8-bit code, then code / 255
     // The bits of 1.0f as a kernel parameter.  The box test merges plane bytes into this word with PRMT; SASS PRMT has one
     // immediate slot, and when ptxas knows the word is a constant it spends the slot on it and re-materialises the four byte
@@ -159,6 +163,8 @@ struct FrameDev {
     float     heatmap_scale;        // ticks that map to heat 1.0
     FrameCounters* counters;
     unsigned int* bounce_hint;      // host-mapped word: bounce rays queued by segment 0 of the latest wavefront frame (optional)
+    unsigned int* overflow_flag;    // host-mapped word, set when a traversal stack overflowed: the frame is incomplete and the
+                                    // next synchronising call of the API reports RT_ERR_OUT_OF_RANGE (optional)
     RayRec*   ray_q[2];
     HitRec*   hit_q;
     // Shadow-ray directions of this frame, [64][64][shadow_rays] float4 indexed by (py & 63, px & 63, sample): the

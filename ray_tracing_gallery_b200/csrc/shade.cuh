@@ -75,25 +75,36 @@ __device__ __forceinline__ F4 sample_image_uniform(const SceneDev& S, uint32_t k
 }
 
 // Bindless fetch with a per-lane image index (`nonuniformEXT`, closest_hit_textured.glsl:50-52).
-// A TEX instruction takes its texture header from a uniform register.  When lanes of a warp hold
-// different handles, the serialising loop nvcc 12.9 generates for sm_100a returned texels of the
-// wrong image for some lanes (measured on B200 with compacted wavefront warps mixing lain and fence
-// hits; an __activemask()/__shfl_sync election did not cure it, diverged groups re-merge inside the
-// sampled block).  So the handle is made *provably* uniform: 1x1 images are constants in the table
-// and need no TEX; for the others the loop below walks the short list of real images with a
-// warp-uniform counter and each lane samples in the iteration that matches its index.
+// A TEX instruction takes its texture header from a uniform register, so lanes holding different images have to take
+// turns.  The turns are made explicit here and cost O(distinct images in the warp), not O(images in the table): the
+// lanes that reached this call together OR their indices into one presence word per 32 table entries (redux.sync), and
+// the loop walks only the set bits; each lane samples in the iteration that names its image.  1x1 images are constants
+// in the table and need no TEX.  (The first version of the wavefront shading kernel returned texels of the wrong image
+// when lanes mixed lain and fence hits, and round 1 therefore walked the whole table with a uniform counter; the
+// stand-alone check of the pattern, tests/cuda/tex_divergent_handles.cu, shows every variant — including this one and
+// the plain per-lane handle — correct on B200 with nvcc 12.9, and the all-table walk 1.5-1.8x slower at 96-128 images:
+// profiles/r02c_tex_repro.txt.  tests/test_gpu_parity.py::test_many_images_in_one_warp holds this path to the oracle
+// with 64+ real images mixed inside single warps.)
 __device__ __forceinline__ F4 sample_texture(const SceneDev& S, uint32_t index, float u, float v) {
     F4 r;
     r.r = r.g = r.b = r.a = 0.0f;
-    if (index >= S.num_textures) return r;  // robustness2 null descriptor, src/main.rs:183-184
-    const TexEntry* t = S.textures + index;
-    if (t->obj == 0) {
-        r.r = t->constant[0]; r.g = t->constant[1]; r.b = t->constant[2]; r.a = t->constant[3];
-        return r;
+    bool need = false;
+    if (index < S.num_textures) {  // else: robustness2 null descriptor, src/main.rs:183-184
+        const TexEntry* t = S.textures + index;
+        if (t->obj == 0) {
+            r.r = t->constant[0]; r.g = t->constant[1]; r.b = t->constant[2]; r.a = t->constant[3];
+        } else {
+            need = true;
+        }
     }
-    for (uint32_t j = 0; j < S.num_real_textures; j++) {
-        uint32_t k = S.real_textures[j];
-        if (k == index) r = sample_image_uniform(S, k, u, v);
+    const uint32_t together = __activemask();
+    for (uint32_t word = 0; word * 32u < S.num_textures; word++) {
+        uint32_t present = __reduce_or_sync(together, (need && (index >> 5) == word) ? 1u << (index & 31u) : 0u);
+        while (present) {
+            const uint32_t k = word * 32u + (uint32_t)__ffs(present) - 1u;
+            present &= present - 1u;
+            if (need && k == index) r = sample_image_uniform(S, k, u, v);
+        }
     }
     return r;
 }

@@ -28,7 +28,6 @@
 
 namespace b200rt {
 
-#define RT_STACK_SIZE 48
 #define RT_NONE 0xFFFFFFFFu
 
 struct Hit {
@@ -53,8 +52,6 @@ __device__ __forceinline__ float safe_rcp(float x) {
     return r;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 // 8-bit mask of non-zero bytes of (lo, hi)
 __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t lo, uint32_t hi) {
     uint32_t a = ((__vcmpne4(lo, 0u) & 0x08040201u) * 0x01010101u) >> 24;
@@ -73,19 +70,12 @@ __device__ __forceinline__ uint32_t permute_by_octant(uint32_t m, uint32_t oct) 
 // byte `SEL` of w placed in the mantissa of 1.0f: 1 + q * 2^-15.  `one` = the bits of 1.0f (SceneDev::one_bits).
 template <int SEL>
 __device__ __forceinline__ float byte_m(uint32_t w, uint32_t one) {
-#ifdef RT_PRMT_CONST_ONE
-    one = 0x3F800000u;
-#endif
     return __uint_as_float(__byte_perm(w, one, 0x7604u | (SEL << 4)));
 }
 
 // Shadow rays stop at the first accepted hit, whatever its distance: their children need no front-to-back order, so
-// the octant permutation of the pending mask is skipped for them (A/B: -DRT_ANY_ORDERED keeps it).
-#ifdef RT_ANY_ORDERED
-#define RT_UNORDERED(ANY) false
-#else
+// the octant permutation of the pending mask is skipped for them (measured: profiles/r01n_ab.txt).
 #define RT_UNORDERED(ANY) (ANY)
-#endif
 
 template <bool ANY, bool COUNT>
 struct Traverser {
@@ -175,7 +165,6 @@ struct Traverser {
     // runs as few passes over the three blocks as its longest ray needs.  Returns true when the ray is finished (then
     // found() tells hit or miss).
     __device__ __forceinline__ bool step(const SceneDev& S, uint2* stack, TraceCounters& tc) {
-#ifndef RT_STEP_POP_LAST
         if ((ng_bits & 0xFFu) == 0u) {
             // ---- current group exhausted: pop
             if (inst_sp >= 0 && sp == inst_sp) {
@@ -187,7 +176,6 @@ struct Traverser {
             if (e.y & 0x80000000u) enter_inst = e.x;
             else { ng_base = e.x; ng_bits = e.y; }
         }
-#endif
         if (ng_bits & 0xFFu) {
             // ---- visit the nearest pending child of the current group
             uint32_t i = __ffs(ng_bits & 0xFFu) - 1;
@@ -224,15 +212,11 @@ struct Traverser {
             float tlimit = hit.t;
             const uint32_t one = S.one_bits;
             uint32_t h = 0;
-#ifdef RT_MASK_SHF
-            // Prepared A/B variant (not measured yet): the hit mask from the sign bits of tf - tn, shifted in with one funnel
-            // shift per child (8 FADD on the fma pipe + 8 SHF instead of 8 FSETP + 8 predicated adds on the alu pipe, which
-            // carries twice the fma pipe's load in this block).  tn >= tmin > 0, so tf - tn is never -0 for a hit; a NaN may
-            // read as a hit, which only costs a wasted visit.  Slots are committed 0..7, so slot s ends up at bit 7 - s.
+            // The hit mask comes from the sign bits of tf - tn, shifted in with one funnel shift per child: 8 FADD on the fma pipe +
+            // 8 SHF instead of 8 FSETP + 8 predicated adds on the alu pipe, which carries twice the fma pipe's load in this
+            // block (profiles/r02a_ab.txt: -0.2 .. -0.6 % frame time on C2..C5).  tn >= tmin > 0, so tf - tn is never -0 for a
+            // hit; a NaN may read as a hit, which only costs a wasted visit.  Slots are committed 0..7: slot s ends at bit 7 - s.
 #define RT_BOX_COMMIT(SLOT, TN, TF) h = __funnelshift_l(__float_as_uint((TF) - (TN)), h, 1);
-#else
-#define RT_BOX_COMMIT(SLOT, TN, TF) if ((TN) <= (TF)) h |= 1u << SLOT;
-#endif
 #define RT_BOX(SLOT, SEL, WNX, WNY, WNZ, WFX, WFY, WFZ)                                                   \
     {                                                                                                    \
         float tn = fmaxf(fmaxf(fmaf(byte_m<SEL>(WNX, one), Ax, Bnx), fmaf(byte_m<SEL>(WNY, one), Ay, Bny)),          \
@@ -252,36 +236,16 @@ struct Traverser {
             RT_BOX(7, 3, nx1, ny1, nz1, fx1, fy1, fz1)
 #undef RT_BOX
 #undef RT_BOX_COMMIT
-#ifdef RT_MASK_SHF
             h = __brev(~h) >> 24;  // sign clear = hit; bit 7 - s -> bit s
-#endif
             uint32_t imask = n0.w >> 24;
             h &= nonzero_bytes(n1.z, n1.w);
             uint32_t hl = h & ~imask;
             ng_base = n1.x;
             ng_bits = (RT_UNORDERED(ANY) ? (h & imask) : permute_by_octant(h & imask, oct)) | (imask << 8);
-#ifdef RT_PREFETCH
-            // Prepared A/B variant (not measured yet): the next child's line is requested before this node's leaves are
-            // tested, so an L1 miss (36 % of node loads on C2) overlaps the triangle tests of the same ray.
-            if (ng_bits & 0xFFu) {
-                uint32_t pi = __ffs(ng_bits & 0xFFu) - 1, ps = RT_UNORDERED(ANY) ? pi : (pi ^ oct);
-                prefetch_l1(nodes + ng_base + __popc(imask & ((1u << ps) - 1u)));
-            }
-#endif
 
             // ---- leaves of this node
             uint64_t meta = ((uint64_t)n1.w << 32) | n1.z;
             if (inst_sp >= 0) {
-#ifdef RT_PREFETCH
-                // every hit leaf's triangle records are requested before the first one is tested: the fetch of the 48-byte
-                // records is the kernel's top stall (profiles/r01r_k_shadow_lines.md: 13 % of samples on their first use)
-                for (uint32_t pl = hl; pl; pl &= pl - 1) {
-                    uint32_t ps = __ffs(pl) - 1, pm = (uint32_t)(meta >> (8 * ps)) & 0xFFu;
-                    const TriRec* pt = S.tris + n1.y + (pm & 31u);
-                    prefetch_l1(pt);
-                    if ((pm >> 5) > 1u) prefetch_l1(pt + 1);
-                }
-#endif
                 while (hl) {
                     uint32_t s = __ffs(hl) - 1;
                     hl &= hl - 1;
@@ -341,33 +305,12 @@ struct Traverser {
                     ng_base = root;
                     ng_bits = (RT_UNORDERED(ANY) ? 1u : (1u << oct)) | (1u << 8);
                     inst_sp = sp;
-#ifdef RT_PREFETCH
-                    prefetch_l1(S.blas_nodes + root);
-#endif
                 }
             }
-#ifdef RT_STEP_POP_LAST
-            return false;
-#endif
         }
 
-#ifdef RT_STEP_POP_LAST
-        if ((ng_bits & 0xFFu) == 0u) {
-            // ---- current group exhausted: pop (the order of the first version, kept for A/B)
-            if (inst_sp >= 0 && sp == inst_sp) {
-                inst_sp = -1;
-                set_space(o, d);
-            }
-            if (sp == 0) return true;
-            uint2 e = stack[--sp];
-            if (e.y & 0x80000000u) enter_inst = e.x;
-            else { ng_base = e.x; ng_bits = e.y; }
-        }
-        return false;
-#else
         // nothing pending and nothing stacked: finished (saves the pass that would only find the stack empty)
         return (ng_bits & 0xFFu) == 0u && sp == 0;
-#endif
     }
 };
 

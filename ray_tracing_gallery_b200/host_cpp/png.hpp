@@ -53,6 +53,11 @@ inline ImageRgba8 decode_png_rgba8(const uint8_t* data, size_t size) {
     if (interlace) throw std::runtime_error("PNG: interlaced images are not supported");
     int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!channels) throw std::runtime_error("PNG: bad colour type");
+    // legal bit depths per colour type (PNG spec 11.2.2): anything else would shift by garbage or divide by zero below
+    const bool depth_ok = ctype == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                        : ctype == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8)
+                                     : (depth == 8 || depth == 16);
+    if (!depth_ok) throw std::runtime_error("PNG: bit depth not allowed for this colour type");
     size_t bpp_bits = (size_t)channels * depth;
     size_t stride = (w * bpp_bits + 7) / 8;
     size_t bpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;  // filter unit in bytes
@@ -109,10 +114,15 @@ inline ImageRgba8 decode_png_rgba8(const uint8_t* data, size_t size) {
                     out[3] = (trns.size() >= 2 && g == (((uint32_t)trns[0] << 8) | trns[1])) ? 0 : 255;
                     break;
                 }
-                case 2:
-                    out[0] = to8(sample(row, 3 * (size_t)x)); out[1] = to8(sample(row, 3 * (size_t)x + 1)); out[2] = to8(sample(row, 3 * (size_t)x + 2));
-                    out[3] = 255;
+                case 2: {
+                    uint32_t r = sample(row, 3 * (size_t)x), g = sample(row, 3 * (size_t)x + 1), b = sample(row, 3 * (size_t)x + 2);
+                    out[0] = to8(r); out[1] = to8(g); out[2] = to8(b);
+                    // tRNS colour key (three 16-bit samples): that exact colour is fully transparent, like image's to_rgba8
+                    const bool key = trns.size() >= 6 && r == (((uint32_t)trns[0] << 8) | trns[1]) && g == (((uint32_t)trns[2] << 8) | trns[3]) &&
+                                     b == (((uint32_t)trns[4] << 8) | trns[5]);
+                    out[3] = key ? 0 : 255;
                     break;
+                }
                 case 3: {
                     uint32_t i = sample(row, x);
                     if (3 * (size_t)i + 2 >= plte.size()) throw std::runtime_error("PNG: palette index out of range");

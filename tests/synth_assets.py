@@ -201,3 +201,52 @@ def build_random_scene(backend, seed: int, width=256, height=144):
                    shadow_rays=int(rng.integers(1, 6)), sun_radius=float(rng.uniform(0.0, 0.08)), description="seeded random stress scene")
     backend.build_tlas(s.instances)
     return s
+
+
+def build_mosaic_scene(backend, n_images=72, cells=(36, 20), width=480, height=270, seed=5):
+    """A wall of small quads, each cell with its own material out of `n_images` real (non-1x1) images, dealt so that
+    neighbouring cells differ: the 8x4-pixel tile a warp traces covers half a dozen images.  Every third material is
+    alpha-masked (random 0 / 255 alpha, NEAREST) so that the any-hit stage samples per-lane images inside traversal; the
+    others alternate LINEAR / NEAREST and sRGB diffuse + metal-rough pairs.  Uses the bindless table up to its 128 entries."""
+    import numpy as np
+
+    from ray_tracing_gallery_b200 import abi
+    from ray_tracing_gallery_b200.gltf import Geometry, ModelArrays
+    from ray_tracing_gallery_b200.scene import Camera, SceneSetup, Sun, load_model, make_instance, mat_rotation_y, mat_scale, mat_translation, push_builtin_images
+
+    rng = np.random.default_rng(seed)
+    push_builtin_images(backend)
+    pid, ph, _ = load_model(backend, "plane.glb", 0)
+    images = []
+    for k in range(n_images):
+        masked = k % 3 == 0
+        tex = rng.integers(0, 256, (4, 4, 4), dtype=np.uint8)
+        tex[..., 3] = rng.choice([0, 255], (4, 4)) if masked else 255
+        images.append(backend.push_image(tex, abi.RT_FORMAT_RGBA8_SRGB, linear=(k % 2 == 1) and not masked))
+    mr = backend.push_image(np.array([[[1.0, 0.6, 0.1, 1.0]]], np.float32), abi.RT_FORMAT_RGBA32_SFLOAT, False)
+    nx, ny = cells
+    pos, nrm, uvs = [], [], []
+    geo_idx = [[] for _ in range(n_images)]
+    for j in range(ny):
+        for i in range(nx):
+            k = (i * 7 + j * 13 + (i * j) % 5) % n_images
+            x0, x1, y0, y1 = i / nx * 6 - 3, (i + 1) / nx * 6 - 3, j / ny * 3.2 + 0.2, (j + 1) / ny * 3.2 + 0.2
+            base = len(pos)
+            pos += [(x0, y0, 0), (x1, y0, 0), (x1, y1, 0), (x0, y1, 0)]
+            nrm += [(0, 0.1, -1)] * 4
+            uvs += [(0, 0), (1, 0), (1, 1), (0, 1)]
+            geo_idx[k] += [base, base + 1, base + 2, base, base + 2, base + 3]
+    geos = [Geometry(np.array(ix, np.uint32), opaque=(k % 3 != 0), diffuse_image_index=images[k], metallic_roughness_image_index=mr,
+                     normal_map_image_index=-1) for k, ix in enumerate(geo_idx)]
+    arrays = ModelArrays("mosaic", np.array(pos, np.float32), np.array(nrm, np.float32), np.array(uvs, np.float32), geos)
+    mid, mh = backend.create_model(arrays)
+    inst = np.stack([
+        make_instance(mat_scale(10.0), pid, ph, abi.RT_HIT_TEXTURED),
+        make_instance(mat_translation(0, 0, 2.0) @ mat_rotation_y(0.15), mid, mh, abi.RT_HIT_TEXTURED, True),
+        make_instance(mat_translation(0.4, 0, 3.5) @ mat_rotation_y(-0.3), mid, mh, abi.RT_HIT_TEXTURED, True),
+    ])
+    s = SceneSetup("mosaic", inst, Camera(eye=(0.0, 1.8, -3.0)), Sun(), width, height, shadow_rays=2, sun_radius=0.05,
+                   description=f"wall of quads over {n_images} real images, a third alpha-masked")
+    backend.build_tlas(s.instances)
+    return s
+

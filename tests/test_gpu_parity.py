@@ -331,6 +331,86 @@ def test_many_instances_tile_parity():
     orc.close(); gpu.close()
 
 
+def test_full_size_c5_tile_parity():
+    """BASELINE configs[4] at its stated size: ALL 1 000 001 instances, 16 soft-shadow rays, a 960x270 tile of the 3840x2160
+    launch against the oracle (the whole frame would be ~140 M oracle rays)."""
+    orc, so, gpu, sg = both("c5", 3840, 2160)
+    assert len(sg.instances) == 1_000_001 and sg.shadow_rays == 16
+    tile = dict(tile_x0=1440, tile_y0=1080, tile_w=960, tile_h=270)
+    want = orc.render(so.uniforms(), so.params(**tile))
+    for pipeline in PIPELINES:
+        got = gpu.render(sg.uniforms(), sg.params(pipeline=pipeline, **tile))
+        st = gpu.stats()
+        ids, within = check_parity(got, want, strict_ids=False)
+        print(f"c5 full size, pipeline {pipeline}: {st.num_instances} instances, tile 960x270 of 3840x2160, rays {got['ray_counts'].tolist()}, "
+              f"hit IDs {ids:.6%}, radiance within 1e-3 {within:.6%}, PSNR {psnr(got['radiance'], want['radiance']):.1f} dB")
+    assert want["ray_counts"][1] > 2_000_000  # the tile really looks at the field
+    orc.close(); gpu.close()
+
+
+def test_full_size_c4_frame_parity_after_refits():
+    """BASELINE configs[3] at its stated size: 10 001 instances, every transform updated per frame, TLAS refit (the reference's
+    in-place UPDATE) for three ticks, then the whole 3840x2160 frame against the oracle (which rebuilds from scratch)."""
+    orc, so, gpu, sg = both("c4", 3840, 2160)
+    assert len(sg.instances) == 10_001
+    for tick in (1, 2, 3):
+        gpu.update_instances(0, sg.animate(tick)); gpu.update_tlas(abi.RT_UPDATE_REFIT)
+        gpu.render(sg.uniforms(frame_index=tick), sg.params(), want=("ray_counts",))
+    orc.update_instances(0, so.animate(3)); orc.update_tlas(abi.RT_UPDATE_REBUILD)
+    want = orc.render(so.uniforms(frame_index=4), so.params())
+    got = gpu.render(sg.uniforms(frame_index=4), sg.params())
+    st = gpu.stats()
+    ids, within = check_parity(got, want, strict_ids=False)
+    print(f"c4 full size after 3 refit ticks: {st.num_instances} instances, 3840x2160, rays {got['ray_counts'].tolist()}, hit IDs {ids:.6%}, "
+          f"radiance within 1e-3 {within:.6%}, PSNR {psnr(got['radiance'], want['radiance']):.1f} dB, refit {st.last_tlas_ms:.3f} ms")
+    orc.close(); gpu.close()
+
+
+def test_many_images_in_one_warp():
+    """72 real images + the built-ins, dealt so that one warp's pixel tile covers several of them, a third alpha-masked
+    (per-lane image indices inside the traversal's any-hit): the bounded bindless fetch of shade.cuh against the oracle."""
+    import synth_assets
+
+    orc, gpu = make_oracle(), make_renderer()
+    so, sg = synth_assets.build_mosaic_scene(orc), synth_assets.build_mosaic_scene(gpu)
+    want = orc.render(so.uniforms(), so.params())
+    assert len(np.unique(want["hit_ids"][:, :, 0, 1])) > 60  # geometry index = material: most images are on screen
+    for pipeline in PIPELINES:
+        got = gpu.render(sg.uniforms(), sg.params(pipeline=pipeline, flags=abi.RT_RENDER_COUNTERS))
+        st = gpu.stats()
+        assert sum(st.anyhit_calls) > 10000
+        check_parity(got, want, strict_ids=False)
+    orc.close(); gpu.close()
+
+
+def test_stack_overflow_is_reported():
+    """A traversal stack that overflows drops a subtree, so the API must refuse the frame instead of returning a wrong image:
+    the same library built with a 3-entry stack (csrc/Makefile libb200rt_stack3.so) renders C3 in a child process."""
+    import os
+    import subprocess
+    import sys
+
+    from ray_tracing_gallery_b200 import native
+
+    lib = os.path.join(os.path.dirname(native.LIB_PATH), "libb200rt_stack3.so")
+    if not os.path.exists(lib):
+        pytest.skip("libb200rt_stack3.so not built (__graft_entry__.build())")
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from ray_tracing_gallery_b200 import native\n"
+        "from ray_tracing_gallery_b200.backend import RtError\n"
+        "from ray_tracing_gallery_b200.scene import build_scene\n"
+        "gpu = native.Renderer(0); s = build_scene(gpu, 'c3', 640, 360)\n"
+        "try:\n"
+        "    gpu.render(s.uniforms(), s.params())\n"
+        "    print('NO ERROR')\n"
+        "except RtError as e:\n"
+        "    print('ERR', e)\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200RT_LIB=lib), capture_output=True, text=True, timeout=300)
+    assert "ERR" in out.stdout and "stack overflowed" in out.stdout, out.stdout + out.stderr
+
+
 def test_show_heatmap_frame():
     """SURVEY 8f-3, Uniforms.show_heatmap (lib.rs:120-124, 174-186; heatmap.rs): the frame shows
     heatmap_temperature(clock ticks of the pixel's ray-gen invocation / heatmap_scale) + 1e-6 * colour.  The clock is the

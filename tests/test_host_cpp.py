@@ -117,6 +117,39 @@ def test_cpp_png_decoder_colour_types(host_dump, tmp_path, mode, depth16):
     assert sec[2000] == want.tobytes()
 
 
+def test_cpp_png_decoder_rgb_colour_key_and_bad_depth(host_dump, tmp_path):
+    """tRNS on colour type 2 = a colour key: that exact RGB is transparent (image's to_rgba8 gives alpha 0 — it matters
+    for alpha-clipped materials).  An IHDR bit depth that is illegal for the colour type must be refused, not crash."""
+    import zlib
+
+    from PIL import Image
+
+    from ray_tracing_gallery_b200.gltf import decode_png_rgba8
+
+    a = np.zeros((5, 7, 3), np.uint8)
+    a[..., 0] = np.arange(7)[None, :] * 30
+    a[2, 3] = (9, 8, 7)
+    a[4, 6] = (9, 8, 7)
+    p = tmp_path / "key.png"
+    Image.fromarray(a, "RGB").save(p, format="PNG", transparency=(9, 8, 7))
+    out = str(tmp_path / "key.bin")
+    subprocess.check_call([host_dump, "png", str(p), out])
+    want = decode_png_rgba8(p.read_bytes())
+    assert want[2, 3, 3] == 0 and want[4, 6, 3] == 0 and want[0, 0, 3] == 255
+    assert read_sections(out)[2000] == want.tobytes()
+
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body))
+
+    for depth, ctype in ((0, 0), (3, 0), (32, 2), (4, 6)):
+        bad = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, depth, ctype, 0, 0, 0)) + \
+            chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+        q = tmp_path / f"bad_{depth}_{ctype}.png"
+        q.write_bytes(bad)
+        r = subprocess.run([host_dump, "png", str(q), str(tmp_path / "bad.bin")], capture_output=True)
+        assert r.returncode not in (0, -8, -11), (depth, ctype, r.returncode)  # an error exit, not SIGFPE / SIGSEGV
+
+
 class Recorder:
     """The Python twin of host_dump's recording backend."""
 

@@ -9,6 +9,7 @@ rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 cur_file, hdr = None, None
 agg, samples, texts = collections.Counter(), collections.Counter(), {}
+threads = collections.Counter()  # thread instructions executed: / warp instructions = active lanes per instruction
 stalls = collections.defaultdict(collections.Counter)
 for r in rows:
     if not r:
@@ -28,10 +29,12 @@ for r in rows:
     try:
         ie = int(float(r[col["Instructions Executed"]] or 0))
         sm = int(float(r[col["# Samples"]] or 0))
+        ti = int(float(r[col["Thread Instructions Executed"]] or 0)) if "Thread Instructions Executed" in col else 0
     except ValueError:
         continue
     key = (cur_file.split("/")[-1], line)
     agg[key] += ie
+    threads[key] += ti
     samples[key] += sm
     texts[key] = r[1].strip()[:110]
     for name, i in col.items():
@@ -41,7 +44,10 @@ for r in rows:
             except ValueError:
                 pass
 tot, ts = sum(agg.values()), sum(samples.values())
-print("total warp-inst", tot, "samples", ts)
+print("total warp-inst", tot, "samples", ts, "active lanes per warp instruction %.2f" % (sum(threads.values()) / max(tot, 1)))
+# idle lane-slots per line: where the SIMD width is lost (32 * warp instructions - thread instructions)
+idle = {k: 32 * agg[k] - threads[k] for k in agg}
+tidle = sum(idle.values()) or 1
 byfile, byfile_s = collections.Counter(), collections.Counter()
 for k, v in agg.items():
     byfile[k[0]] += v
@@ -55,4 +61,4 @@ print("stall samples:", ", ".join(f"{n} {100*c/st:.0f}%" for n, c in allst.most_
 order = sorted(agg, key=lambda k: -(agg[k] / max(tot, 1) + samples[k] / max(ts, 1)))
 for k in order[:top]:
     why = ", ".join(f"{n} {c}" for n, c in stalls[k].most_common(3) if c)
-    print(f"{100*agg[k]/tot:5.1f}% inst {100*samples[k]/max(ts,1):5.1f}% smp  {k[0]}:{k[1]:4d}  {texts[k]}   [{why}]")
+    print(f"{100*agg[k]/tot:5.1f}% inst {100*samples[k]/max(ts,1):5.1f}% smp {threads[k]/max(agg[k],1):5.1f} lanes {100*idle[k]/tidle:5.1f}% idle  {k[0]}:{k[1]:4d}  {texts[k]}   [{why}]")
