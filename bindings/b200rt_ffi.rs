@@ -15,6 +15,17 @@ pub struct RtContext {
     _private: [u8; 0],
 }
 
+/// Several GPUs of one box rendering one frame (`rt_group_*`): one process per GPU, one `RtContext` each.
+#[repr(C)]
+pub struct RtGroup {
+    _private: [u8; 0],
+}
+
+pub const RT_GROUP_ID_BYTES: usize = 128;
+pub const RT_GROUP_STRIP_ROWS: u32 = 8;
+pub const RT_GROUP_MAX_RANKS: usize = 16;
+pub const RT_GROUP_FRAME_SLOTS: u64 = 4;
+
 pub const RT_OK: c_int = 0;
 pub const RT_ERR_INVALID_ARGUMENT: c_int = -1;
 pub const RT_ERR_CUDA: c_int = -2;
@@ -137,6 +148,24 @@ extern "C" {
     pub fn rt_get_stats(ctx: *mut RtContext, out: *mut RtStats) -> c_int;
     pub fn rt_get_push_constants(ctx: *mut RtContext, out: *mut PushConstantBufferAddresses) -> c_int;
     pub fn rt_debug_read_model_info(ctx: *mut RtContext, model_id: u32, out_info: *mut ModelInfo, out_geoms: *mut GeometryInfo, max_geoms: u32) -> c_int;
+    // ---- multi-GPU: device creation (src/main.rs:157-204) and the per-frame scene update (src/scene.rs:167-204) for a group of ranks
+    pub fn rt_group_unique_id(out_id_128_bytes: *mut c_void) -> c_int;
+    pub fn rt_group_create(ctx: *mut RtContext, n_ranks: c_int, rank: c_int, id_128_bytes: *const c_void, width: u32, height: u32,
+                           out: *mut *mut RtGroup) -> c_int;
+    pub fn rt_group_destroy(group: *mut RtGroup);
+    pub fn rt_group_last_error(group: *const RtGroup) -> *const c_char;
+    pub fn rt_group_partition(group: *const RtGroup, params: *mut RtRenderParams) -> u32;
+    pub fn rt_group_update_instances(group: *mut RtGroup, root: c_int, first: u32, count: u32, host_records: *const AccelerationStructureInstance,
+                                     mode: u32) -> c_int; // ncclBroadcast into the TLAS builder's input, then update_tlas on every rank
+    pub fn rt_group_update_instances_device(group: *mut RtGroup, root: c_int, first: u32, count: u32, device_records: *const c_void, mode: u32) -> c_int;
+    pub fn rt_group_render_device(group: *mut RtGroup, seq: u64, uniforms: *const Uniforms, params: *const RtRenderParams) -> c_int;
+    pub fn rt_group_render_host(group: *mut RtGroup, seq: u64, uniforms: *const Uniforms, params: *const RtRenderParams) -> c_int;
+    pub fn rt_group_acquire_device(group: *mut RtGroup, seq: u64, out_device_rgba8: *mut *mut u8) -> c_int;
+    pub fn rt_group_acquire_host(group: *mut RtGroup, seq: u64, timeout_ms: u32, out_host_rgba8: *mut *const u8, ray_counts: *mut u64) -> c_int;
+    pub fn rt_group_release(group: *mut RtGroup, seq: u64) -> c_int;
+    pub fn rt_group_readback(group: *mut RtGroup, seq: u64, host_rgba8: *mut c_void, capacity_bytes: usize) -> c_int;
+    pub fn rt_group_local_ray_counts(group: *mut RtGroup, out_device_counts: *mut *mut u64) -> c_int;
+    pub fn rt_group_barrier(group: *mut RtGroup) -> c_int;
     pub fn rt_kernel_launches() -> u64;
     pub fn rt_version() -> u32;
 }

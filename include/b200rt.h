@@ -238,6 +238,71 @@ int  rt_get_push_constants(RtContext* ctx, RtPushConstantBufferAddresses* out);
  * device tables carry the reference's 32/24-byte layouts). */
 int  rt_debug_read_model_info(RtContext* ctx, uint32_t model_id, RtModelInfo* out_info,
                               RtGeometryInfo* out_geoms, uint32_t max_geoms);
+/* ---------------------------------------------------------------------------------------------------------------
+ * One frame on several GPUs of one box.  The reference is single-GPU: its device creation
+ * (src/main.rs:157-204) and its per-frame scene update (src/scene.rs:167-204) are the two seams a multi-GPU host
+ * goes through, and they map to rt_group_create and rt_group_update_instances.  One process (or thread) per GPU, one
+ * RtContext each, every rank holding the whole scene; a group joins the ranks:
+ *   - image rows are dealt to the ranks in strips of RT_GROUP_STRIP_ROWS rows, round-robin (pixels are independent,
+ *     blue noise is indexed by the global pixel: shaders/closest_hit_textured.glsl:100);
+ *   - on a TLAS change the instance records go from the root rank to all ranks with ONE ncclBroadcast over NVLink that
+ *     lands directly in the buffer the TLAS builder reads, followed by the refit / rebuild on every rank;
+ *   - the frame reaches rank 0 either in DEVICE memory — every rank's render kernels store their rows straight into rank
+ *     0's frame through NVLink peer memory (cudaIpc mapping) and raise a flag there, no collective, no copy kernel — or
+ *     in HOST memory — every rank copies its own strips over its own PCIe link into one page-locked frame shared by
+ *     the ranks (POSIX shared memory, registered with CUDA on every rank), which rank 0 then reads in place.
+ * NCCL is loaded at run time (dlopen of libnccl.so.2, the copy already in the process if there is one); single-GPU
+ * users of this library do not need it.  No torch, no MPI: the only thing the host has to move between the ranks
+ * is the 128-byte id of rt_group_unique_id. */
+typedef struct RtGroup RtGroup;
+enum { RT_GROUP_ID_BYTES = 128, RT_GROUP_STRIP_ROWS = 8, RT_GROUP_MAX_RANKS = 16, RT_GROUP_FRAME_SLOTS = 4 };
+
+/* Rank 0: make the id (ncclGetUniqueId); hand its bytes to every rank by any means. */
+int  rt_group_unique_id(void* out_id_128_bytes);
+/* All ranks, collectively.  `ctx` is this rank's context (its GPU, its scene).  Frames of `width` x `height` pixels. */
+int  rt_group_create(RtContext* ctx, int n_ranks, int rank, const void* id_128_bytes, uint32_t width, uint32_t height,
+                     RtGroup** out);
+void rt_group_destroy(RtGroup* group);
+const char* rt_group_last_error(const RtGroup* group);
+/* Fill the strip fields of `params` for this rank (rows r with (r / 8) % n_ranks == rank); rows this rank renders. */
+uint32_t rt_group_partition(const RtGroup* group, RtRenderParams* params);
+
+/* All ranks, collectively: DefaultScene::write_resources for a multi-GPU box (src/scene.rs:167-204).  `host_records`
+ * (count x 64 bytes, rank `root` only, may be NULL elsewhere) -> ncclBroadcast into the staging instance buffer at
+ * `first` -> rt_update_tlas(mode) on every rank.  Stream-ordered on each rank's context stream. */
+int  rt_group_update_instances(RtGroup* group, int root, uint32_t first, uint32_t count, const RtInstance* host_records,
+                               uint32_t mode /* RtUpdateMode */);
+/* Same, the root's records already in device memory of the root's GPU (the counterpart of rt_update_instances_device). */
+int  rt_group_update_instances_device(RtGroup* group, int root, uint32_t first, uint32_t count, const void* device_records,
+                                      uint32_t mode /* RtUpdateMode */);
+
+/* All ranks: enqueue frame number `seq` (1, 2, 3 ... the same on every rank).  This rank renders its strips; `params`
+ * carries width / height / max_segments / shadow_rays / pipeline / flags, the strip fields are filled by the group.
+ *   rt_group_render_device: rows are stored into rank 0's DEVICE frame (slot seq % RT_GROUP_FRAME_SLOTS) over NVLink
+ *     peer memory, then this rank's arrival flag is raised in rank 0's memory.
+ *   rt_group_render_host: rows are rendered locally and copied into the shared page-locked HOST frame, this rank's
+ *     ray counts next to them; arrival is published from a stream callback.
+ * A slot is reused every RT_GROUP_FRAME_SLOTS frames: the calls wait until rank 0 has released the frame that used it. */
+int  rt_group_render_device(RtGroup* group, uint64_t seq, const RtUniforms* uniforms, const RtRenderParams* params);
+int  rt_group_render_host(RtGroup* group, uint64_t seq, const RtUniforms* uniforms, const RtRenderParams* params);
+/* Rank 0: the finished frame.
+ *   rt_group_acquire_device enqueues, on rank 0's context stream, a wait for every rank's arrival flag of frame `seq`;
+ *     work enqueued on that stream afterwards sees the whole frame at *out_device_rgba8 ([height][width][4]).
+ *   rt_group_acquire_host blocks until every rank's rows of frame `seq` are in host memory (bounded wait: an error
+ *     after `timeout_ms`); *out_host_rgba8 points into the shared frame, ray_counts[2] are summed over the ranks.
+ * rt_group_release(seq) gives the slot back (device path: stream-ordered after what rank 0 enqueued so far). */
+int  rt_group_acquire_device(RtGroup* group, uint64_t seq, uint8_t** out_device_rgba8);
+int  rt_group_acquire_host(RtGroup* group, uint64_t seq, uint32_t timeout_ms, const uint8_t** out_host_rgba8, uint64_t* ray_counts);
+int  rt_group_release(RtGroup* group, uint64_t seq);
+/* Rank 0, for hosts without a CUDA runtime of their own (the counterpart of rt_readback): wait for frame `seq` of the
+ * device path and copy it to host memory (blocking).  Does not release the slot. */
+int  rt_group_readback(RtGroup* group, uint64_t seq, void* host_rgba8, size_t capacity_bytes);
+/* All ranks: ray counts {ray-gen segments, shadow rays} of this rank's share of the last device-path frame (device pointer,
+ * valid in stream order after rt_group_render_device). */
+int  rt_group_local_ray_counts(RtGroup* group, uint64_t** out_device_counts);
+/* All ranks, collectively: every rank's stream work is finished (ncclAllReduce of one word + stream sync). */
+int  rt_group_barrier(RtGroup* group);
+
 /* Number of this library's own kernels launched so far in the process (all contexts). */
 uint64_t rt_kernel_launches(void);
 /* Library/ABI version: (major << 16) | minor. */

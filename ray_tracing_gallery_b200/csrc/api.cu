@@ -435,9 +435,28 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
 
 }  // namespace
 
+// ---- hooks for group.cu (multi-GPU entry points); not part of the C ABI
+namespace b200rt {
+// Where a write of `count` instance records at `first` has to land so that the next rt_update_tlas sees it (the staging
+// TLAS set).  nullptr on error (message in the context).
+RtInstance* internal_stage_instances(RtContext* ctx, uint32_t first, uint32_t count) {
+    if (!ctx) return nullptr;
+    if ((uint64_t)first + count > ctx->num_instances) {
+        fail(ctx, RT_ERR_OUT_OF_RANGE, "instance range outside the instance buffer");
+        return nullptr;
+    }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    if (begin_staging(ctx, first == 0 && count == ctx->num_instances) != RT_OK) return nullptr;
+    ctx->writes_since_build += count;
+    return ctx->sets[ctx->cur ^ 1u].d_instances + first;
+}
+cudaStream_t internal_stream(RtContext* ctx) { return ctx->stream; }
+int internal_device(RtContext* ctx) { return ctx->device; }
+}  // namespace b200rt
+
 extern "C" {
 
-uint32_t rt_version(void) { return (1u << 16) | 0u; }
+uint32_t rt_version(void) { return (1u << 16) | 1u; }
 
 uint64_t rt_kernel_launches(void) { return g_kernel_launches.load(); }
 

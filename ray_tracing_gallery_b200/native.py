@@ -23,7 +23,12 @@ EXPORTS = [
     "rt_update_instances", "rt_update_instances_device", "rt_update_tlas", "rt_render", "rt_render_device", "rt_render_async",
     "rt_wait_frame", "rt_render_device_slot", "rt_host_alloc", "rt_host_free", "rt_readback",
     "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_kernel_launches", "rt_version",
+    "rt_group_unique_id", "rt_group_create", "rt_group_destroy", "rt_group_last_error", "rt_group_partition", "rt_group_update_instances",
+    "rt_group_update_instances_device",
+    "rt_group_render_device", "rt_group_render_host", "rt_group_acquire_device", "rt_group_acquire_host", "rt_group_release",
+    "rt_group_readback", "rt_group_local_ray_counts", "rt_group_barrier",
 ]
+GROUP_ID_BYTES, GROUP_STRIP_ROWS, GROUP_FRAME_SLOTS = 128, 8, 4
 
 
 def build(force: bool = False) -> str:
@@ -59,6 +64,25 @@ def load():
     lib.rt_get_push_constants.argtypes = [p, C.POINTER(abi.RtPushConstantBufferAddresses)]
     lib.rt_debug_read_model_info.argtypes = [p, u32, C.POINTER(abi.RtModelInfo), C.POINTER(abi.RtGeometryInfo), u32]
     lib.rt_version.restype = u32
+    u64 = C.c_uint64
+    lib.rt_group_unique_id.argtypes = [p]
+    lib.rt_group_create.argtypes = [p, C.c_int, C.c_int, p, u32, u32, C.POINTER(p)]
+    lib.rt_group_destroy.argtypes = [p]
+    lib.rt_group_destroy.restype = None
+    lib.rt_group_last_error.argtypes = [p]
+    lib.rt_group_last_error.restype = C.c_char_p
+    lib.rt_group_partition.argtypes = [p, C.POINTER(abi.RtRenderParams)]
+    lib.rt_group_partition.restype = u32
+    lib.rt_group_update_instances.argtypes = [p, C.c_int, u32, u32, p, u32]
+    lib.rt_group_update_instances_device.argtypes = [p, C.c_int, u32, u32, p, u32]
+    lib.rt_group_render_device.argtypes = [p, u64, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams)]
+    lib.rt_group_render_host.argtypes = [p, u64, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams)]
+    lib.rt_group_acquire_device.argtypes = [p, u64, C.POINTER(p)]
+    lib.rt_group_acquire_host.argtypes = [p, u64, u32, C.POINTER(p), C.POINTER(u64)]
+    lib.rt_group_release.argtypes = [p, u64]
+    lib.rt_group_readback.argtypes = [p, u64, p, C.c_size_t]
+    lib.rt_group_local_ray_counts.argtypes = [p, C.POINTER(p)]
+    lib.rt_group_barrier.argtypes = [p]
     lib.rt_kernel_launches.restype = C.c_uint64
     _LIB = lib
     return lib
@@ -137,3 +161,115 @@ class Renderer(CApiBackend):
         geoms = (abi.RtGeometryInfo * max_geoms)()
         self._check(self.lib.rt_debug_read_model_info(self.ctx, model_id, C.byref(info), geoms, max_geoms), "debug_read_model_info")
         return info, geoms
+
+
+_NCCL_PRELOADED = False
+
+
+def _preload_nccl():
+    """The process can hold ONE libnccl.so.2 (the loader goes by SONAME).  When PyTorch's bundled NCCL is installed, load it
+    first: libtorch_cuda needs its symbols, and the C library then finds it with RTLD_NOLOAD.  Without it the C library
+    falls back to the system NCCL on its own."""
+    global _NCCL_PRELOADED
+    if _NCCL_PRELOADED:
+        return
+    _NCCL_PRELOADED = True
+    if os.environ.get("B200RT_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except (ImportError, OSError, AttributeError):
+        pass
+
+
+def group_unique_id() -> bytes:
+    """`rt_group_unique_id` (rank 0): the 128 bytes every rank hands to `Group`."""
+    _preload_nccl()
+    lib = load()
+    buf = C.create_string_buffer(GROUP_ID_BYTES)
+    rc = lib.rt_group_unique_id(buf)
+    if rc != 0:
+        msg = lib.rt_group_last_error(None)
+        raise RtError(f"rt_group_unique_id failed ({rc}): {msg.decode() if msg else ''}")
+    return buf.raw
+
+
+class Group:
+    """`rt_group_*`: one frame on several GPUs of one box (one process per GPU).  Everything that crosses GPUs — the NCCL
+    broadcast of instance records, the peer-memory frame on rank 0, the shared page-locked host frame — lives in the
+    C library; the host only has to get `unique_id` (128 bytes) from rank 0 to every rank."""
+
+    def __init__(self, renderer: "Renderer", n_ranks: int, rank: int, unique_id: bytes, width: int, height: int):
+        _preload_nccl()
+        self.lib, self.renderer, self.n, self.rank, self.width, self.height = renderer.lib, renderer, n_ranks, rank, width, height
+        h = C.c_void_p()
+        idbuf = C.create_string_buffer(bytes(unique_id), GROUP_ID_BYTES)
+        rc = self.lib.rt_group_create(renderer.ctx, n_ranks, rank, idbuf, width, height, C.byref(h))
+        if rc != 0:
+            msg = self.lib.rt_group_last_error(None)
+            raise RtError(f"rt_group_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.h = h
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.rt_group_last_error(self.h)
+            raise RtError(f"rt_group_{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self.h is not None:
+            self.lib.rt_group_destroy(self.h)
+            self.h = None
+
+    def partition(self, params=None) -> int:
+        """Rows this rank renders; fills the strip fields of `params` when given."""
+        return self.lib.rt_group_partition(self.h, C.byref(params) if params is not None else None)
+
+    def update_instances(self, first: int, count: int, host_ptr: int, mode: int, root: int = 0):
+        self._check(self.lib.rt_group_update_instances(self.h, root, first, count, host_ptr or None, mode), "update_instances")
+
+    def update_instances_device(self, first: int, count: int, device_ptr: int, mode: int, root: int = 0):
+        self._check(self.lib.rt_group_update_instances_device(self.h, root, first, count, device_ptr or None, mode), "update_instances_device")
+
+    def render_device(self, seq: int, uniforms, params):
+        self._check(self.lib.rt_group_render_device(self.h, seq, C.byref(uniforms), C.byref(params)), "render_device")
+
+    def render_host(self, seq: int, uniforms, params):
+        self._check(self.lib.rt_group_render_host(self.h, seq, C.byref(uniforms), C.byref(params)), "render_host")
+
+    def acquire_device(self, seq: int) -> int:
+        ptr = C.c_void_p()
+        self._check(self.lib.rt_group_acquire_device(self.h, seq, C.byref(ptr)), "acquire_device")
+        return ptr.value
+
+    def acquire_host(self, seq: int, timeout_ms: int = 10000):
+        """Rank 0: (numpy view of the finished [H, W, 4] frame in the shared host memory, summed ray counts)."""
+        ptr = C.c_void_p()
+        counts = (C.c_uint64 * 2)()
+        self._check(self.lib.rt_group_acquire_host(self.h, seq, timeout_ms, C.byref(ptr), counts), "acquire_host")
+        buf = (C.c_uint8 * (self.width * self.height * 4)).from_address(ptr.value)
+        return np.frombuffer(buf, np.uint8).reshape(self.height, self.width, 4), (int(counts[0]), int(counts[1]))
+
+    def readback(self, seq: int) -> np.ndarray:
+        """Rank 0: wait for frame `seq` of the device path and copy it to host memory."""
+        img = np.zeros((self.height, self.width, 4), np.uint8)
+        self._check(self.lib.rt_group_readback(self.h, seq, img.ctypes.data, img.nbytes), "readback")
+        return img
+
+    def release(self, seq: int):
+        self._check(self.lib.rt_group_release(self.h, seq), "release")
+
+    def local_ray_counts_ptr(self) -> int:
+        ptr = C.c_void_p()
+        self._check(self.lib.rt_group_local_ray_counts(self.h, C.byref(ptr)), "local_ray_counts")
+        return ptr.value
+
+    def barrier(self):
+        self._check(self.lib.rt_group_barrier(self.h), "barrier")
+

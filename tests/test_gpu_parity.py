@@ -411,6 +411,59 @@ def test_stack_overflow_is_reported():
     assert "ERR" in out.stdout and "stack overflowed" in out.stdout, out.stdout + out.stderr
 
 
+def test_group_paths_on_one_rank():
+    """rt_group_* with a group of ONE rank (the 1-GPU box): NCCL comm, broadcast into the staging instance buffer + refit,
+    the device-frame path (flags, acquire, readback, release with slot reuse) and the shared page-locked host frame must
+    reproduce rt_render bit for bit, frame after frame."""
+    from ray_tracing_gallery_b200 import native
+
+    gpu = make_renderer()
+    s = build_scene(gpu, "default", 640, 360)
+    grp = native.Group(gpu, 1, 0, native.group_unique_id(), 640, 360)
+    p = s.params()
+    assert grp.partition(p) == 360 and p.strip_count == 0
+    seq = 0
+    for tick in range(1, 8):  # more frames than slots: release / reuse is exercised
+        rec = np.ascontiguousarray(s.animate(tick)[2:3])
+        grp.update_instances(2, 1, rec.ctypes.data, abi.RT_UPDATE_REFIT)
+        u = s.uniforms(frame_index=tick)
+        want = gpu.render(u, s.params(), want=("rgba8", "ray_counts"))
+        seq += 1
+        grp.render_device(seq, u, s.params())
+        got_dev = grp.readback(seq)
+        grp.release(seq)
+        seq += 1
+        grp.render_host(seq, u, s.params())
+        got_host, counts = grp.acquire_host(seq)
+        assert np.array_equal(got_dev, want["rgba8"]) and np.array_equal(got_host, want["rgba8"]), f"tick {tick}"
+        assert list(counts) == want["ray_counts"].tolist()
+        grp.release(seq)
+    grp.barrier()
+    grp.close(); gpu.close()
+
+
+def test_group_two_ranks_from_cpp():
+    """Two GPUs driven from the C++ host through the C ABI alone (host_cpp/rt_group_demo): NCCL broadcast of the animated
+    instance record, peer-memory device frame and shared host frame, each checked bit for bit against one GPU."""
+    import json
+    import os
+    import subprocess
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ray_tracing_gallery_b200", "host_cpp", "rt_group_demo")
+    if not os.path.exists(exe):
+        pytest.skip("rt_group_demo not built (__graft_entry__.build())")
+    for config, size in (("default", (640, 360)), ("c3", (1001, 563))):  # 563 rows: the last strip is partial
+        out = subprocess.run([exe, "--ranks", "2", "--config", config, "--width", str(size[0]), "--height", str(size[1]), "--frames", "6"],
+                             capture_output=True, text=True, timeout=400)
+        assert out.returncode == 0, out.stdout + out.stderr
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        assert line["ok"] and line["ranks"] == 2 and line["mismatched_frames"] == 0
+
+
 def test_show_heatmap_frame():
     """SURVEY 8f-3, Uniforms.show_heatmap (lib.rs:120-124, 174-186; heatmap.rs): the frame shows
     heatmap_temperature(clock ticks of the pixel's ray-gen invocation / heatmap_scale) + 1e-6 * colour.  The clock is the

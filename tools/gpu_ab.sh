@@ -9,7 +9,7 @@ for w in $WORKLOADS; do
   for v in $VARIANTS; do
     lib=$CSRC/libb200rt.so; [ "$v" != default ] && lib=$CSRC/libb200rt_$v.so
     steps=100; [ "$w" = c4 ] && steps=20; [ "$w" = c5 ] && steps=5
-    B200RT_LIB=$PWD/$lib timeout 200 python bench.py --workload $w --steps $steps --warmup 5 --no-cpu-baseline \
+    B200RT_LIB=$PWD/$lib timeout 200 python bench.py --workload $w --only $w --steps $steps --warmup 5 --no-cpu-baseline \
       > gpurun_out/ab_${TAG}_${v}_$w.json 2> gpurun_out/ab_${TAG}_${v}_$w.err
     python - "$v" "$w" gpurun_out/ab_${TAG}_${v}_$w.json <<'PY'
 import json, sys
