@@ -146,11 +146,17 @@ struct RtGroup {
     uint8_t* h_base = nullptr;
     size_t h_bytes = 0;
     bool h_registered = false;
-    uint8_t* d_local = nullptr;     // this rank's compact rows (host path)
+    // host path: two sets of {compact rows, ray counts}, so that the copy of frame k (on copy_stream, over this rank's PCIe
+    // link) overlaps the rendering of frame k+1
+    uint8_t* d_local[2] = {nullptr, nullptr};
     size_t d_local_bytes = 0;
-    uint64_t* d_counts = nullptr;   // {ray-gen segments, shadow rays} of this rank's share
+    uint64_t* d_counts_host[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+    uint64_t* d_counts = nullptr;   // {ray-gen segments, shadow rays} of this rank's share (device path)
     uint32_t* d_word = nullptr;     // scratch for barriers / the handle exchange (64 B)
-    uint8_t slot_is_host[RT_GROUP_FRAME_SLOTS] = {0, 0, 0, 0};
+
     DevFlags* flags() const { return reinterpret_cast<DevFlags*>(d_base); }
     uint8_t* dev_frame(uint64_t seq) const { return d_base + kDevHeader + (seq % RT_GROUP_FRAME_SLOTS) * frame_bytes; }
     ShmHeader* shm() const { return reinterpret_cast<ShmHeader*>(h_base); }
@@ -251,7 +257,13 @@ void rt_group_destroy(RtGroup* g) {
         if (g->h_registered) cudaHostUnregister(g->h_base);
         munmap(g->h_base, g->h_bytes);
     }
-    cudaFree(g->d_local); cudaFree(g->d_counts); cudaFree(g->d_word);
+    if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
+    for (int b = 0; b < 2; b++) {
+        cudaFree(g->d_local[b]); cudaFree(g->d_counts_host[b]);
+        if (g->rendered[b]) cudaEventDestroy(g->rendered[b]);
+        if (g->copied[b]) cudaEventDestroy(g->copied[b]);
+    }
+    cudaFree(g->d_counts); cudaFree(g->d_word);
     (void)cudaGetLastError();
     delete g;
 }
@@ -349,7 +361,13 @@ int rt_group_create(RtContext* ctx, int n_ranks, int rank, const void* id_bytes,
 
     const Strips s = strips_of(height, n_ranks, rank);
     grp->d_local_bytes = (size_t)(s.rows_own ? s.rows_own : 1u) * width * 4;
-    BCK(cudaMalloc(&grp->d_local, grp->d_local_bytes));
+    BCK(cudaStreamCreateWithFlags(&grp->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        BCK(cudaMalloc(&grp->d_local[b], grp->d_local_bytes));
+        BCK(cudaMalloc(&grp->d_counts_host[b], 16));
+        BCK(cudaEventCreateWithFlags(&grp->rendered[b], cudaEventDisableTiming));
+        BCK(cudaEventCreateWithFlags(&grp->copied[b], cudaEventDisableTiming));
+    }
 #undef BCK
     *out = grp;
     return RT_OK;
@@ -413,7 +431,7 @@ int rt_group_render_device(RtGroup* g, uint64_t seq, const RtUniforms* u, const 
     if (rc) return gfail(g, rc, std::string("rt_group_render_device: ") + rt_last_error(g->ctx));
     k_group_signal<<<1, 1, 0, st>>>(&f->arrived[g->rank], (uint32_t)seq);
     note_launch();
-    if (g->rank == 0) g->slot_is_host[seq % RT_GROUP_FRAME_SLOTS] = 0;
+
     GCK(cudaGetLastError());
     return RT_OK;
 }
@@ -447,26 +465,32 @@ int rt_group_render_host(RtGroup* g, uint64_t seq, const RtUniforms* u, const Rt
     RtRenderParams p = *params;
     rt_group_partition(g, &p);
     p.flags &= ~(uint32_t)RT_RENDER_OUTPUT_IMAGE_ROWS;
+    const int b2 = (int)(seq & 1);
+    if (g->copy_pending[b2]) GCK(cudaStreamWaitEvent(st, g->copied[b2], 0));  // the set's previous frame has left the device
     RtFrameOutputs out;
     memset(&out, 0, sizeof(out));
-    out.rgba8 = g->d_local;
-    out.ray_counts = g->d_counts;
+    out.rgba8 = g->d_local[b2];
+    out.ray_counts = g->d_counts_host[b2];
     int rc = rt_render_device(g->ctx, u, &p, &out);
     if (rc) return gfail(g, rc, std::string("rt_group_render_host: ") + rt_last_error(g->ctx));
-    // this rank's strips -> their rows of the shared host frame, over this rank's own PCIe link
+    GCK(cudaEventRecord(g->rendered[b2], st));
+    // this rank's strips -> their rows of the shared host frame, over this rank's own PCIe link, on the copy stream
+    cudaStream_t cs = g->copy_stream;
+    GCK(cudaStreamWaitEvent(cs, g->rendered[b2], 0));
     const Strips s = strips_of(g->height, g->n, g->rank);
     const size_t strip_bytes = (size_t)RT_GROUP_STRIP_ROWS * g->width * 4;
     uint8_t* dst = g->host_frame(seq) + (size_t)g->rank * strip_bytes;
     const uint32_t full = s.own - ((s.owns_last && s.rows_last < RT_GROUP_STRIP_ROWS) ? 1u : 0u);
-    if (full) GCK(cudaMemcpy2DAsync(dst, strip_bytes * g->n, g->d_local, strip_bytes, strip_bytes, full, cudaMemcpyDeviceToHost, st));
+    if (full) GCK(cudaMemcpy2DAsync(dst, strip_bytes * g->n, g->d_local[b2], strip_bytes, strip_bytes, full, cudaMemcpyDeviceToHost, cs));
     if (full < s.own)
-        GCK(cudaMemcpyAsync(dst + (size_t)full * strip_bytes * g->n, g->d_local + (size_t)full * strip_bytes, (size_t)s.rows_last * g->width * 4,
-                            cudaMemcpyDeviceToHost, st));
-    GCK(cudaMemcpyAsync(&h->ray_counts[seq % RT_GROUP_FRAME_SLOTS][g->rank][0], g->d_counts, 16, cudaMemcpyDeviceToHost, st));
+        GCK(cudaMemcpyAsync(dst + (size_t)full * strip_bytes * g->n, g->d_local[b2] + (size_t)full * strip_bytes, (size_t)s.rows_last * g->width * 4,
+                            cudaMemcpyDeviceToHost, cs));
+    GCK(cudaMemcpyAsync(&h->ray_counts[seq % RT_GROUP_FRAME_SLOTS][g->rank][0], g->d_counts_host[b2], 16, cudaMemcpyDeviceToHost, cs));
     Publish* pub = new (std::nothrow) Publish{h, g->rank, seq};
     if (!pub) return gfail(g, RT_ERR_CUDA, "rt_group_render_host: out of host memory");
-    GCK(cudaLaunchHostFunc(st, publish_arrival, pub));
-    if (g->rank == 0) g->slot_is_host[seq % RT_GROUP_FRAME_SLOTS] = 1;
+    GCK(cudaLaunchHostFunc(cs, publish_arrival, pub));
+    GCK(cudaEventRecord(g->copied[b2], cs));
+    g->copy_pending[b2] = true;
     return RT_OK;
 }
 
@@ -496,14 +520,14 @@ int rt_group_acquire_host(RtGroup* g, uint64_t seq, uint32_t timeout_ms, const u
 int rt_group_release(RtGroup* g, uint64_t seq) {
     if (!g) return RT_ERR_INVALID_ARGUMENT;
     if (g->rank != 0) return gfail(g, RT_ERR_INVALID_ARGUMENT, "rt_group_release: rank 0 owns the frame");
-    if (g->slot_is_host[seq % RT_GROUP_FRAME_SLOTS]) {
-        g->shm()->released.store(seq, std::memory_order_release);
-    } else {
-        GCK(cudaSetDevice(g->device));
-        k_group_signal<<<1, 1, 0, internal_stream(g->ctx)>>>(&g->flags()->released, (uint32_t)seq);
-        note_launch();
-        GCK(cudaGetLastError());
-    }
+    // Frames are numbered across both paths and released in order, so both "released" words advance together: the host
+    // word at once (a frame of the device path never occupied a host slot), the device word in stream order behind
+    // whatever rank 0 enqueued to consume the frame.
+    g->shm()->released.store(seq, std::memory_order_release);
+    GCK(cudaSetDevice(g->device));
+    k_group_signal<<<1, 1, 0, internal_stream(g->ctx)>>>(&g->flags()->released, (uint32_t)seq);
+    note_launch();
+    GCK(cudaGetLastError());
     return RT_OK;
 }
 
@@ -531,6 +555,7 @@ int rt_group_local_ray_counts(RtGroup* g, uint64_t** out) {
 int rt_group_barrier(RtGroup* g) {
     if (!g) return RT_ERR_INVALID_ARGUMENT;
     GCK(cudaSetDevice(g->device));
+    if (g->copy_stream) GCK(cudaStreamSynchronize(g->copy_stream));
     if (g->n > 1) {
         int rc = barrier(g);
         if (rc) return rc;

@@ -216,6 +216,7 @@ class Group:
             msg = self.lib.rt_group_last_error(None)
             raise RtError(f"rt_group_create failed ({rc}): {msg.decode() if msg else ''}")
         self.h = h
+        self._views = {}
 
     def _check(self, rc, what):
         if rc != 0:
@@ -253,8 +254,11 @@ class Group:
         ptr = C.c_void_p()
         counts = (C.c_uint64 * 2)()
         self._check(self.lib.rt_group_acquire_host(self.h, seq, timeout_ms, C.byref(ptr), counts), "acquire_host")
-        buf = (C.c_uint8 * (self.width * self.height * 4)).from_address(ptr.value)
-        return np.frombuffer(buf, np.uint8).reshape(self.height, self.width, 4), (int(counts[0]), int(counts[1]))
+        view = self._views.get(ptr.value)
+        if view is None:  # one numpy view per frame slot of the shared segment
+            buf = (C.c_uint8 * (self.width * self.height * 4)).from_address(ptr.value)
+            view = self._views[ptr.value] = np.frombuffer(buf, np.uint8).reshape(self.height, self.width, 4)
+        return view, (int(counts[0]), int(counts[1]))
 
     def readback(self, seq: int) -> np.ndarray:
         """Rank 0: wait for frame `seq` of the device path and copy it to host memory."""
