@@ -187,6 +187,55 @@ struct Sun {
     }
 };
 
+// ------------------------------------------------------------------------------------------ per-tick control integration
+// `KbdState`, `camera_velocity`, `sun_velocity` and the Event::MainEventsCleared block of the reference (src/main.rs:845-910).
+struct KbdState {
+    bool forward = false, back = false, left = false, right = false, sun_up = false, sun_down = false, sun_cw = false, sun_ccw = false;
+};
+struct Controls {
+    float camera_velocity[3] = {0.0f, 0.0f, 0.0f};
+    float sun_velocity[2] = {0.0f, 0.0f};
+};
+inline void integrate_controls(Camera& camera, Sun& sun, Controls& ctl, const KbdState& kbd) {
+    {
+        const float acc = 0.005f, vmax = 0.2f;
+        float lv[3] = {0.0f, 0.0f, 0.0f};
+        const float cp = (float)std::cos((double)camera.pitch), sp = (float)std::sin((double)camera.pitch);
+        if (kbd.forward) { lv[2] -= acc * cp; lv[1] += acc * sp; }
+        if (kbd.back) { lv[2] += acc * cp; lv[1] -= acc * sp; }
+        if (kbd.left) lv[0] -= acc;
+        if (kbd.right) lv[0] += acc;
+        // Mat3::from_rotation_y(yaw): columns (c,0,-s), (0,1,0), (s,0,c)
+        const float s = (float)std::sin((double)camera.yaw), c = (float)std::cos((double)camera.yaw);
+        const float wv[3] = {c * lv[0] + s * lv[2], lv[1], -s * lv[0] + c * lv[2]};
+        for (int k = 0; k < 3; k++) ctl.camera_velocity[k] += wv[k];
+        float* v = ctl.camera_velocity;
+        const float mag = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (mag > vmax) { const float f = std::fmin(mag, vmax) / mag; for (int k = 0; k < 3; k++) v[k] *= f; }
+        for (int k = 0; k < 3; k++) { camera.eye[k] += v[k]; v[k] *= 0.9f; }
+    }
+    {
+        const float acc = 0.002f, vmax = 0.05f, half_pi = (float)(3.14159265358979323846 / 2.0);
+        float* v = ctl.sun_velocity;
+        if (kbd.sun_up) v[1] += acc;
+        if (kbd.sun_down) v[1] -= acc;
+        if (kbd.sun_cw) v[0] += acc;
+        if (kbd.sun_ccw) v[0] -= acc;
+        const float mag = std::sqrt(v[0] * v[0] + v[1] * v[1]);
+        if (mag > vmax) { const float f = std::fmin(mag, vmax) / mag; v[0] *= f; v[1] *= f; }
+        sun.yaw -= v[0];
+        sun.pitch = std::fmax(std::fmin(sun.pitch + v[1], half_pi), 0.0f);
+        v[0] *= 0.95f; v[1] *= 0.95f;
+    }
+}
+// the fixed key schedule of headless animated runs (scene.py scripted_keys)
+inline KbdState scripted_keys(uint32_t tick) {
+    KbdState k;
+    k.forward = tick < 20; k.right = tick >= 10 && tick < 30; k.sun_cw = tick >= 20 && tick < 40; k.sun_up = tick >= 30 && tick < 45;
+    k.back = tick >= 40 && tick < 50; k.left = tick >= 50 && tick < 55; k.sun_ccw = tick >= 45 && tick < 50; k.sun_down = tick >= 50 && tick < 60;
+    return k;
+}
+
 inline RtUniforms make_uniforms(const Camera& cam, const Sun& sun, uint32_t width, uint32_t height, float sun_radius, uint32_t frame_index) {
     RtUniforms u;
     std::memset(&u, 0, sizeof(u));

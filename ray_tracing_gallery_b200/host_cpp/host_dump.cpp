@@ -4,6 +4,7 @@
 //   host_dump model <file.glb> <fallback_index> <first_image_index> <out.bin>
 //   host_dump scene <config> <assets_dir> <out.bin> [width height]
 //   host_dump png <file.png> <out.bin>
+//   host_dump controls <ticks> <out.bin>      (tag 6000: per tick {eye[3], pitch, yaw, sun pitch, sun yaw} as 7 floats)
 // Section = u32 tag, u64 byte count, payload.  Tags: 1 positions, 2 normals, 3 uvs, 100+g geometry header
 // {opaque, diffuse, metal-rough, normal map}, 200+g indices, 1000+i image header {w, h, format, linear}, 2000+i texels,
 // 5000 instances (64 B each), 5001 uniforms (176 B), 5002 {width, height, shadow_rays, max_segments}.
@@ -72,6 +73,18 @@ int main(int argc, char** argv) {
             uint32_t hdr[4] = {im.width, im.height, 0, 0};
             section(1000, hdr, sizeof(hdr));
             section(2000, im.texels.data(), im.texels.size());
+        } else if (argc >= 4 && std::string(argv[1]) == "controls") {
+            g_out = std::fopen(argv[3], "wb");
+            Camera cam;
+            Sun sun;
+            Controls ctl;
+            std::vector<float> rows;
+            for (uint32_t t = 0; t < (uint32_t)std::atoi(argv[2]); t++) {
+                integrate_controls(cam, sun, ctl, scripted_keys(t));
+                const float r[7] = {cam.eye[0], cam.eye[1], cam.eye[2], cam.pitch, cam.yaw, sun.pitch, sun.yaw};
+                rows.insert(rows.end(), r, r + 7);
+            }
+            section(6000, rows.data(), rows.size() * 4);
         } else if (argc >= 5 && std::string(argv[1]) == "scene") {
             g_out = std::fopen(argv[4], "wb");
             Backend be;

@@ -144,6 +144,79 @@ def make_uniforms(camera: Camera, sun: Sun, width: int, height: int, sun_radius:
     return u
 
 
+# ----------------------------------------------------------------------------- the reference's per-tick control integration
+@dataclass
+class KbdState:
+    """`KbdState` of the reference (src/main.rs: the W/S/A/D and arrow-key flags set by the KeyboardInput events)."""
+
+    forward: bool = False
+    back: bool = False
+    left: bool = False
+    right: bool = False
+    sun_up: bool = False
+    sun_down: bool = False
+    sun_cw: bool = False
+    sun_ccw: bool = False
+
+
+@dataclass
+class Controls:
+    """Camera and sun velocities carried from tick to tick (`camera_velocity`, `sun_velocity`, src/main.rs:600-610)."""
+
+    camera_velocity: np.ndarray = field(default_factory=lambda: np.zeros(3, F))
+    sun_velocity: np.ndarray = field(default_factory=lambda: np.zeros(2, F))
+
+
+def integrate_controls(camera: Camera, sun: Sun, ctl: Controls, kbd: KbdState):
+    """One `Event::MainEventsCleared` tick of the reference (src/main.rs:845-910), float32 like ultraviolet:
+    acceleration 0.005 along the camera's local axes (forward follows the pitch), rotated by `Mat3::from_rotation_y(yaw)`,
+    speed clamped to 0.2, eye += velocity, velocity *= 0.9; sun: acceleration 0.002, speed clamped to 0.05,
+    yaw -= v.x, pitch = clamp(pitch + v.y, 0, pi/2), velocity *= 0.95."""
+    acc, vmax = F(0.005), F(0.2)
+    lv = np.zeros(3, F)
+    cp, sp = F(math.cos(F(camera.pitch))), F(math.sin(F(camera.pitch)))
+    if kbd.forward:
+        lv[2] -= acc * cp
+        lv[1] += acc * sp
+    if kbd.back:
+        lv[2] += acc * cp
+        lv[1] -= acc * sp
+    if kbd.left:
+        lv[0] -= acc
+    if kbd.right:
+        lv[0] += acc
+    ctl.camera_velocity = (ctl.camera_velocity + (mat_rotation_y(camera.yaw)[:3, :3] @ lv).astype(F)).astype(F)
+    mag = F(np.sqrt(np.sum(ctl.camera_velocity * ctl.camera_velocity, dtype=F)))
+    if mag > vmax:
+        ctl.camera_velocity = (ctl.camera_velocity * (min(mag, vmax) / mag)).astype(F)
+    camera.eye = tuple(float(v) for v in (np.asarray(camera.eye, F) + ctl.camera_velocity).astype(F))
+    ctl.camera_velocity = (ctl.camera_velocity * F(0.9)).astype(F)
+
+    acc, vmax = F(0.002), F(0.05)
+    sv = ctl.sun_velocity.copy()
+    if kbd.sun_up:
+        sv[1] += acc
+    if kbd.sun_down:
+        sv[1] -= acc
+    if kbd.sun_cw:
+        sv[0] += acc
+    if kbd.sun_ccw:
+        sv[0] -= acc
+    mag = F(np.sqrt(np.sum(sv * sv, dtype=F)))
+    if mag > vmax:
+        sv = (sv * (min(mag, vmax) / mag)).astype(F)
+    sun.yaw = float(F(sun.yaw) - sv[0])
+    sun.pitch = float(max(min(F(sun.pitch) + sv[1], F(math.pi / 2.0)), F(0.0)))
+    ctl.sun_velocity = (sv * F(0.95)).astype(F)
+
+
+def scripted_keys(tick: int) -> KbdState:
+    """A fixed key schedule for headless animated runs (rt_demo --animate, tests): walk forward, strafe right while the sun
+    turns clockwise and rises, then back off."""
+    return KbdState(forward=tick < 20, right=10 <= tick < 30, sun_cw=20 <= tick < 40, sun_up=30 <= tick < 45, back=40 <= tick < 50,
+                    left=50 <= tick < 55, sun_ccw=45 <= tick < 50, sun_down=50 <= tick < 60)
+
+
 # ----------------------------------------------------------------------------- seeded streams
 def hash_uniform(seed: int, stream: int, n: int) -> np.ndarray:
     """n float64 values in [0,1): splitmix64 over the counter (seed, stream, i)."""

@@ -150,6 +150,46 @@ def test_cpp_png_decoder_rgb_colour_key_and_bad_depth(host_dump, tmp_path):
         assert r.returncode not in (0, -8, -11), (depth, ctype, r.returncode)  # an error exit, not SIGFPE / SIGSEGV
 
 
+def test_control_integration_matches_the_python_host_and_float64(host_dump, tmp_path):
+    """`Event::MainEventsCleared` of the reference (src/main.rs:845-910): camera / sun velocity integration over the fixed key
+    schedule — the C++ host against the Python host tick for tick, and the Python host against a float64 restatement."""
+    import math
+
+    from ray_tracing_gallery_b200.scene import Camera, Controls, Sun, integrate_controls, scripted_keys
+
+    out = str(tmp_path / "ctl.bin")
+    ticks = 70
+    subprocess.check_call([host_dump, "controls", str(ticks), out])
+    cpp = np.frombuffer(read_sections(out)[6000], np.float32).reshape(ticks, 7)
+    cam, sun, ctl = Camera(), Sun(), Controls()
+    eye, pitch, yaw, sp, sy = np.array([0.0, 2.0, -5.0]), 0.0, math.pi, 0.5, 1.0   # float64 twin
+    cv, sv = np.zeros(3), np.zeros(2)
+    for t in range(ticks):
+        k = scripted_keys(t)
+        integrate_controls(cam, sun, ctl, k)
+        got = np.array([*cam.eye, cam.pitch, cam.yaw, sun.pitch, sun.yaw])
+        assert np.allclose(cpp[t], got, rtol=2e-6, atol=2e-6), (t, cpp[t], got)
+        lv = np.zeros(3)
+        if k.forward: lv += (0, 0.005 * math.sin(pitch), -0.005 * math.cos(pitch))
+        if k.back: lv += (0, -0.005 * math.sin(pitch), 0.005 * math.cos(pitch))
+        if k.left: lv[0] -= 0.005
+        if k.right: lv[0] += 0.005
+        s, c = math.sin(yaw), math.cos(yaw)
+        cv += np.array([c * lv[0] + s * lv[2], lv[1], -s * lv[0] + c * lv[2]])
+        m = np.linalg.norm(cv)
+        if m > 0.2: cv *= 0.2 / m
+        eye = eye + cv
+        cv *= 0.9
+        sv += np.array([(0.002 if k.sun_cw else 0) - (0.002 if k.sun_ccw else 0), (0.002 if k.sun_up else 0) - (0.002 if k.sun_down else 0)])
+        m = np.linalg.norm(sv)
+        if m > 0.05: sv *= 0.05 / m
+        sy -= sv[0]
+        sp = max(min(sp + sv[1], math.pi / 2), 0.0)
+        sv *= 0.95
+        assert np.allclose(got, [*eye, pitch, yaw, sp, sy], rtol=1e-4, atol=1e-4), t
+    assert abs(cam.eye[2] + 5.0) > 0.5 and abs(sun.yaw - 1.0) > 0.2  # the schedule really moved camera and sun
+
+
 class Recorder:
     """The Python twin of host_dump's recording backend."""
 
@@ -237,3 +277,36 @@ def test_rt_demo_frame_loop(host_dump, tmp_path):
     want = gpu.render(s.uniforms(frame_index=6), s.params(), want=("rgba8",))["rgba8"][..., :3]
     gpu.close()
     assert np.mean(np.abs(img.astype(int) - want.astype(int)).max(axis=2) <= 1) >= 0.999
+
+
+@pytest.mark.gpu
+def test_rt_demo_animated_run_matches_the_python_host(host_dump, tmp_path):
+    """rt_demo --animate: the reference's whole per-tick loop from C++ (src/main.rs:845-948, src/scene.rs:162-204): control
+    integration from the key schedule, lain's one-record update + in-place TLAS refit, frame_index + 1, two frames in
+    flight.  Its last frame must equal the frame the Python host renders after the same ticks."""
+    import json
+
+    from conftest import make_renderer
+    from ray_tracing_gallery_b200 import abi
+    from ray_tracing_gallery_b200.scene import LAIN_INSTANCE, Controls, integrate_controls, scripted_keys
+
+    frames = 24
+    ppm = str(tmp_path / "anim.ppm")
+    r = subprocess.run([os.path.join(HOST_DIR, "rt_demo"), "--config", "default", "--width", "640", "--height", "360", "--frames", str(frames), "--animate",
+                        "--out", ppm], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["animated"] and line["frames"] == frames
+    data = open(ppm, "rb").read()
+    img = np.frombuffer(data[len(b"P6\n640 360\n255\n"):], np.uint8).reshape(360, 640, 3)
+    gpu = make_renderer()
+    s = build_scene(gpu, "default", 640, 360)
+    ctl = Controls()
+    for k in range(frames):
+        integrate_controls(s.camera, s.sun, ctl, scripted_keys(k))
+    assert np.allclose(line["eye"], s.camera.eye, atol=2e-4) and np.allclose(line["sun"], [s.sun.pitch, s.sun.yaw], atol=2e-4)
+    gpu.update_instances(LAIN_INSTANCE, s.animate(frames)[LAIN_INSTANCE:LAIN_INSTANCE + 1])
+    gpu.update_tlas(abi.RT_UPDATE_REFIT)
+    want = gpu.render(s.uniforms(frame_index=frames), s.params(), want=("rgba8",))["rgba8"][..., :3]
+    gpu.close()
+    assert np.mean(np.abs(img.astype(int) - want.astype(int)).max(axis=2) <= 1) >= 0.995
