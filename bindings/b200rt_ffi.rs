@@ -25,6 +25,7 @@ pub const RT_GROUP_ID_BYTES: usize = 128;
 pub const RT_GROUP_STRIP_ROWS: u32 = 8;
 pub const RT_GROUP_MAX_RANKS: usize = 16;
 pub const RT_GROUP_FRAME_SLOTS: u64 = 4;
+pub const RT_GROUP_BUILD_FORCE_SHARDED: u32 = 1;
 
 pub const RT_OK: c_int = 0;
 pub const RT_ERR_INVALID_ARGUMENT: c_int = -1;
@@ -158,6 +159,7 @@ extern "C" {
     pub fn rt_group_update_instances(group: *mut RtGroup, root: c_int, first: u32, count: u32, host_records: *const AccelerationStructureInstance,
                                      mode: u32) -> c_int; // ncclBroadcast into the TLAS builder's input, then update_tlas on every rank
     pub fn rt_group_update_instances_device(group: *mut RtGroup, root: c_int, first: u32, count: u32, device_records: *const c_void, mode: u32) -> c_int;
+    pub fn rt_group_build_tlas(group: *mut RtGroup, root: c_int, host_records: *const AccelerationStructureInstance, count: u32, flags: u32) -> c_int; // sharded build_tlas
     pub fn rt_group_render_device(group: *mut RtGroup, seq: u64, uniforms: *const Uniforms, params: *const RtRenderParams) -> c_int;
     pub fn rt_group_render_host(group: *mut RtGroup, seq: u64, uniforms: *const Uniforms, params: *const RtRenderParams) -> c_int;
     pub fn rt_group_acquire_device(group: *mut RtGroup, seq: u64, out_device_rgba8: *mut *mut u8) -> c_int;

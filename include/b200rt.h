@@ -276,6 +276,16 @@ int  rt_group_update_instances(RtGroup* group, int root, uint32_t first, uint32_
 int  rt_group_update_instances_device(RtGroup* group, int root, uint32_t first, uint32_t count, const void* device_records,
                                       uint32_t mode /* RtUpdateMode */);
 
+/* All ranks, collectively: build_tlas for a multi-GPU box (src/util_functions.rs:453-510), SHARDED.  The root's
+ * `count` records are broadcast; every rank computes the Morton keys, the ranks agree on n_ranks contiguous key ranges of
+ * equal population, each rank builds the wide BVH of ITS range only (1/N of the sort, hierarchy, SAH collapse), the
+ * treelets are exchanged over NVLink (NCCL broadcasts of exactly the nodes in use) and every rank puts the same top node
+ * over them.  Frames do not depend on topology (closest hit + tie rule), so they equal those of rt_build_tlas bit for
+ * bit; later rt_group_update_instances refits work on the assembled tree.  Falls back to the replicated build for more
+ * than 8 ranks or fewer than 1024 instances per rank, unless RT_GROUP_BUILD_FORCE_SHARDED is set (tests: one rank). */
+enum { RT_GROUP_BUILD_FORCE_SHARDED = 1u };
+int  rt_group_build_tlas(RtGroup* group, int root, const RtInstance* host_records, uint32_t count, uint32_t flags);
+
 /* All ranks: enqueue frame number `seq` (1, 2, 3 ... the same on every rank).  This rank renders its strips; `params`
  * carries width / height / max_segments / shadow_rays / pipeline / flags, the strip fields are filled by the group.
  *   rt_group_render_device: rows are stored into rank 0's DEVICE frame (slot seq % RT_GROUP_FRAME_SLOTS) over NVLink

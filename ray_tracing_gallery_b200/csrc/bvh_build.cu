@@ -587,6 +587,77 @@ __global__ void k_refit(RefitArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------------ sharded TLAS builds
+__device__ __forceinline__ uint32_t shard_bin(uint64_t key) { return (uint32_t)(key >> (63u - RT_SHARD_BITS)); }
+
+__global__ void k_shard_hist(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* hist) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&hist[shard_bin(keys[i])], 1u);
+}
+// bin boundaries b[0..n_shards]: shard r owns bins [b[r], b[r+1]); the boundary goes where the running population first
+// reaches r * n / n_shards.  One thread: 32 k bins, once per build.
+__global__ void k_shard_split(const uint32_t* __restrict__ hist, uint32_t n, uint32_t n_shards, uint32_t* bounds, uint32_t* counts) {
+    uint32_t r = 1, run = 0, last = 0;
+    bounds[0] = 0;
+    for (uint32_t b = 0; b < (1u << RT_SHARD_BITS); b++) {
+        while (r < n_shards && run >= (uint32_t)(((unsigned long long)n * r) / n_shards)) {
+            bounds[r] = b;
+            counts[r - 1] = run - last;
+            last = run;
+            r++;
+        }
+        run += hist[b];
+    }
+    while (r < n_shards) { bounds[r] = 1u << RT_SHARD_BITS; counts[r - 1] = run - last; last = run; r++; }
+    bounds[n_shards] = 1u << RT_SHARD_BITS;
+    counts[n_shards - 1] = run - last;
+    bounds[33] = 0;  // select cursor
+}
+__global__ void k_shard_select(const Aabb* __restrict__ boxes, const uint64_t* __restrict__ keys, uint32_t n, uint32_t* bounds, uint32_t shard,
+                               Aabb* sel_boxes, uint32_t* sel_index) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t bin = shard_bin(keys[i]);
+    if (bin < bounds[shard] || bin >= bounds[shard + 1]) return;
+    const uint32_t pos = atomicAdd(&bounds[33], 1u);
+    sel_boxes[pos] = boxes[i];
+    sel_index[pos] = i;
+}
+__global__ void k_map_order(const uint32_t* __restrict__ treelet_order, const uint32_t* __restrict__ sel_index, uint32_t count, uint32_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = sel_index[treelet_order[i]];
+}
+__global__ void k_treelet_rebase(Node8* nodes, uint32_t root_at, uint32_t rest_at, uint32_t count, uint32_t slot) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // treelet-local node number
+    if (j >= count) return;
+    Node8* nd = &nodes[j == 0 ? root_at : rest_at + (j - 1)];
+    const uint32_t delta = rest_at - 1u;  // local index l >= 1 lives at rest_at + l - 1
+    if (nd->imask) nd->child_base += delta;
+    if (j == 0) { nd->parent = 0u; nd->parent_slot = slot; }
+    else nd->parent = nd->parent == 0u ? root_at : nd->parent + delta;
+}
+__global__ void k_tlas_top(Node8* nodes, uint32_t k, uint32_t total_nodes, uint32_t* node_count) {
+    Node8 nd;
+    memset(&nd, 0, sizeof(nd));
+    Aabb sb[8];
+    uint32_t present = 0;
+    for (uint32_t s = 0; s < k && s < 8; s++) {
+        const Node8& c = nodes[1 + s];
+        for (int a = 0; a < 3; a++) { sb[s].lo[a] = c.lo[a]; sb[s].hi[a] = c.hi[a]; }
+        present |= 1u << s;
+        nd.meta[s] = 0xFF;
+    }
+    quantise_node(nd, sb, present);
+    nd.imask = (uint8_t)present;
+    nd.lmask = 0;
+    nd.child_base = 1;
+    nd.prim_base = 0;
+    nd.parent = 0xFFFFFFFFu;
+    nd.parent_slot = 0;
+    store_node(&nodes[0], nd);
+    if (node_count) *node_count = total_nodes;
+}
+
 template <typename T>
 T* carve(char*& p, size_t count) {
     uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255);
@@ -608,6 +679,7 @@ struct Scratch {
     int* task_node;
     uint32_t* task_parent;
     uint32_t* refit_counters;
+    uint32_t* shard_hist;   // (1 << RT_SHARD_BITS) bins + 64 words: shard bin boundaries [0..32], select cursor [33]
     void* cub_temp;
 };
 
@@ -633,6 +705,7 @@ size_t layout(char* base, uint32_t n, size_t cub_bytes, Scratch& s) {
     s.task_node = carve<int>(p, maxw);
     s.task_parent = carve<uint32_t>(p, maxw);
     s.refit_counters = carve<uint32_t>(p, maxw);
+    s.shard_hist = carve<uint32_t>(p, (1u << RT_SHARD_BITS) + 64);
     s.cub_temp = carve<char>(p, cub_bytes);
     return (size_t)(p - base) + 256;
 }
@@ -749,6 +822,43 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
         }
     }
     if (d_node_count && !count_written) { k_copy_u32<<<1, 1, 0, stream>>>(&s.state[ST_WIDE_COUNT], d_node_count); note_launch(); }
+    return cudaGetLastError();
+}
+
+cudaError_t BvhBuilder::shard_select(const Aabb* d_boxes, uint32_t n, uint32_t n_shards, uint32_t shard, Aabb* d_sel_boxes, uint32_t* d_sel_index,
+                                     uint32_t* d_counts, cudaStream_t stream) {
+    if (n_shards < 1 || n_shards > 32 || shard >= n_shards) return cudaErrorInvalidValue;
+    cudaError_t e = reserve(n);
+    if (e != cudaSuccess) return e;
+    Scratch s;
+    layout(static_cast<char*>(scratch_), cap_, cub_bytes_, s);
+    const int TB = 256;
+    const uint32_t blocks = (n + TB - 1) / TB;
+    k_init_state<<<1, 32, 0, stream>>>(s.bounds, s.state, s.task_node, s.task_parent, 0);
+    cudaMemsetAsync(s.shard_hist, 0, sizeof(uint32_t) * ((1u << RT_SHARD_BITS) + 64), stream);
+    if (n) {
+        k_centroid_bounds<<<blocks, TB, 0, stream>>>(d_boxes, n, s.bounds);
+        k_morton<<<blocks, TB, 0, stream>>>(d_boxes, n, s.bounds, 0u, s.keys_in, s.vals_in);
+        k_shard_hist<<<blocks, TB, 0, stream>>>(s.keys_in, n, s.shard_hist);
+    }
+    uint32_t* bounds = s.shard_hist + (1u << RT_SHARD_BITS);
+    k_shard_split<<<1, 1, 0, stream>>>(s.shard_hist, n, n_shards, bounds, d_counts);
+    if (n) k_shard_select<<<blocks, TB, 0, stream>>>(d_boxes, s.keys_in, n, bounds, shard, d_sel_boxes, d_sel_index);
+    note_launch(n ? 6 : 2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_map_order(const uint32_t* treelet_order, const uint32_t* sel_index, uint32_t count, uint32_t* leaf_order_out, cudaStream_t stream) {
+    if (count) { k_map_order<<<(count + 255) / 256, 256, 0, stream>>>(treelet_order, sel_index, count, leaf_order_out); note_launch(); }
+    return cudaGetLastError();
+}
+cudaError_t launch_treelet_rebase(Node8* nodes, uint32_t root_at, uint32_t rest_at, uint32_t count, uint32_t slot, cudaStream_t stream) {
+    if (count) { k_treelet_rebase<<<(count + 255) / 256, 256, 0, stream>>>(nodes, root_at, rest_at, count, slot); note_launch(); }
+    return cudaGetLastError();
+}
+cudaError_t launch_tlas_top(Node8* nodes, uint32_t k, uint32_t total_nodes, uint32_t* d_node_count, cudaStream_t stream) {
+    k_tlas_top<<<1, 1, 0, stream>>>(nodes, k, total_nodes, d_node_count);
+    note_launch();
     return cudaGetLastError();
 }
 

@@ -37,6 +37,13 @@ public:
     cudaError_t refit(const Aabb* d_boxes_leaf_order, uint32_t n, Node8* nodes_pool, uint32_t node_offset,
                       uint32_t prim_offset, const uint32_t* d_node_count, uint32_t node_capacity, cudaStream_t stream);
 
+    // Sharded builds (rt_group_build_tlas): the 63-bit Morton keys of all n boxes, a histogram of their top RT_SHARD_BITS bits,
+    // `n_shards` contiguous key ranges of (nearly) equal population, and the boxes of range `shard` compacted into
+    // d_sel_boxes (any order) with their input indices in d_sel_index.  d_counts[n_shards] (device) receives every
+    // shard's population; identical on every GPU that runs this over the same boxes.
+    cudaError_t shard_select(const Aabb* d_boxes, uint32_t n, uint32_t n_shards, uint32_t shard, Aabb* d_sel_boxes, uint32_t* d_sel_index,
+                             uint32_t* d_counts, cudaStream_t stream);
+
 private:
     uint32_t cap_ = 0;
     void* scratch_ = nullptr;
@@ -45,5 +52,16 @@ private:
     int coop_blocks_ = 0;
     bool coop_ok_ = true;
 };
+
+// ---- assembling a TLAS from treelets built on different GPUs (bvh_build.cu)
+#define RT_SHARD_BITS 15u
+// leaf_order_out[i] = sel_index[treelet_order[i]]: treelet-local primitive numbers -> input primitive numbers
+cudaError_t launch_map_order(const uint32_t* treelet_order, const uint32_t* sel_index, uint32_t count, uint32_t* leaf_order_out, cudaStream_t stream);
+// A treelet arrives built at node offset 0: its root is stored at nodes[root_at], its other `count - 1` nodes at
+// nodes[rest_at ...] in their original order.  Child indices and parent links are moved accordingly; the root gets
+// parent 0 / parent_slot `slot`.
+cudaError_t launch_treelet_rebase(Node8* nodes, uint32_t root_at, uint32_t rest_at, uint32_t count, uint32_t slot, cudaStream_t stream);
+// nodes[0] = the top node over `k` treelet roots stored at nodes[1 .. k] (their exact bounds are read from the nodes).
+cudaError_t launch_tlas_top(Node8* nodes, uint32_t k, uint32_t total_nodes, uint32_t* d_node_count, cudaStream_t stream);
 
 }  // namespace b200rt

@@ -28,14 +28,18 @@
 #include <string>
 #include <thread>
 
+#include <vector>
+
+#include "context.h"
 #include "launch_count.h"
-#include "render.h"
 
 using namespace b200rt;
 
 namespace b200rt {
 // hooks into api.cu (not part of the C ABI)
 RtInstance* internal_stage_instances(RtContext* ctx, uint32_t first, uint32_t count);
+int internal_begin_full_build(RtContext* ctx, uint32_t count);
+int internal_build_tlas_replicated(RtContext* ctx);
 cudaStream_t internal_stream(RtContext* ctx);
 int internal_device(RtContext* ctx);
 }  // namespace b200rt
@@ -49,6 +53,9 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string& err) {
         if (handle) return true;
@@ -69,6 +76,9 @@ struct NcclApi {
         RT_NCCL_SYM(CommDestroy, "ncclCommDestroy")
         RT_NCCL_SYM(Broadcast, "ncclBroadcast")
         RT_NCCL_SYM(AllReduce, "ncclAllReduce")
+        RT_NCCL_SYM(AllGather, "ncclAllGather")
+        RT_NCCL_SYM(GroupStart, "ncclGroupStart")
+        RT_NCCL_SYM(GroupEnd, "ncclGroupEnd")
         RT_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef RT_NCCL_SYM
         return true;
@@ -408,6 +418,117 @@ int rt_group_update_instances(RtGroup* g, int root, uint32_t first, uint32_t cou
 }
 int rt_group_update_instances_device(RtGroup* g, int root, uint32_t first, uint32_t count, const void* device_records, uint32_t mode) {
     return group_update(g, root, first, count, device_records, cudaMemcpyDeviceToDevice, mode);
+}
+
+int rt_group_build_tlas(RtGroup* g, int root, const RtInstance* host_records, uint32_t count, uint32_t flags) {
+    if (!g) return RT_ERR_INVALID_ARGUMENT;
+    if (root < 0 || root >= g->n) return gfail(g, RT_ERR_INVALID_ARGUMENT, "rt_group_build_tlas: bad root");
+    if (g->rank == root && count && !host_records) return gfail(g, RT_ERR_INVALID_ARGUMENT, "rt_group_build_tlas: the root needs the records");
+    GCK(cudaSetDevice(g->device));
+    RtContext* ctx = g->ctx;
+    cudaStream_t st = ctx->stream;
+    const int N = g->n;
+    // ---- the records: root -> every rank, straight into the instance buffer of the set the build writes
+    int rc = internal_begin_full_build(ctx, count);
+    if (rc) return gfail(g, rc, std::string("rt_group_build_tlas: ") + rt_last_error(ctx));
+    RtContext::TlasSet& D = ctx->sets[ctx->cur];
+    if (count) {
+        if (g->rank == root) GCK(cudaMemcpyAsync(D.d_instances, host_records, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, st));
+        if (N > 1) GNCCL(g_nccl.Broadcast(D.d_instances, D.d_instances, sizeof(RtInstance) * (size_t)count, ncclUint8, root, g->comm, st));
+    }
+    const bool sharded = (flags & RT_GROUP_BUILD_FORCE_SHARDED) ? (N <= 8) : (N > 1 && N <= 8 && count >= 1024u * (uint32_t)N);
+    if (!sharded) {
+        rc = internal_build_tlas_replicated(ctx);
+        if (rc) return gfail(g, rc, std::string("rt_group_build_tlas: ") + rt_last_error(ctx));
+        GCK(cudaStreamSynchronize(st));
+        return RT_OK;
+    }
+    GCK(cudaEventRecord(ctx->ev[2], st));
+    // ---- every rank: traversal records + world boxes of ALL instances (cheap, and the keys need the boxes), then the shard
+    const uint32_t n = count;
+    GCK(launch_prepare_instances(D.d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), nullptr, ctx->d_inst_unsorted, ctx->d_inst_boxes, st));
+    Aabb* d_sel_boxes = nullptr;
+    uint32_t *d_sel_index = nullptr, *d_counts = nullptr, *d_treelet_order = nullptr, *d_cnt = nullptr;
+    Node8* d_treelet = nullptr;
+    auto cleanup = [&]() { cudaFree(d_sel_boxes); cudaFree(d_sel_index); cudaFree(d_counts); cudaFree(d_treelet_order); cudaFree(d_cnt); cudaFree(d_treelet); };
+#define SCK(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess) { (void)cudaGetLastError(); cleanup(); return gfail(g, RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } \
+    } while (0)
+#define SNCCL(call)                                                                                        \
+    do {                                                                                                   \
+        ncclResult_t _r = (call);                                                                          \
+        if (_r != ncclSuccess) { cleanup(); return gfail(g, RT_ERR_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(_r)); } \
+    } while (0)
+    SCK(cudaMalloc(&d_sel_boxes, sizeof(Aabb) * (size_t)(n ? n : 1)));
+    SCK(cudaMalloc(&d_sel_index, sizeof(uint32_t) * (size_t)(n ? n : 1)));
+    SCK(cudaMalloc(&d_counts, sizeof(uint32_t) * 64));
+    SCK(cudaMalloc(&d_cnt, sizeof(uint32_t) * 64));
+    SCK(ctx->builder.shard_select(ctx->d_inst_boxes, n, (uint32_t)N, (uint32_t)g->rank, d_sel_boxes, d_sel_index, d_counts, st));
+    uint32_t counts[32] = {0};
+    SCK(cudaMemcpyAsync(counts, d_counts, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    uint32_t first[33] = {0};
+    for (int r = 0; r < N; r++) first[r + 1] = first[r] + counts[r];
+    if (first[N] != n) { cleanup(); return gfail(g, RT_ERR_CUDA, "rt_group_build_tlas: shard populations do not add up"); }
+    // ---- this rank's treelet: the ordinary builder over its key range, leaf positions offset to its place in the global order
+    const uint32_t mine = counts[g->rank];
+    SCK(cudaMalloc(&d_treelet, sizeof(Node8) * (size_t)max_wide_nodes(mine)));
+    SCK(cudaMalloc(&d_treelet_order, sizeof(uint32_t) * (size_t)(mine ? mine : 1)));
+    uint32_t my_nodes = 0;
+    if (mine) {
+        SCK(ctx->builder.build(d_sel_boxes, mine, 1, d_treelet, 0, first[g->rank], d_treelet_order, d_cnt + 32, true, /*sah_collapse=*/true, st));
+        SCK(launch_map_order(d_treelet_order, d_sel_index, mine, D.d_leaf_order + first[g->rank], st));
+    } else {
+        SCK(cudaMemsetAsync(d_cnt + 32, 0, sizeof(uint32_t), st));
+    }
+    // ---- node counts of all treelets (each rank only knows its own, and only on the device)
+    if (N > 1) SNCCL(g_nccl.AllGather(d_cnt + 32, d_cnt, 1, ncclUint32, g->comm, st));
+    else SCK(cudaMemcpyAsync(d_cnt, d_cnt + 32, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    uint32_t node_counts[32] = {0};
+    SCK(cudaMemcpyAsync(node_counts, d_cnt, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    my_nodes = node_counts[g->rank];
+    // ---- layout: nodes[0] top, nodes[1..K] the roots of the K non-empty treelets, then each treelet's other nodes, compact
+    uint32_t K = 0, root_at[32], rest_at[32], cursor = 1;
+    for (int r = 0; r < N; r++) if (counts[r]) root_at[r] = 1 + K++;
+    cursor = 1 + K;
+    for (int r = 0; r < N; r++) { rest_at[r] = cursor; if (counts[r]) cursor += node_counts[r] - 1; }
+    const uint32_t total_nodes = cursor;
+    if (total_nodes > ctx->tlas_node_cap) { cleanup(); return gfail(g, RT_ERR_OUT_OF_RANGE, "rt_group_build_tlas: node pool too small for the assembled tree"); }
+    // ---- exchange over NVLink: exactly the nodes in use and the leaf-order ranges, one broadcast per treelet part
+    if (N > 1) SNCCL(g_nccl.GroupStart());
+    for (int r = 0; r < N; r++) {
+        if (!counts[r]) continue;
+        const bool me = r == g->rank;
+        if (N > 1) {
+            SNCCL(g_nccl.Broadcast(me ? (const void*)d_treelet : (const void*)(D.d_tlas_nodes + root_at[r]), D.d_tlas_nodes + root_at[r], sizeof(Node8), ncclUint8, r, g->comm, st));
+            if (node_counts[r] > 1)
+                SNCCL(g_nccl.Broadcast(me ? (const void*)(d_treelet + 1) : (const void*)(D.d_tlas_nodes + rest_at[r]), D.d_tlas_nodes + rest_at[r],
+                                       sizeof(Node8) * (size_t)(node_counts[r] - 1), ncclUint8, r, g->comm, st));
+            SNCCL(g_nccl.Broadcast(D.d_leaf_order + first[r], D.d_leaf_order + first[r], sizeof(uint32_t) * (size_t)counts[r], ncclUint8, r, g->comm, st));
+        } else {
+            SCK(cudaMemcpyAsync(D.d_tlas_nodes + root_at[r], d_treelet, sizeof(Node8), cudaMemcpyDeviceToDevice, st));
+            if (my_nodes > 1) SCK(cudaMemcpyAsync(D.d_tlas_nodes + rest_at[r], d_treelet + 1, sizeof(Node8) * (size_t)(my_nodes - 1), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (N > 1) SNCCL(g_nccl.GroupEnd());
+    // ---- every rank: move the links to the assembled layout, put the top node over the treelet roots, records into leaf order
+    uint32_t slot = 0;
+    for (int r = 0; r < N; r++)
+        if (counts[r]) SCK(launch_treelet_rebase(D.d_tlas_nodes, root_at[r], rest_at[r], node_counts[r], slot++, st));
+    SCK(launch_tlas_top(D.d_tlas_nodes, K, total_nodes, D.d_node_count, st));
+    SCK(launch_gather_instances(ctx->d_inst_unsorted, D.d_leaf_order, n, D.d_inst_rt, st));
+    SCK(cudaEventRecord(ctx->ev[3], st));
+    SCK(cudaStreamSynchronize(st));
+#undef SCK
+#undef SNCCL
+    cleanup();
+    ctx->tlas_timed = true;
+    ctx->tlas_built = true;
+    ctx->writes_since_build = 0;
+    return RT_OK;
 }
 
 int rt_group_render_device(RtGroup* g, uint64_t seq, const RtUniforms* u, const RtRenderParams* params) {

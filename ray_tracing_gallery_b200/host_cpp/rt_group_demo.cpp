@@ -2,6 +2,7 @@
 // this program): the multi-GPU seams of the reference's host — device creation (src/main.rs:157-204) and the per-frame
 // scene update (src/scene.rs:167-204) — as rt_group_create / rt_group_update_instances / rt_group_render_*.
 //   rt_group_demo [--ranks N] [--config c2|c3|default] [--width W] [--height H] [--frames F] [--lib path] [--assets dir]
+//                 [--sharded-build] [--instances N]
 // The parent starts one child process per GPU (rank r on CUDA device r).  Rank 0 makes the 128-byte group id and passes
 // it on through a file; from there on everything between the ranks is the library's business (NCCL broadcast of the
 // instance records, peer-memory frame on rank 0, shared page-locked host frame).  Every frame the animated instance record
@@ -30,6 +31,7 @@ struct GroupApi {
     const char* (*last_error)(const void*) = nullptr;
     uint32_t (*partition)(const void*, RtRenderParams*) = nullptr;
     int (*update_instances)(void*, int, uint32_t, uint32_t, const RtInstance*, uint32_t) = nullptr;
+    int (*build_tlas)(void*, int, const RtInstance*, uint32_t, uint32_t) = nullptr;
     int (*render_device)(void*, uint64_t, const RtUniforms*, const RtRenderParams*) = nullptr;
     int (*render_host)(void*, uint64_t, const RtUniforms*, const RtRenderParams*) = nullptr;
     int (*acquire_host)(void*, uint64_t, uint32_t, const uint8_t**, uint64_t*) = nullptr;
@@ -39,6 +41,7 @@ struct GroupApi {
     void bind_all(Backend& be) {
         be.bind(unique_id, "rt_group_unique_id"); be.bind(create, "rt_group_create"); be.bind(destroy, "rt_group_destroy");
         be.bind(last_error, "rt_group_last_error"); be.bind(partition, "rt_group_partition"); be.bind(update_instances, "rt_group_update_instances");
+        be.bind(build_tlas, "rt_group_build_tlas");
         be.bind(render_device, "rt_group_render_device"); be.bind(render_host, "rt_group_render_host"); be.bind(acquire_host, "rt_group_acquire_host");
         be.bind(readback, "rt_group_readback"); be.bind(release, "rt_group_release"); be.bind(barrier, "rt_group_barrier");
     }
@@ -50,7 +53,7 @@ static std::string dir_of(const std::string& path) {
 }
 
 static int run_rank(int rank, int ranks, const std::string& lib, const std::string& assets, const std::string& config, uint32_t width, uint32_t height,
-                    uint32_t frames, const std::string& id_file) {
+                    uint32_t frames, const std::string& id_file, bool sharded_build, uint32_t num_instances) {
     Backend be;
     GroupApi ga;
     void* group = nullptr;
@@ -63,7 +66,7 @@ static int run_rank(int rank, int ranks, const std::string& lib, const std::stri
         be.open_b200rt(lib, rank);
         ga.bind_all(be);
         Host host(be, assets);
-        SceneSetup s = build_scene(host, config, width, height);
+        SceneSetup s = build_scene(host, config, width, height, num_instances);
         // ---- the 128-byte id: rank 0 makes it, the others read it from the file
         unsigned char id[RT_GROUP_ID_BYTES];
         if (rank == 0) {
@@ -86,6 +89,21 @@ static int run_rank(int rank, int ranks, const std::string& lib, const std::stri
         const bool animated = s.instances.size() > 2;
         uint64_t seq = 0, rays_total = 0;
         uint32_t mismatched_frames = 0;
+        if (sharded_build) {
+            // build_tlas for the group: rank 0 hands over the records, every rank builds 1/N of the tree, the treelets
+            // are exchanged over NVLink.  The frame must not change: compare with the frame of the replicated tree built above.
+            std::vector<uint8_t> before(bytes), after(bytes);
+            RtUniforms u = s.uniforms(1);
+            RtFrameOutputs o = {before.data(), nullptr, nullptr, nullptr, nullptr};
+            be.check(be.render(be.ctx, &u, &p, &o), "render");
+            gcheck(ga.build_tlas(group, 0, rank == 0 ? s.instances.data() : nullptr, (uint32_t)s.instances.size(), 1u /* force sharded */), "rt_group_build_tlas");
+            o.rgba8 = after.data();
+            be.check(be.render(be.ctx, &u, &p, &o), "render");
+            if (std::memcmp(before.data(), after.data(), bytes) != 0) {
+                std::fprintf(stderr, "rank %d: the frame changed with the sharded TLAS\n", rank);
+                mismatched_frames++;
+            }
+        }
         auto t0 = std::chrono::steady_clock::now();
         for (uint32_t k = 0; k < frames; k++) {
             // DefaultScene::update + write_resources for the group: ONE 64-byte record from rank 0 to every rank, then refit
@@ -138,9 +156,9 @@ static int run_rank(int rank, int ranks, const std::string& lib, const std::stri
         double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (rank == 0)
             std::printf("{\"host\": \"c++\", \"ranks\": %d, \"config\": \"%s\", \"resolution\": \"%ux%u\", \"frames\": %u, \"rays\": %llu, \"seconds\": %.3f, "
-                        "\"instance_broadcast\": %s, \"mismatched_frames\": %u, \"ok\": %s}\n",
+                        "\"instance_broadcast\": %s, \"sharded_build\": %s, \"instances\": %zu, \"mismatched_frames\": %u, \"ok\": %s}\n",
                         ranks, config.c_str(), s.width, s.height, frames, (unsigned long long)rays_total, sec, animated ? "true" : "false",
-                        mismatched_frames, mismatched_frames == 0 ? "true" : "false");
+                        sharded_build ? "true" : "false", s.instances.size(), mismatched_frames, mismatched_frames == 0 ? "true" : "false");
         ga.destroy(group);
         be.close();
         return mismatched_frames == 0 ? 0 : 3;
@@ -153,8 +171,9 @@ static int run_rank(int rank, int ranks, const std::string& lib, const std::stri
 int main(int argc, char** argv) {
     std::string self = dir_of(argv[0]);
     std::string lib = self + "/../csrc/libb200rt.so", assets = self + "/../../assets", config = "default", id_file;
-    uint32_t width = 640, height = 360, frames = 4;
+    uint32_t width = 640, height = 360, frames = 4, num_instances = 0;
     int ranks = 2, rank = -1;
+    bool sharded_build = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string {
@@ -170,9 +189,11 @@ int main(int argc, char** argv) {
         else if (a == "--frames") frames = (uint32_t)std::atoi(next().c_str());
         else if (a == "--lib") lib = next();
         else if (a == "--assets") assets = next();
+        else if (a == "--sharded-build") sharded_build = true;
+        else if (a == "--instances") num_instances = (uint32_t)std::atoi(next().c_str());
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
-    if (rank >= 0) return run_rank(rank, ranks, lib, assets, config, width, height, frames, id_file);
+    if (rank >= 0) return run_rank(rank, ranks, lib, assets, config, width, height, frames, id_file, sharded_build, num_instances);
     // ---- parent: one fresh process per GPU (exec of this program with --rank r), bounded by an alarm
     char tmpl[] = "/tmp/b200rt_group_id_XXXXXX";
     int fd = mkstemp(tmpl);
@@ -184,7 +205,8 @@ int main(int argc, char** argv) {
         if (pid == 0) {
             std::vector<std::string> args = {argv[0], "--rank", std::to_string(r), "--ranks", std::to_string(ranks), "--id-file", id_file, "--config", config,
                                              "--width", std::to_string(width), "--height", std::to_string(height), "--frames", std::to_string(frames),
-                                             "--lib", lib, "--assets", assets};
+                                             "--lib", lib, "--assets", assets, "--instances", std::to_string(num_instances)};
+            if (sharded_build) args.push_back("--sharded-build");
             std::vector<char*> cargs;
             for (auto& s : args) cargs.push_back(const_cast<char*>(s.c_str()));
             cargs.push_back(nullptr);

@@ -24,7 +24,7 @@ EXPORTS = [
     "rt_wait_frame", "rt_render_device_slot", "rt_host_alloc", "rt_host_free", "rt_readback",
     "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_kernel_launches", "rt_version",
     "rt_group_unique_id", "rt_group_create", "rt_group_destroy", "rt_group_last_error", "rt_group_partition", "rt_group_update_instances",
-    "rt_group_update_instances_device",
+    "rt_group_update_instances_device", "rt_group_build_tlas",
     "rt_group_render_device", "rt_group_render_host", "rt_group_acquire_device", "rt_group_acquire_host", "rt_group_release",
     "rt_group_readback", "rt_group_local_ray_counts", "rt_group_barrier",
 ]
@@ -75,6 +75,7 @@ def load():
     lib.rt_group_partition.restype = u32
     lib.rt_group_update_instances.argtypes = [p, C.c_int, u32, u32, p, u32]
     lib.rt_group_update_instances_device.argtypes = [p, C.c_int, u32, u32, p, u32]
+    lib.rt_group_build_tlas.argtypes = [p, C.c_int, p, u32, u32]
     lib.rt_group_render_device.argtypes = [p, u64, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams)]
     lib.rt_group_render_host.argtypes = [p, u64, C.POINTER(abi.RtUniforms), C.POINTER(abi.RtRenderParams)]
     lib.rt_group_acquire_device.argtypes = [p, u64, C.POINTER(p)]
@@ -231,6 +232,14 @@ class Group:
     def partition(self, params=None) -> int:
         """Rows this rank renders; fills the strip fields of `params` when given."""
         return self.lib.rt_group_partition(self.h, C.byref(params) if params is not None else None)
+
+    def build_tlas(self, instances=None, count: int = 0, root: int = 0, force_sharded: bool = False):
+        """`rt_group_build_tlas`: the root passes the records (numpy, INSTANCE_DTYPE), the other ranks only `count`."""
+        ptr = 0
+        if instances is not None:
+            a = np.ascontiguousarray(instances)
+            ptr, count = a.ctypes.data, len(a)
+        self._check(self.lib.rt_group_build_tlas(self.h, root, ptr or None, count, 1 if force_sharded else 0), "build_tlas")
 
     def update_instances(self, first: int, count: int, host_ptr: int, mode: int, root: int = 0):
         self._check(self.lib.rt_group_update_instances(self.h, root, first, count, host_ptr or None, mode), "update_instances")

@@ -442,6 +442,38 @@ def test_group_paths_on_one_rank():
     grp.close(); gpu.close()
 
 
+@pytest.mark.parametrize("cfg,kw,size", [("c5", dict(num_instances=60000), (960, 540)), ("c4", dict(num_instances=3000), (640, 360)), ("default", {}, (640, 360))])
+def test_group_sharded_tlas_build_on_one_rank(cfg, kw, size):
+    """SURVEY 8f-4 on the 1-GPU box: rt_group_build_tlas with the sharded path forced for a group of one rank — key histogram,
+    range selection, treelet build at its place in the global leaf order, re-linking into the assembled layout, top node.
+    The frame must equal the frame of the ordinary build bit for bit, and a refit of the assembled tree must still match the
+    oracle."""
+    from ray_tracing_gallery_b200 import native
+
+    orc, so, gpu, sg = both(cfg, *size, **kw)
+    before = gpu.render(sg.uniforms(), sg.params())
+    nodes_before = gpu.stats().tlas_nodes
+    grp = native.Group(gpu, 1, 0, native.group_unique_id(), *size)
+    grp.build_tlas(sg.instances, force_sharded=True)
+    after = gpu.render(sg.uniforms(), sg.params())
+    st = gpu.stats()
+    for key in ("rgba8", "hit_ids", "ray_counts", "radiance"):
+        assert np.array_equal(before[key], after[key]), key
+    assert st.tlas_nodes >= 2 and abs(int(st.tlas_nodes) - int(nodes_before)) <= max(8, nodes_before // 4)
+    check_parity(after, orc.render(so.uniforms(), so.params()), strict_ids=False)
+    if sg.dynamic:  # the assembled tree takes refits like any other
+        rec_g, rec_o = sg.animate(3), so.animate(3)
+        if cfg == "default":
+            grp.update_instances(2, 1, np.ascontiguousarray(rec_g[2:3]).ctypes.data, abi.RT_UPDATE_REFIT)
+        else:
+            a = np.ascontiguousarray(rec_g)
+            grp.update_instances(0, len(a), a.ctypes.data, abi.RT_UPDATE_REFIT)
+        orc.update_instances(0, rec_o); orc.update_tlas(abi.RT_UPDATE_REBUILD)
+        check_parity(gpu.render(sg.uniforms(), sg.params()), orc.render(so.uniforms(), so.params()), strict_ids=False)
+        gpu.stats()
+    grp.close(); orc.close(); gpu.close()
+
+
 def test_group_two_ranks_from_cpp():
     """Two GPUs driven from the C++ host through the C ABI alone (host_cpp/rt_group_demo): NCCL broadcast of the animated
     instance record, peer-memory device frame and shared host frame, each checked bit for bit against one GPU."""
@@ -456,8 +488,9 @@ def test_group_two_ranks_from_cpp():
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ray_tracing_gallery_b200", "host_cpp", "rt_group_demo")
     if not os.path.exists(exe):
         pytest.skip("rt_group_demo not built (__graft_entry__.build())")
-    for config, size in (("default", (640, 360)), ("c3", (1001, 563))):  # 563 rows: the last strip is partial
-        out = subprocess.run([exe, "--ranks", "2", "--config", config, "--width", str(size[0]), "--height", str(size[1]), "--frames", "6"],
+    for config, size, extra in (("default", (640, 360), []), ("c3", (1001, 563), []),   # 563 rows: the last strip is partial
+                                ("c3", (640, 360), ["--sharded-build", "--instances", "20000"])):  # each rank builds half of the TLAS
+        out = subprocess.run([exe, "--ranks", "2", "--config", config, "--width", str(size[0]), "--height", str(size[1]), "--frames", "6"] + extra,
                              capture_output=True, text=True, timeout=400)
         assert out.returncode == 0, out.stdout + out.stderr
         line = json.loads(out.stdout.strip().splitlines()[-1])
