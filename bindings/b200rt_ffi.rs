@@ -123,6 +123,18 @@ pub struct RtStats {
     pub segment_hits: [u32; 8],
 }
 
+/// Image-space buffers handed to the shadow-denoise hook (readme.md:17-20 names shadow denoising as the next step).
+#[repr(C)]
+pub struct RtDenoiseBuffers {
+    pub width: u32,
+    pub rows: u32,
+    pub sun_factor: *mut f32,
+    pub position_nol: *const f32,
+    pub shadow_rays: u32,
+    pub frame_index: u32,
+}
+pub type RtDenoiseFn = Option<unsafe extern "C" fn(user: *mut c_void, cuda_stream: *mut c_void, buffers: *const RtDenoiseBuffers) -> c_int>;
+
 extern "C" {
     pub fn rt_create(cuda_device: c_int, out: *mut *mut RtContext) -> c_int; // src/main.rs:157-204,337
     pub fn rt_destroy(ctx: *mut RtContext); // src/main.rs:997-1023
@@ -144,6 +156,8 @@ extern "C" {
                                  params: *const RtRenderParams, out: *const RtFrameOutputs) -> c_int;
     pub fn rt_readback(ctx: *mut RtContext, host_rgba8: *mut c_void, capacity_bytes: usize) -> c_int; // src/command_buffer_recording.rs:165-179
     pub fn rt_sync(ctx: *mut RtContext) -> c_int;
+    pub fn rt_set_denoise_hook(ctx: *mut RtContext, hook: RtDenoiseFn, user: *mut c_void) -> c_int;
+    pub fn rt_denoise_bilateral(user: *mut c_void, cuda_stream: *mut c_void, buffers: *const RtDenoiseBuffers) -> c_int;
     pub fn rt_host_alloc(ctx: *mut RtContext, bytes: usize, out: *mut *mut c_void) -> c_int; // host-visible Buffer, src/util_structs.rs:17-120
     pub fn rt_host_free(ctx: *mut RtContext, ptr: *mut c_void) -> c_int;
     pub fn rt_get_stats(ctx: *mut RtContext, out: *mut RtStats) -> c_int;

@@ -225,6 +225,27 @@ int  rt_readback(RtContext* ctx, void* host_rgba8, size_t capacity_bytes);
 /* Fence wait (src/main.rs:919-923). */
 int  rt_sync(RtContext* ctx);
 
+/* Shadow-denoise hook.  The reference's readme lists "shadow denoising" as its next step (readme.md:17-20); this is the seam
+ * for it in the frame: between the shadow rays of the first ray-gen segment and the colour resolve, the per-pixel sun
+ * factor (`sun_factor = unshadowed / N`, closest_hit_textured.glsl:203) is laid out in image space and handed to the hook,
+ * which may filter it in place with work enqueued on the given stream; the resolve then uses the filtered value.  Pixels
+ * whose first segment has no textured hit hold 1.0 and are not read back.  Wavefront frames only (the megakernel and heat-
+ * map paths shade inside one thread and ignore the hook); bounce segments keep their raw factor.  With an identity
+ * hook the frame is bit-identical to a frame without hook. */
+typedef struct RtDenoiseBuffers {
+    uint32_t width, rows;        /* the rendered rectangle, compact like the frame outputs */
+    float*       sun_factor;     /* [rows][width] in / out */
+    const float* position_nol;   /* [rows][width][4] guide: world-space shadow-ray origin of the hit (xyz) and N.L (w); 0 where no hit */
+    uint32_t     shadow_rays;    /* N of this frame */
+    uint32_t     frame_index;
+} RtDenoiseBuffers;
+typedef int (*RtDenoiseFn)(void* user, void* cuda_stream, const RtDenoiseBuffers* buffers);  /* return 0, or the frame fails */
+int  rt_set_denoise_hook(RtContext* ctx, RtDenoiseFn fn, void* user);   /* fn == NULL removes the hook */
+/* A ready-made hook with the RtDenoiseFn signature: 5x5 cross-bilateral average of the sun factor, weights from the
+ * world-space distance between the hits (`user` points to a float: the distance at which the weight has dropped to 1/e, in scene
+ * units; NULL = 0.25) and from N.L sign agreement. */
+int  rt_denoise_bilateral(void* user, void* cuda_stream, const RtDenoiseBuffers* buffers);
+
 /* Page-locked host memory for frame read-back and instance uploads (what the reference gets from its host-visible
  * `Buffer`s, src/util_structs.rs:17-120): copies to/from it are asynchronous, so rt_render_async really overlaps. */
 int  rt_host_alloc(RtContext* ctx, size_t bytes, void** out);

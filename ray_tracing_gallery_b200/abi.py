@@ -118,6 +118,20 @@ class RtFrameOutputs(C.Structure):
     ]
 
 
+class RtDenoiseBuffers(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32),
+        ("rows", C.c_uint32),
+        ("sun_factor", C.c_void_p),
+        ("position_nol", C.c_void_p),
+        ("shadow_rays", C.c_uint32),
+        ("frame_index", C.c_uint32),
+    ]
+
+
+RT_DENOISE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(RtDenoiseBuffers))
+
+
 class RtStats(C.Structure):
     _fields_ = [
         ("primary_rays", C.c_uint64),

@@ -256,6 +256,19 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
     if (&R == &ctx->main) CK(cudaMemcpyAsync(ctx->d_uniforms, u, sizeof(RtUniforms), cudaMemcpyHostToDevice, R.stream));
     F.bounce_hint = ctx->d_bounce;
     F.overflow_flag = ctx->d_bounce + 1;
+    // denoise hook: wavefront colour frames only
+    const bool hooked = ctx->denoise.fn && p->pipeline == RT_PIPELINE_WAVEFRONT && !u->show_heatmap && pixels > 0;
+    if (hooked) {
+        if (pixels > R.denoise_cap) {
+            size_t cap = R.denoise_cap;
+            CK(grow(R.d_sun_factor, cap, pixels));
+            cap = R.denoise_cap;
+            CK(grow(R.d_position_nol, cap, pixels));
+            R.denoise_cap = pixels;
+        }
+        F.sun_factor = R.d_sun_factor;
+        F.position_nol = R.d_position_nol;
+    }
     bool split_tail = (p->flags & RT_RENDER_SPLIT_TAIL) != 0;
     if (!split_tail && !(p->flags & RT_RENDER_COOP_TAIL)) {
         if (ctx->tail_policy >= 0) split_tail = ctx->tail_policy == 1;
@@ -272,8 +285,11 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
     }
     ctx->timing_valid = timing != nullptr;
     CK(init_launch_geometry(ctx->launch_geometry, ctx->sms));
-    CK(launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, split_tail, (p->flags & RT_RENDER_NO_PDL) != 0, ctx->launch_geometry,
-                    d_ray_counts, timing, R.stream));
+    int hook_status = 0;
+    cudaError_t le = launch_frame(S, F, p->pipeline, (p->flags & RT_RENDER_COUNTERS) != 0, split_tail, (p->flags & RT_RENDER_NO_PDL) != 0, ctx->launch_geometry,
+                                  d_ray_counts, timing, R.stream, hooked ? &ctx->denoise : nullptr, &hook_status);
+    if (hook_status != 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_render: the denoise hook returned " + std::to_string(hook_status));
+    CK(le);
     CK(cudaEventRecord(ctx->ev[1], R.stream));
     ctx->render_timed = true;
     ctx->last_res = &R;
@@ -852,6 +868,13 @@ int rt_sync(RtContext* ctx) {
     for (auto& sl : ctx->dev_slots)
         if (sl.rendering) { CK(cudaEventSynchronize(sl.rendered)); sl.rendering = false; }
     return check_stack_overflow(ctx, "rt_sync");
+}
+
+int rt_set_denoise_hook(RtContext* ctx, RtDenoiseFn fn, void* user) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    ctx->denoise.fn = fn;
+    ctx->denoise.user = fn ? user : nullptr;
+    return RT_OK;
 }
 
 int rt_host_alloc(RtContext* ctx, size_t bytes, void** out) {

@@ -63,8 +63,13 @@ struct FrameResources {
     size_t queue_cap = 0;
     float4* d_sun_dirs = nullptr;
     size_t sun_dirs_cap = 0;
+    float* d_sun_factor = nullptr;       // denoise hook: image-space sun factor + guide of segment 0
+    float4* d_position_nol = nullptr;
+    size_t denoise_cap = 0;
     void release() {
         cudaFree(d_counters); cudaFree(d_ray_q[0]); cudaFree(d_ray_q[1]); cudaFree(d_hit_q); cudaFree(d_sun_dirs);
+        cudaFree(d_sun_factor); cudaFree(d_position_nol);
+        d_sun_factor = nullptr; d_position_nol = nullptr; denoise_cap = 0;
         d_counters = nullptr; d_ray_q[0] = d_ray_q[1] = nullptr; d_hit_q = nullptr; d_sun_dirs = nullptr;
         queue_cap = sun_dirs_cap = 0;
     }
@@ -79,6 +84,7 @@ struct RtContext {
     bool render_timed = false, tlas_timed = false;
     FrameTiming timing;
     bool timing_ready = false, timing_valid = false;
+    DenoiseHook denoise;             // rt_set_denoise_hook
     LaunchGeometry launch_geometry;  // grids of the persistent kernels on this context's device
     // Tail policy.  Bounce segments run either inside the one cooperative k_tail (one launch; best when there are few or no
     // bounce rays: C2 0.453 against 0.505 ms) or as separate launches at each kernel's own occupancy (better when a frame

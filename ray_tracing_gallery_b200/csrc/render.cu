@@ -380,6 +380,7 @@ __device__ __forceinline__ void resolve_phase(const FrameDev& F, uint32_t seg) {
         V3 col = v3(0.f, 0.f, 0.f);
         if (valid) {
             float sun_factor = div_((float)__float_as_uint(r1.w), (float)F.shadow_rays);
+            if (seg == 0 && F.sun_factor) sun_factor = __ldcg(F.sun_factor + __float_as_uint(r0.x));  // what the denoise hook left
             col = shade_finish(sun_factor, r0.y, v3(r1.x, r1.y, r1.z), v3(r2.x, r2.y, r2.z));
         }
         write_pixel(F, __float_as_uint(r0.x), col);
@@ -417,6 +418,51 @@ __device__ __forceinline__ void export_bounce_hint(const FrameDev& F) {
 __global__ void __launch_bounds__(128) k_resolve(FrameDev F, uint32_t seg) {
     if (seg == 0) export_bounce_hint(F);
     resolve_phase(F, seg);
+}
+
+// Denoise hook, segment 0: the sun factor of every textured hit (closest_hit_textured.glsl:203, the same division the resolve
+// phase does) and its guide values in image space, compact pixel order; pixels without a hit keep the 1.0 / 0 fill.
+__global__ void __launch_bounds__(256) k_fill_sun_factor(float* sun_factor, float4* position_nol, uint32_t pixels) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += gridDim.x * blockDim.x) {
+        sun_factor[i] = 1.0f;
+        position_nol[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+__global__ void __launch_bounds__(128) k_export_sun_factor(FrameDev F) {
+    const uint32_t total = *((volatile unsigned int*)&seg_counters(F, 0)->hit_count);
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+        const HitRec* hr = F.hit_q + item;
+        const float4 r0 = __ldcg(reinterpret_cast<const float4*>(hr));
+        const float4 r1 = __ldcg(reinterpret_cast<const float4*>(hr) + 1);
+        const float4 r3 = __ldcg(reinterpret_cast<const float4*>(hr) + 3);
+        if (!(__float_as_uint(r3.w) & 1u)) continue;
+        const uint32_t pixel = __float_as_uint(r0.x);
+        F.sun_factor[pixel] = div_((float)__float_as_uint(r1.w), (float)F.shadow_rays);
+        F.position_nol[pixel] = make_float4(r3.x, r3.y, r3.z, r0.y);
+    }
+}
+// rt_denoise_bilateral: 5x5 cross-bilateral average of the sun factor
+__global__ void __launch_bounds__(256) k_denoise_bilateral(const float* __restrict__ in, float* __restrict__ out, const float4* __restrict__ guide, uint32_t w,
+                                                           uint32_t h, float inv_sigma2) {
+    const uint32_t x = blockIdx.x * 16u + (threadIdx.x & 15u), y = blockIdx.y * 16u + (threadIdx.x >> 4);
+    if (x >= w || y >= h) return;
+    const float4 g0 = guide[(size_t)y * w + x];
+    float acc = 0.f, wsum = 0.f;
+    const bool hit0 = g0.x != 0.f || g0.y != 0.f || g0.z != 0.f || g0.w != 0.f;
+    if (!hit0) { out[(size_t)y * w + x] = in[(size_t)y * w + x]; return; }
+    for (int dy = -2; dy <= 2; dy++)
+        for (int dx = -2; dx <= 2; dx++) {
+            const int xx = (int)x + dx, yy = (int)y + dy;
+            if (xx < 0 || yy < 0 || xx >= (int)w || yy >= (int)h) continue;
+            const float4 g = guide[(size_t)yy * w + xx];
+            if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;   // no textured hit there
+            if ((g.w > 0.f) != (g0.w > 0.f)) continue;                           // lit side / unlit side do not mix
+            const float ddx = g.x - g0.x, ddy = g.y - g0.y, ddz = g.z - g0.z;
+            const float wt = __expf(-(ddx * ddx + ddy * ddy + ddz * ddz) * inv_sigma2);
+            acc += wt * in[(size_t)yy * w + xx];
+            wsum += wt;
+        }
+    out[(size_t)y * w + x] = wsum > 0.f ? acc / wsum : in[(size_t)y * w + x];
 }
 
 // segments >= RT_SEG_SLOTS reuse a counter slot (split-tail path)
@@ -579,7 +625,8 @@ cudaError_t init_launch_geometry(LaunchGeometry& g, int sms) {
 
 cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, bool no_pdl,
                          const LaunchGeometry& geom, uint64_t* d_ray_counts,
-                         FrameTiming* timing, cudaStream_t stream) {
+                         FrameTiming* timing, cudaStream_t stream, const DenoiseHook* hook, int* hook_status) {
+    if (hook_status) *hook_status = 0;
     cudaMemsetAsync(F.counters, 0, sizeof(FrameCounters), stream);
     if (F.hit_ids) cudaMemsetAsync(F.hit_ids, 0xFF, (size_t)F.rows * F.tw * F.max_segments * 3 * sizeof(uint32_t), stream);
     uint32_t tiles = ((F.tw + 7u) / 8u) * ((F.rows + 3u) / 4u);
@@ -636,7 +683,23 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
         else le = launch_pdl(k_shadow<false>, fit(g_shadow[ci], F.shadow_rays), stream, pdl, S, F, 0u);
         if (le != cudaSuccess) return le;
         mark(K_SHADOW);
-        if (F.max_segments == 1 || split_tail) {
+        const bool hooked = hook && hook->fn && F.sun_factor && F.position_nol;
+        if (hooked) {
+            // the sun factor in image space -> the host's filter (enqueues on this stream) -> read back by k_resolve(seg 0)
+            const uint32_t pixels = F.rows * F.tw;
+            k_fill_sun_factor<<<fit(geom.resolve, 1), 256, 0, stream>>>(F.sun_factor, F.position_nol, pixels);
+            k_export_sun_factor<<<fit(geom.resolve, 1), 128, 0, stream>>>(F);
+            note_launch(2);
+            RtDenoiseBuffers db;
+            db.width = F.tw; db.rows = F.rows; db.sun_factor = F.sun_factor; db.position_nol = reinterpret_cast<const float*>(F.position_nol);
+            db.shadow_rays = F.shadow_rays; db.frame_index = F.uniforms.frame_index;
+            const int hs = hook->fn(hook->user, (void*)stream, &db);
+            if (hs != 0) {
+                if (hook_status) *hook_status = hs;
+                return cudaErrorUnknown;
+            }
+        }
+        if (F.max_segments == 1 || split_tail || hooked) {
             k_resolve<<<fit(g_resolve, 1), 128, 0, stream>>>(F, 0);
             mark(K_RESOLVE);
             for (uint32_t seg = 1; seg < F.max_segments; seg++) {
@@ -668,3 +731,20 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
 }
 
 }  // namespace b200rt
+
+extern "C" int rt_denoise_bilateral(void* user, void* cuda_stream, const RtDenoiseBuffers* b) {
+    if (!b || !b->sun_factor || !b->position_nol) return RT_ERR_INVALID_ARGUMENT;
+    const size_t pixels = (size_t)b->width * b->rows;
+    if (!pixels) return RT_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    float* tmp = nullptr;
+    if (cudaMallocAsync(&tmp, pixels * sizeof(float), st) != cudaSuccess) return RT_ERR_CUDA;
+    const float sigma = user ? *static_cast<const float*>(user) : 0.25f;
+    cudaMemcpyAsync(tmp, b->sun_factor, pixels * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    dim3 grid((b->width + 15u) / 16u, (b->rows + 15u) / 16u);
+    b200rt::k_denoise_bilateral<<<grid, 256, 0, st>>>(tmp, b->sun_factor, reinterpret_cast<const float4*>(b->position_nol), b->width, b->rows,
+                                                      1.0f / (sigma * sigma));
+    b200rt::note_launch();
+    cudaFreeAsync(tmp, st);
+    return cudaGetLastError() == cudaSuccess ? RT_OK : RT_ERR_CUDA;
+}

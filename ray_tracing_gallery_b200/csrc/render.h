@@ -22,10 +22,17 @@ struct LaunchGeometry {
 };
 cudaError_t init_launch_geometry(LaunchGeometry& g, int sms);
 
+// Denoise hook of the context (rt_set_denoise_hook): called on the host while the frame is enqueued, between the shadow
+// rays of segment 0 and its resolve; works on F.sun_factor / F.position_nol with work enqueued on the frame's stream.
+struct DenoiseHook {
+    RtDenoiseFn fn = nullptr;
+    void* user = nullptr;
+};
+
 // Enqueue one frame on `stream`.  d_ray_counts (device, optional) receives {ray-gen segments, shadow rays}.
 cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline, bool count, bool split_tail, bool no_pdl,
                          const LaunchGeometry& geom, uint64_t* d_ray_counts,
-                         FrameTiming* timing, cudaStream_t stream);
+                         FrameTiming* timing, cudaStream_t stream, const DenoiseHook* hook = nullptr, int* hook_status = nullptr);
 
 // BLAS input: per flattened triangle (geometry-major) the padded AABB.
 struct ModelGeomDev {

@@ -163,6 +163,9 @@ struct FrameDev {
     float     heatmap_scale;        // ticks that map to heat 1.0
     FrameCounters* counters;
     unsigned int* bounce_hint;      // host-mapped word: bounce rays queued by segment 0 of the latest wavefront frame (optional)
+    // denoise hook (segment 0 only): image-space sun factor written after the shadow rays, read by the resolve phase when set
+    float*    sun_factor;
+    float4*   position_nol;
     unsigned int* overflow_flag;    // host-mapped word, set when a traversal stack overflowed: the frame is incomplete and the
                                     // next synchronising call of the API reports RT_ERR_OUT_OF_RANGE (optional)
     RayRec*   ray_q[2];

@@ -23,6 +23,7 @@ EXPORTS = [
     "rt_update_instances", "rt_update_instances_device", "rt_update_tlas", "rt_render", "rt_render_device", "rt_render_async",
     "rt_wait_frame", "rt_render_device_slot", "rt_host_alloc", "rt_host_free", "rt_readback",
     "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_kernel_launches", "rt_version",
+    "rt_set_denoise_hook", "rt_denoise_bilateral",
     "rt_group_unique_id", "rt_group_create", "rt_group_destroy", "rt_group_last_error", "rt_group_partition", "rt_group_update_instances",
     "rt_group_update_instances_device", "rt_group_build_tlas",
     "rt_group_render_device", "rt_group_render_host", "rt_group_acquire_device", "rt_group_acquire_host", "rt_group_release",
@@ -64,6 +65,8 @@ def load():
     lib.rt_get_push_constants.argtypes = [p, C.POINTER(abi.RtPushConstantBufferAddresses)]
     lib.rt_debug_read_model_info.argtypes = [p, u32, C.POINTER(abi.RtModelInfo), C.POINTER(abi.RtGeometryInfo), u32]
     lib.rt_version.restype = u32
+    lib.rt_set_denoise_hook.argtypes = [p, p, p]
+    lib.rt_denoise_bilateral.argtypes = [p, p, C.POINTER(abi.RtDenoiseBuffers)]
     u64 = C.c_uint64
     lib.rt_group_unique_id.argtypes = [p]
     lib.rt_group_create.argtypes = [p, C.c_int, C.c_int, p, u32, u32, C.POINTER(p)]
@@ -103,6 +106,18 @@ class Renderer(CApiBackend):
             raise RtError(f"rt_create({device}) failed ({rc}): {msg.decode() if msg else ''}")
         super().__init__(lib, ctx)
         self.device = device
+
+    def set_denoise_hook(self, fn=None, user: int = 0):
+        """`rt_set_denoise_hook`.  `fn`: None (remove), "bilateral" (the library's rt_denoise_bilateral; `user` = address of a
+        float sigma or 0), or a Python callable (user, cuda_stream, buffers: POINTER(RtDenoiseBuffers)) -> int."""
+        if fn is None:
+            ptr, self._hook = None, None
+        elif fn == "bilateral":
+            ptr, self._hook = C.cast(self.lib.rt_denoise_bilateral, C.c_void_p), None
+        else:
+            self._hook = abi.RT_DENOISE_FN(fn)  # keep the trampoline alive
+            ptr = C.cast(self._hook, C.c_void_p)
+        self._check(self.lib.rt_set_denoise_hook(self.ctx, ptr, user or None), "set_denoise_hook")
 
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.rt_set_stream(self.ctx, cuda_stream), "set_stream")

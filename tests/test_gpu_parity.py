@@ -497,6 +497,47 @@ def test_group_two_ranks_from_cpp():
         assert line["ok"] and line["ranks"] == 2 and line["mismatched_frames"] == 0
 
 
+def test_shadow_denoise_hook():
+    """SURVEY 8f-4 (readme.md:17-20, "shadow denoising"): the hook sits between segment 0's shadow rays and its resolve.  An
+    identity hook must leave the frame bit-identical; a failing hook must fail the frame; the library's cross-bilateral
+    filter must bring a 2-sample frame closer to the 64-sample frame than the raw 2-sample frame is."""
+    import ctypes as C
+
+    gpu = make_renderer()
+    s = build_scene(gpu, "c2", 960, 540)
+    s.shadow_rays = 2
+    raw = gpu.render(s.uniforms(), s.params())
+    seen = {}
+
+    def identity(user, stream, buffers):
+        b = buffers.contents
+        seen.update(width=b.width, rows=b.rows, n=b.shadow_rays, frame=b.frame_index, ptrs=(b.sun_factor, b.position_nol), stream=stream)
+        return 0
+
+    gpu.set_denoise_hook(identity)
+    same = gpu.render(s.uniforms(), s.params())
+    assert seen["width"] == 960 and seen["rows"] == 540 and seen["n"] == 2 and all(seen["ptrs"]) and seen["frame"] == s.frame_index
+    for key in ("rgba8", "radiance", "hit_ids", "ray_counts"):
+        assert np.array_equal(raw[key], same[key]), key
+    gpu.set_denoise_hook(lambda user, stream, buffers: 7)
+    with pytest.raises(RtError, match="denoise hook returned 7"):
+        gpu.render(s.uniforms(), s.params())
+    sigma = C.c_float(0.3)
+    gpu.set_denoise_hook("bilateral", C.addressof(sigma))
+    den = gpu.render(s.uniforms(), s.params())
+    gpu.set_denoise_hook(None)
+    again = gpu.render(s.uniforms(), s.params())
+    assert np.array_equal(again["radiance"], raw["radiance"])
+    s.shadow_rays = 64
+    ref = gpu.render(s.uniforms(), s.params())["radiance"].astype(np.float64)
+    mse_raw = np.mean((raw["radiance"] - ref) ** 2)
+    mse_den = np.mean((den["radiance"] - ref) ** 2)
+    print(f"shadow denoise: MSE against the 64-sample frame, raw 2 samples {mse_raw:.3e}, bilateral {mse_den:.3e}")
+    assert mse_den < 0.6 * mse_raw
+    assert np.array_equal(den["hit_ids"], raw["hit_ids"]) and np.array_equal(den["ray_counts"], raw["ray_counts"])
+    gpu.close()
+
+
 def test_show_heatmap_frame():
     """SURVEY 8f-3, Uniforms.show_heatmap (lib.rs:120-124, 174-186; heatmap.rs): the frame shows
     heatmap_temperature(clock ticks of the pixel's ray-gen invocation / heatmap_scale) + 1e-6 * colour.  The clock is the
