@@ -215,24 +215,17 @@ def algorithmic_bytes(st, setup, pixels):
     return {"trace": int(trace_b), "prep": int(prep_b), "shadow": int(shadow_b), "resolve": int(resolve_b), "mega": int(mega_b), "tail": int(resolve_b)}
 
 
-def measure_l2_peak(torch, dev, stream):
-    """L2 'peak' the way the HBM peak of MEASURED_PEAKS.json is measured, with a cache-resident working set: a device copy
-    of 16 MiB -> 16 MiB (32 MiB of the 126 MB L2), best of 5 batches of 50 copies, read + write bytes."""
-    n = 16 << 20
-    a = torch.empty(n, dtype=torch.uint8, device=dev).fill_(1)
-    b = torch.empty(n, dtype=torch.uint8, device=dev)
-    for _ in range(10):
-        b.copy_(a)
-    best = 0.0
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(50):
-            b.copy_(a)
-        e1.record(stream)
-        e1.synchronize()
-        best = max(best, 50 * 2 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9)
-    return best
+def measure_l2_peak(local_rank):
+    """L2 read bandwidth of a cache-resident working set (32 MiB of the 126 MB L2, 64 passes of 16-byte ld.global.cg from a
+    full persistent grid): the denominator of `l2_frac`.  `rt_debug_l2_read_bandwidth` in the library, so the number comes
+    from the same process, device and clocks as the frames."""
+    from ray_tracing_gallery_b200 import native
+
+    gpu = native.Renderer(local_rank)
+    try:
+        return gpu.l2_read_bandwidth(32 << 20, 64)
+    finally:
+        gpu.close()
 
 
 class Bench:
@@ -265,7 +258,7 @@ class Bench:
         else:
             self.hbm_peak, self.hbm_src, self.sm_max_mhz = 6650.0, "fallback (B200_PROFILING.md)", 1965.0
         self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
-        self.l2_peak = measure_l2_peak(torch, self.dev, self.stream) if self.rank == 0 else None
+        self.l2_peak = measure_l2_peak(self.local_rank) if self.rank == 0 else None
         ncu_path = os.path.join(ROOT, "profiles", "ncu_counters.json")
         self.ncu = json.load(open(ncu_path)) if os.path.exists(ncu_path) else {}
 
@@ -541,7 +534,7 @@ class Bench:
                     "note": "algorithmic bytes / kernel time against the HBM copy peak: the contract's figure, kept for continuity — the bytes are "
                             "served by L1/L2 (see dram_frac), so this fraction says nothing about how close the kernel is to a limit"},
             "kernel": KERNEL_DESC[kname], "peak_source": f"{self.sms} SMs x 4 schedulers x {self.sm_max_mhz:.0f} MHz; HBM: {self.hbm_src}; "
-                                                         "L2: 16 MiB -> 16 MiB device copy measured at start-up",
+                                                         "L2: rt_debug_l2_read_bandwidth (32 MiB resident, 64 passes) measured at start-up",
             "kernel_ms_per_frame": {n: float(kernel_ms[i] / ksteps) for i, n in enumerate(KERNELS)},
             "kernel_share_of_step": float((kernel_ms[dom] / ksteps) / ms_per_step) if self.world == 1 else None,
             "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_frame": float(launches_per_frame),

@@ -334,6 +334,9 @@ int  rt_group_local_ray_counts(RtGroup* group, uint64_t** out_device_counts);
 /* All ranks, collectively: every rank's stream work is finished (ncclAllReduce of one word + stream sync). */
 int  rt_group_barrier(RtGroup* group);
 
+/* Micro-benchmark behind bench.py's `l2_frac`: read a device buffer of `bytes` (cache-resident when well below the 126 MB L2)
+ * `repeats` times with 16-byte loads from a full persistent grid and report read bytes / kernel time (CUDA events). */
+int  rt_debug_l2_read_bandwidth(RtContext* ctx, size_t bytes, uint32_t repeats, float* out_gb_per_s);
 /* Number of this library's own kernels launched so far in the process (all contexts). */
 uint64_t rt_kernel_launches(void);
 /* Library/ABI version: (major << 16) | minor. */

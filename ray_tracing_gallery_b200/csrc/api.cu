@@ -300,6 +300,19 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ buf, size_t quads, uint32_t repeats, uint32_t* sink) {
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (uint32_t r = 0; r < repeats; r++)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += stride) {
+            const uint4 v = __ldcg(buf + ((i + (size_t)r * 977u) % quads));  // ld.global.cg: L2, not L1
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9E3779B9u) *sink = acc.x;  // keeps the loads alive
+}
+}  // namespace
+
 // ---- hooks for group.cu (multi-GPU entry points); not part of the C ABI
 namespace b200rt {
 // Where a write of `count` instance records at `first` has to land so that the next rt_update_tlas sees it (the staging
@@ -943,6 +956,36 @@ int rt_get_push_constants(RtContext* ctx, RtPushConstantBufferAddresses* out) {
     out->model_info = (uint64_t)(uintptr_t)ctx->d_model_info.ptr;
     out->uniforms = (uint64_t)(uintptr_t)ctx->d_uniforms;
     out->acceleration_structure = (uint64_t)(uintptr_t)ctx->sets[ctx->cur].d_tlas_nodes;
+    return RT_OK;
+}
+
+int rt_debug_l2_read_bandwidth(RtContext* ctx, size_t bytes, uint32_t repeats, float* out_gb_per_s) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!out_gb_per_s || bytes < 4096 || !repeats) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_debug_l2_read_bandwidth: bad argument");
+    CK_DEV(ctx);
+    const size_t quads = bytes / 16;
+    uint4* buf = nullptr;
+    uint32_t* sink = nullptr;
+    CK(cudaMalloc(&buf, quads * 16));
+    CK(cudaMalloc(&sink, 4));
+    CK(cudaMemsetAsync(buf, 1, quads * 16, ctx->stream));
+    const int grid = ctx->sms * 8;
+    k_l2_read<<<grid, 256, 0, ctx->stream>>>(buf, quads, 2, sink);  // warm the cache
+    float best = 0.0f;
+    for (int it = 0; it < 5; it++) {
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_l2_read<<<grid, 256, 0, ctx->stream>>>(buf, quads, repeats, sink);
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        const float gbs = (float)((double)quads * 16.0 * repeats / (ms * 1e-3) / 1e9);
+        if (gbs > best) best = gbs;
+    }
+    note_launch(6);
+    ctx->render_timed = false;
+    cudaFree(buf); cudaFree(sink);
+    *out_gb_per_s = best;
     return RT_OK;
 }
 

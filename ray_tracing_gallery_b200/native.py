@@ -22,7 +22,7 @@ EXPORTS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_push_image", "rt_create_model", "rt_build_tlas",
     "rt_update_instances", "rt_update_instances_device", "rt_update_tlas", "rt_render", "rt_render_device", "rt_render_async",
     "rt_wait_frame", "rt_render_device_slot", "rt_host_alloc", "rt_host_free", "rt_readback",
-    "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_kernel_launches", "rt_version",
+    "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_debug_l2_read_bandwidth", "rt_kernel_launches", "rt_version",
     "rt_set_denoise_hook", "rt_denoise_bilateral",
     "rt_group_unique_id", "rt_group_create", "rt_group_destroy", "rt_group_last_error", "rt_group_partition", "rt_group_update_instances",
     "rt_group_update_instances_device", "rt_group_build_tlas",
@@ -65,6 +65,7 @@ def load():
     lib.rt_get_push_constants.argtypes = [p, C.POINTER(abi.RtPushConstantBufferAddresses)]
     lib.rt_debug_read_model_info.argtypes = [p, u32, C.POINTER(abi.RtModelInfo), C.POINTER(abi.RtGeometryInfo), u32]
     lib.rt_version.restype = u32
+    lib.rt_debug_l2_read_bandwidth.argtypes = [p, C.c_size_t, u32, C.POINTER(C.c_float)]
     lib.rt_set_denoise_hook.argtypes = [p, p, p]
     lib.rt_denoise_bilateral.argtypes = [p, p, C.POINTER(abi.RtDenoiseBuffers)]
     u64 = C.c_uint64
@@ -166,6 +167,12 @@ class Renderer(CApiBackend):
         s = abi.RtStats()
         self._check(self.lib.rt_get_stats(self.ctx, C.byref(s)), "get_stats")
         return s
+
+    def l2_read_bandwidth(self, nbytes: int = 32 << 20, repeats: int = 64) -> float:
+        """`rt_debug_l2_read_bandwidth`: GB/s of 16-byte loads over a cache-resident buffer (bench.py's L2 denominator)."""
+        out = C.c_float()
+        self._check(self.lib.rt_debug_l2_read_bandwidth(self.ctx, nbytes, repeats, C.byref(out)), "debug_l2_read_bandwidth")
+        return float(out.value)
 
     def push_constants(self) -> abi.RtPushConstantBufferAddresses:
         pc = abi.RtPushConstantBufferAddresses()
