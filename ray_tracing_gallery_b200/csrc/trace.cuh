@@ -73,6 +73,61 @@ __device__ __forceinline__ float byte_m(uint32_t w, uint32_t one) {
     return __uint_as_float(__byte_perm(w, one, 0x7604u | (SEL << 4)));
 }
 
+// Hit mask (bit s = slot s) of the eight quantised child boxes of a node against the ray (co, 1/cd = id*, octant oct) on
+// [tmin, tlimit]; empty slots are not masked here (the caller ands with nonzero_bytes(meta)).  FIRST_HIT: no far clamp.
+template <bool FIRST_HIT>
+__device__ __forceinline__ uint32_t node_hit_mask(const uint4& n0, const uint4& n2, const uint4& n3, const uint4& n4, V3 co, float idx, float idy,
+                                                  float idz, uint32_t oct, float tmin, float tlimit, uint32_t one) {
+    // per-axis: A = 2^15 * 2^e / d, B = (origin - o)/d - A, padded outwards by p
+    // (the exponent bytes are stored biased: shifted into place they ARE the cell sizes 2^e)
+    float ax = __uint_as_float((n0.w << 23) & 0x7F800000u) * idx;
+    float ay = __uint_as_float((n0.w << 15) & 0x7F800000u) * idy;
+    float az = __uint_as_float((n0.w << 7) & 0x7F800000u) * idz;
+    float bx = (__uint_as_float(n0.x) - co.x) * idx;
+    float by = (__uint_as_float(n0.y) - co.y) * idy;
+    float bz = (__uint_as_float(n0.z) - co.z) * idz;
+    float Ax = ax * 32768.0f, Ay = ay * 32768.0f, Az = az * 32768.0f;
+    float Bx = fmaf(-32768.0f, ax, bx), By = fmaf(-32768.0f, ay, by), Bz = fmaf(-32768.0f, az, bz);
+    float px = (fabsf(bx) + fabsf(Ax)) * 4.76837158e-7f;
+    float py = (fabsf(by) + fabsf(Ay)) * 4.76837158e-7f;
+    float pz = (fabsf(bz) + fabsf(Az)) * 4.76837158e-7f;
+    float Bnx = Bx - px, Bfx = Bx + px, Bny = By - py, Bfy = By + py, Bnz = Bz - pz, Bfz = Bz + pz;
+    // near / far plane words per axis, chosen by ray direction
+    uint32_t nx0, nx1, fx0, fx1, ny0, ny1, fy0, fy1, nz0, nz1, fz0, fz1;
+    if (oct & 1u) { nx0 = n3.z; nx1 = n3.w; fx0 = n2.x; fx1 = n2.y; } else { nx0 = n2.x; nx1 = n2.y; fx0 = n3.z; fx1 = n3.w; }
+    if (oct & 2u) { ny0 = n4.x; ny1 = n4.y; fy0 = n2.z; fy1 = n2.w; } else { ny0 = n2.z; ny1 = n2.w; fy0 = n4.x; fy1 = n4.y; }
+    if (oct & 4u) { nz0 = n4.z; nz1 = n4.w; fz0 = n3.x; fz1 = n3.y; } else { nz0 = n3.x; nz1 = n3.y; fz0 = n4.z; fz1 = n4.w; }
+    // closest-hit rays cull children beyond the committed hit; first-hit rays keep tmax for the triangles only
+    // (a child box beyond tmax = 10 000 scene units is visited in vain, never wrongly accepted)
+    uint32_t h = 0;
+    // The hit mask comes from the sign bits of tf - tn, shifted in with one funnel shift per child: 8 FADD on the fma pipe +
+    // 8 SHF instead of 8 FSETP + 8 predicated adds on the alu pipe, which carries twice the fma pipe's load in this
+    // block (profiles/r02a_ab.txt: -0.2 .. -0.6 % frame time on C2..C5).  tn >= tmin > 0, so tf - tn is never -0 for a
+    // hit; a NaN may read as a hit, which only costs a wasted visit.  Slots are committed 0..7: slot s ends at bit 7 - s.
+#define RT_BOX_COMMIT(SLOT, TN, TF) h = __funnelshift_l(__float_as_uint((TF) - (TN)), h, 1);
+#define RT_BOX(SLOT, SEL, WNX, WNY, WNZ, WFX, WFY, WFZ)                                                            \
+    {                                                                                                             \
+        float tn = fmaxf(fmaxf(fmaf(byte_m<SEL>(WNX, one), Ax, Bnx), fmaf(byte_m<SEL>(WNY, one), Ay, Bny)),       \
+                         fmaxf(fmaf(byte_m<SEL>(WNZ, one), Az, Bnz), tmin));                                      \
+        float tfz = fmaf(byte_m<SEL>(WFZ, one), Az, Bfz);                                                         \
+        if (!FIRST_HIT) tfz = fminf(tfz, tlimit);                                                                 \
+        float tf = fminf(fminf(fmaf(byte_m<SEL>(WFX, one), Ax, Bfx), fmaf(byte_m<SEL>(WFY, one), Ay, Bfy)), tfz); \
+        RT_BOX_COMMIT(SLOT, tn, tf)                                                                               \
+    }
+    RT_BOX(0, 0, nx0, ny0, nz0, fx0, fy0, fz0)
+    RT_BOX(1, 1, nx0, ny0, nz0, fx0, fy0, fz0)
+    RT_BOX(2, 2, nx0, ny0, nz0, fx0, fy0, fz0)
+    RT_BOX(3, 3, nx0, ny0, nz0, fx0, fy0, fz0)
+    RT_BOX(4, 0, nx1, ny1, nz1, fx1, fy1, fz1)
+    RT_BOX(5, 1, nx1, ny1, nz1, fx1, fy1, fz1)
+    RT_BOX(6, 2, nx1, ny1, nz1, fx1, fy1, fz1)
+    RT_BOX(7, 3, nx1, ny1, nz1, fx1, fy1, fz1)
+#undef RT_BOX
+#undef RT_BOX_COMMIT
+    h = __brev(~h) >> 24;  // sign clear = hit; bit 7 - s -> bit s
+    return h;
+}
+
 // Shadow rays stop at the first accepted hit, whatever its distance: their children need no front-to-back order, so
 // the octant permutation of the pending mask is skipped for them (measured: profiles/r01n_ab.txt).
 #define RT_UNORDERED(ANY) (ANY)
@@ -188,55 +243,7 @@ struct Traverser {
             uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
             if (COUNT) tc.nodes++;
 
-            // per-axis: A = 2^15 * 2^e / d, B = (origin - o)/d - A, padded outwards by p
-            // (the exponent bytes are stored biased: shifted into place they ARE the cell sizes 2^e)
-            float ax = __uint_as_float((n0.w << 23) & 0x7F800000u) * idx;
-            float ay = __uint_as_float((n0.w << 15) & 0x7F800000u) * idy;
-            float az = __uint_as_float((n0.w << 7) & 0x7F800000u) * idz;
-            float bx = (__uint_as_float(n0.x) - co.x) * idx;
-            float by = (__uint_as_float(n0.y) - co.y) * idy;
-            float bz = (__uint_as_float(n0.z) - co.z) * idz;
-            float Ax = ax * 32768.0f, Ay = ay * 32768.0f, Az = az * 32768.0f;
-            float Bx = fmaf(-32768.0f, ax, bx), By = fmaf(-32768.0f, ay, by), Bz = fmaf(-32768.0f, az, bz);
-            float px = (fabsf(bx) + fabsf(Ax)) * 4.76837158e-7f;
-            float py = (fabsf(by) + fabsf(Ay)) * 4.76837158e-7f;
-            float pz = (fabsf(bz) + fabsf(Az)) * 4.76837158e-7f;
-            float Bnx = Bx - px, Bfx = Bx + px, Bny = By - py, Bfy = By + py, Bnz = Bz - pz, Bfz = Bz + pz;
-            // near / far plane words per axis, chosen by ray direction
-            uint32_t nx0, nx1, fx0, fx1, ny0, ny1, fy0, fy1, nz0, nz1, fz0, fz1;
-            if (oct & 1u) { nx0 = n3.z; nx1 = n3.w; fx0 = n2.x; fx1 = n2.y; } else { nx0 = n2.x; nx1 = n2.y; fx0 = n3.z; fx1 = n3.w; }
-            if (oct & 2u) { ny0 = n4.x; ny1 = n4.y; fy0 = n2.z; fy1 = n2.w; } else { ny0 = n2.z; ny1 = n2.w; fy0 = n4.x; fy1 = n4.y; }
-            if (oct & 4u) { nz0 = n4.z; nz1 = n4.w; fz0 = n3.x; fz1 = n3.y; } else { nz0 = n3.x; nz1 = n3.y; fz0 = n4.z; fz1 = n4.w; }
-            // closest-hit rays cull children beyond the committed hit; first-hit rays keep tmax for the triangles only
-            // (a child box beyond tmax = 10 000 scene units is visited in vain, never wrongly accepted)
-            float tlimit = hit.t;
-            const uint32_t one = S.one_bits;
-            uint32_t h = 0;
-            // The hit mask comes from the sign bits of tf - tn, shifted in with one funnel shift per child: 8 FADD on the fma pipe +
-            // 8 SHF instead of 8 FSETP + 8 predicated adds on the alu pipe, which carries twice the fma pipe's load in this
-            // block (profiles/r02a_ab.txt: -0.2 .. -0.6 % frame time on C2..C5).  tn >= tmin > 0, so tf - tn is never -0 for a
-            // hit; a NaN may read as a hit, which only costs a wasted visit.  Slots are committed 0..7: slot s ends at bit 7 - s.
-#define RT_BOX_COMMIT(SLOT, TN, TF) h = __funnelshift_l(__float_as_uint((TF) - (TN)), h, 1);
-#define RT_BOX(SLOT, SEL, WNX, WNY, WNZ, WFX, WFY, WFZ)                                                   \
-    {                                                                                                    \
-        float tn = fmaxf(fmaxf(fmaf(byte_m<SEL>(WNX, one), Ax, Bnx), fmaf(byte_m<SEL>(WNY, one), Ay, Bny)),          \
-                         fmaxf(fmaf(byte_m<SEL>(WNZ, one), Az, Bnz), tmin));                                  \
-        float tfz = fmaf(byte_m<SEL>(WFZ, one), Az, Bfz);                                                \
-        if (!ANY) tfz = fminf(tfz, tlimit);                                                              \
-        float tf = fminf(fminf(fmaf(byte_m<SEL>(WFX, one), Ax, Bfx), fmaf(byte_m<SEL>(WFY, one), Ay, Bfy)), tfz); \
-        RT_BOX_COMMIT(SLOT, tn, tf)                                                                      \
-    }
-            RT_BOX(0, 0, nx0, ny0, nz0, fx0, fy0, fz0)
-            RT_BOX(1, 1, nx0, ny0, nz0, fx0, fy0, fz0)
-            RT_BOX(2, 2, nx0, ny0, nz0, fx0, fy0, fz0)
-            RT_BOX(3, 3, nx0, ny0, nz0, fx0, fy0, fz0)
-            RT_BOX(4, 0, nx1, ny1, nz1, fx1, fy1, fz1)
-            RT_BOX(5, 1, nx1, ny1, nz1, fx1, fy1, fz1)
-            RT_BOX(6, 2, nx1, ny1, nz1, fx1, fy1, fz1)
-            RT_BOX(7, 3, nx1, ny1, nz1, fx1, fy1, fz1)
-#undef RT_BOX
-#undef RT_BOX_COMMIT
-            h = __brev(~h) >> 24;  // sign clear = hit; bit 7 - s -> bit s
+            uint32_t h = node_hit_mask<ANY>(n0, n2, n3, n4, co, idx, idy, idz, oct, tmin, hit.t, S.one_bits);
             uint32_t imask = n0.w >> 24;
             h &= nonzero_bytes(n1.z, n1.w);
             uint32_t hl = h & ~imask;
