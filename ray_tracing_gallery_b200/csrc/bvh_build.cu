@@ -353,8 +353,9 @@ __device__ void quantise_node(Node8& nd, const Aabb* cb, uint32_t present) {
                 ql = (uint8_t)a;
                 qh = (uint8_t)b;
             }
-            nd.qlo[k][s] = ql;
-            nd.qhi[k][s] = qh;
+            // the integers as bf16 bit patterns (exact: q < 256 has at most 8 significant bits)
+            nd.q[2 * k][s] = (uint16_t)(__float_as_uint((float)ql) >> 16);
+            nd.q[2 * k + 1][s] = (uint16_t)(__float_as_uint((float)qh) >> 16);
         }
     }
 }
@@ -363,7 +364,7 @@ __device__ __forceinline__ void store_node(Node8* dst, const Node8& nd) {
     const uint4* s = reinterpret_cast<const uint4*>(&nd);
     uint4* d = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-    for (int i = 0; i < 8; i++) d[i] = s[i];
+    for (int i = 0; i < (int)RT_NODE_QUADS; i++) d[i] = s[i];
 }
 
 // ------------------------------------------------------------------------------------ 6
@@ -553,14 +554,14 @@ __global__ void k_refit(RefitArgs A) {
             const uint4* s = reinterpret_cast<const uint4*>(nd);
             uint4* d = reinterpret_cast<uint4*>(&cur);
 #pragma unroll
-            for (int i = 0; i < 8; i++) d[i] = __ldcg(s + i);
+            for (int i = 0; i < (int)RT_NODE_QUADS; i++) d[i] = __ldcg(s + i);
         }
         Aabb sb[8];
         uint32_t present = cur.imask | cur.lmask, rank = 0;
         for (int s = 0; s < 8; s++) {
             if (cur.imask >> s & 1) {
                 const Node8* c = &A.nodes[cur.child_base + rank++];
-                const float* f = reinterpret_cast<const float*>(c) + 20;  // lo at byte 80
+                const float* f = reinterpret_cast<const float*>(c) + RT_NODE_BOUNDS_FLOAT;  // Node8::lo, ::hi
                 for (int k = 0; k < 3; k++) { sb[s].lo[k] = __ldcg(f + k); sb[s].hi[k] = __ldcg(f + 3 + k); }
             } else if (cur.lmask >> s & 1) {
                 uint32_t off = cur.meta[s] & 31u, c = cur.meta[s] >> 5;
@@ -574,7 +575,7 @@ __global__ void k_refit(RefitArgs A) {
             const uint4* s = reinterpret_cast<const uint4*>(&cur);
             uint4* d = reinterpret_cast<uint4*>(nd);
 #pragma unroll
-            for (int i = 0; i < 8; i++) __stcg(d + i, s[i]);
+            for (int i = 0; i < (int)RT_NODE_QUADS; i++) __stcg(d + i, s[i]);
         }
         if (cur.parent == 0xFFFFFFFFu) return;
         __threadfence();

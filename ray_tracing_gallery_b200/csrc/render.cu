@@ -181,7 +181,10 @@ __device__ __forceinline__ V3 shade_textured(const SceneDev& S, const FrameDev& 
 enum { K_TRACE = 0, K_PREP = 1, K_SHADOW = 2, K_RESOLVE = 3, K_MEGA = 4, K_TAIL = 5 };
 
 #ifndef RT_TRACE_MINB
-#define RT_TRACE_MINB 5
+#define RT_TRACE_MINB 6   // resident blocks per SM asked of k_trace0: 5 / 6 / 7 measured after the bf16 box test, profiles/r02y_ab.txt
+#endif
+#ifndef RT_TRACE_N_MINB
+#define RT_TRACE_N_MINB 6   // same for the bounce-segment launches (k_trace_n): C4 -3 %
 #endif
 #ifndef RT_SHADOW_MINB
 #define RT_SHADOW_MINB 7
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(128, RT_TRACE_MINB) k_trace0(SceneDev S, Frame
 }
 // bounce segment as its own launch (RT_RENDER_SPLIT_TAIL): the ray count is read on the device
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_n(SceneDev S, FrameDev F, uint32_t seg) {
+__global__ void __launch_bounds__(128, RT_TRACE_N_MINB) k_trace_n(SceneDev S, FrameDev F, uint32_t seg) {
     trace_phase<false, COUNT>(S, F, seg, *((volatile unsigned int*)&seg_counters(F, seg - 1u)->ray_count));
 }
 __global__ void __launch_bounds__(128) k_prep(SceneDev S, FrameDev F, uint32_t seg) {
@@ -615,6 +618,7 @@ static int persistent_grid(K kernel, int sms) {
 cudaError_t init_launch_geometry(LaunchGeometry& g, int sms) {
     if (g.ready) return cudaSuccess;
     g.trace0[0] = persistent_grid(k_trace0<false>, sms); g.trace0[1] = persistent_grid(k_trace0<true>, sms);
+    g.trace_n[0] = persistent_grid(k_trace_n<false>, sms); g.trace_n[1] = persistent_grid(k_trace_n<true>, sms);
     g.shadow[0] = persistent_grid(k_shadow<false>, sms); g.shadow[1] = persistent_grid(k_shadow<true>, sms);
     g.tail[0] = persistent_grid(k_tail<false>, sms);     g.tail[1] = persistent_grid(k_tail<true>, sms);
     g.prep = persistent_grid(k_prep, sms);
@@ -704,8 +708,8 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
             mark(K_RESOLVE);
             for (uint32_t seg = 1; seg < F.max_segments; seg++) {
                 if (seg >= RT_SEG_SLOTS) { k_reset_segment<<<1, 1, 0, stream>>>(F.counters, seg); note_launch(); }
-                if (count) k_trace_n<true><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, seg);
-                else k_trace_n<false><<<fit(g_trace0[ci], 1), 128, 0, stream>>>(S, F, seg);
+                if (count) k_trace_n<true><<<fit(geom.trace_n[ci], 1), 128, 0, stream>>>(S, F, seg);
+                else k_trace_n<false><<<fit(geom.trace_n[ci], 1), 128, 0, stream>>>(S, F, seg);
                 mark(K_TRACE);
                 k_prep<<<fit(g_prep, 1), 128, 0, stream>>>(S, F, seg);
                 mark(K_PREP);

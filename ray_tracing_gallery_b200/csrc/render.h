@@ -18,7 +18,7 @@ struct FrameTiming {
 // different host threads, never share them.  [0] = plain kernels, [1] = the RT_RENDER_COUNTERS instantiations.
 struct LaunchGeometry {
     bool ready = false;
-    int trace0[2] = {0, 0}, shadow[2] = {0, 0}, tail[2] = {0, 0}, prep = 0, resolve = 0;
+    int trace0[2] = {0, 0}, trace_n[2] = {0, 0}, shadow[2] = {0, 0}, tail[2] = {0, 0}, prep = 0, resolve = 0;
 };
 cudaError_t init_launch_geometry(LaunchGeometry& g, int sms);
 

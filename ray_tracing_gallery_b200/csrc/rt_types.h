@@ -8,37 +8,39 @@
 namespace b200rt {
 
 // ---------------------------------------------------------------------------------------------
-// Compressed 8-wide BVH node.  One 128-byte, 128-byte-aligned record = one L2 line.
-// Traversal reads bytes 0..79 as five ld.global.nc.v4; bytes 80..127 are build/refit state.
+// Compressed 8-wide BVH node: two 128-byte lines, 256-byte aligned.  Traversal reads the FIRST line only (eight
+// ld.global.nc.v4: header + the near and far planes of the ray's octant); the second line is build / refit state.
 //
 // Child boxes are quantised to 8 bits per plane on a power-of-two grid anchored at `origin`:
-//     plane = origin[k] + q * 2^(exp[k] - 127)
-// The origin is snapped onto that grid and exp is clamped so that every plane is exactly
-// representable in fp32 (builder: quantise_node).  lo planes are rounded down, hi planes up.
-// Slots are assigned by the octant of the child centre relative to the node centre, so that
-// visiting hit slots in order of (slot XOR ray_octant) is front-to-back without sorting.
-// Internal children are stored contiguously from `child_base` in slot order
-// (child index = child_base + popc(imask & ((1<<slot)-1))); leaf primitives are stored
-// contiguously from `prim_base`: meta[slot] = offset (5 bits) | count << 5 (count 1..7) for a leaf
-// slot, 0xFF for an internal slot, 0 for an empty slot (which also has qlo = 255, qhi = 0).
-struct __align__(128) Node8 {
-    float    origin[3];   //  0
-    uint8_t  exp[3];      // 12  biased like an fp32 exponent field: cell size = 2^(exp - 127)
-    uint8_t  imask;       // 15  bit s: slot s is an internal child
-    uint32_t child_base;  // 16
-    uint32_t prim_base;   // 20
-    uint8_t  meta[8];     // 24
-    uint8_t  qlo[3][8];   // 32  [axis][slot]
-    uint8_t  qhi[3][8];   // 56
-    // ---- not read by traversal
-    float    lo[3];       // 80  exact bounds of this node
-    float    hi[3];       // 92
-    uint32_t parent;      // 104 wide-node index of the parent (0xFFFFFFFF for the root)
-    uint32_t parent_slot; // 108
-    uint32_t lmask;       // 112 bit s: slot s is a leaf child
-    uint32_t _pad[3];
+//     plane = origin[k] + q * 2^(exp[k] - 127),   q = 0..255
+// The origin is snapped onto that grid and exp is clamped so that every plane is exactly representable in fp32
+// (builder: quantise_node).  lo planes are rounded down, hi planes up.  The planes are STORED as bf16 numbers (the
+// integer q, exact in bf16's 8 significant bits), two slots per 32-bit word, so that the box test runs on packed
+// bf16x2 arithmetic with no unpacking: one HFMA2.BF16 per two planes (trace.cuh node_hit_mask).
+// Slots are assigned by the octant of the child centre relative to the node centre, so that visiting hit slots in
+// order of (slot XOR ray_octant) is front-to-back without sorting.  Internal children are stored contiguously from
+// `child_base` in slot order (child index = child_base + popc(imask & ((1<<slot)-1))); leaf primitives are stored
+// contiguously from `prim_base`: meta[slot] = offset (5 bits) | count << 5 (count 1..7) for a leaf slot, 0xFF for an
+// internal slot, 0 for an empty slot (which also has q lo = 255, q hi = 0).
+struct __align__(256) Node8 {
+    float    origin[3];   //   0
+    uint8_t  exp[3];      //  12  biased like an fp32 exponent field: cell size = 2^(exp - 127)
+    uint8_t  imask;       //  15  bit s: slot s is an internal child
+    uint32_t child_base;  //  16
+    uint32_t prim_base;   //  20
+    uint8_t  meta[8];     //  24
+    uint16_t q[6][8];     //  32  bf16 bit patterns: [2 * axis] = lo planes, [2 * axis + 1] = hi planes; [slot]
+    // ---- second line: not read by traversal
+    float    lo[3];       // 128  exact bounds of this node
+    float    hi[3];       // 140
+    uint32_t parent;      // 152  wide-node index of the parent (0xFFFFFFFF for the root)
+    uint32_t parent_slot; // 156
+    uint32_t lmask;       // 160  bit s: slot s is a leaf child
+    uint32_t _pad[23];
 };
-static_assert(sizeof(Node8) == 128, "Node8 must be one 128-byte line");
+static_assert(sizeof(Node8) == 256, "Node8 is two 128-byte lines");
+#define RT_NODE_QUADS (sizeof(Node8) / sizeof(uint4))
+#define RT_NODE_BOUNDS_FLOAT 32   // Node8::lo as a float index
 
 // Entries of a ray's traversal stack (trace.cuh): one per visited node that still has other hit children, one per TLAS leaf
 // found but not entered yet.  Typical depth < 10; an overflow is reported by the API (api.cu: check_stack_overflow).

@@ -67,65 +67,108 @@ __device__ __forceinline__ uint32_t permute_by_octant(uint32_t m, uint32_t oct) 
     return m;
 }
 
-// byte `SEL` of w placed in the mantissa of 1.0f: 1 + q * 2^-15.  `one` = the bits of 1.0f (SceneDev::one_bits).
-template <int SEL>
-__device__ __forceinline__ float byte_m(uint32_t w, uint32_t one) {
-    return __uint_as_float(__byte_perm(w, one, 0x7604u | (SEL << 4)));
+// ---- the box test: eight quantised child boxes against one ray, on packed bf16 arithmetic
+//
+// Per axis the ray parameter of grid plane q is t(q) = b + q*a with a = cell/d, b = (origin - o)/d (fp32).  The planes are
+// stored as bf16 integers, two slots per word, so one HFMA2.BF16 evaluates a plane of two children.  bf16 has 8 significant
+// bits; to keep that enough, everything is measured from a reference close to where the ray is inside the node:
+//     t_ref = max(entry of the ray into the node's grid box [0, 255 cells]^3, tmin)      (fp32, guarded downwards)
+//     u(q)  = t(q) - t_ref = c + q*a,  c = b - t_ref
+// At t_ref the ray sits on (or inside) the grid box, i.e. at a cell position q_o in [0, 255] on every axis, and
+// u(q) = (q - q_o)*a: |c| <= 255|a| and |u| <= 255|a| for every plane of the node.  Rounding errors (half an ulp = 2^-9):
+//     a -> bf16:  q * |a| * 2^-9 <= 0.498 |a|          c -/+ pad -> bf16:  (255 + PAD)|a| * 2^-9 <= 0.502 |a|
+//     the fma's own rounding:  |u| * 2^-9 <= 0.502 |a|
+// together at most 1.503 |a| = 1.503 cells of that axis; near planes are therefore evaluated with c - pad, far planes with
+// c + pad, pad = 1.5625 |a| plus the fp32 guard (|b| + |t_ref| + 256|a|) * 2^-21 that the fp32 version of this test carried:
+// the test stays conservative (a child is never missed), its boxes are about 1.6 cells = 0.6 % of the node's extent fatter.
+// A ray that misses the grid box altogether has no such bounds, but then it misses every child: whatever the arithmetic
+// yields is at worst a wasted visit.  min / max are exact; tf - tn >= 0 exactly when tf >= tn (round to nearest, x - x = +0).
+//
+// Cost: 24 HFMA2.BF16 + 22..26 HMNMX2.BF16 + 4 HADD2 for the 48 planes, against 48 PRMT + 48 FFMA + 24 FMNMX(3) + 16 mask
+// instructions of the fp32 version; the alu pipe (PRMT, FMNMX, LOP3, SHF: one warp instruction per two cycles per scheduler)
+// was what bounded a node visit (profiles/r02p_summary.md: alu 71 %, fma 29 %).
+__device__ __forceinline__ uint32_t bf2_fma(uint32_t q, uint32_t a, uint32_t c) {
+    uint32_t r;
+    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(q), "r"(a), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t bf2_max(uint32_t x, uint32_t y) {
+    uint32_t r;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y));
+    return r;
+}
+__device__ __forceinline__ uint32_t bf2_min(uint32_t x, uint32_t y) {
+    uint32_t r;
+    asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y));
+    return r;
+}
+__device__ __forceinline__ uint32_t bf2_sub(uint32_t x, uint32_t y) {
+    uint32_t r;
+    asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y));
+    return r;
+}
+// both halves = x rounded to nearest
+__device__ __forceinline__ uint32_t bf2_splat(float x) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x), "f"(x));
+    return r;
 }
 
-// Hit mask (bit s = slot s) of the eight quantised child boxes of a node against the ray (co, 1/cd = id*, octant oct) on
-// [tmin, tlimit]; empty slots are not masked here (the caller ands with nonzero_bytes(meta)).  FIRST_HIT: no far clamp.
+#ifndef RT_BOX_PAD_CELLS
+#define RT_BOX_PAD_CELLS 1.5625f
+#endif
+
+// Hit mask (bit s = slot s) of the eight child boxes of a node against the ray (origin co, 1 / direction = id*) on
+// [tmin, tlimit].  n0 = the node's first 16 bytes; nx..fz = its near / far planes per axis for this ray (Node8::q rows chosen
+// by the sign of the direction: the caller loads them from octant-dependent addresses).  Empty slots are not masked here
+// (the caller ands with nonzero_bytes(meta)).  FIRST_HIT: no far clamp.
 template <bool FIRST_HIT>
-__device__ __forceinline__ uint32_t node_hit_mask(const uint4& n0, const uint4& n2, const uint4& n3, const uint4& n4, V3 co, float idx, float idy,
-                                                  float idz, uint32_t oct, float tmin, float tlimit, uint32_t one) {
-    // per-axis: A = 2^15 * 2^e / d, B = (origin - o)/d - A, padded outwards by p
+__device__ __forceinline__ uint32_t node_hit_mask(const uint4& n0, const uint4& nx, const uint4& fx, const uint4& ny, const uint4& fy, const uint4& nz,
+                                                  const uint4& fz, V3 co, float idx, float idy, float idz, float tmin, float tlimit) {
     // (the exponent bytes are stored biased: shifted into place they ARE the cell sizes 2^e)
-    float ax = __uint_as_float((n0.w << 23) & 0x7F800000u) * idx;
-    float ay = __uint_as_float((n0.w << 15) & 0x7F800000u) * idy;
-    float az = __uint_as_float((n0.w << 7) & 0x7F800000u) * idz;
-    float bx = (__uint_as_float(n0.x) - co.x) * idx;
-    float by = (__uint_as_float(n0.y) - co.y) * idy;
-    float bz = (__uint_as_float(n0.z) - co.z) * idz;
-    float Ax = ax * 32768.0f, Ay = ay * 32768.0f, Az = az * 32768.0f;
-    float Bx = fmaf(-32768.0f, ax, bx), By = fmaf(-32768.0f, ay, by), Bz = fmaf(-32768.0f, az, bz);
-    float px = (fabsf(bx) + fabsf(Ax)) * 4.76837158e-7f;
-    float py = (fabsf(by) + fabsf(Ay)) * 4.76837158e-7f;
-    float pz = (fabsf(bz) + fabsf(Az)) * 4.76837158e-7f;
-    float Bnx = Bx - px, Bfx = Bx + px, Bny = By - py, Bfy = By + py, Bnz = Bz - pz, Bfz = Bz + pz;
-    // near / far plane words per axis, chosen by ray direction
-    uint32_t nx0, nx1, fx0, fx1, ny0, ny1, fy0, fy1, nz0, nz1, fz0, fz1;
-    if (oct & 1u) { nx0 = n3.z; nx1 = n3.w; fx0 = n2.x; fx1 = n2.y; } else { nx0 = n2.x; nx1 = n2.y; fx0 = n3.z; fx1 = n3.w; }
-    if (oct & 2u) { ny0 = n4.x; ny1 = n4.y; fy0 = n2.z; fy1 = n2.w; } else { ny0 = n2.z; ny1 = n2.w; fy0 = n4.x; fy1 = n4.y; }
-    if (oct & 4u) { nz0 = n4.z; nz1 = n4.w; fz0 = n3.x; fz1 = n3.y; } else { nz0 = n3.x; nz1 = n3.y; fz0 = n4.z; fz1 = n4.w; }
-    // closest-hit rays cull children beyond the committed hit; first-hit rays keep tmax for the triangles only
-    // (a child box beyond tmax = 10 000 scene units is visited in vain, never wrongly accepted)
-    uint32_t h = 0;
-    // The hit mask comes from the sign bits of tf - tn, shifted in with one funnel shift per child: 8 FADD on the fma pipe +
-    // 8 SHF instead of 8 FSETP + 8 predicated adds on the alu pipe, which carries twice the fma pipe's load in this
-    // block (profiles/r02a_ab.txt: -0.2 .. -0.6 % frame time on C2..C5).  tn >= tmin > 0, so tf - tn is never -0 for a
-    // hit; a NaN may read as a hit, which only costs a wasted visit.  Slots are committed 0..7: slot s ends at bit 7 - s.
-#define RT_BOX_COMMIT(SLOT, TN, TF) h = __funnelshift_l(__float_as_uint((TF) - (TN)), h, 1);
-#define RT_BOX(SLOT, SEL, WNX, WNY, WNZ, WFX, WFY, WFZ)                                                            \
-    {                                                                                                             \
-        float tn = fmaxf(fmaxf(fmaf(byte_m<SEL>(WNX, one), Ax, Bnx), fmaf(byte_m<SEL>(WNY, one), Ay, Bny)),       \
-                         fmaxf(fmaf(byte_m<SEL>(WNZ, one), Az, Bnz), tmin));                                      \
-        float tfz = fmaf(byte_m<SEL>(WFZ, one), Az, Bfz);                                                         \
-        if (!FIRST_HIT) tfz = fminf(tfz, tlimit);                                                                 \
-        float tf = fminf(fminf(fmaf(byte_m<SEL>(WFX, one), Ax, Bfx), fmaf(byte_m<SEL>(WFY, one), Ay, Bfy)), tfz); \
-        RT_BOX_COMMIT(SLOT, tn, tf)                                                                               \
+    const float ax = __uint_as_float((n0.w << 23) & 0x7F800000u) * idx;
+    const float ay = __uint_as_float((n0.w << 15) & 0x7F800000u) * idy;
+    const float az = __uint_as_float((n0.w << 7) & 0x7F800000u) * idz;
+    const float bx = (__uint_as_float(n0.x) - co.x) * idx;
+    const float by = (__uint_as_float(n0.y) - co.y) * idy;
+    const float bz = (__uint_as_float(n0.z) - co.z) * idz;
+    // fp32 guards per axis, then the entry into the grid box
+    const float gx = fmaf(fabsf(ax), 256.0f, fabsf(bx)) * 4.76837158e-7f;
+    const float gy = fmaf(fabsf(ay), 256.0f, fabsf(by)) * 4.76837158e-7f;
+    const float gz = fmaf(fabsf(az), 256.0f, fabsf(bz)) * 4.76837158e-7f;
+    const float ex = fminf(bx, fmaf(255.0f, ax, bx)) - gx;
+    const float ey = fminf(by, fmaf(255.0f, ay, by)) - gy;
+    const float ez = fminf(bz, fmaf(255.0f, az, bz)) - gz;
+    const float t_ref = fmaxf(fmaxf(ex, ey), fmaxf(ez, tmin));
+    const float gr = fabsf(t_ref) * 4.76837158e-7f;
+    const float px = fmaf(fabsf(ax), RT_BOX_PAD_CELLS, gx + gr);
+    const float py = fmaf(fabsf(ay), RT_BOX_PAD_CELLS, gy + gr);
+    const float pz = fmaf(fabsf(az), RT_BOX_PAD_CELLS, gz + gr);
+    const float cx = bx - t_ref, cy = by - t_ref, cz = bz - t_ref;
+    const uint32_t Ax = bf2_splat(ax), Ay = bf2_splat(ay), Az = bf2_splat(az);
+    const uint32_t Nx = bf2_splat(cx - px), Ny = bf2_splat(cy - py), Nz = bf2_splat(cz - pz);
+    const uint32_t Fx = bf2_splat(cx + px), Fy = bf2_splat(cy + py), Fz = bf2_splat(cz + pz);
+    // closest-hit rays cull children beyond the committed hit (rounded up); first-hit rays keep tmax for the triangles only
+    uint32_t TL = 0;
+    if (!FIRST_HIT) {
+        const float tl = tlimit - t_ref;
+        TL = bf2_splat(fmaf(fabsf(tl), 0.0078125f, tl) + gr);
     }
-    RT_BOX(0, 0, nx0, ny0, nz0, fx0, fy0, fz0)
-    RT_BOX(1, 1, nx0, ny0, nz0, fx0, fy0, fz0)
-    RT_BOX(2, 2, nx0, ny0, nz0, fx0, fy0, fz0)
-    RT_BOX(3, 3, nx0, ny0, nz0, fx0, fy0, fz0)
-    RT_BOX(4, 0, nx1, ny1, nz1, fx1, fy1, fz1)
-    RT_BOX(5, 1, nx1, ny1, nz1, fx1, fy1, fz1)
-    RT_BOX(6, 2, nx1, ny1, nz1, fx1, fy1, fz1)
-    RT_BOX(7, 3, nx1, ny1, nz1, fx1, fy1, fz1)
-#undef RT_BOX
-#undef RT_BOX_COMMIT
-    h = __brev(~h) >> 24;  // sign clear = hit; bit 7 - s -> bit s
-    return h;
+    // two children per word: .x = slots 0,1  .y = 2,3  .z = 4,5  .w = 6,7 (even slot in the low half)
+#define RT_BOX2(W)                                                                                         \
+    ({                                                                                                     \
+        uint32_t tn = bf2_max(bf2_max(bf2_fma(nx.W, Ax, Nx), bf2_fma(ny.W, Ay, Ny)), bf2_max(bf2_fma(nz.W, Az, Nz), 0u)); \
+        uint32_t tf = bf2_min(bf2_min(bf2_fma(fx.W, Ax, Fx), bf2_fma(fy.W, Ay, Fy)), bf2_fma(fz.W, Az, Fz));               \
+        if (!FIRST_HIT) tf = bf2_min(tf, TL);                                                              \
+        bf2_sub(tf, tn);                                                                                   \
+    })
+    const uint32_t d0 = RT_BOX2(x), d1 = RT_BOX2(y), d2 = RT_BOX2(z), d3 = RT_BOX2(w);
+#undef RT_BOX2
+    // sign bytes of the eight differences (bytes 1 and 3 of each word) -> one bit per slot; sign set = miss
+    const uint32_t s03 = __byte_perm(d0, d1, 0x7531), s47 = __byte_perm(d2, d3, 0x7531);
+    const uint32_t m03 = (((s03 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+    const uint32_t m47 = (((s47 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+    return ~(m03 | (m47 << 4)) & 0xFFu;
 }
 
 // Shadow rays stop at the first accepted hit, whatever its distance: their children need no front-to-back order, so
@@ -169,7 +212,7 @@ struct Traverser {
     // bounds of the TLAS root, padded for the approximate reciprocals).  Saves the 8-child test of the root
     // for sky rays; only worth its ~20 instructions for rays that start outside the scene (primary rays).
     __device__ __forceinline__ bool touches_scene(const SceneDev& S) const {
-        const float4* rb = reinterpret_cast<const float4*>(S.tlas_nodes) + 5;  // bytes 80..111: lo[3], hi[3], parent, slot
+        const float4* rb = reinterpret_cast<const float4*>(S.tlas_nodes) + RT_NODE_BOUNDS_FLOAT / 4;  // Node8::lo[3], hi[3], parent, slot
         float4 a = __ldg(rb), b = __ldg(rb + 1);
         float x0 = (a.x - o.x) * idx, x1 = (a.w - o.x) * idx;
         float y0 = (a.y - o.y) * idy, y1 = (b.x - o.y) * idy;
@@ -240,10 +283,16 @@ struct Traverser {
             if (ng_bits & 0xFFu) push(stack, ng_base, ng_bits, tc);
             const Node8* nodes = inst_sp >= 0 ? S.blas_nodes : S.tlas_nodes;
             const uint4* np = reinterpret_cast<const uint4*>(nodes + child);
-            uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            // header, then per axis the near and the far planes of this ray's octant (Node8::q rows 2k and 2k + 1, swapped
+            // for a negative direction): the choice is made in the address, not with selects afterwards
+            const uint32_t sx = oct & 1u, sy = (oct >> 1) & 1u, sz = oct >> 2;
+            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1);
+            const uint4 nx = __ldg(np + 2 + sx), fx = __ldg(np + 3 - sx);
+            const uint4 ny = __ldg(np + 4 + sy), fy = __ldg(np + 5 - sy);
+            const uint4 nz = __ldg(np + 6 + sz), fz = __ldg(np + 7 - sz);
             if (COUNT) tc.nodes++;
 
-            uint32_t h = node_hit_mask<ANY>(n0, n2, n3, n4, co, idx, idy, idz, oct, tmin, hit.t, S.one_bits);
+            uint32_t h = node_hit_mask<ANY>(n0, nx, fx, ny, fy, nz, fz, co, idx, idy, idz, tmin, hit.t);
             uint32_t imask = n0.w >> 24;
             h &= nonzero_bytes(n1.z, n1.w);
             uint32_t hl = h & ~imask;
