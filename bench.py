@@ -201,10 +201,10 @@ NCU_NAME = {"trace": "k_trace", "prep": "k_prep", "shadow": "k_shadow", "resolve
 def algorithmic_bytes(st, setup, pixels):
     """Algorithmic bytes of one frame per kernel (DESIGN.md 'Roofline accounting').
 
-    Traversal: 80 B read per node visit (the five 16-byte words the box test needs), 64 B per instance entered,
+    Traversal: 128 B read per node visit (the eight 16-byte words of a node's first line: header + bf16 planes), 64 B per instance entered,
     48 B per triangle tested, 12 + 24 + 16 B per any-hit call (indices, 3 uvs, one bilinear tap)."""
     n = setup.shadow_rays
-    trav = [80 * st.nodes_visited[k] + 64 * st.instances_entered[k] + 48 * st.triangles_tested[k] + 52 * st.anyhit_calls[k] for k in (0, 1)]
+    trav = [128 * st.nodes_visited[k] + 64 * st.instances_entered[k] + 48 * st.triangles_tested[k] + 52 * st.anyhit_calls[k] for k in (0, 1)]
     hits = st.textured_hits
     bounces = st.primary_rays - pixels
     trace_b = trav[0] + 64 * bounces + 112 * bounces + 48 * hits + 4 * (pixels - hits)
