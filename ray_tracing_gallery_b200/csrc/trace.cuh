@@ -171,6 +171,37 @@ __device__ __forceinline__ uint32_t node_hit_mask(const uint4& n0, const uint4& 
     return ~(m03 | (m47 << 4)) & 0xFFu;
 }
 
+// The traversal stack of one ray.  RT_SMEM_STACK = N > 0 (A/B): the first N entries live in shared memory (entry e of thread t at
+// [e * 128 + t]: consecutive lanes, consecutive 8-byte words, no bank conflicts), deeper entries in local memory; 0: all of
+// it in local memory.  The top of the stack proper — the node group being worked on — is always in registers (ng_base, ng_bits).
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 0
+#endif
+#define RT_SMEM_ENTRIES (RT_SMEM_STACK < RT_STACK_SIZE ? RT_SMEM_STACK : RT_STACK_SIZE)
+#if RT_SMEM_STACK > 0
+__device__ __forceinline__ uint2* block_stack_base() {
+    __shared__ uint2 s_stack[RT_SMEM_ENTRIES * 128];  // every kernel of the path runs 128-thread blocks
+    return s_stack;
+}
+#endif
+struct RayStack {
+#if RT_SMEM_STACK > 0
+    uint2* sm;
+    uint2 lm[RT_STACK_SIZE > RT_SMEM_ENTRIES ? RT_STACK_SIZE - RT_SMEM_ENTRIES : 1];
+    __device__ __forceinline__ void init() { sm = block_stack_base() + threadIdx.x; }
+    __device__ __forceinline__ void store(int i, uint2 v) {
+        if (i < RT_SMEM_ENTRIES) sm[i * 128] = v;
+        else lm[i - RT_SMEM_ENTRIES] = v;
+    }
+    __device__ __forceinline__ uint2 load(int i) const { return i < RT_SMEM_ENTRIES ? sm[i * 128] : lm[i - RT_SMEM_ENTRIES]; }
+#else
+    uint2 lm[RT_STACK_SIZE];
+    __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ void store(int i, uint2 v) { lm[i] = v; }
+    __device__ __forceinline__ uint2 load(int i) const { return lm[i]; }
+#endif
+};
+
 // Shadow rays stop at the first accepted hit, whatever its distance: their children need no front-to-back order, so
 // the octant permutation of the pending mask is skipped for them (measured: profiles/r01n_ab.txt).
 #define RT_UNORDERED(ANY) (ANY)
@@ -222,8 +253,8 @@ struct Traverser {
         return !(tn > tf + 4e-6f * (fabsf(tn) + fabsf(tf)) + 1e-30f);  // NaN (empty scene bounds) -> traverse
     }
 
-    __device__ __forceinline__ void push(uint2* stack, uint32_t x, uint32_t y, TraceCounters& tc) {
-        if (sp < RT_STACK_SIZE) stack[sp++] = make_uint2(x, y);
+    __device__ __forceinline__ void push(RayStack& stack, uint32_t x, uint32_t y, TraceCounters& tc) {
+        if (sp < RT_STACK_SIZE) stack.store(sp++, make_uint2(x, y));
         else tc.overflow++;
     }
 
@@ -262,7 +293,7 @@ struct Traverser {
     // that a popped group is visited and a popped or freshly found instance is entered in the same step, and the warp
     // runs as few passes over the three blocks as its longest ray needs.  Returns true when the ray is finished (then
     // found() tells hit or miss).
-    __device__ __forceinline__ bool step(const SceneDev& S, uint2* stack, TraceCounters& tc) {
+    __device__ __forceinline__ bool step(const SceneDev& S, RayStack& stack, TraceCounters& tc) {
         if ((ng_bits & 0xFFu) == 0u) {
             // ---- current group exhausted: pop
             if (inst_sp >= 0 && sp == inst_sp) {
@@ -270,7 +301,7 @@ struct Traverser {
                 set_space(o, d);
             }
             if (sp == 0) return true;
-            uint2 e = stack[--sp];
+            uint2 e = stack.load(--sp);
             if (e.y & 0x80000000u) enter_inst = e.x;
             else { ng_base = e.x; ng_bits = e.y; }
         }
@@ -373,7 +404,8 @@ struct Traverser {
 // Run one ray to completion (megakernel path, tests).
 template <bool ANY, bool COUNT, bool OUTSIDE_START = false>
 __device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float tmin, float tmax, Hit& hit, TraceCounters& tc) {
-    uint2 stack[RT_STACK_SIZE];
+    RayStack stack;
+    stack.init();
     Traverser<ANY, COUNT> T;
     T.begin(o, d, tmin, tmax);
     if (OUTSIDE_START && !T.touches_scene(S)) { hit = T.hit; return false; }
