@@ -182,6 +182,8 @@ extern "C" {
     pub fn rt_group_readback(group: *mut RtGroup, seq: u64, host_rgba8: *mut c_void, capacity_bytes: usize) -> c_int;
     pub fn rt_group_local_ray_counts(group: *mut RtGroup, out_device_counts: *mut *mut u64) -> c_int;
     pub fn rt_group_barrier(group: *mut RtGroup) -> c_int;
+    pub fn rt_debug_box_test(ctx: *mut RtContext, tlas: c_int, first_node: u32, num_nodes: u32, rays: *const f32, num_rays: u32, out_masks: *mut u8,
+                             out_node_lines: *mut c_void) -> c_int;
     pub fn rt_debug_l2_read_bandwidth(ctx: *mut RtContext, bytes: usize, repeats: u32, out_gb_per_s: *mut f32) -> c_int;
     pub fn rt_kernel_launches() -> u64;
     pub fn rt_version() -> u32;

@@ -334,6 +334,14 @@ int  rt_group_local_ray_counts(RtGroup* group, uint64_t** out_device_counts);
 /* All ranks, collectively: every rank's stream work is finished (ncclAllReduce of one word + stream sync). */
 int  rt_group_barrier(RtGroup* group);
 
+/* Audit of the traversal's box test (tests/test_gpu_parity.py::test_box_test_is_conservative): runs it — the packed-bf16
+ * node_hit_mask of trace.cuh, exactly as a node visit does — for every pair of `num_rays` rays and wide nodes
+ * [first_node, first_node + num_nodes) of the BLAS pool (tlas == 0) or of the current TLAS (tlas != 0).
+ * rays: num_rays x 8 floats {origin xyz, tmin, direction xyz, tmax}.  out_masks: [num_rays][num_nodes][2] bytes, bit s = child
+ * slot s reported hit (before the empty-slot mask): [0] first-hit form (no far clamp), [1] closest-hit form with the far limit
+ * at tmax.  out_node_lines (optional): the nodes' first 128-byte lines (header + bf16 planes), num_nodes x 128 bytes. */
+int  rt_debug_box_test(RtContext* ctx, int tlas, uint32_t first_node, uint32_t num_nodes, const float* rays, uint32_t num_rays,
+                       uint8_t* out_masks, void* out_node_lines);
 /* Micro-benchmark behind bench.py's `l2_frac`: read a device buffer of `bytes` (cache-resident when well below the 126 MB L2)
  * `repeats` times with 16-byte loads from a full persistent grid and report read bytes / kernel time (CUDA events). */
 int  rt_debug_l2_read_bandwidth(RtContext* ctx, size_t bytes, uint32_t repeats, float* out_gb_per_s);

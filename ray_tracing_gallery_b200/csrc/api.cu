@@ -989,6 +989,41 @@ int rt_debug_l2_read_bandwidth(RtContext* ctx, size_t bytes, uint32_t repeats, f
     return RT_OK;
 }
 
+int rt_debug_box_test(RtContext* ctx, int tlas, uint32_t first_node, uint32_t num_nodes, const float* rays, uint32_t num_rays, uint8_t* out_masks,
+                      void* out_node_lines) {
+    if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+    if (!rays || !out_masks || !num_nodes || !num_rays) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_debug_box_test: bad argument");
+    if ((uint64_t)num_nodes * num_rays > (1ull << 28)) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_debug_box_test: more than 2^28 pairs");
+    CK_DEV(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    const Node8* pool = nullptr;
+    uint64_t have = 0;
+    if (tlas) {
+        if (!ctx->tlas_built) return fail(ctx, RT_ERR_NOT_BUILT, "rt_debug_box_test: no TLAS");
+        uint32_t count = 0;
+        CK(cudaMemcpy(&count, ctx->sets[ctx->cur].d_node_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        pool = ctx->sets[ctx->cur].d_tlas_nodes;
+        have = count;
+    } else {
+        pool = ctx->blas_nodes.ptr;
+        have = ctx->blas_nodes.size;
+    }
+    if ((uint64_t)first_node + num_nodes > have) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_debug_box_test: node range outside the pool");
+    float4* d_rays = nullptr;
+    uint8_t* d_out = nullptr;
+    const size_t pairs = (size_t)num_nodes * num_rays;
+    CK(cudaMalloc(&d_rays, sizeof(float4) * 2 * num_rays));
+    CK(cudaMalloc(&d_out, pairs * 2));
+    CK(cudaMemcpyAsync(d_rays, rays, sizeof(float4) * 2 * num_rays, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_debug_box_test(pool + first_node, num_nodes, d_rays, num_rays, d_out, ctx->stream));
+    CK(cudaMemcpyAsync(out_masks, d_out, pairs * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_node_lines)
+        CK(cudaMemcpy2DAsync(out_node_lines, 128, pool + first_node, sizeof(Node8), 128, num_nodes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_rays); cudaFree(d_out);
+    return RT_OK;
+}
+
 int rt_debug_read_model_info(RtContext* ctx, uint32_t model_id, RtModelInfo* out_info, RtGeometryInfo* out_geoms, uint32_t max_geoms) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
     if (model_id >= ctx->models.size()) return fail(ctx, RT_ERR_OUT_OF_RANGE, "rt_debug_read_model_info: no such model");

@@ -590,6 +590,23 @@ __global__ void k_export_counts(const FrameCounters* c, uint64_t* out) {
     out[1] = c->shadow_rays;
 }
 
+// Box-test audit (rt_debug_box_test): the traversal's node_hit_mask for every (ray, node) pair, first-hit and closest-hit form.
+__global__ void __launch_bounds__(128) k_debug_box_test(const Node8* __restrict__ nodes, uint32_t num_nodes, const float4* __restrict__ rays, uint32_t num_rays,
+                                                        uint8_t* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_rays * num_nodes) return;
+    const uint32_t r = t / num_nodes, nidx = t - r * num_nodes;
+    const float4 ro = rays[2 * r], rd = rays[2 * r + 1];
+    const V3 co = v3(ro.x, ro.y, ro.z), cd = v3(rd.x, rd.y, rd.z);
+    const float idx = safe_rcp(cd.x), idy = safe_rcp(cd.y), idz = safe_rcp(cd.z);
+    const uint32_t sx = cd.x < 0.0f ? 1u : 0u, sy = cd.y < 0.0f ? 1u : 0u, sz = cd.z < 0.0f ? 1u : 0u;
+    const uint4* np = reinterpret_cast<const uint4*>(nodes + nidx);
+    const uint4 n0 = __ldg(np);
+    const uint4 nx = __ldg(np + 2 + sx), fx = __ldg(np + 3 - sx), ny = __ldg(np + 4 + sy), fy = __ldg(np + 5 - sy), nz = __ldg(np + 6 + sz), fz = __ldg(np + 7 - sz);
+    out[2 * (size_t)t] = (uint8_t)node_hit_mask<true>(n0, nx, fx, ny, fy, nz, fz, co, idx, idy, idz, ro.w, rd.w);
+    out[2 * (size_t)t + 1] = (uint8_t)node_hit_mask<false>(n0, nx, fx, ny, fy, nz, fz, co, idx, idy, idz, ro.w, rd.w);
+}
+
 }  // namespace
 
 // Launch with the programmatic-stream-serialisation attribute (see pdl_wait); plain launch when `pdl` is false.
@@ -734,6 +751,14 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
     return cudaGetLastError();
 }
 
+}  // namespace b200rt
+
+namespace b200rt {
+cudaError_t launch_debug_box_test(const Node8* nodes, uint32_t num_nodes, const float4* rays, uint32_t num_rays, uint8_t* out, cudaStream_t stream) {
+    const uint64_t total = (uint64_t)num_nodes * num_rays;
+    if (total) { k_debug_box_test<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(nodes, num_nodes, rays, num_rays, out); note_launch(); }
+    return cudaGetLastError();
+}
 }  // namespace b200rt
 
 extern "C" int rt_denoise_bilateral(void* user, void* cuda_stream, const RtDenoiseBuffers* b) {

@@ -34,6 +34,9 @@ cudaError_t launch_frame(const SceneDev& S, const FrameDev& F, uint32_t pipeline
                          const LaunchGeometry& geom, uint64_t* d_ray_counts,
                          FrameTiming* timing, cudaStream_t stream, const DenoiseHook* hook = nullptr, int* hook_status = nullptr);
 
+// rt_debug_box_test: node_hit_mask of every (ray, node) pair -> out[ray][node][2] (first-hit form, closest-hit form with tlimit = tmax)
+cudaError_t launch_debug_box_test(const Node8* nodes, uint32_t num_nodes, const float4* rays, uint32_t num_rays, uint8_t* out, cudaStream_t stream);
+
 // BLAS input: per flattened triangle (geometry-major) the padded AABB.
 struct ModelGeomDev {
     const float* positions;         // float3 per vertex

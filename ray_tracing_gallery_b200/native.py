@@ -22,7 +22,7 @@ EXPORTS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_push_image", "rt_create_model", "rt_build_tlas",
     "rt_update_instances", "rt_update_instances_device", "rt_update_tlas", "rt_render", "rt_render_device", "rt_render_async",
     "rt_wait_frame", "rt_render_device_slot", "rt_host_alloc", "rt_host_free", "rt_readback",
-    "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_debug_l2_read_bandwidth", "rt_kernel_launches", "rt_version",
+    "rt_sync", "rt_get_stats", "rt_get_push_constants", "rt_debug_read_model_info", "rt_debug_l2_read_bandwidth", "rt_debug_box_test", "rt_kernel_launches", "rt_version",
     "rt_set_denoise_hook", "rt_denoise_bilateral",
     "rt_group_unique_id", "rt_group_create", "rt_group_destroy", "rt_group_last_error", "rt_group_partition", "rt_group_update_instances",
     "rt_group_update_instances_device", "rt_group_build_tlas",
@@ -66,6 +66,7 @@ def load():
     lib.rt_debug_read_model_info.argtypes = [p, u32, C.POINTER(abi.RtModelInfo), C.POINTER(abi.RtGeometryInfo), u32]
     lib.rt_version.restype = u32
     lib.rt_debug_l2_read_bandwidth.argtypes = [p, C.c_size_t, u32, C.POINTER(C.c_float)]
+    lib.rt_debug_box_test.argtypes = [p, C.c_int, u32, u32, p, u32, p, p]
     lib.rt_set_denoise_hook.argtypes = [p, p, p]
     lib.rt_denoise_bilateral.argtypes = [p, p, C.POINTER(abi.RtDenoiseBuffers)]
     u64 = C.c_uint64
@@ -173,6 +174,18 @@ class Renderer(CApiBackend):
         out = C.c_float()
         self._check(self.lib.rt_debug_l2_read_bandwidth(self.ctx, nbytes, repeats, C.byref(out)), "debug_l2_read_bandwidth")
         return float(out.value)
+
+    def box_test(self, rays, first_node: int, num_nodes: int, tlas: bool = False):
+        """`rt_debug_box_test`: rays (n, 8) float32 {origin, tmin, direction, tmax} -> (masks (n, num_nodes, 2) uint8, node lines
+        (num_nodes, 128) uint8): what the traversal's box test reports for every (ray, node) pair."""
+        import numpy as np
+
+        rays = np.ascontiguousarray(rays, dtype=np.float32)
+        masks = np.zeros((len(rays), num_nodes, 2), np.uint8)
+        lines = np.zeros((num_nodes, 128), np.uint8)
+        self._check(self.lib.rt_debug_box_test(self.ctx, 1 if tlas else 0, first_node, num_nodes, rays.ctypes.data, len(rays), masks.ctypes.data,
+                                               lines.ctypes.data), "debug_box_test")
+        return masks, lines
 
     def push_constants(self) -> abi.RtPushConstantBufferAddresses:
         pc = abi.RtPushConstantBufferAddresses()

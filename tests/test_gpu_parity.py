@@ -331,6 +331,91 @@ def test_many_instances_tile_parity():
     orc.close(); gpu.close()
 
 
+def _decode_node_lines(lines):
+    """First 128-byte lines of wide nodes -> (origin (n,3), cell (n,3), lo (n,3,8), hi (n,3,8) plane positions in float64, present (n,8))."""
+    n = len(lines)
+    origin = lines[:, 0:12].copy().view(np.float32).astype(np.float64)
+    exp = lines[:, 12:15].astype(np.int64)
+    cell = np.ldexp(1.0, exp - 127)
+    meta = lines[:, 24:32]
+    q = (lines[:, 32:128].copy().view(np.uint16).astype(np.uint32) << 16).view(np.float32).reshape(n, 6, 8).astype(np.float64)  # bf16 -> value
+    assert np.all(q == np.round(q)) and q.min() >= 0 and q.max() <= 255
+    lo = origin[:, :, None] + q[:, 0::2, :] * cell[:, :, None]
+    hi = origin[:, :, None] + q[:, 1::2, :] * cell[:, :, None]
+    return origin, cell, lo, hi, meta != 0
+
+
+def test_box_test_is_conservative():
+    """The packed-bf16 box test of a node visit (trace.cuh node_hit_mask, through rt_debug_box_test) against an exact float64 slab
+    test of the same quantised child boxes: a child the ray touches on [tmin, tmax] must ALWAYS be reported, for random rays and for
+    the adversarial ones — axis-parallel and nearly parallel directions, rays aimed exactly at box corners and along box faces, origins
+    inside the node, origins ten thousand units away.  Also reports how many extra children the padded test lets through."""
+    gpu = make_renderer()
+    build_scene(gpu, "c2", 64, 64)  # lain's BLAS + a small TLAS
+    st = gpu.stats()
+    rng = np.random.default_rng(7)
+    for tlas, first, count in ((False, 0, min(st.blas_nodes, 400)), (False, max(st.blas_nodes - 300, 0), min(st.blas_nodes, 300)), (True, 0, st.tlas_nodes)):
+        _, lines = gpu.box_test(np.array([[0, 0, 0, 0.01, 0, 0, 1, 1e4]], np.float32), first, count, tlas)
+        origin, cell, lo, hi, present = _decode_node_lines(lines)
+        centre = origin + 127.5 * cell
+        extent = 255.0 * cell
+        rays = []
+        for k in range(count):
+            c, e = centre[k], np.maximum(extent[k], 1e-6)
+            slots = np.flatnonzero(present[k])
+            for _ in range(6):  # random rays through the node's neighbourhood
+                o = c + (rng.random(3) - 0.5) * 3.0 * e
+                t = c + (rng.random(3) - 0.5) * 1.2 * e
+                rays.append((k, o, t - o))
+            for s_ in slots[:4]:  # aimed exactly at a corner of a child box; along one of its faces; parallel to an axis through it
+                corner = np.array([(lo if rng.random() < 0.5 else hi)[k, a, s_] for a in range(3)])
+                o = c + (rng.random(3) - 0.5) * 4.0 * e
+                rays.append((k, o, corner - o))
+                a = rng.integers(3)
+                d = rng.standard_normal(3); d[a] = 0.0
+                o2 = corner - d * 2.0
+                rays.append((k, o2, d))
+                d3 = np.zeros(3); d3[a] = 1.0 if rng.random() < 0.5 else -1.0
+                mid = 0.5 * (lo[k, :, s_] + hi[k, :, s_])
+                rays.append((k, mid - d3 * 3.0 * e, d3))
+                d4 = d3.copy(); d4[(a + 1) % 3] = 1e-9; d4[(a + 2) % 3] = -3e-12
+                rays.append((k, mid - d4 * 2.0 * e, d4))
+            rays.append((k, c + 0.1 * e * (rng.random(3) - 0.5), rng.standard_normal(3)))           # starts inside
+            far = rng.standard_normal(3); far /= np.linalg.norm(far)
+            rays.append((k, c - far * 1.0e4, far * (1.0 + 1e-7 * rng.standard_normal())))           # from far away
+        ray_arr = np.zeros((len(rays), 8), np.float32)
+        for i, (_, o, d) in enumerate(rays):
+            d = d / max(np.linalg.norm(d), 1e-30)
+            ray_arr[i] = (o[0], o[1], o[2], 0.001, d[0], d[1], d[2], 1.0e4 if i % 3 else 50.0)
+        node_of = np.array([k for k, _, _ in rays])
+        masks = np.zeros((len(rays), 2), np.uint8)
+        for k0 in range(0, count, 64):  # ray x node pairs in blocks of nodes (the call tests every pair)
+            sel = np.flatnonzero((node_of >= k0) & (node_of < k0 + 64))
+            m, _ = gpu.box_test(ray_arr[sel], first + k0, min(64, count - k0), tlas)
+            masks[sel] = m[np.arange(len(sel)), node_of[sel] - k0]
+        # exact slab test in float64 on the float32 rays the device saw
+        o = ray_arr[:, 0:3].astype(np.float64); d = ray_arr[:, 4:7].astype(np.float64)
+        tmin = ray_arr[:, 3].astype(np.float64); tmax = ray_arr[:, 7].astype(np.float64)
+        L, H = lo[node_of], hi[node_of]                    # (rays, 3, 8)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t0 = (L - o[:, :, None]) / d[:, :, None]
+            t1 = (H - o[:, :, None]) / d[:, :, None]
+        par = (d == 0.0)[:, :, None] & np.ones((1, 1, 8), bool)
+        inside = (o[:, :, None] >= L) & (o[:, :, None] <= H)
+        near = np.where(par, np.where(inside, -np.inf, np.inf), np.minimum(t0, t1))
+        far_ = np.where(par, np.where(inside, np.inf, -np.inf), np.maximum(t0, t1))
+        tn = np.maximum(near.max(axis=1), tmin[:, None]); tf = np.minimum(far_.min(axis=1), tmax[:, None])
+        exact = (tn <= tf) & present[node_of] & np.all(L <= H, axis=1)
+        for form in (0, 1):
+            got = ((masks[:, form, None] >> np.arange(8)) & 1).astype(bool)
+            missed = exact & ~got
+            assert not missed.any(), f"box test missed {missed.sum()} children (form {form}, tlas {tlas}); first: ray {ray_arr[np.argwhere(missed)[0][0]]}"
+            extra = (got & present[node_of] & ~exact).sum()
+            print(f"{'TLAS' if tlas else 'BLAS'} nodes {first}..{first + count}: {len(rays)} rays, form {form}: {exact.sum()} children touched, all reported; "
+                  f"{extra} reported but not touched ({extra / max(exact.sum(), 1):.1%} of the touched)")
+    gpu.close()
+
+
 def test_full_size_c5_tile_parity():
     """BASELINE configs[4] at its stated size: ALL 1 000 001 instances, 16 soft-shadow rays, a 960x270 tile of the 3840x2160
     launch against the oracle (the whole frame would be ~140 M oracle rays)."""
