@@ -761,6 +761,14 @@ cudaError_t launch_debug_box_test(const Node8* nodes, uint32_t num_nodes, const 
 }
 }  // namespace b200rt
 
+#ifdef RT_LANE_HIST
+extern "C" int rt_debug_lane_hist(unsigned long long* out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, b200rt::g_lane_hist, sizeof(unsigned long long) * 66);
+    if (reset) { unsigned long long z[66] = {}; cudaMemcpyToSymbol(b200rt::g_lane_hist, z, sizeof(z)); }
+    return (int)cudaGetLastError();
+}
+#endif
+
 extern "C" int rt_denoise_bilateral(void* user, void* cuda_stream, const RtDenoiseBuffers* b) {
     if (!b || !b->sun_factor || !b->position_nol) return RT_ERR_INVALID_ARGUMENT;
     const size_t pixels = (size_t)b->width * b->rows;

@@ -401,6 +401,10 @@ struct Traverser {
     }
 };
 
+#ifdef RT_LANE_HIST
+__device__ unsigned long long g_lane_hist[2][33];
+#endif
+
 // Run one ray to completion (megakernel path, tests).
 template <bool ANY, bool COUNT, bool OUTSIDE_START = false>
 __device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float tmin, float tmax, Hit& hit, TraceCounters& tc) {
@@ -409,7 +413,15 @@ __device__ __forceinline__ bool trace_ray(const SceneDev& S, V3 o, V3 d, float t
     Traverser<ANY, COUNT> T;
     T.begin(o, d, tmin, tmax);
     if (OUTSIDE_START && !T.touches_scene(S)) { hit = T.hit; return false; }
+#ifdef RT_LANE_HIST
+    // scratch instrumentation (tools/gpu_lane_hist.py): passes of the batch by the number of lanes still traversing
+    while (!T.step(S, stack, tc)) {
+        const uint32_t m = __activemask();
+        if ((threadIdx.x & 31u) == (uint32_t)(__ffs(m) - 1)) atomicAdd(&g_lane_hist[ANY ? 1 : 0][__popc(m)], 1ull);
+    }
+#else
     while (!T.step(S, stack, tc)) {}
+#endif
     hit = T.hit;
     return T.found();
 }
