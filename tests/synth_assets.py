@@ -138,11 +138,12 @@ def build_bumpy_scene(backend, width=640, height=360, shadow_rays=2):
     return s
 
 
-def build_random_scene(backend, seed: int, width=256, height=144):
+def build_random_scene(backend, seed: int, width=256, height=144, offset=(0.0, 0.0, 0.0)):
     """Seeded random stress scene for the traversal semantics: a triangle soup in two geometries (one alpha-masked with a
     random NEAREST texture), a second model with exactly coincident duplicate triangles (exact t ties: lowest ids must win),
     instances with arbitrary rotations, non-uniform and NEGATIVE scales, mirror / portal / textured hit groups, one
-    degenerate (zero-area) triangle, a camera orbiting the origin."""
+    degenerate (zero-area) triangle, a camera orbiting the origin.  `offset` moves the whole scene (instances and camera) away
+    from the origin: large coordinates against small node grids are where the traversal's box test has least room."""
     from ray_tracing_gallery_b200 import abi
     from ray_tracing_gallery_b200.gltf import Geometry, ModelArrays
     from ray_tracing_gallery_b200.scene import Camera, SceneSetup, Sun, load_model, make_instance, mat_scale, push_builtin_images
@@ -195,8 +196,13 @@ def build_random_scene(backend, seed: int, width=256, height=144):
         kind = (abi.RT_HIT_TEXTURED, abi.RT_HIT_TEXTURED, abi.RT_HIT_MIRROR, abi.RT_HIT_PORTAL)[int(rng.integers(0, 4))]
         inst.append(make_instance(random_transform(), model, handle, kind, True))
     inst.append(inst[3].copy())  # an exact duplicate INSTANCE: every hit on it ties with instance 3, the lower gl_InstanceID wins
+    off = np.float32(offset)
+    if np.any(off != 0):
+        for rec in inst:
+            rec["transform"].reshape(3, 4)[:, 3] += off  # row-major 3x4: translation column
     ang = rng.uniform(0, 2 * np.pi)
-    cam = Camera(eye=(float(9 * np.sin(ang)), float(rng.uniform(2.5, 5.0)), float(-9 * np.cos(ang))), pitch=-0.25, yaw=float(np.pi - ang))
+    cam = Camera(eye=(float(9 * np.sin(ang)) + float(off[0]), float(rng.uniform(2.5, 5.0)) + float(off[1]), float(-9 * np.cos(ang)) + float(off[2])),
+                 pitch=-0.25, yaw=float(np.pi - ang))
     s = SceneSetup(f"random{seed}", np.stack(inst), cam, Sun(pitch=float(rng.uniform(0.3, 1.2)), yaw=float(rng.uniform(0, 6.28))), width, height,
                    shadow_rays=int(rng.integers(1, 6)), sun_radius=float(rng.uniform(0.0, 0.08)), description="seeded random stress scene")
     backend.build_tlas(s.instances)
