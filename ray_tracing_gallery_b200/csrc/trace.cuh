@@ -120,8 +120,8 @@ __device__ __forceinline__ uint32_t bf2_splat(float x) {
 
 // Hit mask (bit s = slot s) of the eight child boxes of a node against the ray (origin co, 1 / direction = id*) on
 // [tmin, tlimit].  n0 = the node's first 16 bytes; nx..fz = its near / far planes per axis for this ray (Node8::q rows chosen
-// by the sign of the direction: the caller loads them from octant-dependent addresses).  Empty slots are not masked here
-// (the caller ands with nonzero_bytes(meta)).  FIRST_HIT: no far clamp.
+// by the sign of the direction: the caller loads them from octant-dependent addresses).  Empty slots are stored as inverted boxes and fail on
+// their own.  FIRST_HIT: no far clamp.
 template <bool FIRST_HIT>
 __device__ __forceinline__ uint32_t node_hit_mask(const uint4& n0, const uint4& nx, const uint4& fx, const uint4& ny, const uint4& fy, const uint4& nz,
                                                   const uint4& fz, V3 co, float idx, float idy, float idz, float tmin, float tlimit) {
@@ -324,8 +324,14 @@ struct Traverser {
             if (COUNT) tc.nodes++;
 
             uint32_t h = node_hit_mask<ANY>(n0, nx, fx, ny, fy, nz, fz, co, idx, idy, idz, tmin, hit.t);
+            // Empty slots need no mask: their boxes are stored inverted (q lo = 255, q hi = 0), 255 cells against a padding of
+            // 1.6 — they fail the test on their own.  Only non-finite arithmetic (a ray that misses the node altogether, at the
+            // edge of the number range) could report one: an empty slot is never an internal child (imask bit clear), its meta
+            // byte is 0 = no triangles in a BLAS, and the TLAS leaf loop below skips meta 0.
+            // First-hit rays leave it at that (-4 % on k_shadow, profiles/r03hij_empty_slot_mask_ab.txt); closest-hit rays keep the explicit
+            // mask from the meta bytes: without it k_trace0 compiles to a 10 % slower kernel at identical counters.
             uint32_t imask = n0.w >> 24;
-            h &= nonzero_bytes(n1.z, n1.w);
+            if (!ANY) h &= nonzero_bytes(n1.z, n1.w);
             uint32_t hl = h & ~imask;
             ng_base = n1.x;
             ng_bits = (RT_UNORDERED(ANY) ? (h & imask) : permute_by_octant(h & imask, oct)) | (imask << 8);
@@ -342,14 +348,16 @@ struct Traverser {
                         if (test_triangle(S, first + k, co, cd, cur_inst_pos, cur_instance_id, cur_custom_sbt, tc) && ANY) return true;
                 }
             } else if (hl) {
-                // TLAS leaves: enter the first now, stack the others
+                // TLAS leaves: enter the first now, stack the others (meta 0: an empty slot reported by non-finite arithmetic)
                 uint32_t s = __ffs(hl) - 1;
                 hl &= hl - 1;
-                enter_inst = n1.y + ((uint32_t)(meta >> (8 * s)) & 31u);
+                uint32_t m = (uint32_t)(meta >> (8 * s)) & 0xFFu;
+                enter_inst = m ? n1.y + (m & 31u) : RT_NONE;
                 while (hl) {
                     s = __ffs(hl) - 1;
                     hl &= hl - 1;
-                    push(stack, n1.y + ((uint32_t)(meta >> (8 * s)) & 31u), 0x80000000u, tc);
+                    m = (uint32_t)(meta >> (8 * s)) & 0xFFu;
+                    if (m) push(stack, n1.y + (m & 31u), 0x80000000u, tc);
                 }
             }
         }
