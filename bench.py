@@ -517,6 +517,9 @@ class Bench:
                 "issue_frac": thread_inst / 32.0 / sec / 1e9 / peak_issue,             # full-width instruction rate / peak
                 "l2_frac": nc["lts_bytes"] * scale / sec / 1e9 / self.l2_peak if self.l2_peak else None,
                 "l2_gbs": nc["lts_bytes"] * scale / sec / 1e9,
+                # L1 data pipe: one wavefront per SM per clock (l1tex__data_pipe_lsu_wavefronts): since the bf16 box test the unit next to
+                # instruction issue (a node visit = eight 16-byte loads per lane)
+                "l1_wavefront_frac": (nc["l1_wavefronts"] * scale / sec / (self.sms * self.sm_max_mhz * 1e6)) if nc.get("l1_wavefronts") else None,
                 "dram_frac": nc["dram_bytes"] * scale / sec / 1e9 / self.hbm_peak,
                 "traffic": nc["dram_bytes"] * scale,
                 "ncu_duration_ms": nc.get("duration_ms"),
@@ -528,6 +531,7 @@ class Bench:
             "achieved": achieved, "peak": peak_issue, "unit": "G warp-instructions/s at full SIMD width (thread instructions / 32)",
             "frac": issue.get("issue_frac"),
             "issue_slot_frac": issue.get("issue_slot_frac"), "active_lanes": issue.get("active_lanes"),
+            "l1_wavefront_frac": issue.get("l1_wavefront_frac"),
             "l2_frac": issue.get("l2_frac"), "l2_gbs": issue.get("l2_gbs"), "l2_peak_gbs": self.l2_peak,
             "dram_frac": issue.get("dram_frac"), "traffic": issue.get("traffic"),
             "hbm": {"bound": "hbm", "achieved": algo_gbs, "peak": self.hbm_peak, "unit": "GB/s", "frac": algo_gbs / self.hbm_peak,

@@ -14,7 +14,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-METRICS = "gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,lts__t_bytes.sum,dram__bytes_read.sum,dram__bytes_write.sum"
+METRICS = ("gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,lts__t_bytes.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
+           "l1tex__data_pipe_lsu_wavefronts.sum")
 FAMILIES = ["k_sun_dirs", "k_trace", "k_prep", "k_shadow", "k_resolve", "k_tail", "k_mega"]
 
 
@@ -79,11 +80,12 @@ def main():
             continue
         fams = {}
         for l in frame:
-            f = fams.setdefault(family(l["name"]), {"warp_inst": 0.0, "thread_inst": 0.0, "lts_bytes": 0.0, "dram_bytes": 0.0, "duration_ms": 0.0, "launches": 0})
+            f = fams.setdefault(family(l["name"]), {"warp_inst": 0.0, "thread_inst": 0.0, "lts_bytes": 0.0, "dram_bytes": 0.0, "l1_wavefronts": 0.0, "duration_ms": 0.0, "launches": 0})
             f["warp_inst"] += l.get("smsp__inst_executed.sum", 0.0)
             f["thread_inst"] += l.get("smsp__thread_inst_executed.sum", 0.0)
             f["lts_bytes"] += l.get("lts__t_bytes.sum", 0.0)
             f["dram_bytes"] += l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0)
+            f["l1_wavefronts"] += l.get("l1tex__data_pipe_lsu_wavefronts.sum", 0.0)
             f["duration_ms"] += l.get("gpu__time_duration.sum", 0.0)
             f["launches"] += 1
         for f in fams.values():
