@@ -138,7 +138,7 @@ typedef struct RtStats {
     float    kernel_ms[6];      /* with RT_RENDER_TIMING: {trace kernels, k_prep, k_shadow, k_resolve (split-tail path only),
                                    k_mega, k_tail (resolve + bounce segments + ray-count export)} */
     uint32_t kernel_launches[6];/* launches behind kernel_ms */
-    uint32_t tlas_nodes;        /* 128-byte wide nodes in the current TLAS */
+    uint32_t tlas_nodes;        /* wide (8-child) nodes in the current TLAS */
     uint32_t blas_nodes;        /* over all models */
     uint32_t num_instances;
     uint32_t num_triangles;     /* over all models */

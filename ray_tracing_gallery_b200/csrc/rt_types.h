@@ -142,10 +142,7 @@ struct SceneDev {
     const TexEntry*   textures;
     uint32_t          num_textures;
     const float*      srgb_lut;      // 512 floats: sRGB EOTF per 8-bit code, then code / 255
-    // The bits of 1.0f as a kernel parameter.  The box test merges plane bytes into this word with PRMT; SASS PRMT has one
-    // immediate slot, and when ptxas knows the word is a constant it spends the slot on it and re-materialises the four byte
-    // selectors into registers before most of the 48 PRMTs of a node visit.  Coming from the constant bank, the word is
-    // a plain operand and the selectors stay immediates (A/B: -DRT_PRMT_CONST_ONE).
+    // (round 1's fp32 box test merged plane bytes into this word, the bits of 1.0f, with PRMT; unused since the bf16 test)
     uint32_t          one_bits;
 };
 

@@ -11,18 +11,14 @@
 //   * shadow rays (ANY = true) stop at the first accepted candidate.
 //
 // Mechanics: one thread per ray, written as a resumable state machine (`Traverser::step` = one
-// node visit, instance entry or stack pop) so that persistent warps can swap finished rays for
-// new ones between steps.  A node visit is five ld.global.nc.v4 (80 of the node's 128 bytes).
+// node visit, instance entry or stack pop).  A node visit is eight ld.global.nc.v4: the first 128-byte
+// line of the node (header + bf16 planes; the near / far rows of the ray's octant are chosen in the address).
 // The stack holds "node groups" — (child_base, pending-hit mask, imask) — so a node costs one
 // slot however many of its children were hit; slots were assigned at build time by child octant,
 // so visiting pending bits in order of (slot XOR ray_octant) is front-to-back with no distance
 // sort.  TLAS leaves (instances) that are hit but not entered yet are stacked as single entries.
 //
-// Box test: child planes are bytes q on the node grid, t = q*a + b with a = 2^e/d, b = (origin-o)/d.
-// The byte is dropped into the mantissa of 1.0 (m = 1 + q*2^-15, one PRMT, no int->float convert)
-// and t = fma(m, A, B) with A = 2^15*a, B = b - A.  B's rounding error is <= (|b|+|A|)*2^-24, i.e.
-// at most 1/512 of a grid cell; near planes use B - p and far planes B + p with
-// p = (|b|+|A|)*2^-21, so the test stays conservative.
+// Box test: packed bf16, two children per instruction — see node_hit_mask below.
 #pragma once
 #include "shade.cuh"
 
@@ -84,7 +80,7 @@ __device__ __forceinline__ uint32_t permute_by_octant(uint32_t m, uint32_t oct) 
 // A ray that misses the grid box altogether has no such bounds, but then it misses every child: whatever the arithmetic
 // yields is at worst a wasted visit.  min / max are exact; tf - tn >= 0 exactly when tf >= tn (round to nearest, x - x = +0).
 //
-// Cost: 24 HFMA2.BF16 + 22..26 HMNMX2.BF16 + 4 HADD2 for the 48 planes, against 48 PRMT + 48 FFMA + 24 FMNMX(3) + 16 mask
+// Cost: 24 HFMA2.BF16 + 8 VHMNMX.BF16 (3-input) + 4..8 HMNMX2.BF16 + 4 HADD2 for the 48 planes, against 48 PRMT + 48 FFMA + 24 FMNMX(3) + 16 mask
 // instructions of the fp32 version; the alu pipe (PRMT, FMNMX, LOP3, SHF: one warp instruction per two cycles per scheduler)
 // was what bounded a node visit (profiles/r02p_summary.md: alu 71 %, fma 29 %).
 __device__ __forceinline__ uint32_t bf2_fma(uint32_t q, uint32_t a, uint32_t c) {
