@@ -228,7 +228,6 @@ int render_common(RtContext* ctx, FrameResources& R, const RtUniforms* u, const 
     S.textures = ctx->d_textures;
     S.num_textures = (uint32_t)ctx->tex_host.size();
     S.srgb_lut = ctx->d_srgb_lut;
-    S.one_bits = 0x3F800000u;
     FrameDev F;
     memset(&F, 0, sizeof(F));
     F.uniforms = *u;

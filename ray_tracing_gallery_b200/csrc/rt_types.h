@@ -142,8 +142,6 @@ struct SceneDev {
     const TexEntry*   textures;
     uint32_t          num_textures;
     const float*      srgb_lut;      // 512 floats: sRGB EOTF per 8-bit code, then code / 255
-    // (round 1's fp32 box test merged plane bytes into this word, the bits of 1.0f, with PRMT; unused since the bf16 test)
-    uint32_t          one_bits;
 };
 
 struct FrameDev {
