@@ -640,7 +640,8 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     m.blas.root = node_offset;
     m.blas.num_tris = nt;
     m.blas.tri_first = prim_offset;
-    m.blas._pad = 0;
+    m.blas.num_verts = nv <= RT_TIGHT_BOX_MAX_VERTS ? nv : 0;
+    m.blas.verts = m.positions;
     for (int k = 0; k < 3; k++) { m.blas.lo[k] = root.lo[k]; m.blas.hi[k] = root.hi[k]; }
 
     // ---- ModelInfo / BlasInfo tables (reference layout, device pointers in the u64 fields)

@@ -141,6 +141,64 @@ __global__ void k_prepare_instances(const RtInstance* __restrict__ instances, ui
     out_boxes[slot] = wb;
 }
 
+// Exact world bounds for the instances of small models: one warp per instance walks the model's vertices through the
+// instance transform.  The box of the eight transformed corners of the object-space bounds (k_prepare_instances, what a
+// Vulkan driver's TLAS build uses) is up to 1.41x too wide per axis for a rotated model — every instance box of C4 / C5 is a
+// torus pair turned about y — and a wider leaf box is entered by rays that have no business inside the BLAS.  Triangles lie in
+// the convex hull of their vertices, so the result (padded like the corner box and intersected with it) stays conservative;
+// vertices that are not finite can only belong to inactive triangles and are skipped.
+__device__ __forceinline__ int ordered_int(float f) {
+    int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7FFFFFFF);
+}
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7FFFFFFF)); }
+
+__global__ void __launch_bounds__(256) k_tighten_instance_boxes(const RtInstance* __restrict__ instances, uint32_t n,
+                                                                const BlasInfo* __restrict__ blas, uint32_t num_models,
+                                                                const uint32_t* __restrict__ leaf_order, Aabb* boxes) {
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (slot >= n) return;
+    const uint32_t id = leaf_order ? leaf_order[slot] : slot;
+    const uint4* rp = reinterpret_cast<const uint4*>(instances + id);
+    const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+    const uint64_t handle = ((uint64_t)q3.w << 32) | q3.z;
+    const uint32_t model = (uint32_t)(handle & 0xFFFFFFFFu) - 1u;
+    if ((handle >> 48) != 0xB200u || model >= num_models) return;
+    const uint32_t nv = blas[model].num_verts;
+    const float* __restrict__ verts = blas[model].verts;
+    if (nv == 0 || blas[model].num_tris == 0) return;
+    const float m00 = __uint_as_float(q0.x), m01 = __uint_as_float(q0.y), m02 = __uint_as_float(q0.z), m03 = __uint_as_float(q0.w);
+    const float m10 = __uint_as_float(q1.x), m11 = __uint_as_float(q1.y), m12 = __uint_as_float(q1.z), m13 = __uint_as_float(q1.w);
+    const float m20 = __uint_as_float(q2.x), m21 = __uint_as_float(q2.y), m22 = __uint_as_float(q2.z), m23 = __uint_as_float(q2.w);
+    float lx = CUDART_INF_F, ly = CUDART_INF_F, lz = CUDART_INF_F, hx = -CUDART_INF_F, hy = -CUDART_INF_F, hz = -CUDART_INF_F;
+#pragma unroll 4
+    for (uint32_t v = lane; v < nv; v += 32) {
+        const float px = __ldg(verts + 3 * (size_t)v), py = __ldg(verts + 3 * (size_t)v + 1), pz = __ldg(verts + 3 * (size_t)v + 2);
+        const float wx = m00 * px + m01 * py + m02 * pz + m03;
+        const float wy = m10 * px + m11 * py + m12 * pz + m13;
+        const float wz = m20 * px + m21 * py + m22 * pz + m23;
+        if (isfinite(wx) && isfinite(wy) && isfinite(wz)) {  // (a non-finite vertex gives non-finite sums)
+            lx = fminf(lx, wx); hx = fmaxf(hx, wx);
+            ly = fminf(ly, wy); hy = fmaxf(hy, wy);
+            lz = fminf(lz, wz); hz = fmaxf(hz, wz);
+        }
+    }
+    Aabb t;
+    t.lo[0] = ordered_float(__reduce_min_sync(0xFFFFFFFFu, ordered_int(lx)));
+    t.lo[1] = ordered_float(__reduce_min_sync(0xFFFFFFFFu, ordered_int(ly)));
+    t.lo[2] = ordered_float(__reduce_min_sync(0xFFFFFFFFu, ordered_int(lz)));
+    t.hi[0] = ordered_float(__reduce_max_sync(0xFFFFFFFFu, ordered_int(hx)));
+    t.hi[1] = ordered_float(__reduce_max_sync(0xFFFFFFFFu, ordered_int(hy)));
+    t.hi[2] = ordered_float(__reduce_max_sync(0xFFFFFFFFu, ordered_int(hz)));
+    if (lane != 0) return;
+    Aabb c = boxes[slot];
+    if (!(c.lo[0] <= c.hi[0]) || !(t.lo[0] <= t.hi[0])) return;  // instance without geometry / refused by k_prepare_instances; no usable vertex
+    pad_box(t);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { c.lo[k] = fmaxf(c.lo[k], t.lo[k]); c.hi[k] = fminf(c.hi[k], t.hi[k]); }
+    boxes[slot] = c;
+}
+
 __global__ void k_gather_instances(const InstRT* __restrict__ in, const uint32_t* __restrict__ leaf_order, uint32_t n, InstRT* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -189,7 +247,14 @@ cudaError_t launch_gather_triangles(const ModelGeomDev& M, const uint32_t* leaf_
 }
 cudaError_t launch_prepare_instances(const RtInstance* instances, uint32_t n, const BlasInfo* blas, uint32_t num_models,
                                      const uint32_t* leaf_order, InstRT* out_rt, Aabb* out_boxes, cudaStream_t stream) {
-    if (n) { k_prepare_instances<<<(n + 127) / 128, 128, 0, stream>>>(instances, n, blas, num_models, leaf_order, out_rt, out_boxes); note_launch(); }
+    if (n) {
+        k_prepare_instances<<<(n + 127) / 128, 128, 0, stream>>>(instances, n, blas, num_models, leaf_order, out_rt, out_boxes);
+        note_launch();
+#ifndef RT_NO_TIGHT_BOXES
+        k_tighten_instance_boxes<<<(uint32_t)(((size_t)n * 32 + 255) / 256), 256, 0, stream>>>(instances, n, blas, num_models, leaf_order, out_boxes);
+        note_launch();
+#endif
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_gather_instances(const InstRT* in, const uint32_t* leaf_order, uint32_t n, InstRT* out, cudaStream_t stream) {
