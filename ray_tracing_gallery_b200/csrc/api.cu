@@ -80,7 +80,7 @@ int ensure_instance_capacity(RtContext* ctx, uint32_t n) {
 // Build (or refit) the TLAS of set `dst` from dst's instance records.  A refit keeps the topology of set `src`
 // (VK mode UPDATE with src == dst in the reference, src/util_structs.rs:309-319; here src may be the other set, whose
 // nodes, leaf order and node count are copied over first).
-int build_tlas_now(RtContext* ctx, uint32_t mode, uint32_t src, uint32_t dst) {
+int build_tlas_now(RtContext* ctx, uint32_t mode, uint32_t src, uint32_t dst, bool static_build = false) {
     uint32_t n = ctx->num_instances;
     cudaStream_t st = ctx->stream;
     RtContext::TlasSet& D = ctx->sets[dst];
@@ -98,7 +98,8 @@ int build_tlas_now(RtContext* ctx, uint32_t mode, uint32_t src, uint32_t dst) {
     } else {
         CK(launch_prepare_instances(D.d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), nullptr,
                                     ctx->d_inst_unsorted, ctx->d_inst_boxes, st));
-        CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, D.d_tlas_nodes, 0, 0, D.d_leaf_order, D.d_node_count, true, /*sah_collapse=*/true, st));
+        CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, D.d_tlas_nodes, 0, 0, D.d_leaf_order, D.d_node_count, true, /*sah_collapse=*/true, st,
+                               /*sah_splits=*/static_build && RT_TLAS_SAH));
         CK(launch_gather_instances(ctx->d_inst_unsorted, D.d_leaf_order, n, D.d_inst_rt, st));
         ctx->writes_since_build = 0;
     }
@@ -340,7 +341,7 @@ int internal_begin_full_build(RtContext* ctx, uint32_t count) {
     return RT_OK;
 }
 // the ordinary (every rank builds everything) build over the records already in the current set
-int internal_build_tlas_replicated(RtContext* ctx) { return build_tlas_now(ctx, RT_UPDATE_REBUILD, ctx->cur, ctx->cur); }
+int internal_build_tlas_replicated(RtContext* ctx) { return build_tlas_now(ctx, RT_UPDATE_REBUILD, ctx->cur, ctx->cur, /*static_build=*/true); }
 cudaStream_t internal_stream(RtContext* ctx) { return ctx->stream; }
 int internal_device(RtContext* ctx) { return ctx->device; }
 }  // namespace b200rt
@@ -617,7 +618,8 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     M.positions = m.positions; M.indices = d_index_ptrs; M.geom_start = d_geom_start; M.geom_opaque = d_geom_opaque;
     M.num_geoms = ng; M.num_tris = nt; M.num_vertices = nv;
     CKT(launch_triangle_boxes(M, d_boxes, st));
-    CKT(ctx->builder.build(d_boxes, nt, RT_BLAS_LEAF_TRIS, ctx->blas_nodes.ptr, node_offset, prim_offset, d_leaf_order, d_count, false, /*sah_collapse=*/false, st));
+    CKT(ctx->builder.build(d_boxes, nt, RT_BLAS_LEAF_TRIS, ctx->blas_nodes.ptr, node_offset, prim_offset, d_leaf_order, d_count, false, /*sah_collapse=*/RT_BLAS_SAH_COLLAPSE != 0, st,
+                           /*sah_splits=*/RT_BLAS_SAH != 0));
     CKT(launch_gather_triangles(M, d_leaf_order, ctx->tris.ptr + prim_offset, st));
     uint32_t node_count = 0;
     Node8 root;
@@ -677,7 +679,7 @@ int rt_build_tlas(RtContext* ctx, const RtInstance* instances, uint32_t count) {
     ctx->tlas_built = false;
     ctx->staged = false;
     if (count) CK(cudaMemcpyAsync(ctx->sets[ctx->cur].d_instances, instances, sizeof(RtInstance) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-    rc = build_tlas_now(ctx, RT_UPDATE_REBUILD, ctx->cur, ctx->cur);
+    rc = build_tlas_now(ctx, RT_UPDATE_REBUILD, ctx->cur, ctx->cur, /*static_build=*/true);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));  // the caller may free `instances` now
     return RT_OK;

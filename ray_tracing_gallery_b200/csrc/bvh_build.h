@@ -29,8 +29,11 @@ public:
     // sah_collapse: children of each wide node from the SAH-optimal cut table (else greedy largest-area expansion).
     // fast_sort: Morton keys keep only as many bits as n needs (fewer radix passes; per-frame TLAS rebuilds).
     // Everything is enqueued on `stream`; no host synchronisation.
+    // sah_splits: the binary tree is grown top-down with binned-SAH splits instead of the Morton radix tree (one-time builds:
+    // every BLAS).  This variant synchronises the stream once per tree level.
     cudaError_t build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
-                      uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, bool sah_collapse, cudaStream_t stream);
+                      uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, bool sah_collapse, cudaStream_t stream,
+                      bool sah_splits = false);
 
     // Refit in place: recompute boxes bottom-up for a tree built by build() whose leaf order is
     // unchanged.  d_boxes_leaf_order[i] = new box of the primitive at leaf position i.

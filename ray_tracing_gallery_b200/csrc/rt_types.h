@@ -63,6 +63,19 @@ static_assert(sizeof(TriRec) == 48, "TriRec is 48 bytes");
 // visit and culls nothing, so small leaves win (profiles/r01_notes.md).
 #define RT_BLAS_LEAF_TRIS 2u
 
+// Binary tree under the wide nodes (bvh_build.cu): top-down binned-SAH splits (step 4b) for one-time builds — every BLAS, the TLAS of
+// rt_build_tlas / rt_group_build_tlas — and the Morton radix tree for per-frame rebuilds (rt_update_tlas REBUILD).  Measured
+// (profiles/r04cd_sah_builder_ab.txt): C5 55.8 -> 42.8 ms, C4 7.61 -> 6.31 ms with both, of which the TLAS is the larger part.
+#ifndef RT_BLAS_SAH
+#define RT_BLAS_SAH 1
+#endif
+#ifndef RT_BLAS_SAH_COLLAPSE
+#define RT_BLAS_SAH_COLLAPSE 0
+#endif
+#ifndef RT_TLAS_SAH
+#define RT_TLAS_SAH 1
+#endif
+
 // Per-instance traversal record in TLAS leaf order: four float4.
 struct __align__(16) InstRT {
     float    inv[12];      // world -> object, row-major 3x4

@@ -209,6 +209,53 @@ def build_random_scene(backend, seed: int, width=256, height=144, offset=(0.0, 0
     return s
 
 
+def build_rod_scene(backend, seed=11, width=320, height=180):
+    """Instances whose exact world bounds are far smaller than the box of their transformed object-space corners: thin rods along
+    the body diagonal of their box, under arbitrary rotations, shears and mirrorings (k_tighten_instance_boxes walks the vertices of
+    models with <= 4096 of them).  The rod model carries two vertices no triangle references — one NaN, one 1e30 — and a second
+    soup model has 4 500 vertices, so its instances keep the corner box."""
+    from ray_tracing_gallery_b200 import abi
+    from ray_tracing_gallery_b200.gltf import Geometry, ModelArrays
+    from ray_tracing_gallery_b200.scene import Camera, SceneSetup, Sun, load_model, make_instance, mat_scale, push_builtin_images
+
+    rng = np.random.default_rng(seed)
+    push_builtin_images(backend)
+    pid, ph, _ = load_model(backend, "plane.glb", 0)
+    mr = backend.push_image(np.asarray([1.0, 0.5, 0.2, 1.0], np.float32).reshape(1, 1, 4), abi.RT_FORMAT_RGBA32_SFLOAT, False)
+
+    def soup(centres, size):
+        v = centres[:, None, :] + rng.uniform(-size, size, (len(centres), 3, 3))
+        pos = v.reshape(-1, 3).astype(np.float32)
+        nrm = np.repeat(np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]), 3, axis=0).astype(np.float32)
+        nrm[np.all(nrm == 0, axis=1)] = (0, 1, 0)
+        return pos, nrm, rng.uniform(0, 1, (len(pos), 2)).astype(np.float32)
+
+    t = rng.uniform(-1.0, 1.0, (220, 1))
+    pos, nrm, uv = soup(t * np.float64([1.5, 1.0, 1.2]), 0.06)
+    n_ref = len(pos)
+    pos = np.concatenate([pos, np.float32([[np.nan, 0, 0], [1e30, -1e30, 1e30]])])
+    nrm = np.concatenate([nrm, np.float32([[0, 1, 0], [0, 1, 0]])])
+    uv = np.concatenate([uv, np.zeros((2, 2), np.float32)])
+    rid, rh = backend.create_model(ModelArrays("rod", pos, nrm, uv, [Geometry(np.arange(n_ref, dtype=np.uint32), True, 1, mr, -1)]))
+    pos, nrm, uv = soup(rng.uniform(-1.0, 1.0, (1500, 3)) * np.float64([1.0, 0.15, 1.0]), 0.05)
+    bid, bh = backend.create_model(ModelArrays("slab", pos, nrm, uv, [Geometry(np.arange(len(pos), dtype=np.uint32), True, 0, mr, -1)]))
+
+    inst = [make_instance(mat_scale(10.0), pid, ph, abi.RT_HIT_TEXTURED)]
+    for k in range(40):
+        a = rng.normal(size=(3, 3))
+        q, _ = np.linalg.qr(a)
+        shear = np.eye(3); shear[0, 1] = rng.uniform(-0.5, 0.5)
+        m = np.eye(4, dtype=np.float32)
+        m[:3, :3] = (q @ shear * rng.uniform(0.3, 1.0, 3) * rng.choice([1.0, -1.0], 3)).astype(np.float32)
+        m[:3, 3] = (rng.uniform(-4.0, 4.0, 3) * np.float64([1, 0.3, 1]) + np.float64([0, 1.8, 0])).astype(np.float32)
+        model, handle = ((rid, rh), (bid, bh))[k % 5 == 4]
+        inst.append(make_instance(m, model, handle, (abi.RT_HIT_TEXTURED, abi.RT_HIT_MIRROR)[k % 7 == 3], True))
+    s = SceneSetup("rods", np.stack(inst), Camera(eye=(0.5, 4.0, -9.0), pitch=-0.3), Sun(pitch=0.8, yaw=1.0), width, height,
+                   shadow_rays=3, sun_radius=0.04, description="rods: exact instance bounds against corner boxes")
+    backend.build_tlas(s.instances)
+    return s
+
+
 def build_mosaic_scene(backend, n_images=72, cells=(36, 20), width=480, height=270, seed=5):
     """A wall of small quads, each cell with its own material out of `n_images` real (non-1x1) images, dealt so that
     neighbouring cells differ: the 8x4-pixel tile a warp traces covers half a dozen images.  Every third material is
