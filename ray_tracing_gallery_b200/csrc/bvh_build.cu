@@ -31,6 +31,12 @@ namespace cg = cooperative_groups;
 namespace b200rt {
 namespace {
 
+// Slot assignment refined by pairwise exchanges (collapse_task): 0 = off, 1 = BLASes only (shipped: C2's closest-hit rays -14 %, the
+// TLAS of C5 loses 2 % with it), 2 = every tree.  profiles/r04ef_slot_assignment_ab.txt
+#ifndef RT_SLOT_OPT
+#define RT_SLOT_OPT 1
+#endif
+
 enum { ST_LEVEL_BEGIN = 0, ST_LEVEL_END = 1, ST_WIDE_COUNT = 2, ST_PRIM_CURSOR = 3 };
 
 __device__ __forceinline__ int f2ord(float f) {
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) 
     if (tid < 3) s_cb[tid] = f2ord(CUDART_INF_F);
     else if (tid < 6) s_cb[tid] = f2ord(-CUDART_INF_F);
     for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += 128) { (&s_lo[0][0][0])[i] = f2ord(CUDART_INF_F); (&s_hi[0][0][0])[i] = f2ord(-CUDART_INF_F); }
-    if (tid < 3 * SAH_BINS) (&s_cnt[0][0])[tid] = 0;
+    for (uint32_t i = tid; i < 3 * SAH_BINS; i += 128) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     // ---- centroid bounds of the node's valid primitives
     {
@@ -315,8 +321,8 @@ __global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) 
     }
     __syncthreads();
     // ---- the 3 x (SAH_BINS - 1) candidate planes
-    if (tid < 3 * (SAH_BINS - 1)) {
-        const int k = tid / (SAH_BINS - 1), sp = tid % (SAH_BINS - 1);  // left = bins 0..sp
+    for (int cand = (int)tid; cand < 3 * (SAH_BINS - 1); cand += 128) {
+        const int k = cand / (SAH_BINS - 1), sp = cand % (SAH_BINS - 1);  // left = bins 0..sp
         Aabb L = box_empty(), R = box_empty();
         uint32_t nl = 0, nr = 0;
         for (int bI = 0; bI < SAH_BINS; bI++) {
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) 
             for (int j = 0; j < 3; j++) { bb.lo[j] = ord2f(s_lo[k][bI][j]); bb.hi[j] = ord2f(s_hi[k][bI][j]); }
             if (bI <= sp) { box_grow(L, bb); nl += s_cnt[k][bI]; } else { box_grow(R, bb); nr += s_cnt[k][bI]; }
         }
-        s_cost[tid] = (nl == 0 || nr == 0) ? CUDART_INF_F : box_area(L) * (float)nl + box_area(R) * (float)nr;
+        s_cost[cand] = (nl == 0 || nr == 0) ? CUDART_INF_F : box_area(L) * (float)nl + box_area(R) * (float)nr;
     }
     __syncthreads();
     if (tid == 0) {
@@ -650,6 +656,29 @@ __device__ void collapse_task(const CollapseArgs& A, uint32_t w) {
         }
         child_at[best] = j;
     }
+#if RT_SLOT_OPT
+    if (RT_SLOT_OPT == 2 || A.max_leaf > 1)
+    {   // pairwise-exchange refinement of the slot assignment.  Score of child j in slot s = dot(centre_j - cn, sign vector of s)
+        // (Ylitie et al. 2017, sec. 3.2: the assignment that maximises the sum orders the children best for all eight ray octants).
+        float rel[8][3];
+        for (int j = 0; j < cnt; j++)
+            for (int k = 0; k < 3; k++) rel[j][k] = box_valid(cb[j]) ? 0.5f * cb[j].lo[k] + 0.5f * cb[j].hi[k] - cn[k] : 0.0f;
+        auto score = [&](int j, int sl) -> float {
+            if (j < 0) return 0.0f;
+            return ((sl & 1) ? rel[j][0] : -rel[j][0]) + ((sl & 2) ? rel[j][1] : -rel[j][1]) + ((sl & 4) ? rel[j][2] : -rel[j][2]);
+        };
+        for (int sweep = 0; sweep < 6; sweep++) {
+            bool changed = false;
+            for (int a = 0; a < 8; a++)
+                for (int b = a + 1; b < 8; b++) {
+                    const int ja = child_at[a], jb = child_at[b];
+                    if (ja < 0 && jb < 0) continue;
+                    if (score(ja, b) + score(jb, a) > score(ja, a) + score(jb, b) + 1e-12f) { child_at[a] = jb; child_at[b] = ja; changed = true; }
+                }
+            if (!changed) break;
+        }
+    }
+#endif
     uint32_t k_int = 0, total_prims = 0;
     for (int j = 0; j < cnt; j++) {
         if (internal[j]) k_int++;
