@@ -98,7 +98,7 @@ int build_tlas_now(RtContext* ctx, uint32_t mode, uint32_t src, uint32_t dst, bo
     } else {
         CK(launch_prepare_instances(D.d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), nullptr,
                                     ctx->d_inst_unsorted, ctx->d_inst_boxes, st));
-        CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, D.d_tlas_nodes, 0, 0, D.d_leaf_order, D.d_node_count, true, /*sah_collapse=*/true, st,
+        CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, D.d_tlas_nodes, 0, 0, D.d_leaf_order, D.d_node_count, true, /*sah_collapse=*/RT_TLAS_SAH_COLLAPSE != 0, st,
                                /*sah_splits=*/static_build && RT_TLAS_SAH));
         CK(launch_gather_instances(ctx->d_inst_unsorted, D.d_leaf_order, n, D.d_inst_rt, st));
         ctx->writes_since_build = 0;

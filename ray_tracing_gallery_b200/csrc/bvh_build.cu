@@ -19,6 +19,9 @@
 //
 // What the Vulkan driver does for the reference at src/util_structs.rs:269-274 / :345-354.
 #include <cooperative_groups.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <math_constants.h>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -258,7 +261,8 @@ __global__ void k_sah_init(SahArgs A, uint32_t n) {
     }
 }
 
-__global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) {
+template <int TB>
+__global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count) {
     if (blockIdx.x >= q_count) return;
     const uint4 item = A.q_in[blockIdx.x];
     const uint32_t node = item.x, f = item.y, c = item.z;
@@ -268,17 +272,25 @@ __global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) 
     __shared__ uint32_t s_cnt[3][SAH_BINS];
     __shared__ float s_cost[3 * (SAH_BINS - 1)];
     __shared__ int s_axis, s_split;
-    __shared__ uint32_t s_wl[4];
+    __shared__ uint32_t s_wl[TB / 32];
+    if (c == 2u) {  // two primitives: two leaves (a third of all nodes)
+        if (tid == 0) {
+            A.first[node] = f; A.last[node] = f + 1u;
+            A.left[node] = ~(int)f; A.right[node] = ~(int)(f + 1u);
+            A.parent_leaf[f] = (int)node; A.parent_leaf[f + 1u] = (int)node;
+        }
+        return;
+    }
 
     if (tid < 3) s_cb[tid] = f2ord(CUDART_INF_F);
     else if (tid < 6) s_cb[tid] = f2ord(-CUDART_INF_F);
-    for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += 128) { (&s_lo[0][0][0])[i] = f2ord(CUDART_INF_F); (&s_hi[0][0][0])[i] = f2ord(-CUDART_INF_F); }
-    for (uint32_t i = tid; i < 3 * SAH_BINS; i += 128) (&s_cnt[0][0])[i] = 0;
+    for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += TB) { (&s_lo[0][0][0])[i] = f2ord(CUDART_INF_F); (&s_hi[0][0][0])[i] = f2ord(-CUDART_INF_F); }
+    for (uint32_t i = tid; i < 3 * SAH_BINS; i += TB) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     // ---- centroid bounds of the node's valid primitives
     {
         float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-        for (uint32_t i = tid; i < c; i += 128) {
+        for (uint32_t i = tid; i < c; i += TB) {
             const Aabb b = A.boxes[A.order[f + i]];
             if (box_valid(b)) {
 #pragma unroll
@@ -306,7 +318,7 @@ __global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) 
         if (!isfinite(cmn[k])) cmn[k] = 0.0f;  // (no valid primitive at all)
     }
     // ---- binning (primitives without a valid box count in bin 0 and contribute no area)
-    for (uint32_t i = tid; i < c; i += 128) {
+    for (uint32_t i = tid; i < c; i += TB) {
         const Aabb b = A.boxes[A.order[f + i]];
         const bool ok = box_valid(b);
 #pragma unroll
@@ -321,7 +333,7 @@ __global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) 
     }
     __syncthreads();
     // ---- the 3 x (SAH_BINS - 1) candidate planes
-    for (int cand = (int)tid; cand < 3 * (SAH_BINS - 1); cand += 128) {
+    for (int cand = (int)tid; cand < 3 * (SAH_BINS - 1); cand += TB) {
         const int k = cand / (SAH_BINS - 1), sp = cand % (SAH_BINS - 1);  // left = bins 0..sp
         Aabb L = box_empty(), R = box_empty();
         uint32_t nl = 0, nr = 0;
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) 
         for (int bI = 0; bI < SAH_BINS; bI++) total_left += bI <= split ? s_cnt[axis][bI] : 0u;
         n_left = total_left;
         uint32_t done_l = 0, done_r = 0;
-        for (uint32_t base = 0; base < c; base += 128) {
+        for (uint32_t base = 0; base < c; base += TB) {
             const uint32_t i = base + tid;
             bool in = i < c, goes_left = false;
             uint32_t prim = 0;
@@ -368,7 +380,7 @@ __global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) 
             __syncthreads();
             uint32_t before_l = 0, before_a = 0, all_l = 0, all_a = 0;
 #pragma unroll
-            for (uint32_t w = 0; w < 4; w++) {
+            for (uint32_t w = 0; w < TB / 32; w++) {
                 const uint32_t v = s_wl[w];
                 if (w < warp) { before_l += v & 0xFFFFu; before_a += v >> 16; }
                 all_l += v & 0xFFFFu; all_a += v >> 16;
@@ -386,7 +398,7 @@ __global__ void __launch_bounds__(128) k_sah_level(SahArgs A, uint32_t q_count) 
             if (tid == 0) atomicExch(&A.counters[2], 1u);
             n_left = c / 2;
         } else {
-            for (uint32_t i = tid; i < c; i += 128) A.order[f + i] = A.tmp[f + i];
+            for (uint32_t i = tid; i < c; i += TB) A.order[f + i] = A.tmp[f + i];
         }
     }
     // ---- children
@@ -1003,17 +1015,25 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
         note_launch();
         uint32_t count = 1, levels = 0;
         bool ok = true;
+        const bool trace = getenv("B200RT_SAH_TRACE") != nullptr;  // per-level wall times on stderr (tools/gpu_build_time.py)
         while (count > 0) {
+            const auto t_level = std::chrono::steady_clock::now();
+            const uint32_t level_nodes = count;
             if (++levels > 64) { ok = false; break; }
             e = cudaMemsetAsync(&S.counters[1], 0, sizeof(uint32_t), stream);
             if (e != cudaSuccess) return e;
-            k_sah_level<<<count, 128, 0, stream>>>(S, count);
+            // the first levels hold few, large nodes: one SM's worth of threads each; later levels many small ones
+            if (levels <= 8 && n > 16384u) k_sah_level<1024><<<count, 1024, 0, stream>>>(S, count);
+            else k_sah_level<128><<<count, 128, 0, stream>>>(S, count);
             note_launch();
             e = cudaMemcpyAsync(&count, &S.counters[1], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
             if (e != cudaSuccess) return e;
             e = cudaStreamSynchronize(stream);
             if (e != cudaSuccess) return e;
             const uint4* t = S.q_in; S.q_in = S.q_out; S.q_out = const_cast<uint4*>(t);
+            if (trace)
+                fprintf(stderr, "sah level %u: %u nodes, %.3f ms\n", levels, level_nodes,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_level).count());
         }
         uint32_t err = 0;
         e = cudaMemcpy(&err, &S.counters[2], sizeof(uint32_t), cudaMemcpyDeviceToHost);

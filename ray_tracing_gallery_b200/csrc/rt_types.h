@@ -61,7 +61,9 @@ static_assert(sizeof(TriRec) == 48, "TriRec is 48 bytes");
 #define RT_TINY_BLAS_TRIS 4u
 // Triangles per BLAS leaf slot.  Measured on C2/C4 with 2/4/6/7: a triangle test costs about a third of a node
 // visit and culls nothing, so small leaves win (profiles/r01_notes.md).
+#ifndef RT_BLAS_LEAF_TRIS
 #define RT_BLAS_LEAF_TRIS 2u
+#endif
 
 // Binary tree under the wide nodes (bvh_build.cu): top-down binned-SAH splits (step 4b) for one-time builds — every BLAS, the TLAS of
 // rt_build_tlas / rt_group_build_tlas — and the Morton radix tree for per-frame rebuilds (rt_update_tlas REBUILD).  Measured
@@ -71,6 +73,9 @@ static_assert(sizeof(TriRec) == 48, "TriRec is 48 bytes");
 #endif
 #ifndef RT_BLAS_SAH_COLLAPSE
 #define RT_BLAS_SAH_COLLAPSE 0
+#endif
+#ifndef RT_TLAS_SAH_COLLAPSE
+#define RT_TLAS_SAH_COLLAPSE 1
 #endif
 #ifndef RT_TLAS_SAH
 #define RT_TLAS_SAH 1
