@@ -438,7 +438,7 @@ void rt_destroy(RtContext* ctx) {
         if (t.array) cudaFreeArray(t.array);
     }
     for (auto& m : ctx->models) {
-        cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.geom_info);
+        cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.geom_info); cudaFree(m.bound_pts);
         for (auto* p : m.index_bufs) cudaFree(p);
     }
     ctx->d_model_info.release(); ctx->d_blas_info.release(); ctx->blas_nodes.release(); ctx->tris.release();
@@ -548,7 +548,7 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     ModelRes m;
     m.num_geoms = ng;
     auto cleanup = [&]() {
-        cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.geom_info);
+        cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.geom_info); cudaFree(m.bound_pts);
         for (auto* p : m.index_bufs) cudaFree(p);
     };
 #define CKM(call)                                                                                          \
@@ -642,8 +642,29 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     m.blas.root = node_offset;
     m.blas.num_tris = nt;
     m.blas.tri_first = prim_offset;
-    m.blas.num_verts = nv <= RT_TIGHT_BOX_MAX_VERTS ? nv : 0;
-    m.blas.verts = m.positions;
+    // ---- the points that bound the model: finite vertices referenced by some triangle (exact instance bounds, k_tighten_instance_boxes)
+    m.blas.num_verts = 0;
+    m.blas.verts = nullptr;
+    {
+        std::vector<uint8_t> used(nv ? nv : 1, 0);
+        for (uint32_t g = 0; g < ng; g++)
+            for (uint32_t i = 0; i < desc->geometries[g].num_indices; i++) used[desc->geometries[g].indices[i]] = 1;
+        std::vector<float4> pts;
+        bool few = true;
+        for (uint32_t v = 0; v < nv && few; v++) {
+            const float* q = desc->positions + 3 * (size_t)v;
+            if (!used[v] || !std::isfinite(q[0]) || !std::isfinite(q[1]) || !std::isfinite(q[2])) continue;
+            if (pts.size() == RT_TIGHT_BOX_MAX_VERTS) few = false;
+            else pts.push_back(make_float4(q[0], q[1], q[2], 0.0f));
+        }
+        if (few && !pts.empty()) {
+            CKM(cudaMalloc(&m.bound_pts, sizeof(float4) * pts.size()));
+            CKM(cudaMemcpyAsync(m.bound_pts, pts.data(), sizeof(float4) * pts.size(), cudaMemcpyHostToDevice, st));
+            CKM(cudaStreamSynchronize(st));
+            m.blas.num_verts = (uint32_t)pts.size();
+            m.blas.verts = m.bound_pts;
+        }
+    }
     for (int k = 0; k < 3; k++) { m.blas.lo[k] = root.lo[k]; m.blas.hi[k] = root.hi[k]; }
 
     // ---- ModelInfo / BlasInfo tables (reference layout, device pointers in the u64 fields)

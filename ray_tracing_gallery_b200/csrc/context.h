@@ -38,6 +38,7 @@ struct DevVec {  // growable device array; indices stay valid across growth
 
 struct ModelRes {
     float *positions = nullptr, *normals = nullptr, *uvs = nullptr;
+    float4* bound_pts = nullptr;  // finite vertices some triangle references, when there are few enough (BlasInfo::verts)
     RtGeometryInfo* geom_info = nullptr;
     std::vector<uint32_t*> index_bufs;
     uint32_t num_geoms = 0;

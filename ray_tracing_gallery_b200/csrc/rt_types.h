@@ -97,10 +97,10 @@ struct BlasInfo {
     uint32_t tri_first;  // index of the model's first TriRec
     uint32_t num_verts;  // > 0: `verts` may be walked for exact instance bounds (k_tighten_instance_boxes), 0: corners of lo / hi only
     float    lo[3], hi[3];
-    const float* verts;  // the model's positions (f32x3)
+    const float4* verts; // the finite vertices some triangle references (xyz, w unused)
 };
 
-// Instances of a BLAS with at most this many vertices get the exact world bounds of their transformed vertices instead of
+// Instances of a BLAS with at most this many referenced vertices get the exact world bounds of their transformed vertices instead of
 // the bounds of the eight transformed box corners (a model rotated by 45 degrees: up to 1.41x per axis).
 #ifndef RT_TIGHT_BOX_MAX_VERTS
 #define RT_TIGHT_BOX_MAX_VERTS 4096u

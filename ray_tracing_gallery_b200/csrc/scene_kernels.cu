@@ -145,8 +145,8 @@ __global__ void k_prepare_instances(const RtInstance* __restrict__ instances, ui
 // instance transform.  The box of the eight transformed corners of the object-space bounds (k_prepare_instances, what a
 // Vulkan driver's TLAS build uses) is up to 1.41x too wide per axis for a rotated model — every instance box of C4 / C5 is a
 // torus pair turned about y — and a wider leaf box is entered by rays that have no business inside the BLAS.  Triangles lie in
-// the convex hull of their vertices, so the result (padded like the corner box and intersected with it) stays conservative;
-// vertices that are not finite can only belong to inactive triangles and are skipped.
+// the convex hull of their vertices, so the result (padded like the corner box and intersected with it) stays conservative.
+// The point list (rt_create_model) holds the finite vertices that some triangle references, as float4.
 __device__ __forceinline__ int ordered_int(float f) {
     int i = __float_as_int(f);
     return i ^ ((i >> 31) & 0x7FFFFFFF);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) k_tighten_instance_boxes(const RtInstance
     const uint32_t model = (uint32_t)(handle & 0xFFFFFFFFu) - 1u;
     if ((handle >> 48) != 0xB200u || model >= num_models) return;
     const uint32_t nv = blas[model].num_verts;
-    const float* __restrict__ verts = blas[model].verts;
+    const float4* __restrict__ verts = blas[model].verts;
     if (nv == 0 || blas[model].num_tris == 0) return;
     const float m00 = __uint_as_float(q0.x), m01 = __uint_as_float(q0.y), m02 = __uint_as_float(q0.z), m03 = __uint_as_float(q0.w);
     const float m10 = __uint_as_float(q1.x), m11 = __uint_as_float(q1.y), m12 = __uint_as_float(q1.z), m13 = __uint_as_float(q1.w);
@@ -173,15 +173,13 @@ __global__ void __launch_bounds__(256) k_tighten_instance_boxes(const RtInstance
     float lx = CUDART_INF_F, ly = CUDART_INF_F, lz = CUDART_INF_F, hx = -CUDART_INF_F, hy = -CUDART_INF_F, hz = -CUDART_INF_F;
 #pragma unroll 4
     for (uint32_t v = lane; v < nv; v += 32) {
-        const float px = __ldg(verts + 3 * (size_t)v), py = __ldg(verts + 3 * (size_t)v + 1), pz = __ldg(verts + 3 * (size_t)v + 2);
-        const float wx = m00 * px + m01 * py + m02 * pz + m03;
-        const float wy = m10 * px + m11 * py + m12 * pz + m13;
-        const float wz = m20 * px + m21 * py + m22 * pz + m23;
-        if (isfinite(wx) && isfinite(wy) && isfinite(wz)) {  // (a non-finite vertex gives non-finite sums)
-            lx = fminf(lx, wx); hx = fmaxf(hx, wx);
-            ly = fminf(ly, wy); hy = fmaxf(hy, wy);
-            lz = fminf(lz, wz); hz = fmaxf(hz, wz);
-        }
+        const float4 p = __ldg(verts + v);
+        const float wx = fmaf(m00, p.x, fmaf(m01, p.y, fmaf(m02, p.z, m03)));
+        const float wy = fmaf(m10, p.x, fmaf(m11, p.y, fmaf(m12, p.z, m13)));
+        const float wz = fmaf(m20, p.x, fmaf(m21, p.y, fmaf(m22, p.z, m23)));
+        lx = fminf(lx, wx); hx = fmaxf(hx, wx);
+        ly = fminf(ly, wy); hy = fmaxf(hy, wy);
+        lz = fminf(lz, wz); hz = fmaxf(hz, wz);
     }
     Aabb t;
     t.lo[0] = ordered_float(__reduce_min_sync(0xFFFFFFFFu, ordered_int(lx)));
@@ -192,7 +190,9 @@ __global__ void __launch_bounds__(256) k_tighten_instance_boxes(const RtInstance
     t.hi[2] = ordered_float(__reduce_max_sync(0xFFFFFFFFu, ordered_int(hz)));
     if (lane != 0) return;
     Aabb c = boxes[slot];
-    if (!(c.lo[0] <= c.hi[0]) || !(t.lo[0] <= t.hi[0])) return;  // instance without geometry / refused by k_prepare_instances; no usable vertex
+    if (!(c.lo[0] <= c.hi[0])) return;  // instance without geometry / refused by k_prepare_instances
+    // (the points are finite; a transform that overflows on one of them gives an infinite or empty bound here: keep the corner box)
+    if (!(isfinite(t.lo[0]) && isfinite(t.lo[1]) && isfinite(t.lo[2]) && isfinite(t.hi[0]) && isfinite(t.hi[1]) && isfinite(t.hi[2]))) return;
     pad_box(t);
 #pragma unroll
     for (int k = 0; k < 3; k++) { c.lo[k] = fmaxf(c.lo[k], t.lo[k]); c.hi[k] = fminf(c.hi[k], t.hi[k]); }
