@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--update-mode", default="refit", choices=["rebuild", "refit", "auto"],
-                    help="dynamic scenes: refit = the reference's in-place UPDATE (src/util_structs.rs:309), rebuild = full LBVH build")
+                    help="dynamic scenes: refit = the reference's in-place UPDATE (src/util_structs.rs:309), rebuild = full radix-tree rebuild")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end pass (profiling runs)")
     return ap.parse_args()

@@ -68,7 +68,7 @@ typedef enum RtUpdateMode {
     RT_UPDATE_AUTO = 0,     /* library picks: refit, and a full rebuild once the instance records written since the last
                                build add up to 4x the instance count (topology drift) */
     RT_UPDATE_REFIT = 1,    /* keep topology, refit boxes: VK mode UPDATE, src/util_structs.rs:309 */
-    RT_UPDATE_REBUILD = 2   /* full LBVH rebuild */
+    RT_UPDATE_REBUILD = 2   /* full rebuild on the Morton radix tree (stream-ordered; the SAH build of rt_build_tlas is for one-time builds) */
 } RtUpdateMode;
 
 typedef enum RtPipeline {
@@ -179,7 +179,8 @@ int  rt_push_image(RtContext* ctx, const void* texels, uint32_t width, uint32_t 
 int  rt_create_model(RtContext* ctx, const RtModelDesc* desc,
                      uint32_t* out_model_id, uint64_t* out_blas_handle);
 
-/* build_tlas (src/util_functions.rs:453-510; caller src/main.rs:524-530). */
+/* build_tlas (src/util_functions.rs:453-510; caller src/main.rs:524-530).  The one-time, PREFER_FAST_TRACE build: binned-SAH
+ * tree (blocking; 1 ms for 10 k instances, 26 ms for 1 M).  Per-frame changes go through rt_update_tlas. */
 int  rt_build_tlas(RtContext* ctx, const RtInstance* instances, uint32_t count);
 
 /* Buffer::write_mapped on the instance buffer (src/scene.rs:177-181) ... */
@@ -299,7 +300,7 @@ int  rt_group_update_instances_device(RtGroup* group, int root, uint32_t first, 
 
 /* All ranks, collectively: build_tlas for a multi-GPU box (src/util_functions.rs:453-510), SHARDED.  The root's
  * `count` records are broadcast; every rank computes the Morton keys, the ranks agree on n_ranks contiguous key ranges of
- * equal population, each rank builds the wide BVH of ITS range only (1/N of the sort, hierarchy, SAH collapse), the
+ * equal population, each rank builds the wide BVH of ITS range only (1/N of the SAH tree, fit, SAH collapse), the
  * treelets are exchanged over NVLink (NCCL broadcasts of exactly the nodes in use) and every rank puts the same top node
  * over them.  Frames do not depend on topology (closest hit + tie rule), so they equal those of rt_build_tlas bit for
  * bit; later rt_group_update_instances refits work on the assembled tree.  Falls back to the replicated build for more
