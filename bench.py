@@ -138,8 +138,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def oracle_sample(workload, args, threads=0, steps=1, warmup=0):
-    """Time the CPU restatement (oracle/) on a bounded sample of the workload.  Returns (Mrays/s, info)."""
+def oracle_sample(workload, args, threads=0, steps=1, warmup=0, min_secs=0.0):
+    """Time the CPU restatement (oracle/) on a bounded sample of the workload.  Returns (Mrays/s, info).
+    min_secs: keep adding frames (at most 64) until the timed sample is that long."""
     from oracle.binding import Oracle
     from ray_tracing_gallery_b200.scene import build_scene
 
@@ -152,7 +153,8 @@ def oracle_sample(workload, args, threads=0, steps=1, warmup=0):
         tile = dict(tile_x0=(s.width - tw) // 2, tile_y0=(s.height - th) // 2 + s.height // 8, tile_w=tw, tile_h=th)
     p = s.params(**tile)
     rays, secs = 0, 0.0
-    for i in range(warmup + steps):
+    i = 0
+    while i < warmup + steps or (secs < min_secs and i < warmup + 64):
         u = s.uniforms(frame_index=1 + i)
         t0 = time.perf_counter()
         r = orc.render(u, p, want=("rgba8", "ray_counts"))
@@ -160,6 +162,8 @@ def oracle_sample(workload, args, threads=0, steps=1, warmup=0):
         if i >= warmup:
             rays += int(r["ray_counts"].sum())
             secs += dt
+        i += 1
+    steps = i - warmup
     cores = orc.threads
     orc.close()
     sample = (f"{steps} frame(s) of {s.name} at {s.width}x{s.height}" +
@@ -574,7 +578,9 @@ def run_ours(args):
         # ---- CPU baseline: the oracle on a bounded sample of each workload (rank 0, N = 1 only)
         if world == 1 and not args.no_cpu_baseline:
             for name in names:
-                v, info = oracle_sample(name, args, steps=5 if name in ("c1", "c2", "c3", "default") else 1, warmup=1 if name in ("c1", "c2", "c3") else 0)
+                # the headline workload gets a 10-second sample, the others a second or two each
+                v, info = oracle_sample(name, args, steps=5 if name in ("c1", "c2", "c3", "default") else 1, warmup=1 if name in ("c1", "c2", "c3") else 0,
+                                        min_secs=10.0 if name == args.workload else 0.0)
                 results[name]["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
         head = results[args.workload]
         line = {
