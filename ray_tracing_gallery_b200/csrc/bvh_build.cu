@@ -1,9 +1,11 @@
-// bvh_build.cu — LBVH -> SAH-guided collapse -> compressed 8-wide BVH, entirely on the GPU.
+// bvh_build.cu — binary tree (binned SAH or Morton radix tree) -> SAH-guided collapse -> compressed 8-wide BVH, entirely on the GPU.
 //
 //   1. centroid bounds            k_centroid_bounds    (warp shuffles + ordered-int atomics)
 //   2. 63-bit Morton keys         k_morton
 //   3. radix sort                 cub::DeviceRadixSort::SortPairs (64-bit key, 32-bit payload)
 //   4. binary radix tree          k_hierarchy          (Karras 2012, index tie-break for duplicates)
+//   4b. INSTEAD of 1-4 for one-time builds (every BLAS, static TLAS builds): top-down binned SAH, k_sah_level —
+//      level-synchronous, one block per node, 32 bins per axis; the radix tree stays for per-frame rebuilds
 //   5. bottom-up AABB fit         k_fit                (one atomic flag per internal node)
 //      + in the same pass: SAH-optimal collapse table per binary node (dynamic programme of
 //        Ylitie et al. 2017, "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide
@@ -13,7 +15,8 @@
 //                                                      task index == wide-node index, so the BFS
 //                                                      queue IS the node array; grid.sync per level)
 //      - children of a wide node: the 8-slot cut of the binary tree the table says is cheapest
-//      - slots assigned by child-centre octant => front-to-back order is (slot XOR ray octant)
+//      - slots assigned by child-centre octant => front-to-back order is (slot XOR ray octant);
+//        for BLASes the assignment is refined by pairwise exchanges (RT_SLOT_OPT)
 //      - boxes quantised to 8 bits on an exactly representable power-of-two grid
 //   7. refit (TLAS update)        k_refit              (bottom-up over wide nodes)
 //
