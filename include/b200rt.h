@@ -68,7 +68,7 @@ typedef enum RtUpdateMode {
     RT_UPDATE_AUTO = 0,     /* library picks: refit, and a full rebuild once the instance records written since the last
                                build add up to 4x the instance count (topology drift) */
     RT_UPDATE_REFIT = 1,    /* keep topology, refit boxes: VK mode UPDATE, src/util_structs.rs:309 */
-    RT_UPDATE_REBUILD = 2   /* full rebuild on the Morton radix tree (stream-ordered; the SAH build of rt_build_tlas is for one-time builds) */
+    RT_UPDATE_REBUILD = 2   /* full rebuild, stream-ordered: SAH tree up to 65 536 instances (one cooperative launch), Morton radix tree above */
 } RtUpdateMode;
 
 typedef enum RtPipeline {

@@ -99,7 +99,7 @@ int build_tlas_now(RtContext* ctx, uint32_t mode, uint32_t src, uint32_t dst, bo
         CK(launch_prepare_instances(D.d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), nullptr,
                                     ctx->d_inst_unsorted, ctx->d_inst_boxes, st));
         CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, D.d_tlas_nodes, 0, 0, D.d_leaf_order, D.d_node_count, true, /*sah_collapse=*/RT_TLAS_SAH_COLLAPSE != 0, st,
-                               /*sah_splits=*/static_build && RT_TLAS_SAH));
+                               /*sah_splits=*/!RT_TLAS_SAH ? SAH_NEVER : static_build ? SAH_ALWAYS : SAH_IF_STREAM_ORDERED));
         CK(launch_gather_instances(ctx->d_inst_unsorted, D.d_leaf_order, n, D.d_inst_rt, st));
         ctx->writes_since_build = 0;
     }
@@ -619,7 +619,7 @@ int rt_create_model(RtContext* ctx, const RtModelDesc* desc, uint32_t* out_model
     M.num_geoms = ng; M.num_tris = nt; M.num_vertices = nv;
     CKT(launch_triangle_boxes(M, d_boxes, st));
     CKT(ctx->builder.build(d_boxes, nt, RT_BLAS_LEAF_TRIS, ctx->blas_nodes.ptr, node_offset, prim_offset, d_leaf_order, d_count, false, /*sah_collapse=*/RT_BLAS_SAH_COLLAPSE != 0, st,
-                           /*sah_splits=*/RT_BLAS_SAH != 0));
+                           /*sah_splits=*/RT_BLAS_SAH ? SAH_ALWAYS : SAH_NEVER));
     CKT(launch_gather_triangles(M, d_leaf_order, ctx->tris.ptr + prim_offset, st));
     uint32_t node_count = 0;
     Node8 root;

@@ -243,7 +243,7 @@ struct SahArgs {
     uint32_t *order, *tmp;
     const uint4* q_in;   // (node, first, count, -)
     uint4* q_out;
-    uint32_t* counters;  // [0] next internal node id, [1] length of q_out, [2] error flag
+    uint32_t* counters;  // [0] next internal node id, [1] length of q_out ([1] / [3] by level parity in k_sah_coop), [2] error flag
     int *left, *right, *parent_int, *parent_leaf;
     uint32_t *first, *last;
 };
@@ -258,16 +258,16 @@ __global__ void k_sah_init(SahArgs A, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) A.order[i] = i;
     if (i == 0) {
-        A.counters[0] = 1; A.counters[1] = 0; A.counters[2] = 0;
+        A.counters[0] = 1; A.counters[1] = 0; A.counters[2] = 0; A.counters[3] = 0;
         A.parent_int[0] = -1;
         const_cast<uint4*>(A.q_in)[0] = make_uint4(0u, 0u, n, 0u);
     }
 }
 
+// One node of the level: called by all TB threads of a block.  q_out / q_len: where nodes of the next level are queued.
+// halve: no SAH, the range is cut in the middle (depth limit of the single-launch build).
 template <int TB>
-__global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count) {
-    if (blockIdx.x >= q_count) return;
-    const uint4 item = A.q_in[blockIdx.x];
+__device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 item, uint4* q_out, uint32_t* q_len, const bool halve) {
     const uint32_t node = item.x, f = item.y, c = item.z;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     __shared__ int s_cb[6];
@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count) {
         return;
     }
 
+    int axis = -1, split = 0;
+    float cmn[3] = {0.0f, 0.0f, 0.0f}, scale[3] = {0.0f, 0.0f, 0.0f};
+    if (!halve) {
     if (tid < 3) s_cb[tid] = f2ord(CUDART_INF_F);
     else if (tid < 6) s_cb[tid] = f2ord(-CUDART_INF_F);
     for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += TB) { (&s_lo[0][0][0])[i] = f2ord(CUDART_INF_F); (&s_hi[0][0][0])[i] = f2ord(-CUDART_INF_F); }
@@ -311,7 +314,6 @@ __global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count) {
         }
     }
     __syncthreads();
-    float cmn[3], scale[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         cmn[k] = ord2f(s_cb[k]);
@@ -358,7 +360,8 @@ __global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count) {
         s_split = bi < 0 ? 0 : bi % (SAH_BINS - 1);
     }
     __syncthreads();
-    const int axis = s_axis, split = s_split;
+    axis = s_axis; split = s_split;
+    }
     uint32_t n_left = c / 2;  // no usable plane (coincident centroids): halve the range as it stands
     if (axis >= 0) {
         // ---- stable partition of order[f .. f + c) through tmp
@@ -417,10 +420,39 @@ __global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count) {
                 const uint32_t id = atomicAdd(&A.counters[0], 1u);
                 ref = (int)id;
                 A.parent_int[id] = (int)node;
-                A.q_out[atomicAdd(&A.counters[1], 1u)] = make_uint4(id, cf, cc, 0u);
+                q_out[atomicAdd(q_len, 1u)] = make_uint4(id, cf, cc, 0u);
             }
             if (side) A.right[node] = ref; else A.left[node] = ref;
         }
+    }
+}
+
+template <int TB>
+__global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count) {
+    if (blockIdx.x >= q_count) return;
+    sah_split_node<TB>(A, A.q_in[blockIdx.x], A.q_out, &A.counters[1], false);
+}
+
+// The whole tree in ONE cooperative launch (builds of up to RT_SAH_COOP_MAX primitives: nothing for the host to follow, so per-frame
+// TLAS rebuilds can afford SAH trees too).  Blocks share the nodes of a level; the two queues and their two length words (counters[1]
+// and [3], by level parity) alternate; below level 48 ranges are halved, which bounds the depth at 48 + log2(n).
+#define SAH_COOP_TB 128
+__global__ void __launch_bounds__(SAH_COOP_TB) k_sah_coop(SahArgs A) {
+    cg::grid_group grid = cg::this_grid();
+    const uint4* q_in = A.q_in;
+    uint4* q_out = A.q_out;
+    uint32_t count = 1;
+    for (uint32_t level = 1; count > 0; level++) {
+        uint32_t* len_next = &A.counters[(level & 1u) ? 1 : 3];
+        if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[(level & 1u) ? 3 : 1] = 0;  // the word of level + 1 (everybody has read it: they passed the last grid.sync)
+        for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
+            sah_split_node<SAH_COOP_TB>(A, q_in[q], q_out, len_next, level > 48u);
+            __syncthreads();  // shared bins are reused by the block's next node
+        }
+        grid.sync();
+        count = *((volatile uint32_t*)len_next);
+        const uint4* t = q_in; q_in = q_out; q_out = const_cast<uint4*>(t);
+        grid.sync();  // nobody may queue nodes of the next level before everybody has read this one's length
     }
 }
 
@@ -983,13 +1015,17 @@ cudaError_t BvhBuilder::reserve(uint32_t n) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse_coop, 128, 0);
         coop_blocks_ = sms * (per_sm > 0 ? per_sm : 1);
         coop_ok_ = coop != 0 && per_sm > 0;
+        int sah_per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sah_per_sm, k_sah_coop, SAH_COOP_TB, 0);
+        if (sah_per_sm > 4) sah_per_sm = 4;  // grid.sync gets dearer with the grid; four blocks per SM serve the widest levels of a 64 k-primitive tree
+        sah_coop_blocks_ = coop != 0 && sah_per_sm > 0 ? sms * sah_per_sm : 0;
     }
     return cudaSuccess;
 }
 
 cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
                               uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, bool sah_collapse, cudaStream_t stream,
-                              bool sah_splits) {
+                              int sah_splits) {
     cudaError_t e = reserve(n);
     if (e != cudaSuccess) return e;
     Scratch s;
@@ -1005,20 +1041,34 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
     }
     uint32_t blocks = (n + TB - 1) / TB;
     bool radix_tree = true;
-    if (sah_splits && n >= 2) {
-        // top-down binned SAH (step 4b); the host follows the level sizes.  A tree deeper than 64 levels (pathological input)
-        // is dropped for the radix tree below: the traversal stack is sized for trees of ordinary depth.
+    const bool sah_single_launch = sah_splits != SAH_NEVER && n >= 2 && n <= RT_SAH_COOP_MAX && sah_coop_blocks_ > 0;
+    if (sah_single_launch || (sah_splits == SAH_ALWAYS && n >= 2)) {
+        // top-down binned SAH (step 4b)
         SahArgs S;
         S.boxes = d_boxes; S.order = s.vals_out; S.tmp = s.vals_in;
         uint4* q[2] = {reinterpret_cast<uint4*>(s.keys_in), reinterpret_cast<uint4*>(s.keys_out)};  // <= n / 2 entries of 16 bytes
-        S.counters = s.state + 4;  // words 4..6 of the state block (k_init_state zeroes all eight)
+        S.counters = s.state + 4;  // words 4..7 of the state block (k_init_state zeroes all eight)
         S.left = s.left; S.right = s.right; S.parent_int = s.parent_int; S.parent_leaf = s.parent_leaf; S.first = s.first; S.last = s.last;
         S.q_in = q[0]; S.q_out = q[1];
         k_sah_init<<<blocks, TB, 0, stream>>>(S, n);
         note_launch();
+        radix_tree = false;
+        bool launched = false;
+        if (sah_single_launch) {
+            // small trees: every level inside one cooperative launch, nothing for the host to wait for
+            void* args[] = {&S};
+            uint32_t want = (n + 3u) / 4u;
+            uint32_t grid = want < (uint32_t)sah_coop_blocks_ ? want : (uint32_t)sah_coop_blocks_;
+            cudaError_t ce = cudaLaunchCooperativeKernel((void*)k_sah_coop, dim3(grid), dim3(SAH_COOP_TB), args, 0, stream);
+            if (ce == cudaSuccess) { launched = true; note_launch(); }
+            else { (void)cudaGetLastError(); sah_coop_blocks_ = 0; radix_tree = sah_splits != SAH_ALWAYS; }
+        }
+        if (!launched && !radix_tree) {
+        // large trees: the host follows the level sizes.  A tree deeper than 64 levels (pathological input) is dropped for the
+        // radix tree below: the traversal stack is sized for trees of ordinary depth.
+        const bool trace = getenv("B200RT_SAH_TRACE") != nullptr;  // per-level wall times on stderr (tools/gpu_build_time.py)
         uint32_t count = 1, levels = 0;
         bool ok = true;
-        const bool trace = getenv("B200RT_SAH_TRACE") != nullptr;  // per-level wall times on stderr (tools/gpu_build_time.py)
         while (count > 0) {
             const auto t_level = std::chrono::steady_clock::now();
             const uint32_t level_nodes = count;
@@ -1042,6 +1092,7 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
         e = cudaMemcpy(&err, &S.counters[2], sizeof(uint32_t), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return e;
         radix_tree = !ok || err != 0;
+        }
     }
     if (radix_tree) {
     k_centroid_bounds<<<blocks, TB, 0, stream>>>(d_boxes, n, s.bounds);

@@ -11,6 +11,12 @@ namespace b200rt {
 // (n - 1 of them) and the cost-driven cut gives no tighter guarantee.
 inline uint32_t max_wide_nodes(uint32_t n) { return n + 8; }
 
+// BvhBuilder::build, sah_splits
+enum { SAH_NEVER = 0, SAH_IF_STREAM_ORDERED = 1, SAH_ALWAYS = 2 };
+#ifndef RT_SAH_COOP_MAX
+#define RT_SAH_COOP_MAX 65536u
+#endif
+
 class BvhBuilder {
 public:
     BvhBuilder() = default;
@@ -29,11 +35,12 @@ public:
     // sah_collapse: children of each wide node from the SAH-optimal cut table (else greedy largest-area expansion).
     // fast_sort: Morton keys keep only as many bits as n needs (fewer radix passes; per-frame TLAS rebuilds).
     // Everything is enqueued on `stream`; no host synchronisation.
-    // sah_splits: the binary tree is grown top-down with binned-SAH splits instead of the Morton radix tree (one-time builds:
-    // every BLAS).  This variant synchronises the stream once per tree level.
+    // sah_splits: the binary tree is grown top-down with binned-SAH splits instead of the Morton radix tree.  Up to
+    // RT_SAH_COOP_MAX primitives that is one cooperative launch (stream-ordered like everything else); larger SAH builds
+    // synchronise the stream once per tree level and are only done for SAH_ALWAYS (one-time builds).
     cudaError_t build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
                       uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, bool sah_collapse, cudaStream_t stream,
-                      bool sah_splits = false);
+                      int sah_splits = SAH_NEVER);
 
     // Refit in place: recompute boxes bottom-up for a tree built by build() whose leaf order is
     // unchanged.  d_boxes_leaf_order[i] = new box of the primitive at leaf position i.
@@ -54,6 +61,7 @@ private:
     size_t cub_bytes_ = 0;
     int coop_blocks_ = 0;
     bool coop_ok_ = true;
+    int sah_coop_blocks_ = 0;
 };
 
 // ---- assembling a TLAS from treelets built on different GPUs (bvh_build.cu)

@@ -478,7 +478,7 @@ int rt_group_build_tlas(RtGroup* g, int root, const RtInstance* host_records, ui
     SCK(cudaMalloc(&d_treelet_order, sizeof(uint32_t) * (size_t)(mine ? mine : 1)));
     uint32_t my_nodes = 0;
     if (mine) {
-        SCK(ctx->builder.build(d_sel_boxes, mine, 1, d_treelet, 0, first[g->rank], d_treelet_order, d_cnt + 32, true, /*sah_collapse=*/true, st, /*sah_splits=*/RT_TLAS_SAH != 0));
+        SCK(ctx->builder.build(d_sel_boxes, mine, 1, d_treelet, 0, first[g->rank], d_treelet_order, d_cnt + 32, true, /*sah_collapse=*/true, st, /*sah_splits=*/RT_TLAS_SAH ? SAH_ALWAYS : SAH_NEVER));
         SCK(launch_map_order(d_treelet_order, d_sel_index, mine, D.d_leaf_order + first[g->rank], st));
     } else {
         SCK(cudaMemsetAsync(d_cnt + 32, 0, sizeof(uint32_t), st));
