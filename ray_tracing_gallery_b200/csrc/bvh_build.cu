@@ -235,9 +235,7 @@ __global__ void k_hierarchy(Tree2 T) {
 // `order` (through `tmp`), two children.  Ranges stay contiguous, single primitives become leaves, internal nodes are numbered
 // from an atomic counter (root = 0): the same Tree2 conventions as the radix tree, so that k_fit and the collapse run unchanged.
 // Measured against the radix tree: sum of internal-node areas -22 % (tori) / -31 % (lain).
-#ifndef SAH_BINS
-#define SAH_BINS 32  // 16 -> 32: C5 -2.8 %, C4 -1.9 % (profiles/r04cd_sah_builder_ab.txt)
-#endif
+#define SAH_BINS 32  // = the warp width: one warp scans the bins of an axis.  16 -> 32: C5 -2.8 %, C4 -1.9 %; 64: within noise (profiles/r04cd_sah_builder_ab.txt, r04ef)
 struct SahArgs {
     const Aabb* boxes;
     uint32_t *order, *tmp;
@@ -273,7 +271,8 @@ __device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 ite
     __shared__ int s_cb[6];
     __shared__ int s_lo[3][SAH_BINS][3], s_hi[3][SAH_BINS][3];
     __shared__ uint32_t s_cnt[3][SAH_BINS];
-    __shared__ float s_cost[3 * (SAH_BINS - 1)];
+    __shared__ float s_cost[3];
+    __shared__ int s_best_split[3];
     __shared__ int s_axis, s_split;
     __shared__ uint32_t s_wl[TB / 32];
     if (c == 2u) {  // two primitives: two leaves (a third of all nodes)
@@ -337,27 +336,54 @@ __device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 ite
         }
     }
     __syncthreads();
-    // ---- the 3 x (SAH_BINS - 1) candidate planes
-    for (int cand = (int)tid; cand < 3 * (SAH_BINS - 1); cand += TB) {
-        const int k = cand / (SAH_BINS - 1), sp = cand % (SAH_BINS - 1);  // left = bins 0..sp
-        Aabb L = box_empty(), R = box_empty();
-        uint32_t nl = 0, nr = 0;
-        for (int bI = 0; bI < SAH_BINS; bI++) {
-            Aabb bb;
+    // ---- the 3 x 31 candidate planes: warp k scans the 32 bins of axis k (lane = bin) — an inclusive prefix of boxes and counts from
+    //      the left, one from the right (shuffles) — lane sp prices the plane after bin sp, the warp keeps its cheapest (lowest sp wins ties)
+    if (warp < 3) {
+        const int k = (int)warp;
+        float llo[3], lhi[3], rlo[3], rhi[3];
 #pragma unroll
-            for (int j = 0; j < 3; j++) { bb.lo[j] = ord2f(s_lo[k][bI][j]); bb.hi[j] = ord2f(s_hi[k][bI][j]); }
-            if (bI <= sp) { box_grow(L, bb); nl += s_cnt[k][bI]; } else { box_grow(R, bb); nr += s_cnt[k][bI]; }
+        for (int j = 0; j < 3; j++) { llo[j] = rlo[j] = ord2f(s_lo[k][lane][j]); lhi[j] = rhi[j] = ord2f(s_hi[k][lane][j]); }
+        uint32_t nl = s_cnt[k][lane], nr = nl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const float a0 = __shfl_up_sync(0xFFFFFFFFu, llo[j], o), a1 = __shfl_up_sync(0xFFFFFFFFu, lhi[j], o);
+                const float b0 = __shfl_down_sync(0xFFFFFFFFu, rlo[j], o), b1 = __shfl_down_sync(0xFFFFFFFFu, rhi[j], o);
+                if ((int)lane >= o) { llo[j] = fminf(llo[j], a0); lhi[j] = fmaxf(lhi[j], a1); }
+                if ((int)lane + o < 32) { rlo[j] = fminf(rlo[j], b0); rhi[j] = fmaxf(rhi[j], b1); }
+            }
+            const uint32_t cl = __shfl_up_sync(0xFFFFFFFFu, nl, o), cr = __shfl_down_sync(0xFFFFFFFFu, nr, o);
+            if ((int)lane >= o) nl += cl;
+            if ((int)lane + o < 32) nr += cr;
         }
-        s_cost[cand] = (nl == 0 || nr == 0) ? CUDART_INF_F : box_area(L) * (float)nl + box_area(R) * (float)nr;
+        // (bins without primitives keep +inf / -inf planes: an empty side has area 0 and count 0)
+        auto area = [](const float* lo, const float* hi) -> float {
+            const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+            return (dx >= 0.0f && dy >= 0.0f && dz >= 0.0f) ? dx * dy + dy * dz + dz * dx : 0.0f;
+        };
+        const float right_cost = area(rlo, rhi) * (float)nr;   // bins lane .. 31
+        const float rc = __shfl_down_sync(0xFFFFFFFFu, right_cost, 1);
+        const uint32_t rn = __shfl_down_sync(0xFFFFFFFFu, nr, 1);
+        float cost = (lane == 31u || nl == 0u || rn == 0u) ? CUDART_INF_F : area(llo, lhi) * (float)nl + rc;
+        if (!(cost == cost)) cost = CUDART_INF_F;
+        uint32_t sp = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float oc = __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+            const uint32_t os = __shfl_xor_sync(0xFFFFFFFFu, sp, o);
+            if (oc < cost || (oc == cost && os < sp)) { cost = oc; sp = os; }
+        }
+        if (lane == 0) { s_cost[k] = cost; s_best_split[k] = (int)sp; }
     }
     __syncthreads();
     if (tid == 0) {
+        int bk = -1;
         float best = CUDART_INF_F;
-        int bi = -1;
-        for (int i = 0; i < 3 * (SAH_BINS - 1); i++)
-            if (s_cost[i] < best) { best = s_cost[i]; bi = i; }
-        s_axis = bi < 0 ? -1 : bi / (SAH_BINS - 1);
-        s_split = bi < 0 ? 0 : bi % (SAH_BINS - 1);
+        for (int k = 0; k < 3; k++)
+            if (s_cost[k] < best) { best = s_cost[k]; bk = k; }
+        s_axis = bk;
+        s_split = bk < 0 ? 0 : s_best_split[bk];
     }
     __syncthreads();
     axis = s_axis; split = s_split;
@@ -436,7 +462,12 @@ __global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count) {
 // The whole tree in ONE cooperative launch (builds of up to RT_SAH_COOP_MAX primitives: nothing for the host to follow, so per-frame
 // TLAS rebuilds can afford SAH trees too).  Blocks share the nodes of a level; the two queues and their two length words (counters[1]
 // and [3], by level parity) alternate; below level 48 ranges are halved, which bounds the depth at 48 + log2(n).
+#ifndef SAH_COOP_TB
 #define SAH_COOP_TB 128
+#endif
+#ifndef SAH_COOP_PER_SM
+#define SAH_COOP_PER_SM 4
+#endif
 __global__ void __launch_bounds__(SAH_COOP_TB) k_sah_coop(SahArgs A) {
     cg::grid_group grid = cg::this_grid();
     const uint4* q_in = A.q_in;
@@ -1017,7 +1048,7 @@ cudaError_t BvhBuilder::reserve(uint32_t n) {
         coop_ok_ = coop != 0 && per_sm > 0;
         int sah_per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sah_per_sm, k_sah_coop, SAH_COOP_TB, 0);
-        if (sah_per_sm > 4) sah_per_sm = 4;  // grid.sync gets dearer with the grid; four blocks per SM serve the widest levels of a 64 k-primitive tree
+        if (sah_per_sm > SAH_COOP_PER_SM) sah_per_sm = SAH_COOP_PER_SM;  // grid.sync gets dearer with the grid; four blocks per SM serve the widest levels of a 64 k-primitive tree
         sah_coop_blocks_ = coop != 0 && sah_per_sm > 0 ? sms * sah_per_sm : 0;
     }
     return cudaSuccess;
