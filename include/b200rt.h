@@ -180,7 +180,7 @@ int  rt_create_model(RtContext* ctx, const RtModelDesc* desc,
                      uint32_t* out_model_id, uint64_t* out_blas_handle);
 
 /* build_tlas (src/util_functions.rs:453-510; caller src/main.rs:524-530).  The one-time, PREFER_FAST_TRACE build: binned-SAH
- * tree (0.8 ms for 10 k instances, 21 ms for 1 M).  Per-frame changes go through rt_update_tlas. */
+ * tree (0.8 ms for 10 k instances, 7 ms for 1 M).  Per-frame changes go through rt_update_tlas. */
 int  rt_build_tlas(RtContext* ctx, const RtInstance* instances, uint32_t count);
 
 /* Buffer::write_mapped on the instance buffer (src/scene.rs:177-181) ... */

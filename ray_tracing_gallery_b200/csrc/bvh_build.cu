@@ -262,88 +262,46 @@ __global__ void k_sah_init(SahArgs A, uint32_t n) {
     }
 }
 
-// One node of the level: called by all TB threads of a block.  q_out / q_len: where nodes of the next level are queued.
-// halve: no SAH, the range is cut in the middle (depth limit of the single-launch build).
-template <int TB>
-__device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 item, uint4* q_out, uint32_t* q_len, const bool halve) {
-    const uint32_t node = item.x, f = item.y, c = item.z;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    __shared__ int s_cb[6];
-    __shared__ int s_lo[3][SAH_BINS][3], s_hi[3][SAH_BINS][3];
-    __shared__ uint32_t s_cnt[3][SAH_BINS];
-    __shared__ float s_cost[3];
-    __shared__ int s_best_split[3];
-    __shared__ int s_axis, s_split;
-    __shared__ uint32_t s_wl[TB / 32];
-    if (c == 2u) {  // two primitives: two leaves (a third of all nodes)
-        if (tid == 0) {
-            A.first[node] = f; A.last[node] = f + 1u;
-            A.left[node] = ~(int)f; A.right[node] = ~(int)(f + 1u);
-            A.parent_leaf[f] = (int)node; A.parent_leaf[f + 1u] = (int)node;
-        }
-        return;
-    }
+// Shared memory of a block that splits a node: centroid bounds, the bins of the three axes, the outcome of the plane search.
+struct SahBins {
+    int cb[6];                                       // centroid bounds (ordered ints): lo xyz, hi xyz
+    int lo[3][SAH_BINS][3], hi[3][SAH_BINS][3];      // [axis][bin][xyz], ordered ints
+    uint32_t cnt[3][SAH_BINS];
+    float cost[3];
+    int best_split[3];
+    int axis, split;                                 // axis < 0: no usable plane
+};
 
-    int axis = -1, split = 0;
-    float cmn[3] = {0.0f, 0.0f, 0.0f}, scale[3] = {0.0f, 0.0f, 0.0f};
-    if (!halve) {
-    if (tid < 3) s_cb[tid] = f2ord(CUDART_INF_F);
-    else if (tid < 6) s_cb[tid] = f2ord(-CUDART_INF_F);
-    for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += TB) { (&s_lo[0][0][0])[i] = f2ord(CUDART_INF_F); (&s_hi[0][0][0])[i] = f2ord(-CUDART_INF_F); }
-    for (uint32_t i = tid; i < 3 * SAH_BINS; i += TB) (&s_cnt[0][0])[i] = 0;
-    __syncthreads();
-    // ---- centroid bounds of the node's valid primitives
-    {
-        float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-        for (uint32_t i = tid; i < c; i += TB) {
-            const Aabb b = A.boxes[A.order[f + i]];
-            if (box_valid(b)) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) { float ck = centroid_k(b, k); lo[k] = fminf(lo[k], ck); hi[k] = fmaxf(hi[k], ck); }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o));
-                hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o));
-            }
-            if (lane == 0) { atomicMin(&s_cb[k], f2ord(lo[k])); atomicMax(&s_cb[3 + k], f2ord(hi[k])); }
-        }
-    }
-    __syncthreads();
+__device__ __forceinline__ void sah_bins_clear(SahBins& B, uint32_t tid, uint32_t nthreads) {
+    if (tid < 3) B.cb[tid] = f2ord(CUDART_INF_F);
+    else if (tid < 6) B.cb[tid] = f2ord(-CUDART_INF_F);
+    for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += nthreads) { (&B.lo[0][0][0])[i] = f2ord(CUDART_INF_F); (&B.hi[0][0][0])[i] = f2ord(-CUDART_INF_F); }
+    for (uint32_t i = tid; i < 3 * SAH_BINS; i += nthreads) (&B.cnt[0][0])[i] = 0;
+}
+
+// bin = (centroid - cmn) * scale, from the centroid bounds of the node (every pass over a node's primitives derives it the same way)
+__device__ __forceinline__ void sah_bin_scale(const int* cb, float* cmn, float* scale) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        cmn[k] = ord2f(s_cb[k]);
-        const float ext = ord2f(s_cb[3 + k]) - cmn[k];
+        cmn[k] = ord2f(cb[k]);
+        const float ext = ord2f(cb[3 + k]) - cmn[k];
         scale[k] = (ext > 0.0f && isfinite(ext)) ? (float)SAH_BINS * 0.999999f / ext : 0.0f;  // 0: every primitive in bin 0, no split on this axis
         if (!isfinite(scale[k])) scale[k] = 0.0f;
         if (!isfinite(cmn[k])) cmn[k] = 0.0f;  // (no valid primitive at all)
     }
-    // ---- binning (primitives without a valid box count in bin 0 and contribute no area)
-    for (uint32_t i = tid; i < c; i += TB) {
-        const Aabb b = A.boxes[A.order[f + i]];
-        const bool ok = box_valid(b);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int bin = ok ? sah_bin(centroid_k(b, k), cmn[k], scale[k]) : 0;
-            atomicAdd(&s_cnt[k][bin], 1u);
-            if (ok) {
-#pragma unroll
-                for (int j = 0; j < 3; j++) { atomicMin(&s_lo[k][bin][j], f2ord(b.lo[j])); atomicMax(&s_hi[k][bin][j], f2ord(b.hi[j])); }
-            }
-        }
-    }
-    __syncthreads();
-    // ---- the 3 x 31 candidate planes: warp k scans the 32 bins of axis k (lane = bin) — an inclusive prefix of boxes and counts from
-    //      the left, one from the right (shuffles) — lane sp prices the plane after bin sp, the warp keeps its cheapest (lowest sp wins ties)
+}
+
+// The 3 x 31 candidate planes over filled bins (all threads of a block of >= 3 warps; B.axis / B.split on return): warp k scans the
+// 32 bins of axis k (lane = bin) — an inclusive prefix of boxes and counts from the left, one from the right (shuffles) — lane sp
+// prices the plane after bin sp, the warp keeps its cheapest (lowest sp wins ties), thread 0 the cheapest axis (lowest wins ties).
+__device__ __forceinline__ void sah_pick_plane(SahBins& B) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (warp < 3) {
         const int k = (int)warp;
         float llo[3], lhi[3], rlo[3], rhi[3];
 #pragma unroll
-        for (int j = 0; j < 3; j++) { llo[j] = rlo[j] = ord2f(s_lo[k][lane][j]); lhi[j] = rhi[j] = ord2f(s_hi[k][lane][j]); }
-        uint32_t nl = s_cnt[k][lane], nr = nl;
+        for (int j = 0; j < 3; j++) { llo[j] = rlo[j] = ord2f(B.lo[k][lane][j]); lhi[j] = rhi[j] = ord2f(B.hi[k][lane][j]); }
+        uint32_t nl = B.cnt[k][lane], nr = nl;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
@@ -374,26 +332,107 @@ __device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 ite
             const uint32_t os = __shfl_xor_sync(0xFFFFFFFFu, sp, o);
             if (oc < cost || (oc == cost && os < sp)) { cost = oc; sp = os; }
         }
-        if (lane == 0) { s_cost[k] = cost; s_best_split[k] = (int)sp; }
+        if (lane == 0) { B.cost[k] = cost; B.best_split[k] = (int)sp; }
     }
     __syncthreads();
     if (tid == 0) {
         int bk = -1;
         float best = CUDART_INF_F;
         for (int k = 0; k < 3; k++)
-            if (s_cost[k] < best) { best = s_cost[k]; bk = k; }
-        s_axis = bk;
-        s_split = bk < 0 ? 0 : s_best_split[bk];
+            if (B.cost[k] < best) { best = B.cost[k]; bk = k; }
+        B.axis = bk;
+        B.split = bk < 0 ? 0 : B.best_split[bk];
     }
     __syncthreads();
-    axis = s_axis; split = s_split;
+}
+
+// The two children of `node` = order[f .. f + c), cut after n_left primitives (one thread)
+__device__ __forceinline__ void sah_emit_children(const SahArgs& A, uint32_t node, uint32_t f, uint32_t c, uint32_t n_left, uint4* q_out, uint32_t* q_len) {
+    A.first[node] = f;
+    A.last[node] = f + c - 1u;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const uint32_t cf = side ? f + n_left : f, cc = side ? c - n_left : n_left;
+        int ref;
+        if (cc == 1u) { ref = ~(int)cf; A.parent_leaf[cf] = (int)node; }
+        else {
+            const uint32_t id = atomicAdd(&A.counters[0], 1u);
+            ref = (int)id;
+            A.parent_int[id] = (int)node;
+            q_out[atomicAdd(q_len, 1u)] = make_uint4(id, cf, cc, 0u);
+        }
+        if (side) A.right[node] = ref; else A.left[node] = ref;
+    }
+}
+
+// One node of the level: called by all TB threads of a block.  q_out / q_len: where nodes of the next level are queued.
+// halve: no SAH, the range is cut in the middle (depth limit of the single-launch build).
+template <int TB>
+__device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 item, uint4* q_out, uint32_t* q_len, const bool halve) {
+    const uint32_t node = item.x, f = item.y, c = item.z;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    __shared__ SahBins B;
+    __shared__ uint32_t s_wl[TB / 32];
+    if (c == 2u) {  // two primitives: two leaves (a third of all nodes)
+        if (tid == 0) {
+            A.first[node] = f; A.last[node] = f + 1u;
+            A.left[node] = ~(int)f; A.right[node] = ~(int)(f + 1u);
+            A.parent_leaf[f] = (int)node; A.parent_leaf[f + 1u] = (int)node;
+        }
+        return;
+    }
+
+    int axis = -1, split = 0;
+    float cmn[3] = {0.0f, 0.0f, 0.0f}, scale[3] = {0.0f, 0.0f, 0.0f};
+    if (!halve) {
+    sah_bins_clear(B, tid, TB);
+    __syncthreads();
+    // ---- centroid bounds of the node's valid primitives
+    {
+        float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+        for (uint32_t i = tid; i < c; i += TB) {
+            const Aabb b = A.boxes[A.order[f + i]];
+            if (box_valid(b)) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { float ck = centroid_k(b, k); lo[k] = fminf(lo[k], ck); hi[k] = fmaxf(hi[k], ck); }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o));
+                hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o));
+            }
+            if (lane == 0) { atomicMin(&B.cb[k], f2ord(lo[k])); atomicMax(&B.cb[3 + k], f2ord(hi[k])); }
+        }
+    }
+    __syncthreads();
+    sah_bin_scale(B.cb, cmn, scale);
+    // ---- binning (primitives without a valid box count in bin 0 and contribute no area)
+    for (uint32_t i = tid; i < c; i += TB) {
+        const Aabb b = A.boxes[A.order[f + i]];
+        const bool ok = box_valid(b);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int bin = ok ? sah_bin(centroid_k(b, k), cmn[k], scale[k]) : 0;
+            atomicAdd(&B.cnt[k][bin], 1u);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) { atomicMin(&B.lo[k][bin][j], f2ord(b.lo[j])); atomicMax(&B.hi[k][bin][j], f2ord(b.hi[j])); }
+            }
+        }
+    }
+    __syncthreads();
+    sah_pick_plane(B);
+    axis = B.axis; split = B.split;
     }
     uint32_t n_left = c / 2;  // no usable plane (coincident centroids): halve the range as it stands
     if (axis >= 0) {
         // ---- stable partition of order[f .. f + c) through tmp
         uint32_t total_left = 0;
 #pragma unroll
-        for (int bI = 0; bI < SAH_BINS; bI++) total_left += bI <= split ? s_cnt[axis][bI] : 0u;
+        for (int bI = 0; bI < SAH_BINS; bI++) total_left += bI <= split ? B.cnt[axis][bI] : 0u;
         n_left = total_left;
         uint32_t done_l = 0, done_r = 0;
         for (uint32_t base = 0; base < c; base += TB) {
@@ -433,30 +472,163 @@ __device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 ite
             for (uint32_t i = tid; i < c; i += TB) A.order[f + i] = A.tmp[f + i];
         }
     }
-    // ---- children
-    if (tid == 0) {
-        A.first[node] = f;
-        A.last[node] = f + c - 1u;
+    if (tid == 0) sah_emit_children(A, node, f, c, n_left, q_out, q_len);
+}
+
+// skip_from: nodes of at least this many primitives are left to the k_sahbig_* launches of the same level
+template <int TB>
+__global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count, uint32_t skip_from) {
+    if (blockIdx.x >= q_count) return;
+    const uint4 item = A.q_in[blockIdx.x];
+    if (item.z >= skip_from) return;
+    sah_split_node<TB>(A, item, A.q_out, &A.counters[1], false);
+}
+
+// ---- nodes too large for one block (first levels of a big tree): the same split spread over the grid.  Per node, in stream order:
+//      k_sahbig_init -> k_sahbig_bounds -> k_sahbig_bin (shared bins per block, flushed with global atomics) -> k_sahbig_split (one
+//      block: plane search, children) -> k_sahbig_partition (blocks claim output ranges with two atomic cursors) -> k_sahbig_copy.
+#define SAH_BIG_MIN 32768u    // nodes of at least this many primitives take this path (when the host knows the level's nodes)
+struct SahBig {
+    int cb[6];
+    int lo[3][SAH_BINS][3], hi[3][SAH_BINS][3];
+    uint32_t cnt[3][SAH_BINS];
+    uint32_t cur[2];   // primitives written to the left / right part so far
+    int axis, split;
+    uint32_t n_left, _pad;
+};
+
+static_assert(sizeof(SahBig) <= 1024 * sizeof(uint32_t), "SahBig fits the scratch words reserved for it");
+
+__global__ void k_sahbig_init(SahBig* G) {
+    const uint32_t tid = threadIdx.x;
+    if (tid < 3) G->cb[tid] = f2ord(CUDART_INF_F);
+    else if (tid < 6) G->cb[tid] = f2ord(-CUDART_INF_F);
+    for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += blockDim.x) { (&G->lo[0][0][0])[i] = f2ord(CUDART_INF_F); (&G->hi[0][0][0])[i] = f2ord(-CUDART_INF_F); }
+    for (uint32_t i = tid; i < 3 * SAH_BINS; i += blockDim.x) (&G->cnt[0][0])[i] = 0;
+    if (tid == 0) { G->cur[0] = G->cur[1] = 0; G->axis = -1; G->split = 0; G->n_left = 0; }
+}
+
+__global__ void __launch_bounds__(256) k_sahbig_bounds(SahArgs A, SahBig* G, uint32_t f, uint32_t c) {
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c; i += gridDim.x * blockDim.x) {
+        const Aabb b = A.boxes[A.order[f + i]];
+        if (box_valid(b)) {
 #pragma unroll
-        for (int side = 0; side < 2; side++) {
-            const uint32_t cf = side ? f + n_left : f, cc = side ? c - n_left : n_left;
-            int ref;
-            if (cc == 1u) { ref = ~(int)cf; A.parent_leaf[cf] = (int)node; }
-            else {
-                const uint32_t id = atomicAdd(&A.counters[0], 1u);
-                ref = (int)id;
-                A.parent_int[id] = (int)node;
-                q_out[atomicAdd(q_len, 1u)] = make_uint4(id, cf, cc, 0u);
+            for (int k = 0; k < 3; k++) { float ck = centroid_k(b, k); lo[k] = fminf(lo[k], ck); hi[k] = fmaxf(hi[k], ck); }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o));
+        }
+        if ((threadIdx.x & 31u) == 0) { atomicMin(&G->cb[k], f2ord(lo[k])); atomicMax(&G->cb[3 + k], f2ord(hi[k])); }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sahbig_bin(SahArgs A, SahBig* G, uint32_t f, uint32_t c) {
+    __shared__ SahBins B;
+    const uint32_t tid = threadIdx.x;
+    sah_bins_clear(B, tid, blockDim.x);
+    __syncthreads();
+    float cmn[3], scale[3];
+    sah_bin_scale(G->cb, cmn, scale);
+    for (uint32_t i = blockIdx.x * blockDim.x + tid; i < c; i += gridDim.x * blockDim.x) {
+        const Aabb b = A.boxes[A.order[f + i]];
+        const bool ok = box_valid(b);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int bin = ok ? sah_bin(centroid_k(b, k), cmn[k], scale[k]) : 0;
+            atomicAdd(&B.cnt[k][bin], 1u);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) { atomicMin(&B.lo[k][bin][j], f2ord(b.lo[j])); atomicMax(&B.hi[k][bin][j], f2ord(b.hi[j])); }
             }
-            if (side) A.right[node] = ref; else A.left[node] = ref;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < 3 * SAH_BINS; i += blockDim.x) {
+        const uint32_t n = (&B.cnt[0][0])[i];
+        if (n == 0) continue;
+        atomicAdd(&(&G->cnt[0][0])[i], n);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            atomicMin(&(&G->lo[0][0][0])[3 * i + j], (&B.lo[0][0][0])[3 * i + j]);
+            atomicMax(&(&G->hi[0][0][0])[3 * i + j], (&B.hi[0][0][0])[3 * i + j]);
         }
     }
 }
 
-template <int TB>
-__global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count) {
-    if (blockIdx.x >= q_count) return;
-    sah_split_node<TB>(A, A.q_in[blockIdx.x], A.q_out, &A.counters[1], false);
+__global__ void __launch_bounds__(128) k_sahbig_split(SahArgs A, SahBig* G, uint32_t node, uint32_t f, uint32_t c) {
+    __shared__ SahBins B;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += 128) { (&B.lo[0][0][0])[i] = (&G->lo[0][0][0])[i]; (&B.hi[0][0][0])[i] = (&G->hi[0][0][0])[i]; }
+    for (uint32_t i = tid; i < 3 * SAH_BINS; i += 128) (&B.cnt[0][0])[i] = (&G->cnt[0][0])[i];
+    __syncthreads();
+    sah_pick_plane(B);
+    if (tid == 0) {
+        uint32_t n_left = c / 2;
+        if (B.axis >= 0) {
+            n_left = 0;
+            for (int bI = 0; bI <= B.split; bI++) n_left += B.cnt[B.axis][bI];
+        }
+        G->axis = B.axis; G->split = B.split; G->n_left = n_left;
+        sah_emit_children(A, node, f, c, n_left, A.q_out, &A.counters[1]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sahbig_partition(SahArgs A, SahBig* G, uint32_t f, uint32_t c) {
+    const int axis = G->axis, split = G->split;
+    if (axis < 0) return;  // halved as it stands
+    const uint32_t n_left = G->n_left;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    __shared__ uint32_t s_wl[8], s_base[2];
+    float cmn[3], scale[3];
+    sah_bin_scale(G->cb, cmn, scale);
+    const uint32_t per_block = ((c + gridDim.x - 1) / gridDim.x + 255u) & ~255u;
+    const uint32_t begin = blockIdx.x * per_block, end = begin + per_block < c ? begin + per_block : c;
+    for (uint32_t base = begin; base < end; base += 256) {
+        const uint32_t i = base + tid;
+        bool in = i < end, goes_left = false;
+        uint32_t prim = 0;
+        if (in) {
+            prim = A.order[f + i];
+            const Aabb b = A.boxes[prim];
+            const int bin = box_valid(b) ? sah_bin(centroid_k(b, axis), cmn[axis], scale[axis]) : 0;
+            goes_left = bin <= split;
+        }
+        const uint32_t ml = __ballot_sync(0xFFFFFFFFu, in && goes_left), ma = __ballot_sync(0xFFFFFFFFu, in);
+        __syncthreads();  // (s_wl / s_base of the previous chunk have been read)
+        if (lane == 0) s_wl[warp] = (uint32_t)__popc(ml) | ((uint32_t)__popc(ma) << 16);
+        __syncthreads();
+        uint32_t before_l = 0, before_a = 0, all_l = 0, all_a = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < 8; w++) {
+            const uint32_t v = s_wl[w];
+            if (w < warp) { before_l += v & 0xFFFFu; before_a += v >> 16; }
+            all_l += v & 0xFFFFu; all_a += v >> 16;
+        }
+        if (tid == 0) { s_base[0] = atomicAdd(&G->cur[0], all_l); s_base[1] = atomicAdd(&G->cur[1], all_a - all_l); }
+        __syncthreads();
+        if (in) {
+            const uint32_t below = (1u << lane) - 1u;
+            const uint32_t rank_l = before_l + (uint32_t)__popc(ml & below);
+            const uint32_t rank_r = (before_a - before_l) + (uint32_t)__popc((ma & ~ml) & below);
+            const uint32_t dst = goes_left ? s_base[0] + rank_l : n_left + s_base[1] + rank_r;
+            if (dst < c) A.tmp[f + dst] = prim;  // (a disagreement of the passes is caught by k_sahbig_copy; never write outside the range)
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sahbig_copy(SahArgs A, SahBig* G, uint32_t f, uint32_t c) {
+    if (G->axis < 0) return;
+    if (G->cur[0] != G->n_left || G->cur[0] + G->cur[1] != c) {  // the passes disagree: cannot happen with the explicitly rounded bin arithmetic
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(&A.counters[2], 1u);
+        return;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c; i += gridDim.x * blockDim.x) A.order[f + i] = A.tmp[f + i];
 }
 
 // The whole tree in ONE cooperative launch (builds of up to RT_SAH_COOP_MAX primitives: nothing for the host to follow, so per-frame
@@ -983,6 +1155,7 @@ struct Scratch {
     int* task_node;
     uint32_t* task_parent;
     uint32_t* refit_counters;
+    uint32_t* sah_big;      // one SahBig record (bins of a node that is split by the whole grid)
     uint32_t* shard_hist;   // (1 << RT_SHARD_BITS) bins + 64 words: shard bin boundaries [0..32], select cursor [33]
     void* cub_temp;
 };
@@ -1009,6 +1182,7 @@ size_t layout(char* base, uint32_t n, size_t cub_bytes, Scratch& s) {
     s.task_node = carve<int>(p, maxw);
     s.task_parent = carve<uint32_t>(p, maxw);
     s.refit_counters = carve<uint32_t>(p, maxw);
+    s.sah_big = carve<uint32_t>(p, 1024);
     s.shard_hist = carve<uint32_t>(p, (1u << RT_SHARD_BITS) + 64);
     s.cub_temp = carve<char>(p, cub_bytes);
     return (size_t)(p - base) + 256;
@@ -1106,9 +1280,36 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
             if (++levels > 64) { ok = false; break; }
             e = cudaMemsetAsync(&S.counters[1], 0, sizeof(uint32_t), stream);
             if (e != cudaSuccess) return e;
-            // the first levels hold few, large nodes: one SM's worth of threads each; later levels many small ones
-            if (levels <= 8 && n > 16384u) k_sah_level<1024><<<count, 1024, 0, stream>>>(S, count);
-            else k_sah_level<128><<<count, 128, 0, stream>>>(S, count);
+            // the first levels hold few, large nodes.  While the level is short the host fetches its nodes and gives the largest
+            // ones the whole grid (k_sahbig_*); the others get one SM's worth of threads each, later levels 128 threads per node.
+            uint32_t skip_from = 0xFFFFFFFFu;
+            if (count <= 64 && n >= SAH_BIG_MIN) {
+                uint4 items[64];
+                if (levels == 1) items[0] = make_uint4(0u, 0u, n, 0u);
+                else {
+                    e = cudaMemcpyAsync(items, S.q_in, sizeof(uint4) * count, cudaMemcpyDeviceToHost, stream);
+                    if (e != cudaSuccess) return e;
+                    e = cudaStreamSynchronize(stream);
+                    if (e != cudaSuccess) return e;
+                }
+                skip_from = SAH_BIG_MIN;
+                SahBig* G = reinterpret_cast<SahBig*>(s.sah_big);
+                for (uint32_t qi = 0; qi < count; qi++) {
+                    const uint32_t bn = items[qi].x, bf = items[qi].y, bc = items[qi].z;
+                    if (bc < SAH_BIG_MIN) continue;
+                    uint32_t grid = (bc + 2047u) / 2048u;
+                    if (grid > 1184u) grid = 1184u;
+                    k_sahbig_init<<<1, 256, 0, stream>>>(G);
+                    k_sahbig_bounds<<<grid, 256, 0, stream>>>(S, G, bf, bc);
+                    k_sahbig_bin<<<grid, 256, 0, stream>>>(S, G, bf, bc);
+                    k_sahbig_split<<<1, 128, 0, stream>>>(S, G, bn, bf, bc);
+                    k_sahbig_partition<<<grid, 256, 0, stream>>>(S, G, bf, bc);
+                    k_sahbig_copy<<<grid, 256, 0, stream>>>(S, G, bf, bc);
+                    note_launch(6);
+                }
+            }
+            if (levels <= 8 && n > 16384u) k_sah_level<1024><<<count, 1024, 0, stream>>>(S, count, skip_from);
+            else k_sah_level<128><<<count, 128, 0, stream>>>(S, count, skip_from);
             note_launch();
             e = cudaMemcpyAsync(&count, &S.counters[1], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
             if (e != cudaSuccess) return e;
