@@ -257,6 +257,41 @@ def test_tiles_and_strips_reassemble_the_full_frame():
     gpu.close()
 
 
+def test_sah_trees_are_built_and_pay():
+    """The builder's three ways to a binary tree, held against each other on one scene (C5 with 80 000 instances, above the single-launch
+    limit): rt_build_tlas = host-followed SAH levels with grid-wide splits of the large nodes, rt_update_tlas REBUILD = Morton radix tree;
+    and with 40 000 instances REBUILD = the single-launch SAH build.  Frames must be identical whatever the tree (closest hit + tie rule),
+    and the SAH trees must need clearly fewer node visits per ray than the radix tree — a silent fall-back to the radix tree (depth limit,
+    disagreement flag) would pass every parity test and only show up here."""
+    def nodes_per_ray(gpu, s):
+        out = gpu.render(s.uniforms(), s.params(flags=abi.RT_RENDER_COUNTERS))
+        st = gpu.stats()
+        return sum(st.nodes_visited) / max(1, st.primary_rays + st.shadow_rays), out
+
+    gpu = make_renderer()
+    s = build_scene(gpu, "c5", 640, 360, num_instances=80000)
+    sah_big, frame_sah = nodes_per_ray(gpu, s)
+    gpu.update_instances(0, s.instances); gpu.update_tlas(abi.RT_UPDATE_REBUILD)
+    radix, frame_radix = nodes_per_ray(gpu, s)
+    gpu.update_instances(0, s.instances); gpu.update_tlas(abi.RT_UPDATE_REFIT)
+    radix_refit, frame_refit = nodes_per_ray(gpu, s)
+    for k in ("rgba8", "hit_ids", "ray_counts"):
+        assert np.array_equal(frame_sah[k], frame_radix[k]) and np.array_equal(frame_sah[k], frame_refit[k]), k
+    assert abs(radix_refit - radix) < 1e-9
+    gpu.close()
+    gpu = make_renderer()
+    s = build_scene(gpu, "c5", 640, 360, num_instances=40000)
+    built, frame_a = nodes_per_ray(gpu, s)
+    gpu.update_instances(0, s.instances); gpu.update_tlas(abi.RT_UPDATE_REBUILD)   # single cooperative launch
+    rebuilt, frame_b = nodes_per_ray(gpu, s)
+    for k in ("rgba8", "hit_ids", "ray_counts"):
+        assert np.array_equal(frame_a[k], frame_b[k]), k
+    gpu.close()
+    print(f"nodes per ray, 80 k instances: SAH build {sah_big:.2f}, radix rebuild {radix:.2f}; 40 k instances: SAH build {built:.2f}, single-launch SAH rebuild {rebuilt:.2f}")
+    assert sah_big < 0.9 * radix
+    assert abs(rebuilt - built) < 0.02 * built   # the same algorithm (node numbering may differ, the splits do not)
+
+
 @pytest.mark.parametrize("mode", [abi.RT_UPDATE_REBUILD, abi.RT_UPDATE_REFIT, abi.RT_UPDATE_AUTO])
 def test_tlas_update_parity(mode):
     """C4 in small: every transform changes each tick, then rt_update_instances + rt_update_tlas
