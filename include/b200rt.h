@@ -68,7 +68,7 @@ typedef enum RtUpdateMode {
     RT_UPDATE_AUTO = 0,     /* library picks: refit, and a full rebuild once the instance records written since the last
                                build add up to 4x the instance count (topology drift) */
     RT_UPDATE_REFIT = 1,    /* keep topology, refit boxes: VK mode UPDATE, src/util_structs.rs:309 */
-    RT_UPDATE_REBUILD = 2   /* full rebuild, stream-ordered: SAH tree up to 65 536 instances (one cooperative launch), Morton radix tree above */
+    RT_UPDATE_REBUILD = 2   /* full rebuild, stream-ordered: a new binned-SAH tree in one cooperative launch (0.75 ms for 10 k instances, 9 ms for 1 M) */
 } RtUpdateMode;
 
 typedef enum RtPipeline {
@@ -180,7 +180,7 @@ int  rt_create_model(RtContext* ctx, const RtModelDesc* desc,
                      uint32_t* out_model_id, uint64_t* out_blas_handle);
 
 /* build_tlas (src/util_functions.rs:453-510; caller src/main.rs:524-530).  The one-time, PREFER_FAST_TRACE build: binned-SAH
- * tree (0.8 ms for 10 k instances, 7 ms for 1 M).  Per-frame changes go through rt_update_tlas. */
+ * tree (0.75 ms for 10 k instances, 9 ms for 1 M; stream-ordered).  Per-frame changes go through rt_update_tlas. */
 int  rt_build_tlas(RtContext* ctx, const RtInstance* instances, uint32_t count);
 
 /* Buffer::write_mapped on the instance buffer (src/scene.rs:177-181) ... */

@@ -4,8 +4,8 @@
 //   2. 63-bit Morton keys         k_morton
 //   3. radix sort                 cub::DeviceRadixSort::SortPairs (64-bit key, 32-bit payload)
 //   4. binary radix tree          k_hierarchy          (Karras 2012, index tie-break for duplicates)
-//   4b. INSTEAD of 1-4 for one-time builds (every BLAS, static TLAS builds): top-down binned SAH, k_sah_level —
-//      level-synchronous, one block per node, 32 bins per axis; the radix tree stays for per-frame rebuilds
+//   4b. INSTEAD of 1-4: top-down binned SAH in one cooperative launch, k_sah_tree — level by level, one block per node (the
+//      whole grid for large nodes), 32 bins per axis; 1-4 remain as the path without cooperative launches
 //   5. bottom-up AABB fit         k_fit                (one atomic flag per internal node)
 //      + in the same pass: SAH-optimal collapse table per binary node (dynamic programme of
 //        Ylitie et al. 2017, "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide
@@ -22,9 +22,6 @@
 //
 // What the Vulkan driver does for the reference at src/util_structs.rs:269-274 / :345-354.
 #include <cooperative_groups.h>
-#include <chrono>
-#include <cstdio>
-#include <cstdlib>
 #include <math_constants.h>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -228,20 +225,17 @@ __global__ void k_hierarchy(Tree2 T) {
 
 
 // ------------------------------------------------------------------------------------ 4b: top-down binned SAH
-// The high-quality alternative to steps 2-4 for builds that happen once (every BLAS: the reference asks the driver for
-// PREFER_FAST_TRACE, src/util_structs.rs:236): the binary tree is grown top-down, every split the cheapest of 3 x 31 binned
-// surface-area-heuristic candidates (32 bins per axis over the centroid bounds; Wald 2007).  Level-synchronous, one block per
-// node of the level: centroid bounds, binning with shared-memory atomics, split choice, stable partition of the node's range of
-// `order` (through `tmp`), two children.  Ranges stay contiguous, single primitives become leaves, internal nodes are numbered
-// from an atomic counter (root = 0): the same Tree2 conventions as the radix tree, so that k_fit and the collapse run unchanged.
-// Measured against the radix tree: sum of internal-node areas -22 % (tori) / -31 % (lain).
+// The binary tree under the wide nodes (the reference asks its driver for PREFER_FAST_TRACE, src/util_structs.rs:236): grown top-down,
+// every split the cheapest of 3 x 31 binned surface-area-heuristic candidates (32 bins per axis over the centroid bounds; Wald 2007).
+// Per node: centroid bounds, binning with shared-memory atomics, plane search by warp scans, stable partition of the node's range of
+// `order` (through `tmp`), two children.  Ranges stay contiguous, single primitives become leaves, internal nodes are numbered from an
+// atomic counter (root = 0): the same Tree2 conventions as the radix tree, so that k_fit and the collapse run unchanged.
+// Measured against the radix tree: sum of internal-node areas -22 % (tori) / -31 % (lain); node visits per ray -22 % (C5) / -31 % (C4).
 #define SAH_BINS 32  // = the warp width: one warp scans the bins of an axis.  16 -> 32: C5 -2.8 %, C4 -1.9 %; 64: within noise (profiles/r04cd_sah_builder_ab.txt, r04ef)
 struct SahArgs {
     const Aabb* boxes;
     uint32_t *order, *tmp;
-    const uint4* q_in;   // (node, first, count, -)
-    uint4* q_out;
-    uint32_t* counters;  // [0] next internal node id, [1] length of q_out ([1] / [3] by level parity in k_sah_coop), [2] error flag
+    uint32_t* counters;  // [0] next internal node id, [2] set when the two passes over a node disagree (cannot happen; the node is then halved)
     int *left, *right, *parent_int, *parent_leaf;
     uint32_t *first, *last;
 };
@@ -250,16 +244,6 @@ __device__ __forceinline__ float centroid_k(const Aabb& b, int k) { return __fad
 __device__ __forceinline__ int sah_bin(float c, float cmn, float scale) {
     int b = (int)__fmul_rn(__fsub_rn(c, cmn), scale);
     return b < 0 ? 0 : b > SAH_BINS - 1 ? SAH_BINS - 1 : b;
-}
-
-__global__ void k_sah_init(SahArgs A, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) A.order[i] = i;
-    if (i == 0) {
-        A.counters[0] = 1; A.counters[1] = 0; A.counters[2] = 0; A.counters[3] = 0;
-        A.parent_int[0] = -1;
-        const_cast<uint4*>(A.q_in)[0] = make_uint4(0u, 0u, n, 0u);
-    }
 }
 
 // Shared memory of a block that splits a node: centroid bounds, the bins of the three axes, the outcome of the plane search.
@@ -346,8 +330,16 @@ __device__ __forceinline__ void sah_pick_plane(SahBins& B) {
     __syncthreads();
 }
 
+// Where the nodes of the next level are queued: nodes of at least big_min primitives go to a queue of their own (k_sah_tree splits
+// them with the whole grid); big_min = 0xFFFFFFFF: one queue.
+struct SahRoute {
+    uint4* q_small; uint32_t* len_small;
+    uint4* q_big;   uint32_t* len_big;
+    uint32_t big_min;
+};
+
 // The two children of `node` = order[f .. f + c), cut after n_left primitives (one thread)
-__device__ __forceinline__ void sah_emit_children(const SahArgs& A, uint32_t node, uint32_t f, uint32_t c, uint32_t n_left, uint4* q_out, uint32_t* q_len) {
+__device__ __forceinline__ void sah_emit_children(const SahArgs& A, uint32_t node, uint32_t f, uint32_t c, uint32_t n_left, const SahRoute& R) {
     A.first[node] = f;
     A.last[node] = f + c - 1u;
 #pragma unroll
@@ -359,16 +351,17 @@ __device__ __forceinline__ void sah_emit_children(const SahArgs& A, uint32_t nod
             const uint32_t id = atomicAdd(&A.counters[0], 1u);
             ref = (int)id;
             A.parent_int[id] = (int)node;
-            q_out[atomicAdd(q_len, 1u)] = make_uint4(id, cf, cc, 0u);
+            if (cc >= R.big_min) R.q_big[atomicAdd(R.len_big, 1u)] = make_uint4(id, cf, cc, 0u);
+            else R.q_small[atomicAdd(R.len_small, 1u)] = make_uint4(id, cf, cc, 0u);
         }
         if (side) A.right[node] = ref; else A.left[node] = ref;
     }
 }
 
-// One node of the level: called by all TB threads of a block.  q_out / q_len: where nodes of the next level are queued.
+// One node of the level: called by all TB threads of a block.  R: where nodes of the next level are queued.
 // halve: no SAH, the range is cut in the middle (depth limit of the single-launch build).
 template <int TB>
-__device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 item, uint4* q_out, uint32_t* q_len, const bool halve) {
+__device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 item, const SahRoute& R, const bool halve) {
     const uint32_t node = item.x, f = item.y, c = item.z;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     __shared__ SahBins B;
@@ -472,22 +465,10 @@ __device__ __forceinline__ void sah_split_node(const SahArgs& A, const uint4 ite
             for (uint32_t i = tid; i < c; i += TB) A.order[f + i] = A.tmp[f + i];
         }
     }
-    if (tid == 0) sah_emit_children(A, node, f, c, n_left, q_out, q_len);
+    if (tid == 0) sah_emit_children(A, node, f, c, n_left, R);
 }
 
-// skip_from: nodes of at least this many primitives are left to the k_sahbig_* launches of the same level
-template <int TB>
-__global__ void __launch_bounds__(TB) k_sah_level(SahArgs A, uint32_t q_count, uint32_t skip_from) {
-    if (blockIdx.x >= q_count) return;
-    const uint4 item = A.q_in[blockIdx.x];
-    if (item.z >= skip_from) return;
-    sah_split_node<TB>(A, item, A.q_out, &A.counters[1], false);
-}
-
-// ---- nodes too large for one block (first levels of a big tree): the same split spread over the grid.  Per node, in stream order:
-//      k_sahbig_init -> k_sahbig_bounds -> k_sahbig_bin (shared bins per block, flushed with global atomics) -> k_sahbig_split (one
-//      block: plane search, children) -> k_sahbig_partition (blocks claim output ranges with two atomic cursors) -> k_sahbig_copy.
-#define SAH_BIG_MIN 32768u    // nodes of at least this many primitives take this path (when the host knows the level's nodes)
+// Record of a node that is split by the whole grid (global memory): what SahBins is to a block, plus the partition cursors
 struct SahBig {
     int cb[6];
     int lo[3][SAH_BINS][3], hi[3][SAH_BINS][3];
@@ -497,165 +478,229 @@ struct SahBig {
     uint32_t n_left, _pad;
 };
 
-static_assert(sizeof(SahBig) <= 1024 * sizeof(uint32_t), "SahBig fits the scratch words reserved for it");
+// ---- The whole tree in one cooperative launch (k_sah_tree): nothing for the host to follow, so static builds and per-frame rebuilds
+//      alike are stream-ordered.  Level by level; the blocks share the nodes of a level (two alternating queues with alternating length
+//      words, grid.sync() between levels); below level 48 ranges are halved, which bounds the depth at 48 + log2(n).  Nodes of at
+//      least SAH_TREE_BIG_MIN primitives are queued apart and split by the whole grid, all large nodes of a level together, phase
+//      by phase with grid.sync() between the phases — records cleared / centroid bounds / bins (per chunk in shared memory, flushed with
+//      global atomics) / plane search + children / partition (blocks claim output ranges from the node's two cursors) / copy back —
+//      each over the flattened list of (node, 4 096-primitive chunk) pairs, so the grid is busy however the primitives are spread.
+#define SAH_TB 128
+#define SAH_BLOCKS_PER_SM 4
+#define SAH_CHUNK 4096u
+#ifndef SAH_TREE_BIG_MIN
+#define SAH_TREE_BIG_MIN 8192u
+#endif
+#define SAH_BIG_WORDS 704u   // one SahBig record, padded
+static_assert(sizeof(SahBig) <= SAH_BIG_WORDS * sizeof(uint32_t), "SahBig record size");
 
-__global__ void k_sahbig_init(SahBig* G) {
-    const uint32_t tid = threadIdx.x;
-    if (tid < 3) G->cb[tid] = f2ord(CUDART_INF_F);
-    else if (tid < 6) G->cb[tid] = f2ord(-CUDART_INF_F);
-    for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += blockDim.x) { (&G->lo[0][0][0])[i] = f2ord(CUDART_INF_F); (&G->hi[0][0][0])[i] = f2ord(-CUDART_INF_F); }
-    for (uint32_t i = tid; i < 3 * SAH_BINS; i += blockDim.x) (&G->cnt[0][0])[i] = 0;
-    if (tid == 0) { G->cur[0] = G->cur[1] = 0; G->axis = -1; G->split = 0; G->n_left = 0; }
+struct SahTreeArgs {
+    SahArgs A;
+    uint4* qs[2];        // queues of small nodes: level L reads qs[(L & 1) ^ 1], fills qs[L & 1]
+    uint4* qb[2];        // queues of large nodes, likewise
+    uint32_t* words;     // [p] / [2 + p]: length of qs[p] / qb[p]
+    uint32_t* big;       // SAH_BIG_WORDS words per large node of a level
+};
+
+__global__ void k_sah_tree_init(SahTreeArgs P, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) P.A.order[i] = i;
+    if (i == 0) {
+        P.A.counters[0] = 1; P.A.counters[1] = 0; P.A.counters[2] = 0; P.A.counters[3] = 0;
+        P.A.parent_int[0] = -1;
+        P.words[0] = P.words[1] = P.words[2] = P.words[3] = 0;
+        if (n >= SAH_TREE_BIG_MIN) { P.qb[0][0] = make_uint4(0u, 0u, n, 0u); P.words[2] = 1; }
+        else { P.qs[0][0] = make_uint4(0u, 0u, n, 0u); P.words[0] = 1; }
+    }
 }
 
-__global__ void __launch_bounds__(256) k_sahbig_bounds(SahArgs A, SahBig* G, uint32_t f, uint32_t c) {
-    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c; i += gridDim.x * blockDim.x) {
-        const Aabb b = A.boxes[A.order[f + i]];
-        if (box_valid(b)) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) { float ck = centroid_k(b, k); lo[k] = fminf(lo[k], ck); hi[k] = fmaxf(hi[k], ck); }
+// chunk `t` of the level's large nodes -> node j, primitives [begin, end) of its range; false: t is past the last chunk
+__device__ __forceinline__ bool sah_locate_chunk(const uint4* qb, uint32_t n_big, uint32_t t, uint32_t& j, uint32_t& begin, uint32_t& end) {
+    uint32_t first = 0;
+    for (j = 0; j < n_big; j++) {
+        const uint32_t c = qb[j].z, chunks = (c + SAH_CHUNK - 1u) / SAH_CHUNK;
+        if (t < first + chunks) {
+            begin = (t - first) * SAH_CHUNK;
+            end = begin + SAH_CHUNK < c ? begin + SAH_CHUNK : c;
+            return true;
         }
+        first += chunks;
     }
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o));
-            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o));
-        }
-        if ((threadIdx.x & 31u) == 0) { atomicMin(&G->cb[k], f2ord(lo[k])); atomicMax(&G->cb[3 + k], f2ord(hi[k])); }
-    }
+    return false;
 }
 
-__global__ void __launch_bounds__(256) k_sahbig_bin(SahArgs A, SahBig* G, uint32_t f, uint32_t c) {
+__global__ void __launch_bounds__(SAH_TB) k_sah_tree(SahTreeArgs P) {
+    cg::grid_group grid = cg::this_grid();
+    const SahArgs& A = P.A;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     __shared__ SahBins B;
-    const uint32_t tid = threadIdx.x;
-    sah_bins_clear(B, tid, blockDim.x);
-    __syncthreads();
-    float cmn[3], scale[3];
-    sah_bin_scale(G->cb, cmn, scale);
-    for (uint32_t i = blockIdx.x * blockDim.x + tid; i < c; i += gridDim.x * blockDim.x) {
-        const Aabb b = A.boxes[A.order[f + i]];
-        const bool ok = box_valid(b);
+    __shared__ uint32_t s_wl[SAH_TB / 32], s_base[2];
+    uint32_t n_small = *((volatile uint32_t*)&P.words[0]), n_big = *((volatile uint32_t*)&P.words[2]);
+    grid.sync();  // (everybody has read the lengths of level 1 before block 0 clears them below)
+    for (uint32_t level = 1; n_small + n_big > 0; level++) {
+        const uint32_t w = level & 1u;
+        const uint4* qs_in = P.qs[w ^ 1u];
+        const uint4* qb_in = P.qb[w ^ 1u];
+        const SahRoute R = {P.qs[w], &P.words[w], P.qb[w], &P.words[2u + w], SAH_TREE_BIG_MIN};
+        const bool halve = level > 48u;
+        if (blockIdx.x == 0 && tid == 0) { P.words[w ^ 1u] = 0; P.words[2u + (w ^ 1u)] = 0; }  // the words level + 1 will fill (their old values, this level's lengths, have been read)
+        if (n_big > 0) {
+            // ---- 0: records
+            for (uint32_t j = blockIdx.x; j < n_big; j += gridDim.x) {
+                SahBig* G = reinterpret_cast<SahBig*>(P.big + (size_t)j * SAH_BIG_WORDS);
+                if (tid < 3) G->cb[tid] = f2ord(CUDART_INF_F);
+                else if (tid < 6) G->cb[tid] = f2ord(-CUDART_INF_F);
+                for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += SAH_TB) { (&G->lo[0][0][0])[i] = f2ord(CUDART_INF_F); (&G->hi[0][0][0])[i] = f2ord(-CUDART_INF_F); }
+                for (uint32_t i = tid; i < 3 * SAH_BINS; i += SAH_TB) (&G->cnt[0][0])[i] = 0;
+                if (tid == 0) { G->cur[0] = G->cur[1] = 0; G->axis = -1; G->split = 0; G->n_left = 0; }
+            }
+            grid.sync();
+            uint32_t j, begin, end;
+            if (!halve) {
+                // ---- 1: centroid bounds
+                for (uint32_t t = blockIdx.x; sah_locate_chunk(qb_in, n_big, t, j, begin, end); t += gridDim.x) {
+                    SahBig* G = reinterpret_cast<SahBig*>(P.big + (size_t)j * SAH_BIG_WORDS);
+                    const uint32_t f = qb_in[j].y;
+                    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+                    for (uint32_t i = begin + tid; i < end; i += SAH_TB) {
+                        const Aabb b = A.boxes[A.order[f + i]];
+                        if (box_valid(b)) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int bin = ok ? sah_bin(centroid_k(b, k), cmn[k], scale[k]) : 0;
-            atomicAdd(&B.cnt[k][bin], 1u);
-            if (ok) {
+                            for (int k = 0; k < 3; k++) { float ck = centroid_k(b, k); lo[k] = fminf(lo[k], ck); hi[k] = fmaxf(hi[k], ck); }
+                        }
+                    }
 #pragma unroll
-                for (int j = 0; j < 3; j++) { atomicMin(&B.lo[k][bin][j], f2ord(b.lo[j])); atomicMax(&B.hi[k][bin][j], f2ord(b.hi[j])); }
+                    for (int k = 0; k < 3; k++) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o));
+                            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o));
+                        }
+                        if (lane == 0) { atomicMin(&G->cb[k], f2ord(lo[k])); atomicMax(&G->cb[3 + k], f2ord(hi[k])); }
+                    }
+                }
+                grid.sync();
+                // ---- 2: bins (per chunk in shared memory, then into the node's record)
+                for (uint32_t t = blockIdx.x; sah_locate_chunk(qb_in, n_big, t, j, begin, end); t += gridDim.x) {
+                    SahBig* G = reinterpret_cast<SahBig*>(P.big + (size_t)j * SAH_BIG_WORDS);
+                    const uint32_t f = qb_in[j].y;
+                    sah_bins_clear(B, tid, SAH_TB);
+                    __syncthreads();
+                    float cmn[3], scale[3];
+                    sah_bin_scale(G->cb, cmn, scale);
+                    for (uint32_t i = begin + tid; i < end; i += SAH_TB) {
+                        const Aabb b = A.boxes[A.order[f + i]];
+                        const bool ok = box_valid(b);
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const int bin = ok ? sah_bin(centroid_k(b, k), cmn[k], scale[k]) : 0;
+                            atomicAdd(&B.cnt[k][bin], 1u);
+                            if (ok) {
+#pragma unroll
+                                for (int jj = 0; jj < 3; jj++) { atomicMin(&B.lo[k][bin][jj], f2ord(b.lo[jj])); atomicMax(&B.hi[k][bin][jj], f2ord(b.hi[jj])); }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    for (uint32_t i = tid; i < 3 * SAH_BINS; i += SAH_TB) {
+                        const uint32_t cnt = (&B.cnt[0][0])[i];
+                        if (cnt == 0) continue;
+                        atomicAdd(&(&G->cnt[0][0])[i], cnt);
+#pragma unroll
+                        for (int jj = 0; jj < 3; jj++) {
+                            atomicMin(&(&G->lo[0][0][0])[3 * i + jj], (&B.lo[0][0][0])[3 * i + jj]);
+                            atomicMax(&(&G->hi[0][0][0])[3 * i + jj], (&B.hi[0][0][0])[3 * i + jj]);
+                        }
+                    }
+                    __syncthreads();  // B is cleared again for the block's next chunk
+                }
+                grid.sync();
+            }
+            // ---- 3: plane search and children, one block per node
+            for (uint32_t jn = blockIdx.x; jn < n_big; jn += gridDim.x) {
+                SahBig* G = reinterpret_cast<SahBig*>(P.big + (size_t)jn * SAH_BIG_WORDS);
+                const uint4 item = qb_in[jn];
+                if (!halve) {
+                    for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += SAH_TB) { (&B.lo[0][0][0])[i] = (&G->lo[0][0][0])[i]; (&B.hi[0][0][0])[i] = (&G->hi[0][0][0])[i]; }
+                    for (uint32_t i = tid; i < 3 * SAH_BINS; i += SAH_TB) (&B.cnt[0][0])[i] = (&G->cnt[0][0])[i];
+                    __syncthreads();
+                    sah_pick_plane(B);
+                }
+                if (tid == 0) {
+                    uint32_t n_left = item.z / 2;
+                    int axis = -1, split = 0;
+                    if (!halve && B.axis >= 0) {
+                        axis = B.axis; split = B.split;
+                        n_left = 0;
+                        for (int bI = 0; bI <= split; bI++) n_left += B.cnt[axis][bI];
+                    }
+                    G->axis = axis; G->split = split; G->n_left = n_left;
+                    sah_emit_children(A, item.x, item.y, item.z, n_left, R);
+                }
+                __syncthreads();
+            }
+            if (!halve) {
+                grid.sync();
+                // ---- 4: partition: a block claims the output ranges of its 128 primitives from the node's two cursors
+                for (uint32_t t = blockIdx.x; sah_locate_chunk(qb_in, n_big, t, j, begin, end); t += gridDim.x) {
+                    SahBig* G = reinterpret_cast<SahBig*>(P.big + (size_t)j * SAH_BIG_WORDS);
+                    const int axis = G->axis, split = G->split;
+                    if (axis < 0) continue;  // halved as it stands (block-uniform)
+                    const uint32_t f = qb_in[j].y, c = qb_in[j].z, n_left = G->n_left;
+                    float cmn[3], scale[3];
+                    sah_bin_scale(G->cb, cmn, scale);
+                    for (uint32_t base = begin; base < end; base += SAH_TB) {
+                        const uint32_t i = base + tid;
+                        bool in = i < end, goes_left = false;
+                        uint32_t prim = 0;
+                        if (in) {
+                            prim = A.order[f + i];
+                            const Aabb b = A.boxes[prim];
+                            const int bin = box_valid(b) ? sah_bin(centroid_k(b, axis), cmn[axis], scale[axis]) : 0;
+                            goes_left = bin <= split;
+                        }
+                        const uint32_t ml = __ballot_sync(0xFFFFFFFFu, in && goes_left), ma = __ballot_sync(0xFFFFFFFFu, in);
+                        __syncthreads();  // (s_wl / s_base of the previous round have been read)
+                        if (lane == 0) s_wl[warp] = (uint32_t)__popc(ml) | ((uint32_t)__popc(ma) << 16);
+                        __syncthreads();
+                        uint32_t before_l = 0, before_a = 0, all_l = 0, all_a = 0;
+#pragma unroll
+                        for (uint32_t ww = 0; ww < SAH_TB / 32; ww++) {
+                            const uint32_t v = s_wl[ww];
+                            if (ww < warp) { before_l += v & 0xFFFFu; before_a += v >> 16; }
+                            all_l += v & 0xFFFFu; all_a += v >> 16;
+                        }
+                        if (tid == 0) { s_base[0] = atomicAdd(&G->cur[0], all_l); s_base[1] = atomicAdd(&G->cur[1], all_a - all_l); }
+                        __syncthreads();
+                        if (in) {
+                            const uint32_t below = (1u << lane) - 1u;
+                            const uint32_t rank_l = before_l + (uint32_t)__popc(ml & below);
+                            const uint32_t rank_r = (before_a - before_l) + (uint32_t)__popc((ma & ~ml) & below);
+                            const uint32_t dst = goes_left ? s_base[0] + rank_l : n_left + s_base[1] + rank_r;
+                            if (dst < c) A.tmp[f + dst] = prim;
+                        }
+                    }
+                }
+                grid.sync();
+                // ---- 5: copy back (a node whose two passes disagree — cannot happen with the explicitly rounded bin arithmetic — keeps its order)
+                for (uint32_t t = blockIdx.x; sah_locate_chunk(qb_in, n_big, t, j, begin, end); t += gridDim.x) {
+                    const SahBig* G = reinterpret_cast<const SahBig*>(P.big + (size_t)j * SAH_BIG_WORDS);
+                    const uint32_t f = qb_in[j].y, c = qb_in[j].z;
+                    if (G->axis < 0) continue;
+                    if (G->cur[0] != G->n_left || G->cur[0] + G->cur[1] != c) { if (tid == 0) atomicExch(&A.counters[2], 1u); continue; }
+                    for (uint32_t i = begin + tid; i < end; i += SAH_TB) A.order[f + i] = A.tmp[f + i];
+                }
             }
         }
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < 3 * SAH_BINS; i += blockDim.x) {
-        const uint32_t n = (&B.cnt[0][0])[i];
-        if (n == 0) continue;
-        atomicAdd(&(&G->cnt[0][0])[i], n);
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            atomicMin(&(&G->lo[0][0][0])[3 * i + j], (&B.lo[0][0][0])[3 * i + j]);
-            atomicMax(&(&G->hi[0][0][0])[3 * i + j], (&B.hi[0][0][0])[3 * i + j]);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128) k_sahbig_split(SahArgs A, SahBig* G, uint32_t node, uint32_t f, uint32_t c) {
-    __shared__ SahBins B;
-    const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < 3 * SAH_BINS * 3; i += 128) { (&B.lo[0][0][0])[i] = (&G->lo[0][0][0])[i]; (&B.hi[0][0][0])[i] = (&G->hi[0][0][0])[i]; }
-    for (uint32_t i = tid; i < 3 * SAH_BINS; i += 128) (&B.cnt[0][0])[i] = (&G->cnt[0][0])[i];
-    __syncthreads();
-    sah_pick_plane(B);
-    if (tid == 0) {
-        uint32_t n_left = c / 2;
-        if (B.axis >= 0) {
-            n_left = 0;
-            for (int bI = 0; bI <= B.split; bI++) n_left += B.cnt[B.axis][bI];
-        }
-        G->axis = B.axis; G->split = B.split; G->n_left = n_left;
-        sah_emit_children(A, node, f, c, n_left, A.q_out, &A.counters[1]);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_sahbig_partition(SahArgs A, SahBig* G, uint32_t f, uint32_t c) {
-    const int axis = G->axis, split = G->split;
-    if (axis < 0) return;  // halved as it stands
-    const uint32_t n_left = G->n_left;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    __shared__ uint32_t s_wl[8], s_base[2];
-    float cmn[3], scale[3];
-    sah_bin_scale(G->cb, cmn, scale);
-    const uint32_t per_block = ((c + gridDim.x - 1) / gridDim.x + 255u) & ~255u;
-    const uint32_t begin = blockIdx.x * per_block, end = begin + per_block < c ? begin + per_block : c;
-    for (uint32_t base = begin; base < end; base += 256) {
-        const uint32_t i = base + tid;
-        bool in = i < end, goes_left = false;
-        uint32_t prim = 0;
-        if (in) {
-            prim = A.order[f + i];
-            const Aabb b = A.boxes[prim];
-            const int bin = box_valid(b) ? sah_bin(centroid_k(b, axis), cmn[axis], scale[axis]) : 0;
-            goes_left = bin <= split;
-        }
-        const uint32_t ml = __ballot_sync(0xFFFFFFFFu, in && goes_left), ma = __ballot_sync(0xFFFFFFFFu, in);
-        __syncthreads();  // (s_wl / s_base of the previous chunk have been read)
-        if (lane == 0) s_wl[warp] = (uint32_t)__popc(ml) | ((uint32_t)__popc(ma) << 16);
-        __syncthreads();
-        uint32_t before_l = 0, before_a = 0, all_l = 0, all_a = 0;
-#pragma unroll
-        for (uint32_t w = 0; w < 8; w++) {
-            const uint32_t v = s_wl[w];
-            if (w < warp) { before_l += v & 0xFFFFu; before_a += v >> 16; }
-            all_l += v & 0xFFFFu; all_a += v >> 16;
-        }
-        if (tid == 0) { s_base[0] = atomicAdd(&G->cur[0], all_l); s_base[1] = atomicAdd(&G->cur[1], all_a - all_l); }
-        __syncthreads();
-        if (in) {
-            const uint32_t below = (1u << lane) - 1u;
-            const uint32_t rank_l = before_l + (uint32_t)__popc(ml & below);
-            const uint32_t rank_r = (before_a - before_l) + (uint32_t)__popc((ma & ~ml) & below);
-            const uint32_t dst = goes_left ? s_base[0] + rank_l : n_left + s_base[1] + rank_r;
-            if (dst < c) A.tmp[f + dst] = prim;  // (a disagreement of the passes is caught by k_sahbig_copy; never write outside the range)
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_sahbig_copy(SahArgs A, SahBig* G, uint32_t f, uint32_t c) {
-    if (G->axis < 0) return;
-    if (G->cur[0] != G->n_left || G->cur[0] + G->cur[1] != c) {  // the passes disagree: cannot happen with the explicitly rounded bin arithmetic
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(&A.counters[2], 1u);
-        return;
-    }
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c; i += gridDim.x * blockDim.x) A.order[f + i] = A.tmp[f + i];
-}
-
-// The whole tree in ONE cooperative launch (builds of up to RT_SAH_COOP_MAX primitives: nothing for the host to follow, so per-frame
-// TLAS rebuilds can afford SAH trees too).  Blocks share the nodes of a level; the two queues and their two length words (counters[1]
-// and [3], by level parity) alternate; below level 48 ranges are halved, which bounds the depth at 48 + log2(n).
-#ifndef SAH_COOP_TB
-#define SAH_COOP_TB 128
-#endif
-#ifndef SAH_COOP_PER_SM
-#define SAH_COOP_PER_SM 4
-#endif
-__global__ void __launch_bounds__(SAH_COOP_TB) k_sah_coop(SahArgs A) {
-    cg::grid_group grid = cg::this_grid();
-    const uint4* q_in = A.q_in;
-    uint4* q_out = A.q_out;
-    uint32_t count = 1;
-    for (uint32_t level = 1; count > 0; level++) {
-        uint32_t* len_next = &A.counters[(level & 1u) ? 1 : 3];
-        if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[(level & 1u) ? 3 : 1] = 0;  // the word of level + 1 (everybody has read it: they passed the last grid.sync)
-        for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
-            sah_split_node<SAH_COOP_TB>(A, q_in[q], q_out, len_next, level > 48u);
+        // ---- small nodes: one block each
+        for (uint32_t q = blockIdx.x; q < n_small; q += gridDim.x) {
+            sah_split_node<SAH_TB>(A, qs_in[q], R, halve);
             __syncthreads();  // shared bins are reused by the block's next node
         }
         grid.sync();
-        count = *((volatile uint32_t*)len_next);
-        const uint4* t = q_in; q_in = q_out; q_out = const_cast<uint4*>(t);
-        grid.sync();  // nobody may queue nodes of the next level before everybody has read this one's length
+        n_small = *((volatile uint32_t*)&P.words[w]);
+        n_big = *((volatile uint32_t*)&P.words[2u + w]);
+        grid.sync();  // nobody may queue nodes of the next level (or clear this level's lengths) before everybody has read them
     }
 }
 
@@ -1155,7 +1200,7 @@ struct Scratch {
     int* task_node;
     uint32_t* task_parent;
     uint32_t* refit_counters;
-    uint32_t* sah_big;      // one SahBig record (bins of a node that is split by the whole grid)
+    uint32_t* sah_tree;     // k_sah_tree: 16 length words, two queues of large nodes, one SahBig record per large node of a level
     uint32_t* shard_hist;   // (1 << RT_SHARD_BITS) bins + 64 words: shard bin boundaries [0..32], select cursor [33]
     void* cub_temp;
 };
@@ -1182,7 +1227,7 @@ size_t layout(char* base, uint32_t n, size_t cub_bytes, Scratch& s) {
     s.task_node = carve<int>(p, maxw);
     s.task_parent = carve<uint32_t>(p, maxw);
     s.refit_counters = carve<uint32_t>(p, maxw);
-    s.sah_big = carve<uint32_t>(p, 1024);
+    s.sah_tree = carve<uint32_t>(p, 16 + (size_t)(n / SAH_TREE_BIG_MIN + 2) * (SAH_BIG_WORDS + 8));
     s.shard_hist = carve<uint32_t>(p, (1u << RT_SHARD_BITS) + 64);
     s.cub_temp = carve<char>(p, cub_bytes);
     return (size_t)(p - base) + 256;
@@ -1220,10 +1265,10 @@ cudaError_t BvhBuilder::reserve(uint32_t n) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_collapse_coop, 128, 0);
         coop_blocks_ = sms * (per_sm > 0 ? per_sm : 1);
         coop_ok_ = coop != 0 && per_sm > 0;
-        int sah_per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sah_per_sm, k_sah_coop, SAH_COOP_TB, 0);
-        if (sah_per_sm > SAH_COOP_PER_SM) sah_per_sm = SAH_COOP_PER_SM;  // grid.sync gets dearer with the grid; four blocks per SM serve the widest levels of a 64 k-primitive tree
-        sah_coop_blocks_ = coop != 0 && sah_per_sm > 0 ? sms * sah_per_sm : 0;
+        int tree_per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tree_per_sm, k_sah_tree, SAH_TB, 0);
+        if (tree_per_sm > SAH_BLOCKS_PER_SM) tree_per_sm = SAH_BLOCKS_PER_SM;  // grid.sync gets dearer with the grid; 128 x 4 / 256 x 4 / 512 x 2 measured within 15 % (profiles/r04gh_sah_build_time.txt)
+        sah_tree_blocks_ = coop != 0 && tree_per_sm > 0 ? sms * tree_per_sm : 0;
     }
     return cudaSuccess;
 }
@@ -1246,85 +1291,26 @@ cudaError_t BvhBuilder::build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf
     }
     uint32_t blocks = (n + TB - 1) / TB;
     bool radix_tree = true;
-    const bool sah_single_launch = sah_splits != SAH_NEVER && n >= 2 && n <= RT_SAH_COOP_MAX && sah_coop_blocks_ > 0;
-    if (sah_single_launch || (sah_splits == SAH_ALWAYS && n >= 2)) {
-        // top-down binned SAH (step 4b)
-        SahArgs S;
-        S.boxes = d_boxes; S.order = s.vals_out; S.tmp = s.vals_in;
-        uint4* q[2] = {reinterpret_cast<uint4*>(s.keys_in), reinterpret_cast<uint4*>(s.keys_out)};  // <= n / 2 entries of 16 bytes
-        S.counters = s.state + 4;  // words 4..7 of the state block (k_init_state zeroes all eight)
-        S.left = s.left; S.right = s.right; S.parent_int = s.parent_int; S.parent_leaf = s.parent_leaf; S.first = s.first; S.last = s.last;
-        S.q_in = q[0]; S.q_out = q[1];
-        k_sah_init<<<blocks, TB, 0, stream>>>(S, n);
+    if (sah_splits != SAH_NEVER && n >= 2 && sah_tree_blocks_ > 0) {
+        // top-down binned SAH (step 4b), every level inside one cooperative launch whatever the size: nothing for the host to follow
+        SahTreeArgs P;
+        P.A.boxes = d_boxes; P.A.order = s.vals_out; P.A.tmp = s.vals_in;
+        P.A.counters = s.state + 4;
+        P.A.left = s.left; P.A.right = s.right; P.A.parent_int = s.parent_int; P.A.parent_leaf = s.parent_leaf; P.A.first = s.first; P.A.last = s.last;
+        P.qs[0] = reinterpret_cast<uint4*>(s.keys_in); P.qs[1] = reinterpret_cast<uint4*>(s.keys_out);  // <= n / 2 entries of 16 bytes
+        const size_t big_cap = (size_t)cap_ / SAH_TREE_BIG_MIN + 2;
+        P.words = s.sah_tree;
+        P.qb[0] = reinterpret_cast<uint4*>(s.sah_tree + 16);
+        P.qb[1] = P.qb[0] + big_cap;
+        P.big = s.sah_tree + 16 + 8 * big_cap;
+        k_sah_tree_init<<<blocks, TB, 0, stream>>>(P, n);
         note_launch();
-        radix_tree = false;
-        bool launched = false;
-        if (sah_single_launch) {
-            // small trees: every level inside one cooperative launch, nothing for the host to wait for
-            void* args[] = {&S};
-            uint32_t want = (n + 3u) / 4u;
-            uint32_t grid = want < (uint32_t)sah_coop_blocks_ ? want : (uint32_t)sah_coop_blocks_;
-            cudaError_t ce = cudaLaunchCooperativeKernel((void*)k_sah_coop, dim3(grid), dim3(SAH_COOP_TB), args, 0, stream);
-            if (ce == cudaSuccess) { launched = true; note_launch(); }
-            else { (void)cudaGetLastError(); sah_coop_blocks_ = 0; radix_tree = sah_splits != SAH_ALWAYS; }
-        }
-        if (!launched && !radix_tree) {
-        // large trees: the host follows the level sizes.  A tree deeper than 64 levels (pathological input) is dropped for the
-        // radix tree below: the traversal stack is sized for trees of ordinary depth.
-        const bool trace = getenv("B200RT_SAH_TRACE") != nullptr;  // per-level wall times on stderr (tools/gpu_build_time.py)
-        uint32_t count = 1, levels = 0;
-        bool ok = true;
-        while (count > 0) {
-            const auto t_level = std::chrono::steady_clock::now();
-            const uint32_t level_nodes = count;
-            if (++levels > 64) { ok = false; break; }
-            e = cudaMemsetAsync(&S.counters[1], 0, sizeof(uint32_t), stream);
-            if (e != cudaSuccess) return e;
-            // the first levels hold few, large nodes.  While the level is short the host fetches its nodes and gives the largest
-            // ones the whole grid (k_sahbig_*); the others get one SM's worth of threads each, later levels 128 threads per node.
-            uint32_t skip_from = 0xFFFFFFFFu;
-            if (count <= 64 && n >= SAH_BIG_MIN) {
-                uint4 items[64];
-                if (levels == 1) items[0] = make_uint4(0u, 0u, n, 0u);
-                else {
-                    e = cudaMemcpyAsync(items, S.q_in, sizeof(uint4) * count, cudaMemcpyDeviceToHost, stream);
-                    if (e != cudaSuccess) return e;
-                    e = cudaStreamSynchronize(stream);
-                    if (e != cudaSuccess) return e;
-                }
-                skip_from = SAH_BIG_MIN;
-                SahBig* G = reinterpret_cast<SahBig*>(s.sah_big);
-                for (uint32_t qi = 0; qi < count; qi++) {
-                    const uint32_t bn = items[qi].x, bf = items[qi].y, bc = items[qi].z;
-                    if (bc < SAH_BIG_MIN) continue;
-                    uint32_t grid = (bc + 2047u) / 2048u;
-                    if (grid > 1184u) grid = 1184u;
-                    k_sahbig_init<<<1, 256, 0, stream>>>(G);
-                    k_sahbig_bounds<<<grid, 256, 0, stream>>>(S, G, bf, bc);
-                    k_sahbig_bin<<<grid, 256, 0, stream>>>(S, G, bf, bc);
-                    k_sahbig_split<<<1, 128, 0, stream>>>(S, G, bn, bf, bc);
-                    k_sahbig_partition<<<grid, 256, 0, stream>>>(S, G, bf, bc);
-                    k_sahbig_copy<<<grid, 256, 0, stream>>>(S, G, bf, bc);
-                    note_launch(6);
-                }
-            }
-            if (levels <= 8 && n > 16384u) k_sah_level<1024><<<count, 1024, 0, stream>>>(S, count, skip_from);
-            else k_sah_level<128><<<count, 128, 0, stream>>>(S, count, skip_from);
-            note_launch();
-            e = cudaMemcpyAsync(&count, &S.counters[1], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
-            if (e != cudaSuccess) return e;
-            e = cudaStreamSynchronize(stream);
-            if (e != cudaSuccess) return e;
-            const uint4* t = S.q_in; S.q_in = S.q_out; S.q_out = const_cast<uint4*>(t);
-            if (trace)
-                fprintf(stderr, "sah level %u: %u nodes, %.3f ms\n", levels, level_nodes,
-                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_level).count());
-        }
-        uint32_t err = 0;
-        e = cudaMemcpy(&err, &S.counters[2], sizeof(uint32_t), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return e;
-        radix_tree = !ok || err != 0;
-        }
+        void* args[] = {&P};
+        uint32_t want = (n + 3u) / 4u;
+        uint32_t grid = want < (uint32_t)sah_tree_blocks_ ? want : (uint32_t)sah_tree_blocks_;
+        cudaError_t ce = cudaLaunchCooperativeKernel((void*)k_sah_tree, dim3(grid), dim3(SAH_TB), args, 0, stream);
+        if (ce == cudaSuccess) { radix_tree = false; note_launch(); }
+        else { (void)cudaGetLastError(); sah_tree_blocks_ = 0; }  // no cooperative launch: the radix tree below
     }
     if (radix_tree) {
     k_centroid_bounds<<<blocks, TB, 0, stream>>>(d_boxes, n, s.bounds);

@@ -11,11 +11,8 @@ namespace b200rt {
 // (n - 1 of them) and the cost-driven cut gives no tighter guarantee.
 inline uint32_t max_wide_nodes(uint32_t n) { return n + 8; }
 
-// BvhBuilder::build, sah_splits
+// BvhBuilder::build, sah_splits (the two SAH values are the same thing since the build is one stream-ordered launch)
 enum { SAH_NEVER = 0, SAH_IF_STREAM_ORDERED = 1, SAH_ALWAYS = 2 };
-#ifndef RT_SAH_COOP_MAX
-#define RT_SAH_COOP_MAX 65536u
-#endif
 
 class BvhBuilder {
 public:
@@ -35,9 +32,8 @@ public:
     // sah_collapse: children of each wide node from the SAH-optimal cut table (else greedy largest-area expansion).
     // fast_sort: Morton keys keep only as many bits as n needs (fewer radix passes; per-frame TLAS rebuilds).
     // Everything is enqueued on `stream`; no host synchronisation.
-    // sah_splits: the binary tree is grown top-down with binned-SAH splits instead of the Morton radix tree.  Up to
-    // RT_SAH_COOP_MAX primitives that is one cooperative launch (stream-ordered like everything else); larger SAH builds
-    // synchronise the stream once per tree level and are only done for SAH_ALWAYS (one-time builds).
+    // sah_splits: the binary tree is grown top-down with binned-SAH splits (one cooperative launch, stream-ordered like
+    // everything else) instead of the Morton radix tree, which remains for devices without cooperative launches.
     cudaError_t build(const Aabb* d_boxes, uint32_t n, uint32_t max_leaf, Node8* nodes_pool, uint32_t node_offset,
                       uint32_t prim_offset, uint32_t* d_leaf_order, uint32_t* d_node_count, bool fast_sort, bool sah_collapse, cudaStream_t stream,
                       int sah_splits = SAH_NEVER);
@@ -61,7 +57,7 @@ private:
     size_t cub_bytes_ = 0;
     int coop_blocks_ = 0;
     bool coop_ok_ = true;
-    int sah_coop_blocks_ = 0;
+    int sah_tree_blocks_ = 0;
 };
 
 // ---- assembling a TLAS from treelets built on different GPUs (bvh_build.cu)

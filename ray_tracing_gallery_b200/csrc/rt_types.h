@@ -65,9 +65,9 @@ static_assert(sizeof(TriRec) == 48, "TriRec is 48 bytes");
 #define RT_BLAS_LEAF_TRIS 2u
 #endif
 
-// Binary tree under the wide nodes (bvh_build.cu): top-down binned-SAH splits (step 4b) for one-time builds — every BLAS, the TLAS of
-// rt_build_tlas / rt_group_build_tlas — and the Morton radix tree for per-frame rebuilds (rt_update_tlas REBUILD).  Measured
-// (profiles/r04cd_sah_builder_ab.txt): C5 55.8 -> 42.8 ms, C4 7.61 -> 6.31 ms with both, of which the TLAS is the larger part.
+// Binary tree under the wide nodes (bvh_build.cu): top-down binned-SAH splits (step 4b, one cooperative launch) for every BLAS and every
+// TLAS build or rebuild; 0 = the Morton radix tree (A/B runs).  Measured (profiles/r04cd_sah_builder_ab.txt): C5 55.8 -> 42.8 ms,
+// C4 7.61 -> 6.31 ms with both, of which the TLAS is the larger part.
 #ifndef RT_BLAS_SAH
 #define RT_BLAS_SAH 1
 #endif

@@ -258,38 +258,34 @@ def test_tiles_and_strips_reassemble_the_full_frame():
 
 
 def test_sah_trees_are_built_and_pay():
-    """The builder's three ways to a binary tree, held against each other on one scene (C5 with 80 000 instances, above the single-launch
-    limit): rt_build_tlas = host-followed SAH levels with grid-wide splits of the large nodes, rt_update_tlas REBUILD = Morton radix tree;
-    and with 40 000 instances REBUILD = the single-launch SAH build.  Frames must be identical whatever the tree (closest hit + tie rule),
-    and the SAH trees must need clearly fewer node visits per ray than the radix tree — a silent fall-back to the radix tree (depth limit,
-    disagreement flag) would pass every parity test and only show up here."""
+    """Static builds (rt_build_tlas) and per-frame rebuilds (rt_update_tlas REBUILD) both grow binned-SAH trees in one cooperative
+    launch; above 8 192 primitives the large nodes of a level are split by the whole grid.  On one scene (C5's slab with 80 000 and with
+    4 000 instances, i.e. with and without large nodes): build, rebuild and refit must give identical frames (closest hit + tie rule:
+    frames do not depend on the tree), the rebuilt tree must cost what the built one costs, and the node visits per ray must be those of
+    a SAH tree — the Morton radix tree of the same 80 000 instances needs 32.4 per ray, the SAH tree 18.9: a silent fall-back to the
+    radix tree (no cooperative launch, depth limit) would pass every parity test and only show up here."""
     def nodes_per_ray(gpu, s):
         out = gpu.render(s.uniforms(), s.params(flags=abi.RT_RENDER_COUNTERS))
         st = gpu.stats()
         return sum(st.nodes_visited) / max(1, st.primary_rays + st.shadow_rays), out
 
-    gpu = make_renderer()
-    s = build_scene(gpu, "c5", 640, 360, num_instances=80000)
-    sah_big, frame_sah = nodes_per_ray(gpu, s)
-    gpu.update_instances(0, s.instances); gpu.update_tlas(abi.RT_UPDATE_REBUILD)
-    radix, frame_radix = nodes_per_ray(gpu, s)
-    gpu.update_instances(0, s.instances); gpu.update_tlas(abi.RT_UPDATE_REFIT)
-    radix_refit, frame_refit = nodes_per_ray(gpu, s)
-    for k in ("rgba8", "hit_ids", "ray_counts"):
-        assert np.array_equal(frame_sah[k], frame_radix[k]) and np.array_equal(frame_sah[k], frame_refit[k]), k
-    assert abs(radix_refit - radix) < 1e-9
-    gpu.close()
-    gpu = make_renderer()
-    s = build_scene(gpu, "c5", 640, 360, num_instances=40000)
-    built, frame_a = nodes_per_ray(gpu, s)
-    gpu.update_instances(0, s.instances); gpu.update_tlas(abi.RT_UPDATE_REBUILD)   # single cooperative launch
-    rebuilt, frame_b = nodes_per_ray(gpu, s)
-    for k in ("rgba8", "hit_ids", "ray_counts"):
-        assert np.array_equal(frame_a[k], frame_b[k]), k
-    gpu.close()
-    print(f"nodes per ray, 80 k instances: SAH build {sah_big:.2f}, radix rebuild {radix:.2f}; 40 k instances: SAH build {built:.2f}, single-launch SAH rebuild {rebuilt:.2f}")
-    assert sah_big < 0.9 * radix
-    assert abs(rebuilt - built) < 0.02 * built   # the same algorithm (node numbering may differ, the splits do not)
+    seen = {}
+    for n in (80000, 4000):
+        gpu = make_renderer()
+        s = build_scene(gpu, "c5", 640, 360, num_instances=n)
+        built, frame_a = nodes_per_ray(gpu, s)
+        gpu.update_instances(0, s.instances); gpu.update_tlas(abi.RT_UPDATE_REBUILD)
+        rebuilt, frame_b = nodes_per_ray(gpu, s)
+        gpu.update_instances(0, s.instances); gpu.update_tlas(abi.RT_UPDATE_REFIT)
+        refitted, frame_c = nodes_per_ray(gpu, s)
+        for k in ("rgba8", "hit_ids", "ray_counts"):
+            assert np.array_equal(frame_a[k], frame_b[k]) and np.array_equal(frame_a[k], frame_c[k]), k
+        assert abs(rebuilt - built) < 0.02 * built   # the same algorithm (node numbering may differ, the splits do not)
+        assert abs(refitted - rebuilt) < 1e-9
+        seen[n] = built
+        gpu.close()
+    print(f"nodes per ray: 80 k instances {seen[80000]:.2f} (radix tree: 32.4), 4 k instances {seen[4000]:.2f}")
+    assert seen[80000] < 24.0
 
 
 @pytest.mark.parametrize("mode", [abi.RT_UPDATE_REBUILD, abi.RT_UPDATE_REFIT, abi.RT_UPDATE_AUTO])
