@@ -55,8 +55,8 @@ def parse():
     ap.add_argument("--instances", type=int, default=0, help="override the instance count of c3/c4/c5")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
-    ap.add_argument("--update-mode", default="refit", choices=["rebuild", "refit", "auto"],
-                    help="dynamic scenes: refit = the reference's in-place UPDATE (src/util_structs.rs:309), rebuild = full radix-tree rebuild")
+    ap.add_argument("--update-mode", default="refit", choices=["rebuild", "rebuild_fast", "refit", "auto"],
+                    help="dynamic scenes: refit = the reference's in-place UPDATE (src/util_structs.rs:309), rebuild = full SAH rebuild, rebuild_fast = full radix-tree rebuild")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end pass (profiling runs)")
     return ap.parse_args()
@@ -298,7 +298,7 @@ class Bench:
         s = build_scene(gpu, name, args.width or None, args.height or None, num_instances=args.instances or None)
         W, H = s.width, s.height
         pipeline = abi.RT_PIPELINE_MEGAKERNEL if args.pipeline == "mega" else abi.RT_PIPELINE_WAVEFRONT
-        update_mode = {"refit": abi.RT_UPDATE_REFIT, "rebuild": abi.RT_UPDATE_REBUILD, "auto": abi.RT_UPDATE_AUTO}[args.update_mode]
+        update_mode = {"refit": abi.RT_UPDATE_REFIT, "rebuild": abi.RT_UPDATE_REBUILD, "rebuild_fast": abi.RT_UPDATE_REBUILD_FAST, "auto": abi.RT_UPDATE_AUTO}[args.update_mode]
         group = None
         if world > 1:
             idt = torch.zeros(native.GROUP_ID_BYTES, dtype=torch.uint8, device=dev)

@@ -41,6 +41,7 @@ pub const RT_FORMAT_RGBA32_SFLOAT: u32 = 2;
 pub const RT_UPDATE_AUTO: u32 = 0;
 pub const RT_UPDATE_REFIT: u32 = 1; // vk::BuildAccelerationStructureModeKHR::UPDATE, src/util_structs.rs:309
 pub const RT_UPDATE_REBUILD: u32 = 2;
+pub const RT_UPDATE_REBUILD_FAST: u32 = 3; // Morton radix tree instead of the SAH tree (vk PREFER_FAST_BUILD)
 
 pub const RT_PIPELINE_WAVEFRONT: u32 = 0;
 pub const RT_PIPELINE_MEGAKERNEL: u32 = 1;

@@ -156,7 +156,7 @@ class RtStats(C.Structure):
 
 RT_FORMAT_RGBA8_UNORM, RT_FORMAT_RGBA8_SRGB, RT_FORMAT_RGBA32_SFLOAT = 0, 1, 2
 RT_HIT_TEXTURED, RT_HIT_MIRROR, RT_HIT_PORTAL = 0, 1, 2
-RT_UPDATE_AUTO, RT_UPDATE_REFIT, RT_UPDATE_REBUILD = 0, 1, 2
+RT_UPDATE_AUTO, RT_UPDATE_REFIT, RT_UPDATE_REBUILD, RT_UPDATE_REBUILD_FAST = 0, 1, 2, 3
 RT_PIPELINE_WAVEFRONT, RT_PIPELINE_MEGAKERNEL = 0, 1
 RT_RENDER_COUNTERS = 1
 RT_RENDER_TIMING = 2

@@ -99,7 +99,7 @@ int build_tlas_now(RtContext* ctx, uint32_t mode, uint32_t src, uint32_t dst, bo
         CK(launch_prepare_instances(D.d_instances, n, ctx->d_blas_info.ptr, (uint32_t)ctx->models.size(), nullptr,
                                     ctx->d_inst_unsorted, ctx->d_inst_boxes, st));
         CK(ctx->builder.build(ctx->d_inst_boxes, n, 1, D.d_tlas_nodes, 0, 0, D.d_leaf_order, D.d_node_count, true, /*sah_collapse=*/RT_TLAS_SAH_COLLAPSE != 0, st,
-                               /*sah_splits=*/!RT_TLAS_SAH ? SAH_NEVER : static_build ? SAH_ALWAYS : SAH_IF_STREAM_ORDERED));
+                               /*sah_splits=*/(!RT_TLAS_SAH || mode == RT_UPDATE_REBUILD_FAST) ? SAH_NEVER : static_build ? SAH_ALWAYS : SAH_IF_STREAM_ORDERED));
         CK(launch_gather_instances(ctx->d_inst_unsorted, D.d_leaf_order, n, D.d_inst_rt, st));
         ctx->writes_since_build = 0;
     }
@@ -735,7 +735,7 @@ int rt_update_instances_device(RtContext* ctx, uint32_t first, uint32_t count, c
 
 int rt_update_tlas(RtContext* ctx, uint32_t mode) {
     if (!ctx) return RT_ERR_INVALID_ARGUMENT;
-    if (mode > RT_UPDATE_REBUILD) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_tlas: unknown mode");
+    if (mode > RT_UPDATE_REBUILD_FAST) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rt_update_tlas: unknown mode");
     if (!ctx->tlas_built) return fail(ctx, RT_ERR_NOT_BUILT, "rt_update_tlas before rt_build_tlas");
     CK_DEV(ctx);
     { int w = begin_staging(ctx, false); if (w) return w; }  // an update without instance writes still builds into the other set

@@ -119,7 +119,7 @@ def test_rust_binding_file_declares_every_export_and_matches_the_layouts():
         fields = re.findall(r"pub ([a-z_0-9]+):", body)
         assert fields == [f[0] for f in cls._fields_], name
     for const in ("RT_RENDER_COUNTERS", "RT_RENDER_TIMING", "RT_RENDER_SPLIT_TAIL", "RT_RENDER_NO_PDL", "RT_RENDER_OUTPUT_IMAGE_ROWS", "RT_RENDER_COOP_TAIL",
-                  "RT_UPDATE_AUTO", "RT_UPDATE_REFIT", "RT_UPDATE_REBUILD", "RT_FORMAT_RGBA8_UNORM", "RT_FORMAT_RGBA8_SRGB", "RT_FORMAT_RGBA32_SFLOAT"):
+                  "RT_UPDATE_AUTO", "RT_UPDATE_REFIT", "RT_UPDATE_REBUILD", "RT_UPDATE_REBUILD_FAST", "RT_FORMAT_RGBA8_UNORM", "RT_FORMAT_RGBA8_SRGB", "RT_FORMAT_RGBA32_SFLOAT"):
         m = re.search(r"pub const %s: u32 = (\d+);" % const, rs)
         assert m and int(m.group(1)) == getattr(abi, const), const
 
