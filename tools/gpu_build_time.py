@@ -1,5 +1,5 @@
 """Build times on the GPU box: every BLAS of the bundled assets (rt_create_model, wall clock) and the static TLAS build of C4 / C5
-(rt_build_tlas: `last_tlas_ms` of rt_get_stats = CUDA events around the build, host round trips of the SAH levels included), then
+(rt_build_tlas: `last_tlas_ms` of rt_get_stats = CUDA events around the build), then
 rebuild / refit through rt_update_tlas.   usage: [B200RT_LIB=...] python tools/gpu_build_time.py"""
 import os
 import sys
