@@ -92,6 +92,22 @@ def test_ctypes_mirrors_match_the_headers_field_by_field(tmp_path):
     assert C.sizeof(abi.RtFrameOutputs) == 40 and abi.RtFrameOutputs.cost_cycles.offset == 32
 
 
+def test_constants_match_the_headers(tmp_path):
+    """Every RT_* integer constant that abi.py defines and include/*.h mention (enum values, flag bits, limits) must have the
+    header's value: compiled and printed by a C program, like the layouts above."""
+    header = open(os.path.join(ROOT, "include", "b200rt.h")).read() + open(os.path.join(ROOT, "include", "rt_abi.h")).read()
+    names = sorted(n for n in dir(abi) if re.fullmatch(r"RT_[A-Z0-9_]+", n) and isinstance(getattr(abi, n), int) and re.search(r"\b%s\b" % n, header))
+    assert {"RT_UPDATE_AUTO", "RT_UPDATE_REFIT", "RT_UPDATE_REBUILD", "RT_UPDATE_REBUILD_FAST", "RT_RENDER_COUNTERS", "RT_FORMAT_RGBA8_SRGB"} <= set(names)
+    lines = ['#include <stdio.h>', '#include "b200rt.h"', "int main(void){"] + [f'printf("{n} %lld\\n", (long long)({n}));' for n in names] + ["return 0;}"]
+    src = tmp_path / "consts.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "consts"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n in names:
+        assert int(got[n]) == getattr(abi, n), n
+
+
 def declared_functions():
     text = open(os.path.join(ROOT, "include", "b200rt.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
